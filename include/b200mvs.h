@@ -1,0 +1,132 @@
+/*
+ * b200mvs.h — C-ABI of the B200-native dense depth estimation engine.
+ *
+ * Drop-in boundary for the accelerator seam of cdcseacave/openMVS:
+ *   class PatchMatchCUDA { PatchMatchCUDA(int device); void Init(bool bGeomConsistency);
+ *                          void Release(); void EstimateDepthMap(DepthData&); }
+ *   (libs/MVS/PatchMatchCUDA.inl:78-131), owned by DepthMapsData::pmCUDA
+ *   (libs/MVS/SceneDensify.h:89-92) and called from DepthMapsData::EstimateDepthMap
+ *   (libs/MVS/SceneDensify.cpp:618-623), plus the SGM pair matcher
+ *   SemiGlobalMatcher::Match(...) (libs/MVS/SemiGlobalMatcher.cpp:863-1302).
+ *
+ * Plain C: opaque context, POD structs, caller-owned buffers, int status codes
+ * (0 = success; the reference exits the process on CUDA errors, libs/Common/UtilCUDA.h:81-91,
+ * the adapter maps non-zero to EVT_FAIL instead).  No C++/torch types cross this boundary.
+ * INTEGRATION.md shows the C++ adapter a maintainer adds on the reference side.
+ */
+#ifndef B200MVS_H_
+#define B200MVS_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MVS_MAX_VIEWS 32 /* neighbours per reference view (MAX_VIEWS, PatchMatchCUDA.inl:35) */
+
+typedef struct b200mvs_ctx b200mvs_ctx;
+
+enum {
+	B200MVS_OK = 0,
+	B200MVS_ERR_ARG = 1,     /* invalid argument */
+	B200MVS_ERR_CUDA = 2,    /* CUDA runtime error; see b200mvs_last_error() */
+	B200MVS_ERR_NOGPU = 3,   /* no usable device */
+	B200MVS_ERR_ALLOC = 4
+};
+
+/* One view of a DepthData (DepthData::ViewData, libs/MVS/DepthMap.h:158-185): gray float
+ * image in [0,1] (Image32F from toGray(...,true), SceneDensify.cpp:324), camera K (already
+ * scaled to this image size), R, C in double; optional known depth-map of the view and its
+ * camera for the geometric-consistency pass (depthMap/cameraDepthMap).  views[0] is the
+ * reference view. */
+typedef struct {
+	const float* image;   /* row-major */
+	int width, height;
+	int stride_bytes;     /* bytes between rows (cv::Mat::step); 0 = width*4 */
+	double K[9], R[9], C[3];
+	const float* depth;   /* nullable: enables the geometric term for this view */
+	int dwidth, dheight, dstride_bytes;
+	double Kd[9], Rd[9], Cd[3];
+} b200mvs_view;
+
+/* Snapshot of the OPTDENSE knobs the estimator consumes (libs/MVS/DepthMap.cpp:69-114),
+ * taken at call time because the reference mutates some of them during a run
+ * (fNCCThresholdKeep, SceneDensify.cpp:775-796). */
+typedef struct {
+	int nEstimationIters;                   /* 3  */
+	int nEstimationGeometricIters;          /* 2  */
+	int nRandomIters;                       /* 6  */
+	int nSubResolutionLevels;               /* 2  */
+	float fNCCThresholdKeep;                /* 0.9 */
+	float fDescriptorMinMagnitudeThreshold; /* 0.02 */
+	float fRandomDepthRatio;                /* 0.003 */
+	float fRandomAngle1Range;               /* 16 (deg) */
+	float fRandomAngle2Range;               /* 10 (deg) */
+	float fRandomSmoothDepth;               /* 0.02 */
+	float fRandomSmoothNormal;              /* 13 (deg) */
+	float fRandomSmoothBonus;               /* 0.93 */
+	float fEstimationGeometricWeight;       /* 0.1 */
+	/* engine schedule (not OPTDENSE): a reference iteration is nSweepsPerIter red-black
+	 * sweeps, each trying ceil(nRandomIters/nSweepsPerIter) refinement hypotheses */
+	int nSweepsPerIter;                     /* 2  */
+	int nPropagation;                       /* 4: all 4-neighbours; 2: causal pair only */
+	uint32_t seed;                          /* Philox key */
+} b200mvs_params;
+
+typedef struct {
+	double ms_total;      /* wall time of the call (host clock) */
+	double ms_device;     /* device time between first and last kernel (CUDA events) */
+	uint64_t bytes_h2d, bytes_d2h;
+	int kernel_launches;
+	int levels;
+} b200mvs_stats;
+
+/* ---- lifetime (PatchMatchCUDA ctor / Init / Release, PatchMatchCUDA.cpp:60-117) ---- */
+int  b200mvs_create(int device, b200mvs_ctx** ctx);
+int  b200mvs_destroy(b200mvs_ctx* ctx);
+void b200mvs_default_params(b200mvs_params* p);
+int  b200mvs_set_params(b200mvs_ctx* ctx, const b200mvs_params* p);
+const char* b200mvs_last_error(const b200mvs_ctx* ctx);
+int  b200mvs_device_count(void);
+
+/* ---- DepthMapsData::EstimateDepthMap(idxImage, nGeometricIter) replacement ------------
+ * (SceneDensify.cpp:616-805 / PatchMatchCUDA::EstimateDepthMap, PatchMatchCUDA.cpp:174-416)
+ * HOST buffers.  depth/normal are in/out (initial estimate; depth outside [dMin,dMax) =>
+ * random init), conf and viewsMap out.  nGeometricIter < 0: photometric pass with the
+ * scale loop; >= 0: one geometric-consistency iteration (views[i].depth required).
+ * Output follows EndDepthMapTmp: rejected pixels have depth=0, normal=0, conf=0; others
+ * conf = 1-cost.  viewsMap (nullable): 4 x uint8 per pixel, the neighbour indices that
+ * produced the score, 255 padding (PatchMatchCUDA.cpp:374-391). */
+int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
+	float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf, uint8_t* viewsMap, b200mvs_stats* stats);
+
+/* Same, but every pointer inside `views` and the map pointers are DEVICE pointers on the
+ * context's device (data resident in HBM); work is enqueued on `stream` (cudaStream_t) and
+ * the call returns after enqueueing unless stats != NULL (then it synchronises). */
+int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
+	float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf, uint8_t* viewsMap, void* stream, b200mvs_stats* stats);
+
+/* ---- building blocks (device pointers), exposed for parity tests ----------------------
+ * state: plane = float4 {nx,ny,nz,depth} per pixel, cost = raw score in [0,2]. */
+int b200mvs_pm_pack(b200mvs_ctx* ctx, int width, int height, const float* depth, const float* normal,
+	float* plane4, void* stream);
+int b200mvs_pm_unpack(b200mvs_ctx* ctx, int width, int height, const float* plane4,
+	float* depth, float* normal, void* stream);
+/* pass A — ScoreDepthMapTmp (SceneDensify.cpp:490-517) */
+int b200mvs_pm_score(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
+	const float* lowres, float* plane4, float* cost, void* stream);
+/* pass B — one red-black sweep `sweep` (EstimateDepthMapTmp/ProcessPixel); half = -1 both
+ * colours, 0/1 a single colour */
+int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
+	const float* lowres, int sweep, int half, int nRandomIters, float* plane4, float* cost, void* stream);
+/* pass C — EndDepthMapTmp (SceneDensify.cpp:528-548) */
+int b200mvs_pm_finalize(b200mvs_ctx* ctx, int width, int height, float keepThreshold,
+	const float* plane4, const float* cost, float* depth, float* normal, float* conf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MVS_H_ */

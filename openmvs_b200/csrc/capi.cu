@@ -1,0 +1,498 @@
+// capi.cu — host side of the C-ABI declared in include/b200mvs.h.
+//
+// Mirrors the control flow of DepthMapsData::EstimateDepthMap (libs/MVS/SceneDensify.cpp:616-805)
+// and of the accelerator seam PatchMatchCUDA::EstimateDepthMap (libs/MVS/PatchMatchCUDA.cpp:174-416):
+// scale loop -> pass A (score) -> pass B (sweeps) -> pass C (threshold), all on one stream,
+// no host synchronisation between kernels.
+#include "../../include/b200mvs.h"
+#include "pm_common.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <chrono>
+#include <algorithm>
+
+cudaError_t pm_launch_score(const PMParams& P, bool geom, cudaStream_t s);
+cudaError_t pm_launch_sweep(const PMParams& P, bool geom, cudaStream_t s);
+cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
+	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s);
+cudaError_t pm_launch_pack(int n, const float* depth, const float* normal, float4* plane, cudaStream_t s);
+cudaError_t pm_launch_unpack(int n, const float4* plane, float* depth, float* normal, cudaStream_t s);
+cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, cudaStream_t s);
+cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
+cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s);
+cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, cudaStream_t s);
+
+namespace {
+
+struct DevBuf {
+	void* p = nullptr; size_t cap = 0;
+	cudaError_t reserve(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		cudaError_t e = cudaMalloc(&p, n);
+		if (e == cudaSuccess) cap = n;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <typename T> T* as() const { return (T*)p; }
+};
+
+void mul33(const double* A, const double* B, double* C) {
+	double T[9];
+	for (int i=0;i<3;++i) for (int j=0;j<3;++j) T[i*3+j] = A[i*3]*B[j] + A[i*3+1]*B[3+j] + A[i*3+2]*B[6+j];
+	memcpy(C, T, sizeof(T));
+}
+void mul31(const double* A, const double* v, double* r) {
+	double t[3];
+	for (int i=0;i<3;++i) t[i] = A[i*3]*v[0] + A[i*3+1]*v[1] + A[i*3+2]*v[2];
+	memcpy(r, t, sizeof(t));
+}
+void transpose33(const double* A, double* T) {
+	double R[9];
+	for (int i=0;i<3;++i) for (int j=0;j<3;++j) R[j*3+i] = A[i*3+j];
+	memcpy(T, R, sizeof(R));
+}
+void inv33(const double* A, double* I) {
+	const double a=A[0],b=A[1],c=A[2],d=A[3],e=A[4],f=A[5],g=A[6],h=A[7],i=A[8];
+	const double id = 1.0/(a*(e*i-f*h) - b*(d*i-f*g) + c*(d*h-e*g));
+	double R[9] = {(e*i-f*h)*id, (c*h-b*i)*id, (b*f-c*e)*id, (f*g-d*i)*id, (a*i-c*g)*id, (c*d-a*f)*id, (d*h-e*g)*id, (b*g-a*h)*id, (a*e-b*d)*id};
+	memcpy(I, R, sizeof(R));
+}
+// Camera::ScaleK (libs/MVS/Camera.h:160-173)
+void scaleK(const double* K, int sw, int sh, int dw, int dh, double* Ko) {
+	const double sx = (double)dw/sw, sy = (double)dh/sh;
+	Ko[0] = K[0]*sx; Ko[1] = K[1]*sx; Ko[2] = (K[2]+0.5)*sx-0.5;
+	Ko[3] = 0; Ko[4] = K[4]*sy; Ko[5] = (K[5]+0.5)*sy-0.5;
+	Ko[6] = 0; Ko[7] = 0; Ko[8] = 1;
+}
+inline float d2r(float d) { return d*(3.14159265358979323846f/180.f); }
+
+// a view whose image (and optional depth-map) pointers are device pointers, pitch in floats
+struct DView {
+	const float* img; int w, h, pitch;
+	double K[9], R[9], C[3];
+	const float* dmap; int dw, dh, dpitch;
+	double Kd[9], Rd[9], Cd[3];
+};
+
+} // namespace
+
+struct b200mvs_ctx {
+	int device = 0;
+	b200mvs_params prm;
+	std::string err;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// grow-only device scratch
+	std::vector<DevBuf> imgs, dmaps;          // staged images / depth-maps (host API)
+	std::vector<DevBuf> pyr;                  // per-view pyramid levels (all levels packed)
+	DevBuf plane, cost, best, prior, lowPlane;
+	DevBuf dDepth, dNormal, dConf, dViews;    // level scratch / staging of the maps (host API)
+	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
+	int launches = 0;
+};
+
+namespace {
+
+int fail(b200mvs_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+	if (c) {
+		c->err = what;
+		if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+	}
+	return code;
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(ctx, B200MVS_ERR_CUDA, #call, _e); } while (0)
+
+// fill the kernel parameter block for one resolution level (DepthEstimator ctor constants,
+// libs/MVS/DepthMap.cpp:361-412, and ViewData::Init, libs/MVS/DepthMap.h:175-185)
+void build_params(const b200mvs_params& o, const DView* v, int nViews, float dMin, float dMax,
+	const float* lowres, float4* plane, float* cost, uint32_t* best, PMParams& P, bool& geom)
+{
+	memset(&P, 0, sizeof(P));
+	P.img0 = v[0].img; P.W = v[0].w; P.H = v[0].h; P.pitch0 = v[0].pitch;
+	P.nViews = nViews-1;
+	const double* K = v[0].K;
+	P.ifx = (float)(1.0/K[0]); P.sk = (float)(-K[1]/(K[0]*K[4])); P.ox = (float)((K[1]*K[5]-K[2]*K[4])/(K[0]*K[4]));
+	P.ify = (float)(1.0/K[4]); P.oy = (float)(-K[5]/K[4]);
+	P.dMin = dMin; P.dMax = dMax; P.dMinSqr = std::sqrt(dMin); P.dMaxSqr = std::sqrt(dMax);
+	P.keep = o.fNCCThresholdKeep;
+	P.thMagnitudeSq = o.fDescriptorMinMagnitudeThreshold > 0 ? o.fDescriptorMinMagnitudeThreshold*o.fDescriptorMinMagnitudeThreshold : -1.f;
+	P.thConfSmall = o.fNCCThresholdKeep*0.66f; P.thConfBig = o.fNCCThresholdKeep*0.9f;
+	P.thConfRand = o.fNCCThresholdKeep*1.1f; P.thRobust = o.fNCCThresholdKeep*4.f/3.f;
+	P.smoothBonusDepth = 1.f-o.fRandomSmoothBonus; P.smoothBonusNormal = (1.f-o.fRandomSmoothBonus)*0.96f;
+	P.smoothSigmaDepth = -1.f/(2.f*o.fRandomSmoothDepth*o.fRandomSmoothDepth);
+	P.smoothSigmaNormal = -1.f/(2.f*d2r(o.fRandomSmoothNormal)*d2r(o.fRandomSmoothNormal));
+	P.depthRatio = o.fRandomDepthRatio; P.angle1Range = d2r(o.fRandomAngle1Range); P.angle2Range = d2r(o.fRandomAngle2Range);
+	P.geomWeight = o.fEstimationGeometricWeight;
+	P.nRandomIters = o.nRandomIters; P.propagation = o.nPropagation;
+	P.seed = o.seed;
+	P.lowres = lowres; P.plane = plane; P.cost = cost; P.bestViews = best;
+	double RrT[9], Hr[9], KrRr[9];
+	transpose33(v[0].R, RrT);
+	inv33(v[0].K, Hr);
+	mul33(v[0].K, v[0].R, KrRr);
+	geom = false;
+	for (int i = 1; i < nViews; ++i) {
+		PMView& V = P.views[i-1];
+		double KR[9], Hl[9], A[9], dC[3], Hm[3];
+		mul33(v[i].K, v[i].R, KR);
+		mul33(KR, RrT, Hl);
+		mul33(Hl, Hr, A);
+		for (int k=0;k<3;++k) dC[k] = v[0].C[k]-v[i].C[k];
+		mul31(KR, dC, Hm);
+		for (int k=0;k<9;++k) V.A[k] = (float)A[k];
+		for (int k=0;k<3;++k) V.Hm[k] = (float)Hm[k];
+		V.img = v[i].img; V.w = v[i].w; V.h = v[i].h; V.pitch = v[i].pitch;
+		V.dmap = v[i].dmap; V.dw = v[i].dw; V.dh = v[i].dh; V.dpitch = v[i].dpitch;
+		if (v[i].dmap) {
+			geom = true;
+			double KdRd[9], T[9], t[3], RdT[9], iKd[9];
+			mul33(v[i].Kd, v[i].Rd, KdRd);
+			mul33(KdRd, RrT, T);
+			for (int k=0;k<9;++k) V.Tl[k] = (float)T[k];
+			for (int k=0;k<3;++k) dC[k] = v[0].C[k]-v[i].Cd[k];
+			mul31(KdRd, dC, t);
+			for (int k=0;k<3;++k) V.Tm[k] = (float)t[k];
+			transpose33(v[i].Rd, RdT);
+			inv33(v[i].Kd, iKd);
+			mul33(KrRr, RdT, T); mul33(T, iKd, T);
+			for (int k=0;k<9;++k) V.Tr[k] = (float)T[k];
+			for (int k=0;k<3;++k) dC[k] = v[i].Cd[k]-v[0].C[k];
+			mul31(KrRr, dC, t);
+			for (int k=0;k<3;++k) V.Tn[k] = (float)t[k];
+		}
+	}
+}
+
+int check_views(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews) {
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!views || nViews < 2 || nViews > B200MVS_MAX_VIEWS+1)
+		return fail(ctx, B200MVS_ERR_ARG, "need 2..33 views (reference first)");
+	for (int i = 0; i < nViews; ++i)
+		if (!views[i].image || views[i].width < 2*PM_HALF+2 || views[i].height < 2*PM_HALF+2)
+			return fail(ctx, B200MVS_ERR_ARG, "view without image or image too small");
+	return B200MVS_OK;
+}
+
+void to_dview(const b200mvs_view& s, const float* img, int pitch, const float* dmap, int dpitch, DView& d) {
+	d.img = img; d.w = s.width; d.h = s.height; d.pitch = pitch;
+	memcpy(d.K, s.K, sizeof(d.K)); memcpy(d.R, s.R, sizeof(d.R)); memcpy(d.C, s.C, sizeof(d.C));
+	d.dmap = dmap; d.dw = s.dwidth; d.dh = s.dheight; d.dpitch = dpitch;
+	memcpy(d.Kd, s.Kd, sizeof(d.Kd)); memcpy(d.Rd, s.Rd, sizeof(d.Rd)); memcpy(d.Cd, s.Cd, sizeof(d.Cd));
+}
+
+inline int cvRoundI(double v) { return (int)std::nearbyint(v); }
+
+// The whole EstimateDepthMap on device-resident views.  d_depth/d_normal hold the initial
+// estimate (full resolution) and receive the result together with d_conf / d_views.
+int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float dMin, float dMax, int nGeometricIter,
+	float* d_depth, float* d_normal, float* d_conf, uint32_t* d_views, cudaStream_t s)
+{
+	const b200mvs_params& o = ctx->prm;
+	const int W = views[0].w, H = views[0].h;
+	const int spi = std::max(1, o.nSweepsPerIter);
+	const int nR = (o.nRandomIters+spi-1)/spi;
+	const int iterBegin = nGeometricIter < 0 ? 0 : o.nEstimationIters+nGeometricIter;
+	const int iterEnd = nGeometricIter < 0 ? o.nEstimationIters : iterBegin+1;
+	const int totalScale = nGeometricIter < 0 ? std::max(0, o.nSubResolutionLevels) : 0;
+	const size_t P0 = (size_t)W*H;
+	CK(ctx->plane.reserve(P0*sizeof(float4)));
+	CK(ctx->cost.reserve(P0*sizeof(float)));
+	CK(ctx->best.reserve(P0*sizeof(uint32_t)));
+	if (totalScale > 0) {
+		CK(ctx->prior.reserve(P0*sizeof(float)));
+		CK(ctx->lowPlane.reserve((size_t)(W/2+2)*(H/2+2)*sizeof(float4)));
+		if ((int)ctx->pyr.size() < nViews) ctx->pyr.resize(nViews);
+	}
+	float4* plane = ctx->plane.as<float4>();
+	float* cost = ctx->cost.as<float>();
+	uint32_t* best = ctx->best.as<uint32_t>();
+	int lowW = 0, lowH = 0;
+	for (int sc = totalScale; sc >= 0; --sc) {
+		// ScaleDepthData (SceneDensify.cpp:578-601): INTER_AREA images, rescaled K
+		std::vector<DView> lv(views, views+nViews);
+		if (sc > 0) {
+			const double scale = 1.0/(double)(1<<sc);
+			for (int i = 0; i < nViews; ++i) {
+				const int dw = cvRoundI(views[i].w*scale), dh = cvRoundI(views[i].h*scale);
+				if (dw < 2*PM_HALF+2 || dh < 2*PM_HALF+2)
+					return fail(ctx, B200MVS_ERR_ARG, "image too small for nSubResolutionLevels");
+				const size_t need = (size_t)dw*dh*sizeof(float)*(views[i].dmap ? 2 : 1);
+				CK(ctx->pyr[i].reserve(need));
+				float* im = ctx->pyr[i].as<float>();
+				CK(rs_launch_area(views[i].img, views[i].w, views[i].h, views[i].pitch, im, dw, dh, s)); ++ctx->launches;
+				lv[i].img = im; lv[i].w = dw; lv[i].h = dh; lv[i].pitch = dw;
+				scaleK(views[i].K, views[i].w, views[i].h, dw, dh, lv[i].K);
+				if (views[i].dmap) {
+					float* dm = im + (size_t)dw*dh;
+					CK(rs_launch_area(views[i].dmap, views[i].dw, views[i].dh, views[i].dpitch, dm, dw, dh, s)); ++ctx->launches;
+					lv[i].dmap = dm; lv[i].dw = dw; lv[i].dh = dh; lv[i].dpitch = dw;
+					scaleK(views[i].Kd, views[i].dw, views[i].dh, dw, dh, lv[i].Kd);
+				}
+			}
+		}
+		const int w = lv[0].w, h = lv[0].h;
+		const float* lowres = nullptr;
+		if (sc != totalScale) {
+			// depth LINEAR / normal NEAREST up-sampling of the coarser level; the up-sampled
+			// depth is also the prior of this level (SceneDensify.cpp:660-664)
+			CK(rs_launch_plane_up(ctx->lowPlane.as<float4>(), lowW, lowH, plane, ctx->prior.as<float>(), w, h, s)); ++ctx->launches;
+			lowres = ctx->prior.as<float>();
+		} else if (sc == 0) {
+			CK(pm_launch_pack((int)P0, d_depth, d_normal, plane, s)); ++ctx->launches;
+		} else {
+			// coarsest level: the caller's initial estimate, NEAREST down-sampled
+			CK(ctx->dDepth.reserve((size_t)w*h*sizeof(float)));
+			CK(ctx->dNormal.reserve((size_t)w*h*3*sizeof(float)));
+			CK(rs_launch_nearest(d_depth, W, H, 1, ctx->dDepth.as<float>(), w, h, s));
+			CK(rs_launch_nearest(d_normal, W, H, 3, ctx->dNormal.as<float>(), w, h, s));
+			CK(pm_launch_pack(w*h, ctx->dDepth.as<float>(), ctx->dNormal.as<float>(), plane, s)); ctx->launches += 3;
+		}
+		PMParams P; bool geom;
+		build_params(o, lv.data(), nViews, dMin, dMax, lowres, plane, cost, best, P, geom);
+		P.nRandomIters = nR;
+		CK(pm_launch_score(P, geom, s)); ++ctx->launches;
+		for (int it = iterBegin; it < iterEnd; ++it) {
+			for (int k = 0; k < spi; ++k) {
+				P.sweep = it*spi+k;
+				for (int colour = 0; colour < 2; ++colour) {
+					P.colour = colour;
+					CK(pm_launch_sweep(P, geom, s)); ++ctx->launches;
+				}
+			}
+		}
+		if (sc > 0) {
+			CK(cudaMemcpyAsync(ctx->lowPlane.p, plane, (size_t)w*h*sizeof(float4), cudaMemcpyDeviceToDevice, s));
+			lowW = w; lowH = h;
+		}
+	}
+	float keep = o.fNCCThresholdKeep;
+	if (nGeometricIter < 0 && o.nEstimationGeometricIters)
+		keep *= 1.333f;
+	CK(pm_launch_finalize((int)P0, keep, plane, cost, best, d_depth, d_normal, d_conf, d_views, s)); ++ctx->launches;
+	return B200MVS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200mvs_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+void b200mvs_default_params(b200mvs_params* p) {
+	p->nEstimationIters = 3; p->nEstimationGeometricIters = 2; p->nRandomIters = 6; p->nSubResolutionLevels = 2;
+	p->fNCCThresholdKeep = 0.9f; p->fDescriptorMinMagnitudeThreshold = 0.02f;
+	p->fRandomDepthRatio = 0.003f; p->fRandomAngle1Range = 16.f; p->fRandomAngle2Range = 10.f;
+	p->fRandomSmoothDepth = 0.02f; p->fRandomSmoothNormal = 13.f; p->fRandomSmoothBonus = 0.93f;
+	p->fEstimationGeometricWeight = 0.1f;
+	p->nSweepsPerIter = 2; p->nPropagation = 4; p->seed = 1234u;
+}
+
+int b200mvs_create(int device, b200mvs_ctx** out) {
+	if (!out) return B200MVS_ERR_ARG;
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+		return B200MVS_ERR_NOGPU; // never falls back to a CPU path
+	if (device < 0) device = 0;
+	if (device >= n) return B200MVS_ERR_ARG;
+	if (cudaSetDevice(device) != cudaSuccess) return B200MVS_ERR_CUDA;
+	b200mvs_ctx* c = new b200mvs_ctx();
+	c->device = device;
+	b200mvs_default_params(&c->prm);
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+		cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+		delete c;
+		return B200MVS_ERR_CUDA;
+	}
+	*out = c;
+	return B200MVS_OK;
+}
+
+int b200mvs_destroy(b200mvs_ctx* c) {
+	if (!c) return B200MVS_ERR_ARG;
+	cudaSetDevice(c->device);
+	for (auto& b: c->imgs) b.release();
+	for (auto& b: c->dmaps) b.release();
+	for (auto& b: c->pyr) b.release();
+	c->plane.release(); c->cost.release(); c->best.release(); c->prior.release(); c->lowPlane.release();
+	c->dDepth.release(); c->dNormal.release(); c->dConf.release(); c->dViews.release(); c->mapD.release(); c->mapN.release();
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+	return B200MVS_OK;
+}
+
+int b200mvs_set_params(b200mvs_ctx* ctx, const b200mvs_params* p) {
+	if (!ctx || !p) return B200MVS_ERR_ARG;
+	if (p->nEstimationIters < 0 || p->nRandomIters < 0 || p->nSweepsPerIter < 1 || (p->nPropagation != 2 && p->nPropagation != 4) ||
+		p->nSubResolutionLevels < 0 || !(p->fNCCThresholdKeep > 0))
+		return fail(ctx, B200MVS_ERR_ARG, "invalid parameter block");
+	ctx->prm = *p;
+	return B200MVS_OK;
+}
+
+const char* b200mvs_last_error(const b200mvs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf, uint8_t* viewsMap, void* stream, b200mvs_stats* stats)
+{
+	int rc = check_views(ctx, views, nViews);
+	if (rc) return rc;
+	if (!depth || !normal || !conf || !(dMin > 0 && dMin < dMax))
+		return fail(ctx, B200MVS_ERR_ARG, "null map pointer or invalid depth range");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	std::vector<DView> dv(nViews);
+	for (int i = 0; i < nViews; ++i)
+		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
+			views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
+	const auto t0 = std::chrono::steady_clock::now();
+	ctx->launches = 0;
+	if (stats) CK(cudaEventRecord(ctx->ev0, s));
+	rc = estimate_on_device(ctx, dv.data(), nViews, dMin, dMax, nGeometricIter, depth, normal, conf, (uint32_t*)viewsMap, s);
+	if (rc) return rc;
+	if (stats) {
+		CK(cudaEventRecord(ctx->ev1, s));
+		CK(cudaStreamSynchronize(s));
+		float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		memset(stats, 0, sizeof(*stats));
+		stats->ms_device = ms;
+		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
+		stats->kernel_launches = ctx->launches;
+		stats->levels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
+	}
+	return B200MVS_OK;
+}
+
+int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf, uint8_t* viewsMap, b200mvs_stats* stats)
+{
+	int rc = check_views(ctx, views, nViews);
+	if (rc) return rc;
+	if (!depth || !normal || !conf || !(dMin > 0 && dMin < dMax))
+		return fail(ctx, B200MVS_ERR_ARG, "null map pointer or invalid depth range");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	const auto t0 = std::chrono::steady_clock::now();
+	if ((int)ctx->imgs.size() < nViews) { ctx->imgs.resize(nViews); ctx->dmaps.resize(nViews); }
+	std::vector<DView> dv(nViews);
+	uint64_t h2d = 0, d2h = 0;
+	for (int i = 0; i < nViews; ++i) {
+		const b200mvs_view& v = views[i];
+		const size_t row = (size_t)v.width*sizeof(float);
+		CK(ctx->imgs[i].reserve(row*v.height));
+		CK(cudaMemcpy2DAsync(ctx->imgs[i].p, row, v.image, v.stride_bytes ? v.stride_bytes : row, row, v.height, cudaMemcpyHostToDevice, s));
+		h2d += row*v.height;
+		const float* dm = nullptr;
+		if (v.depth) {
+			const size_t drow = (size_t)v.dwidth*sizeof(float);
+			CK(ctx->dmaps[i].reserve(drow*v.dheight));
+			CK(cudaMemcpy2DAsync(ctx->dmaps[i].p, drow, v.depth, v.dstride_bytes ? v.dstride_bytes : drow, drow, v.dheight, cudaMemcpyHostToDevice, s));
+			h2d += drow*v.dheight;
+			dm = ctx->dmaps[i].as<float>();
+		}
+		to_dview(v, ctx->imgs[i].as<float>(), v.width, dm, v.dwidth, dv[i]);
+	}
+	const size_t P0 = (size_t)views[0].width*views[0].height;
+	DevBuf& dD = ctx->mapD; DevBuf& dN = ctx->mapN;
+	CK(dD.reserve(P0*sizeof(float))); CK(dN.reserve(P0*3*sizeof(float)));
+	CK(ctx->dConf.reserve(P0*sizeof(float))); CK(ctx->dViews.reserve(P0*sizeof(uint32_t)));
+	CK(cudaMemcpyAsync(dD.p, depth, P0*sizeof(float), cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(dN.p, normal, P0*3*sizeof(float), cudaMemcpyHostToDevice, s));
+	h2d += P0*16;
+	ctx->launches = 0;
+	CK(cudaEventRecord(ctx->ev0, s));
+	rc = estimate_on_device(ctx, dv.data(), nViews, dMin, dMax, nGeometricIter, dD.as<float>(), dN.as<float>(),
+		ctx->dConf.as<float>(), ctx->dViews.as<uint32_t>(), s);
+	if (rc) return rc;
+	CK(cudaEventRecord(ctx->ev1, s));
+	CK(cudaMemcpyAsync(depth, dD.p, P0*sizeof(float), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(normal, dN.p, P0*3*sizeof(float), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(conf, ctx->dConf.p, P0*sizeof(float), cudaMemcpyDeviceToHost, s));
+	d2h += P0*20;
+	if (viewsMap) { CK(cudaMemcpyAsync(viewsMap, ctx->dViews.p, P0*4, cudaMemcpyDeviceToHost, s)); d2h += P0*4; }
+	CK(cudaStreamSynchronize(s));
+	if (stats) {
+		float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		memset(stats, 0, sizeof(*stats));
+		stats->ms_device = ms;
+		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
+		stats->bytes_h2d = h2d; stats->bytes_d2h = d2h;
+		stats->kernel_launches = ctx->launches;
+		stats->levels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
+	}
+	return B200MVS_OK;
+}
+
+// ---- building blocks ----------------------------------------------------------------------
+int b200mvs_pm_pack(b200mvs_ctx* ctx, int width, int height, const float* depth, const float* normal, float* plane4, void* stream) {
+	if (!ctx || !depth || !normal || !plane4) return B200MVS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(pm_launch_pack(width*height, depth, normal, (float4*)plane4, stream ? (cudaStream_t)stream : ctx->stream));
+	return B200MVS_OK;
+}
+int b200mvs_pm_unpack(b200mvs_ctx* ctx, int width, int height, const float* plane4, float* depth, float* normal, void* stream) {
+	if (!ctx || !depth || !normal || !plane4) return B200MVS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(pm_launch_unpack(width*height, (const float4*)plane4, depth, normal, stream ? (cudaStream_t)stream : ctx->stream));
+	return B200MVS_OK;
+}
+static int block_params(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax, const float* lowres,
+	float* plane4, float* cost, PMParams& P, bool& geom)
+{
+	int rc = check_views(ctx, views, nViews);
+	if (rc) return rc;
+	if (!plane4 || !cost) return fail(ctx, B200MVS_ERR_ARG, "null state pointer");
+	std::vector<DView> dv(nViews);
+	for (int i = 0; i < nViews; ++i)
+		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
+			views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
+	build_params(ctx->prm, dv.data(), nViews, dMin, dMax, lowres, (float4*)plane4, cost, nullptr, P, geom);
+	return B200MVS_OK;
+}
+int b200mvs_pm_score(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
+	const float* lowres, float* plane4, float* cost, void* stream)
+{
+	PMParams P; bool geom;
+	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, P, geom);
+	if (rc) return rc;
+	CK(cudaSetDevice(ctx->device));
+	CK(pm_launch_score(P, geom, stream ? (cudaStream_t)stream : ctx->stream));
+	return B200MVS_OK;
+}
+int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
+	const float* lowres, int sweep, int half, int nRandomIters, float* plane4, float* cost, void* stream)
+{
+	PMParams P; bool geom;
+	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, P, geom);
+	if (rc) return rc;
+	CK(cudaSetDevice(ctx->device));
+	P.sweep = sweep; P.nRandomIters = nRandomIters;
+	for (int colour = 0; colour < 2; ++colour) {
+		if (half >= 0 && half != colour) continue;
+		P.colour = colour;
+		CK(pm_launch_sweep(P, geom, stream ? (cudaStream_t)stream : ctx->stream));
+	}
+	return B200MVS_OK;
+}
+int b200mvs_pm_finalize(b200mvs_ctx* ctx, int width, int height, float keep, const float* plane4, const float* cost,
+	float* depth, float* normal, float* conf, void* stream)
+{
+	if (!ctx || !plane4 || !cost || !depth || !normal || !conf) return B200MVS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(pm_launch_finalize(width*height, keep, (const float4*)plane4, cost, nullptr, depth, normal, conf, nullptr,
+		stream ? (cudaStream_t)stream : ctx->stream));
+	return B200MVS_OK;
+}
+
+} // extern "C"

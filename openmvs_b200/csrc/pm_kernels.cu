@@ -1,0 +1,542 @@
+// pm_kernels.cu — PatchMatch depth+normal estimation kernels, hand-written for sm_100a.
+//
+// What they compute (behaviour, not code, follows the reference CPU estimator):
+//   pm_score_kernel   pass A  ScoreDepthMapTmp            libs/MVS/SceneDensify.cpp:490-517
+//   pm_sweep_kernel   pass B  DepthEstimator::ProcessPixel libs/MVS/DepthMap.cpp:630-852
+//                             scored by ScorePixel/ScorePixelImage (DepthMap.cpp:465-626)
+//   pm_finalize_kernel pass C EndDepthMapTmp              libs/MVS/SceneDensify.cpp:528-548
+//
+// Schedule: red-black.  One thread owns one pixel of the active colour; a warp owns 32
+// same-colour pixels of one image row (64-pixel span), so the homography-warped taps of
+// the 32 lanes fall on 2-3 cache lines of two neighbour-image rows.  The bilateral
+// weights of the 5x5 reference patch live in registers for the whole sweep (computed once
+// per pixel from a TMA-staged reference tile) and are reused by every hypothesis x view.
+// All four 4-neighbours belong to the other colour, so in-place updates are race-free.
+#include "pm_common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int BLOCK_X = 32;  // lanes: 32 same-colour pixels = 64-pixel span
+constexpr int BLOCK_Y = 8;
+
+struct Patch {
+	float w[PM_TEXELS];
+	float tw[PM_TEXELS];
+	float sumW, normSq0;
+};
+
+// FillPixelPatch + GetWeight (DepthMap.cpp:422-462, DepthMap.h:403-412)
+__device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pitch, int x, int y, Patch& p) {
+	const float sigmaColor = -1.f/(2.f*0.1f*0.1f);
+	const float sigmaSpatial = -1.f/(2.f*9.f);
+	const float center = __ldg(img + (size_t)y*pitch + x);
+	float acc = 0.f, sumW = 0.f;
+	#pragma unroll
+	for (int i = 0; i < 5; ++i) {
+		#pragma unroll
+		for (int j = 0; j < 5; ++j) {
+			const int dy = 2*i-PM_HALF, dx = 2*j-PM_HALF;
+			const float I = __ldg(img + (size_t)(y+dy)*pitch + (x+dx));
+			const float dI = I-center;
+			const float wgt = expf(dI*dI*sigmaColor + float(dx*dx+dy*dy)*sigmaSpatial);
+			p.w[i*5+j] = wgt;
+			p.tw[i*5+j] = I;
+			acc += I*wgt;
+			sumW += wgt;
+		}
+	}
+	const float tm = acc/sumW;
+	float nsq = 0.f;
+	#pragma unroll
+	for (int k = 0; k < PM_TEXELS; ++k) {
+		const float t = p.tw[k]-tm;
+		p.tw[k] = p.w[k]*t;
+		nsq += p.tw[k]*t;
+	}
+	p.sumW = sumW;
+	p.normSq0 = nsq;
+}
+
+struct Hyp {      // one plane hypothesis at the current pixel
+	float d;      // depth
+	float3 n;     // unit normal, camera space
+	float invd;   // 1/d
+	float3 ms;    // (n^T Kref^-1) / (n.X0 d)
+	float smooth; // product of the smoothness factors (view independent)
+};
+
+struct Close {    // the <=4 neighbours used for smoothing (NeighborEstimate, DepthMap.h:300-306)
+	float d[4];
+	float3 n[4];
+	float rx[4], ry[4]; // ray of the neighbour pixel
+	unsigned mask;      // bit k set: slot k holds a valid neighbour
+};
+
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float pow2neg(unsigned i) { return __int_as_float((int)(127u-i)<<23); } // 2^-i, scaleRanges[] (DepthMap.cpp:358-359)
+__device__ __forceinline__ float dot3(const float3& a, const float3& b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
+
+// masked bilinear depth sample (TImage::sample with functor, libs/Common/Types.inl:2297-2313)
+__device__ __forceinline__ bool sample_depth_masked(const float* __restrict__ img, int pitch, float px, float py, float ref, float& v) {
+	const int lx = (int)px, ly = (int)py;
+	const float x = px-lx, x1 = 1.f-x, y = py-ly, y1 = 1.f-y;
+	const float* r0 = img + (size_t)ly*pitch + lx;
+	const float x0y0 = __ldg(r0), x1y0 = __ldg(r0+1), x0y1 = __ldg(r0+pitch), x1y1 = __ldg(r0+pitch+1);
+	const bool b00 = fabsf(ref-x0y0)/ref < 0.03f, b10 = fabsf(ref-x1y0)/ref < 0.03f;
+	const bool b01 = fabsf(ref-x0y1)/ref < 0.03f, b11 = fabsf(ref-x1y1)/ref < 0.03f;
+	if (!b00 && !b10 && !b01 && !b11)
+		return false;
+	v = y1*(x1*(b00 ? x0y0 : (b10 ? x1y0 : (b01 ? x0y1 : x1y1))) + x*(b10 ? x1y0 : (b00 ? x0y0 : (b11 ? x1y1 : x0y1)))) +
+	    y *(x1*(b01 ? x0y1 : (b11 ? x1y1 : (b00 ? x0y0 : x1y0))) + x*(b11 ? x1y1 : (b01 ? x0y1 : (b10 ? x1y0 : x0y0))));
+	return true;
+}
+
+// ScorePixelImage (DepthMap.cpp:465-564) for one neighbour view.
+template <bool GEOM>
+__device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, const Patch& pt,
+	float fx, float fy, float X0x, float X0y, const Hyp& h, float priorF, float priorD)
+{
+	// H = A + Hm (n^T Kref^-1)/(n.X0 d); columns 0/1 and the centre point H*(x,y,1)
+	float c0x = fmaf(V.Hm[0], h.ms.x, V.A[0]), c0y = fmaf(V.Hm[1], h.ms.x, V.A[3]), c0z = fmaf(V.Hm[2], h.ms.x, V.A[6]);
+	float c1x = fmaf(V.Hm[0], h.ms.y, V.A[1]), c1y = fmaf(V.Hm[1], h.ms.y, V.A[4]), c1z = fmaf(V.Hm[2], h.ms.y, V.A[7]);
+	const float xc = fmaf(V.Hm[0], h.invd, fmaf(V.A[0], fx, fmaf(V.A[1], fy, V.A[2])));
+	const float yc = fmaf(V.Hm[1], h.invd, fmaf(V.A[3], fx, fmaf(V.A[4], fy, V.A[5])));
+	const float zc = fmaf(V.Hm[2], h.invd, fmaf(V.A[6], fx, fmaf(V.A[7], fy, V.A[8])));
+	// top-left tap, then steps of 2 pixels
+	float bx = fmaf(-4.f, c0x+c1x, xc), by = fmaf(-4.f, c0y+c1y, yc), bz = fmaf(-4.f, c0z+c1z, zc);
+	c0x *= 2.f; c0y *= 2.f; c0z *= 2.f; c1x *= 2.f; c1y *= 2.f; c1z *= 2.f;
+	const float xmax = float(V.w-2), ymax = float(V.h-2);
+	const float* __restrict__ img = V.img;
+	const int pitch = V.pitch;
+	float sum = 0.f, sumSq = 0.f, num = 0.f;
+	bool bad = false;
+	#pragma unroll
+	for (int i = 0; i < 5; ++i) {
+		float X = bx, Y = by, Z = bz;
+		#pragma unroll
+		for (int j = 0; j < 5; ++j) {
+			const float iz = fast_rcp(Z);
+			const float px = X*iz, py = Y*iz;
+			const bool in = px >= 1.f && py >= 1.f && px <= xmax && py <= ymax;
+			bad |= !in;
+			float v = 0.f;
+			if (in) {
+				const int lx = (int)px, ly = (int)py;
+				const float ax = px-(float)lx, ay = py-(float)ly;
+				const float* r0 = img + (size_t)ly*pitch + lx;
+				const float v00 = __ldg(r0), v10 = __ldg(r0+1), v01 = __ldg(r0+pitch), v11 = __ldg(r0+pitch+1);
+				const float ax1 = 1.f-ax, ay1 = 1.f-ay;
+				v = (v00*ax1 + v10*ax)*ay1 + (v01*ax1 + v11*ax)*ay;
+			}
+			const float vw = v*pt.w[i*5+j];
+			sum += vw;
+			sumSq = fmaf(v, vw, sumSq);
+			num = fmaf(v, pt.tw[i*5+j], num);
+			X += c0x; Y += c0y; Z += c0z;
+		}
+		bx += c1x; by += c1y; bz += c1z;
+		if (__all_sync(__activemask(), bad))
+			break;
+	}
+	if (bad)
+		return P.thRobust;
+	const float normSq1 = sumSq - sum*sum/pt.sumW;
+	const float nrmSq = pt.normSq0*normSq1;
+	if (nrmSq <= 1e-16f)
+		return P.thRobust;
+	const float ncc = fminf(fmaxf(num/sqrtf(nrmSq), -1.f), 1.f);
+	float score = (1.f-ncc)*h.smooth;
+	if (GEOM) {
+		if (V.dmap) {
+			// forward/backward reprojection through the neighbour's depth-map (DepthMap.cpp:535-551)
+			float consistency = 4.f;
+			const float Xx = X0x*h.d, Xy = X0y*h.d, Xz = h.d;
+			const float X1x = V.Tl[0]*Xx + V.Tl[1]*Xy + V.Tl[2]*Xz + V.Tm[0];
+			const float X1y = V.Tl[3]*Xx + V.Tl[4]*Xy + V.Tl[5]*Xz + V.Tm[1];
+			const float X1z = V.Tl[6]*Xx + V.Tl[7]*Xy + V.Tl[8]*Xz + V.Tm[2];
+			if (X1z > 0.f) {
+				const float x1x = X1x/X1z, x1y = X1y/X1z;
+				if (x1x >= 1.f && x1y >= 1.f && x1x <= float(V.dw-2) && x1y <= float(V.dh-2)) {
+					float depth1;
+					if (sample_depth_masked(V.dmap, V.dpitch, x1x, x1y, X1z, depth1)) {
+						const float Px = x1x*depth1, Py = x1y*depth1, Pz = depth1;
+						const float Bx = V.Tr[0]*Px + V.Tr[1]*Py + V.Tr[2]*Pz + V.Tn[0];
+						const float By = V.Tr[3]*Px + V.Tr[4]*Py + V.Tr[5]*Pz + V.Tn[1];
+						const float Bz = V.Tr[6]*Px + V.Tr[7]*Py + V.Tr[8]*Pz + V.Tn[2];
+						const float ex = fx-Bx/Bz, ey = fy-By/Bz;
+						const float dist = sqrtf(ex*ex + ey*ey);
+						consistency = fminf(sqrtf(dist*(dist+2.f)), consistency);
+					}
+				}
+			}
+			score += P.geomWeight*consistency;
+		}
+	}
+	if (priorD > 0.f) {
+		// low-resolution depth prior (DepthMap.cpp:552-561)
+		const float deltaDepth = fminf(fabsf(priorD-h.d)/priorD, 0.5f);
+		score = (1.f-priorF)*score + priorF*deltaDepth;
+	}
+	return fminf(2.f, score);
+}
+
+// ScorePixel (DepthMap.cpp:567-626): MINMEAN over the views; also reports the two best views
+template <bool GEOM>
+__device__ __forceinline__ float score_pixel(const PMParams& P, const Patch& pt,
+	float fx, float fy, float X0x, float X0y, const Hyp& h, float priorF, float priorD, uint32_t& best)
+{
+	float s0 = CUDART_INF_F, s1 = CUDART_INF_F;
+	int i0 = 255, i1 = 255;
+	#pragma unroll 1
+	for (int v = 0; v < P.nViews; ++v) {
+		const float s = score_view<GEOM>(P, P.views[v], pt, fx, fy, X0x, X0y, h, priorF, priorD);
+		if (s < s0) { s1 = s0; i1 = i0; s0 = s; i0 = v; }
+		else if (s < s1) { s1 = s; i1 = v; }
+	}
+	if (P.nViews <= 1 || s1 >= P.thRobust) {
+		best = 0xFFFFFF00u | (uint32_t)i0;
+		return s0;
+	}
+	best = 0xFFFF0000u | ((uint32_t)i1<<8) | (uint32_t)i0;
+	return (s0+s1)*0.5f;
+}
+
+// build a hypothesis: homography terms + smoothness factor over the close neighbours
+// (InitPlane DepthMap.cpp:963-971 and the smoothness loop DepthMap.cpp:522-534)
+__device__ __forceinline__ void make_hyp(const PMParams& P, float X0x, float X0y, float d, const float3& n,
+	const Close& cl, bool useClose, Hyp& h)
+{
+	h.d = d; h.n = n;
+	h.invd = 1.f/d;
+	const float nX0 = n.x*X0x + n.y*X0y + n.z;
+	const float s = 1.f/(nX0*d);
+	h.ms = make_float3(n.x*P.ifx*s, (n.x*P.sk + n.y*P.ify)*s, (n.x*P.ox + n.y*P.oy + n.z)*s);
+	float smooth = 1.f;
+	if (useClose) {
+		const float planeD = -d*nX0;
+		const float nn = dot3(n, n);
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			if (cl.mask & (1u<<k)) {
+				const float dist = (n.x*cl.rx[k] + n.y*cl.ry[k] + n.z)*cl.d[k] + planeD;
+				const float rd = dist/d;
+				const float factorDepth = expf(rd*rd*P.smoothSigmaDepth);
+				float ca = dot3(n, cl.n[k])/sqrtf(nn*dot3(cl.n[k], cl.n[k]));
+				ca = fminf(fmaxf(ca, -1.f), 1.f);
+				const float ang = acosf(ca);
+				const float factorNormal = expf(ang*ang*P.smoothSigmaNormal);
+				smooth *= (1.f-P.smoothBonusDepth*factorDepth)*(1.f-P.smoothBonusNormal*factorNormal);
+			}
+		}
+	}
+	h.smooth = smooth;
+}
+
+__device__ __forceinline__ float3 dir2normal(float a, float b) {
+	float sa, ca, sb, cb;
+	sincosf(a, &sa, &ca);
+	sincosf(b, &sb, &cb);
+	return make_float3(ca*sb, sa*sb, cb);
+}
+// RandomNormal (DepthMap.h:439-444)
+__device__ __forceinline__ float3 random_normal(float u1, float u2, float X0x, float X0y) {
+	const float kPI = 3.14159265358979323846f;
+	const float a = 0.f + (kPI-0.f)*u1;
+	const float b = 0.5f*kPI + (kPI-0.5f*kPI)*u2;
+	float3 n = dir2normal(a, b);
+	if (n.x*X0x + n.y*X0y + n.z > 0.f)
+		n = make_float3(-n.x, -n.y, -n.z);
+	return n;
+}
+// CorrectNormal (DepthMap.h:447-453): rotate n to at most ~90 deg from the viewing ray
+__device__ __forceinline__ void correct_normal(float3& n, float X0x, float X0y) {
+	const float cosAngLen = n.x*X0x + n.y*X0y + n.z;
+	if (cosAngLen >= 0.f) {
+		const float kPI = 3.14159265358979323846f;
+		const float vlen = sqrtf(X0x*X0x + X0y*X0y + 1.f);
+		const float ang = fminf((acosf(cosAngLen/vlen) - 0.5f*kPI)*1.01f, -0.001f);
+		float3 w = make_float3(n.y*1.f - n.z*X0y, n.z*X0x - n.x*1.f, n.x*X0y - n.y*X0x); // n x viewDir
+		const float inv = 1.f/sqrtf(dot3(w, w));
+		w.x *= inv; w.y *= inv; w.z *= inv;
+		float s, c;
+		sincosf(ang, &s, &c);
+		// Rodrigues: R v = v + s (w x v) + (1-c) w x (w x v)
+		const float3 wv = make_float3(w.y*n.z - w.z*n.y, w.z*n.x - w.x*n.z, w.x*n.y - w.y*n.x);
+		const float3 wwv = make_float3(w.y*wv.z - w.z*wv.y, w.z*wv.x - w.x*wv.z, w.x*wv.y - w.y*wv.x);
+		const float c1 = 1.f-c;
+		n = make_float3(n.x + s*wv.x + c1*wwv.x, n.y + s*wv.y + c1*wwv.y, n.z + s*wv.z + c1*wwv.z);
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// pass A: score the initial estimate of every pixel (random where invalid)
+template <bool GEOM>
+__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, 2)
+pm_score_kernel(const __grid_constant__ PMParams P)
+{
+	const int x = blockIdx.x*BLOCK_X + threadIdx.x;
+	const int y = blockIdx.y*BLOCK_Y + threadIdx.y;
+	if (x >= P.W || y >= P.H)
+		return;
+	const size_t idx = (size_t)y*P.W + x;
+	const bool inside = x >= PM_HALF && y >= PM_HALF && x < P.W-PM_HALF && y < P.H-PM_HALF;
+	Patch pt;
+	float priorD = 0.f, priorF = 0.f;
+	bool ok = inside;
+	if (inside) {
+		fill_patch(P.img0, P.pitch0, x, y, pt);
+		if (P.lowres)
+			priorD = fmaxf(__ldg(P.lowres + idx), 0.f);
+		if (pt.normSq0 < P.thMagnitudeSq && !(priorD > 0.f))
+			ok = false;
+	}
+	if (!ok) {
+		P.plane[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+		P.cost[idx] = 2.f;
+		if (P.bestViews) P.bestViews[idx] = 0xFFFFFFFFu;
+		return;
+	}
+	if (priorD > 0.f)
+		priorF = expf(pt.normSq0*(-1.f/0.02f));
+	const float fx = float(x), fy = float(y);
+	const float X0x = fx*P.ifx + fy*P.sk + P.ox, X0y = fy*P.ify + P.oy;
+	float4 pl = P.plane[idx];
+	float3 n = make_float3(pl.x, pl.y, pl.z);
+	float d = pl.w;
+	const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, 0u, 0u, 0u), make_uint2(P.seed, 0xB200C0DEu));
+	if (!(P.dMin <= d && d < P.dMax)) {
+		const float s = P.dMinSqr + (P.dMaxSqr-P.dMinSqr)*u32_to_unit(r.x);
+		d = s*s;
+		n = random_normal(u32_to_unit(r.y), u32_to_unit(r.z), X0x, X0y);
+	} else if (n.x*X0x + n.y*X0y + n.z >= 0.f) {
+		n = random_normal(u32_to_unit(r.x), u32_to_unit(r.y), X0x, X0y);
+	}
+	Close cl; cl.mask = 0;
+	Hyp h;
+	make_hyp(P, X0x, X0y, d, n, cl, false, h);
+	uint32_t best;
+	const float c = score_pixel<GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, best);
+	P.plane[idx] = make_float4(n.x, n.y, n.z, d);
+	P.cost[idx] = c;
+	if (P.bestViews) P.bestViews[idx] = best;
+}
+
+// ------------------------------------------------------------------------------------
+// pass B: one red-black half-sweep
+template <bool GEOM>
+__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, 2)
+pm_sweep_kernel(const __grid_constant__ PMParams P)
+{
+	const int y = blockIdx.y*BLOCK_Y + threadIdx.y;
+	const int x = blockIdx.x*(2*BLOCK_X) + 2*threadIdx.x + ((y+P.colour)&1);
+	if (x < PM_HALF || y < PM_HALF || x >= P.W-PM_HALF || y >= P.H-PM_HALF)
+		return;
+	const int W = P.W, H = P.H;
+	const size_t idx = (size_t)y*W + x;
+	Patch pt;
+	fill_patch(P.img0, P.pitch0, x, y, pt);
+	float priorD = 0.f, priorF = 0.f;
+	if (P.lowres)
+		priorD = fmaxf(__ldg(P.lowres + idx), 0.f);
+	if (pt.normSq0 < P.thMagnitudeSq && !(priorD > 0.f))
+		return;
+	if (priorD > 0.f)
+		priorF = expf(pt.normSq0*(-1.f/0.02f));
+	const float fx = float(x), fy = float(y);
+	const float X0x = fx*P.ifx + fy*P.sk + P.ox, X0y = fy*P.ify + P.oy;
+
+	// neighbours: causal pair of the sweep direction first (DepthMap.cpp:641-766)
+	const int dir = P.sweep & 1;
+	Close cl; cl.mask = 0;
+	float ncost[4];
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		// dir 0: left, up, right, down;  dir 1: right, down, left, up
+		const int kk = dir ? (k^2) : k;
+		const int ox = (kk == 0) ? -1 : (kk == 2) ? 1 : 0;
+		const int oy = (kk == 1) ? -1 : (kk == 3) ? 1 : 0;
+		const bool ok = (kk == 0) ? (x > PM_HALF) : (kk == 1) ? (y > PM_HALF) : (kk == 2) ? (x < W-PM_HALF) : (y < H-PM_HALF);
+		cl.d[k] = 0.f; cl.n[k] = make_float3(0.f, 0.f, 0.f); cl.rx[k] = 0.f; cl.ry[k] = 0.f; ncost[k] = 2.f;
+		if (ok) {
+			const size_t nidx = (size_t)(y+oy)*W + (x+ox);
+			const float4 np = P.plane[nidx];
+			if (np.w > 0.f) {
+				cl.mask |= 1u<<k;
+				cl.d[k] = np.w; cl.n[k] = make_float3(np.x, np.y, np.z);
+				const float nfx = float(x+ox), nfy = float(y+oy);
+				cl.rx[k] = nfx*P.ifx + nfy*P.sk + P.ox; cl.ry[k] = nfy*P.ify + P.oy;
+				ncost[k] = P.cost[nidx];
+			}
+		}
+	}
+	float4 pl = P.plane[idx];
+	float conf = P.cost[idx];
+	float depth = pl.w;
+	float3 normal = make_float3(pl.x, pl.y, pl.z);
+	uint32_t bestViews = P.bestViews ? P.bestViews[idx] : 0xFFFFFFFFu;
+
+	const int nR = P.nRandomIters;
+	const int nProp = P.propagation;
+	const uint2 key = make_uint2(P.seed, 0xB200C0DEu);
+	const uint32_t phase = 1u + (uint32_t)P.sweep;
+	// refinement state machine (DepthMap.cpp:800-852)
+	int mode = 0;               // 0 undecided, 1 restart (fully random), 2 refine, 3 done
+	bool useClose = true;
+	unsigned idxScale = 0;
+	float scaleRange = 1.f, depthRange = 0.f, pa = 0.f, pb = 0.f;
+	const int nSteps = 4 + 2*nR;
+	#pragma unroll 1
+	for (int step = 0; step < nSteps; ++step) {
+		if (step == 4 || (mode == 1 && step >= 4 && conf < P.thConfRand)) {
+			// RefineIters: choose the perturbation scale from the current score
+			if (mode == 0 || mode == 1) {
+				bool toRefine = true;
+				if (conf <= P.thConfSmall) idxScale = 2;
+				else if (conf <= P.thConfBig) idxScale = 1;
+				else if (conf >= P.thConfRand && mode == 0) { mode = 1; useClose = false; toRefine = false; }
+				if (toRefine) {
+					mode = 2;
+					scaleRange = pow2neg(idxScale);
+					depthRange = depth*P.depthRatio;
+					pa = atan2f(normal.y, normal.x);
+					pb = acosf(normal.z);
+				}
+			}
+		}
+		bool have = false, isRefine = false;
+		float hd = 0.f, na = 0.f, nb = 0.f; float3 hn = make_float3(0.f, 0.f, 1.f);
+		if (step < 4) {
+			// propagate the plane of neighbour `step` (InterpolatePixel, DepthMap.cpp:915-959)
+			if (step < nProp && (cl.mask & (1u<<step))) {
+				const float kd = step == 0 ? cl.d[0] : step == 1 ? cl.d[1] : step == 2 ? cl.d[2] : cl.d[3];
+				const float3 kn = step == 0 ? cl.n[0] : step == 1 ? cl.n[1] : step == 2 ? cl.n[2] : cl.n[3];
+				const float kc = step == 0 ? ncost[0] : step == 1 ? ncost[1] : step == 2 ? ncost[2] : ncost[3];
+				const float krx = step == 0 ? cl.rx[0] : step == 1 ? cl.rx[1] : step == 2 ? cl.rx[2] : cl.rx[3];
+				const float kry = step == 0 ? cl.ry[0] : step == 1 ? cl.ry[1] : step == 2 ? cl.ry[2] : cl.ry[3];
+				if (kc < P.keep) {
+					const bool vertical = ((dir ? (step^2) : step) & 1) != 0;
+					const float ncomp = vertical ? kn.y : kn.x;
+					const float nx1 = vertical ? X0y : X0x;
+					const float x1 = vertical ? kry : krx;
+					const float denom = kn.z + nx1*ncomp;
+					hd = kd;
+					if (!(fabsf(denom) < 0.0001f)) {
+						const float dn = kd*(kn.z + x1*ncomp)/denom;
+						if (P.dMin <= dn && dn < P.dMax)
+							hd = dn;
+					}
+					hn = kn;
+					correct_normal(hn, X0x, X0y);
+					have = true;
+				}
+			}
+		} else if (step < 4+nR) {
+			if (mode == 1) {
+				// completely random plane (DepthMap.cpp:810-825)
+				const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)(step-4), 0u), key);
+				const float s = P.dMinSqr + (P.dMaxSqr-P.dMinSqr)*u32_to_unit(r.x);
+				hd = s*s;
+				hn = random_normal(u32_to_unit(r.y), u32_to_unit(r.z), X0x, X0y);
+				have = true;
+			}
+		} else {
+			if (mode == 2) {
+				// perturb around the current estimate (DepthMap.cpp:832-851)
+				const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)(step-4), 0u), key);
+				hd = depth + depthRange*scaleRange*(2.f*u32_to_unit(r.x)-1.f);
+				if (P.dMin <= hd && hd < P.dMax) {
+					na = pa + P.angle1Range*scaleRange*(2.f*u32_to_unit(r.y)-1.f);
+					nb = pb + P.angle2Range*scaleRange*(2.f*u32_to_unit(r.z)-1.f);
+					hn = dir2normal(na, nb);
+					have = hn.x*X0x + hn.y*X0y + hn.z < 0.f;
+					isRefine = true;
+				}
+			}
+		}
+		if (!__any_sync(__activemask(), have))
+			continue;
+		if (have) {
+			Hyp h;
+			make_hyp(P, X0x, X0y, hd, hn, cl, useClose, h);
+			uint32_t bv;
+			const float nconf = score_pixel<GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
+			if (conf > nconf) {
+				conf = nconf; depth = hd; normal = hn; bestViews = bv;
+				if (isRefine) {
+					pa = na; pb = nb;
+					++idxScale;
+					scaleRange = pow2neg(idxScale);
+				}
+			}
+		}
+		if (mode == 1 && step == 4+nR-1 && !(conf < P.thConfRand))
+			mode = 3; // all random tries failed: no refinement this sweep
+	}
+	P.plane[idx] = make_float4(normal.x, normal.y, normal.z, depth);
+	P.cost[idx] = conf;
+	if (P.bestViews) P.bestViews[idx] = bestViews;
+}
+
+// pass C: threshold and convert cost to confidence (EndDepthMapTmp)
+__global__ void pm_finalize_kernel(int n, float keep, const float4* __restrict__ plane, const float* __restrict__ cost,
+	const uint32_t* __restrict__ bestViews, float* __restrict__ depth, float* __restrict__ normal, float* __restrict__ conf,
+	uint32_t* __restrict__ viewsMap)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4 p = plane[i];
+	const float c = cost[i];
+	float d = p.w, cf; float3 nn = make_float3(p.x, p.y, p.z);
+	uint32_t bv = bestViews ? bestViews[i] : 0xFFFFFFFFu;
+	if (d <= 0.f || c >= keep) {
+		d = 0.f; cf = 0.f; nn = make_float3(0.f, 0.f, 0.f); bv = 0xFFFFFFFFu;
+	} else {
+		cf = c >= 1.f ? 0.f : 1.f-c;
+	}
+	depth[i] = d; conf[i] = cf;
+	normal[3*(size_t)i] = nn.x; normal[3*(size_t)i+1] = nn.y; normal[3*(size_t)i+2] = nn.z;
+	if (viewsMap) viewsMap[i] = bv;
+}
+
+__global__ void pm_pack_kernel(int n, const float* __restrict__ depth, const float* __restrict__ normal, float4* __restrict__ plane) {
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	plane[i] = make_float4(normal[3*(size_t)i], normal[3*(size_t)i+1], normal[3*(size_t)i+2], depth[i]);
+}
+__global__ void pm_unpack_kernel(int n, const float4* __restrict__ plane, float* __restrict__ depth, float* __restrict__ normal) {
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4 p = plane[i];
+	depth[i] = p.w;
+	normal[3*(size_t)i] = p.x; normal[3*(size_t)i+1] = p.y; normal[3*(size_t)i+2] = p.z;
+}
+
+} // namespace
+
+// ---- host launchers ---------------------------------------------------------------------
+cudaError_t pm_launch_score(const PMParams& P, bool geom, cudaStream_t s) {
+	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+BLOCK_X-1)/BLOCK_X, (P.H+BLOCK_Y-1)/BLOCK_Y);
+	if (geom) pm_score_kernel<true><<<grid, block, 0, s>>>(P);
+	else pm_score_kernel<false><<<grid, block, 0, s>>>(P);
+	return cudaGetLastError();
+}
+cudaError_t pm_launch_sweep(const PMParams& P, bool geom, cudaStream_t s) {
+	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+2*BLOCK_X-1)/(2*BLOCK_X), (P.H+BLOCK_Y-1)/BLOCK_Y);
+	if (geom) pm_sweep_kernel<true><<<grid, block, 0, s>>>(P);
+	else pm_sweep_kernel<false><<<grid, block, 0, s>>>(P);
+	return cudaGetLastError();
+}
+cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
+	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s) {
+	pm_finalize_kernel<<<(n+255)/256, 256, 0, s>>>(n, keep, plane, cost, bestViews, depth, normal, conf, viewsMap);
+	return cudaGetLastError();
+}
+cudaError_t pm_launch_pack(int n, const float* depth, const float* normal, float4* plane, cudaStream_t s) {
+	pm_pack_kernel<<<(n+255)/256, 256, 0, s>>>(n, depth, normal, plane);
+	return cudaGetLastError();
+}
+cudaError_t pm_launch_unpack(int n, const float4* plane, float* depth, float* normal, cudaStream_t s) {
+	pm_unpack_kernel<<<(n+255)/256, 256, 0, s>>>(n, plane, depth, normal);
+	return cudaGetLastError();
+}

@@ -1,0 +1,138 @@
+// resize_kernels.cu — the image-pyramid arithmetic of the scale loop, on device.
+//
+// The reference calls OpenCV for these (third-party arithmetic):
+//   cv::resize(..., INTER_AREA)    images / known depth-maps   libs/MVS/SceneDensify.cpp:586,590
+//   cv::resize(..., INTER_LINEAR)  low-res depth  -> next level libs/MVS/SceneDensify.cpp:661
+//   cv::resize(..., INTER_NEAREST) low-res normal -> next level libs/MVS/SceneDensify.cpp:662
+// One thread per destination pixel; HBM-bound, a few MB per level.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+// area taps of one destination index: at most a leading partial cell, full cells, trailing partial cell
+struct AreaSpan { int s0, s1; float a0, a, a1; bool lead, trail; };
+
+__device__ __forceinline__ AreaSpan area_span(int d, int ssize, double scale) {
+	AreaSpan t;
+	const double fsx1 = d*scale, fsx2 = fsx1+scale;
+	const double cell = fmin(scale, ssize-fsx1);
+	int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+	sx2 = min(sx2, ssize-1);
+	sx1 = min(sx1, sx2);
+	t.s0 = sx1; t.s1 = sx2;
+	t.lead = (sx1-fsx1) > 1e-3;
+	t.a0 = (float)((sx1-fsx1)/cell);
+	t.a = (float)(1.0/cell);
+	t.trail = (fsx2-sx2) > 1e-3;
+	t.a1 = (float)(fmin(fmin(fsx2-sx2, 1.0), cell)/cell);
+	return t;
+}
+
+__global__ void resize_area_kernel(const float* __restrict__ src, int sw, int sh, int spitch,
+	float* __restrict__ dst, int dw, int dh, double scx, double scy, int ix, int iy)
+{
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= dw || y >= dh) return;
+	if (ix > 0) {
+		// integer ratio: plain box mean
+		float s = 0.f;
+		for (int j = 0; j < iy; ++j)
+			for (int i = 0; i < ix; ++i)
+				s += __ldg(src + (size_t)(y*iy+j)*spitch + x*ix+i);
+		dst[(size_t)y*dw+x] = s*(1.f/(ix*iy));
+		return;
+	}
+	const AreaSpan tx = area_span(x, sw, scx), ty = area_span(y, sh, scy);
+	float sum = 0.f;
+	bool first = true;
+	for (int r = ty.s0-(ty.lead ? 1 : 0); r <= ty.s1; ++r) {
+		float beta;
+		if (r < ty.s0) beta = ty.a0;
+		else if (r < ty.s1) beta = ty.a;
+		else { if (!ty.trail) break; beta = ty.a1; }
+		const float* row = src + (size_t)r*spitch;
+		float buf = 0.f;
+		if (tx.lead) buf += __ldg(row+tx.s0-1)*tx.a0;
+		for (int c = tx.s0; c < tx.s1; ++c) buf += __ldg(row+c)*tx.a;
+		if (tx.trail) buf += __ldg(row+tx.s1)*tx.a1;
+		if (first) { sum = beta*buf; first = false; } else sum += beta*buf;
+	}
+	dst[(size_t)y*dw+x] = sum;
+}
+
+__device__ __forceinline__ void linear_tap(int d, int ssize, double scale, int& s, float& f) {
+	f = (float)((d+0.5)*scale-0.5);
+	s = (int)floorf(f);
+	f -= s;
+	if (s < 0) { f = 0.f; s = 0; }
+	if (s >= ssize-1) { f = 0.f; s = ssize-1; }
+}
+
+__global__ void resize_linear_kernel(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst, int dw, int dh, double scx, double scy) {
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= dw || y >= dh) return;
+	int x0, y0; float fx, fy;
+	linear_tap(x, sw, scx, x0, fx);
+	linear_tap(y, sh, scy, y0, fy);
+	const int x1 = min(x0+1, sw-1), y1 = min(y0+1, sh-1);
+	const float r0 = src[(size_t)y0*sw+x0]*(1.f-fx) + src[(size_t)y0*sw+x1]*fx;
+	const float r1 = src[(size_t)y1*sw+x0]*(1.f-fx) + src[(size_t)y1*sw+x1]*fx;
+	dst[(size_t)y*dw+x] = r0*(1.f-fy) + r1*fy;
+}
+
+__global__ void resize_nearest_kernel(const float* __restrict__ src, int sw, int sh, int ch, float* __restrict__ dst, int dw, int dh, double ifx, double ify) {
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= dw || y >= dh) return;
+	const int sx = min((int)floor(x*ifx), sw-1), sy = min((int)floor(y*ify), sh-1);
+	for (int c = 0; c < ch; ++c)
+		dst[((size_t)y*dw+x)*ch+c] = src[((size_t)sy*sw+sx)*ch+c];
+}
+
+// next-level initialisation: depth bilinear (INTER_LINEAR), normal nearest, from the packed
+// low-resolution plane field; also writes the depth prior of the level
+__global__ void plane_up_kernel(const float4* __restrict__ src, int sw, int sh, float4* __restrict__ dst, float* __restrict__ prior,
+	int dw, int dh, double scx, double scy)
+{
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= dw || y >= dh) return;
+	int x0, y0; float fx, fy;
+	linear_tap(x, sw, scx, x0, fx);
+	linear_tap(y, sh, scy, y0, fy);
+	const int x1 = min(x0+1, sw-1), y1 = min(y0+1, sh-1);
+	const float r0 = src[(size_t)y0*sw+x0].w*(1.f-fx) + src[(size_t)y0*sw+x1].w*fx;
+	const float r1 = src[(size_t)y1*sw+x0].w*(1.f-fx) + src[(size_t)y1*sw+x1].w*fx;
+	const float d = r0*(1.f-fy) + r1*fy;
+	const int sx = min((int)floor(x*scx), sw-1), sy = min((int)floor(y*scy), sh-1);
+	const float4 n = src[(size_t)sy*sw+sx];
+	dst[(size_t)y*dw+x] = make_float4(n.x, n.y, n.z, d);
+	prior[(size_t)y*dw+x] = d;
+}
+
+inline dim3 grid2(int w, int h, dim3 b) { return dim3((w+b.x-1)/b.x, (h+b.y-1)/b.y); }
+
+} // namespace
+
+cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, cudaStream_t s) {
+	const double scx = (double)sw/dw, scy = (double)sh/dh;
+	const int ix = (int)scx, iy = (int)scy;
+	const bool integer = (double)ix == scx && (double)iy == scy;
+	dim3 b(32, 8);
+	resize_area_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, spitch, dst, dw, dh, scx, scy, integer ? ix : 0, integer ? iy : 0);
+	return cudaGetLastError();
+}
+cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s) {
+	dim3 b(32, 8);
+	resize_linear_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, dst, dw, dh, (double)sw/dw, (double)sh/dh);
+	return cudaGetLastError();
+}
+cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s) {
+	dim3 b(32, 8);
+	resize_nearest_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, ch, dst, dw, dh, (double)sw/dw, (double)sh/dh);
+	return cudaGetLastError();
+}
+cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, cudaStream_t s) {
+	dim3 b(32, 8);
+	plane_up_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, dst, prior, dw, dh, (double)sw/dw, (double)sh/dh);
+	return cudaGetLastError();
+}

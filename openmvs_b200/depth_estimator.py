@@ -1,0 +1,263 @@
+"""Host-side mirror of the reference interface of the hot path.
+
+Names, argument meaning and error behaviour follow the reference so that the parity tests
+read like tests of the reference:
+
+  OPTDENSE            option namespace              libs/MVS/DepthMap.cpp:69-114
+  Camera              K, R, C                       libs/MVS/Camera.h
+  ViewData, DepthData in/out container              libs/MVS/DepthMap.h:157-271
+  PatchMatchB200      the PatchMatchCUDA seam       libs/MVS/PatchMatchCUDA.inl:78-131
+                      (ctor(device), Init(bGeomConsistency), Release(), EstimateDepthMap(DepthData&))
+  DepthMapsData       EstimateDepthMap(idxImage, nGeometricIter)   libs/MVS/SceneDensify.cpp:616-805
+
+Everything here is plumbing above the C-ABI (include/b200mvs.h); the arithmetic runs in the
+CUDA kernels of openmvs_b200/csrc.  numpy arrays take the host path (H2D/D2H inside the
+call, like the reference seam); torch CUDA tensors take the device-resident path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import List, Optional
+
+import numpy as np
+
+from . import lib as _lib
+
+
+class OPTDENSE:
+	"""The OPTDENSE knobs the estimator consumes, with the reference defaults
+	(libs/MVS/DepthMap.cpp:69-114).  Class attributes, like the reference's globals."""
+	nSubResolutionLevels = 2
+	nNumViews = 0
+	nEstimationIters = 3
+	nEstimationGeometricIters = 2
+	fEstimationGeometricWeight = 0.1
+	nRandomIters = 6
+	fNCCThresholdKeep = 0.9
+	fDescriptorMinMagnitudeThreshold = 0.02
+	fRandomDepthRatio = 0.003
+	fRandomAngle1Range = 16.0
+	fRandomAngle2Range = 10.0
+	fRandomSmoothDepth = 0.02
+	fRandomSmoothNormal = 13.0
+	fRandomSmoothBonus = 0.93
+	# engine schedule (not in the reference): red-black sweeps per reference iteration
+	nSweepsPerIter = 2
+	nPropagation = 4
+	nSeed = 1234
+
+	@classmethod
+	def snapshot(cls) -> _lib.Params:
+		p = _lib.Params()
+		for name, _ in _lib.Params._fields_:
+			if name == "seed":
+				p.seed = cls.nSeed
+			else:
+				setattr(p, name, getattr(cls, name))
+		return p
+
+
+@dataclasses.dataclass
+class Camera:
+	K: np.ndarray
+	R: np.ndarray
+	C: np.ndarray
+
+
+@dataclasses.dataclass
+class ViewData:
+	"""DepthData::ViewData: gray float image in [0,1] + camera (+ known depth-map and its camera)."""
+	image: object            # (H, W) float32 numpy array or torch CUDA tensor
+	camera: Camera
+	depthMap: object = None  # optional (H, W) float32
+	cameraDepthMap: Optional[Camera] = None
+
+
+@dataclasses.dataclass
+class DepthData:
+	images: List[ViewData]   # reference view first
+	dMin: float
+	dMax: float
+	depthMap: object = None
+	normalMap: object = None
+	confMap: object = None
+	viewsMap: object = None
+
+	def IsValid(self) -> bool:
+		return len(self.images) > 0
+
+	def IsEmpty(self) -> bool:
+		return self.depthMap is None
+
+
+def _is_torch(a) -> bool:
+	return type(a).__module__.startswith("torch")
+
+
+def _make_views(images: List[ViewData]):
+	"""-> (ctypes View array, keepalive list, on_device flag)"""
+	n = len(images)
+	arr = (_lib.View*n)()
+	keep = []
+	dev = _is_torch(images[0].image)
+	for i, v in enumerate(images):
+		o = arr[i]
+		if dev != _is_torch(v.image):
+			raise ValueError("mixing host and device images in one DepthData")
+		if dev:
+			img = v.image
+			if img.dtype.__str__() != "torch.float32" or not img.is_cuda or img.dim() != 2 or img.stride(1) != 1:
+				raise ValueError("device image must be a 2-D float32 CUDA tensor with unit column stride")
+			keep.append(img)
+			o.image = img.data_ptr(); o.height, o.width = img.shape; o.stride_bytes = img.stride(0)*4
+		else:
+			img = np.asarray(v.image)
+			if img.dtype != np.float32 or img.ndim != 2 or img.strides[1] != 4:
+				raise ValueError("image must be a 2-D float32 array with contiguous rows (Image32F)")
+			keep.append(img)
+			o.image = img.ctypes.data; o.height, o.width = img.shape; o.stride_bytes = img.strides[0]
+		o.K[:] = np.asarray(v.camera.K, np.float64).ravel()
+		o.R[:] = np.asarray(v.camera.R, np.float64).ravel()
+		o.C[:] = np.asarray(v.camera.C, np.float64).ravel()
+		o.depth = None
+		if v.depthMap is not None and i > 0:
+			cam = v.cameraDepthMap or v.camera
+			if dev:
+				dm = v.depthMap
+				keep.append(dm)
+				o.depth = dm.data_ptr(); o.dheight, o.dwidth = dm.shape; o.dstride_bytes = dm.stride(0)*4
+			else:
+				dm = np.ascontiguousarray(v.depthMap, np.float32)
+				keep.append(dm)
+				o.depth = dm.ctypes.data; o.dheight, o.dwidth = dm.shape; o.dstride_bytes = dm.strides[0]
+			o.Kd[:] = np.asarray(cam.K, np.float64).ravel()
+			o.Rd[:] = np.asarray(cam.R, np.float64).ravel()
+			o.Cd[:] = np.asarray(cam.C, np.float64).ravel()
+	return arr, keep, dev
+
+
+class PatchMatchB200:
+	"""Drop-in for the reference's `PatchMatchCUDA` (libs/MVS/PatchMatchCUDA.inl:78-131)."""
+
+	def __init__(self, device: int = 0):
+		self._lib = _lib.load()
+		self._ctx = C.c_void_p()
+		rc = self._lib.b200mvs_create(int(device), C.byref(self._ctx))
+		if rc != 0:
+			raise _lib.B200MVSError("b200mvs_create(device=%d) failed with status %d (no GPU => no fallback)" % (device, rc))
+		self.device = int(device)
+		self.bGeomConsistency = False
+		self.stats = _lib.Stats()
+
+	def Init(self, bGeomConsistency: bool = False):
+		"""PatchMatchCUDA::Init: select photometric (false) or geometric-consistency (true) passes."""
+		self.bGeomConsistency = bool(bGeomConsistency)
+
+	def Release(self):
+		if self._ctx:
+			self._lib.b200mvs_destroy(self._ctx)
+			self._ctx = C.c_void_p()
+
+	def __del__(self):
+		try:
+			self.Release()
+		except Exception:
+			pass
+
+	def _set_params(self):
+		p = OPTDENSE.snapshot()
+		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_params(self._ctx, C.byref(p)), "b200mvs_set_params")
+
+	def EstimateDepthMap(self, depthData: DepthData, nGeometricIter: Optional[int] = None, stream=None, sync: bool = True):
+		"""PatchMatchCUDA::EstimateDepthMap(DepthData&): estimate depthMap/normalMap/confMap/viewsMap
+		of depthData in place.  nGeometricIter defaults to -1 (photometric) or 0 (after Init(true))."""
+		if not depthData.IsValid() or len(depthData.images) < 2:
+			raise ValueError("DepthData needs the reference view and at least one neighbour")
+		if nGeometricIter is None:
+			nGeometricIter = 0 if self.bGeomConsistency else -1
+		self._set_params()
+		arr, keep, dev = _make_views(depthData.images)
+		h, w = depthData.images[0].image.shape
+		if dev:
+			import torch
+			t0 = depthData.images[0].image
+			def dmap(a, shape, dtype):
+				if a is None:
+					return torch.zeros(shape, dtype=dtype, device=t0.device)
+				if tuple(a.shape) != tuple(shape) or not a.is_contiguous():
+					raise ValueError("map has the wrong shape or is not contiguous")
+				return a
+			depthData.depthMap = dmap(depthData.depthMap, (h, w), torch.float32)
+			depthData.normalMap = dmap(depthData.normalMap, (h, w, 3), torch.float32)
+			depthData.confMap = dmap(depthData.confMap, (h, w), torch.float32)
+			depthData.viewsMap = dmap(depthData.viewsMap, (h, w, 4), torch.uint8)
+			if stream is None:
+				stream = torch.cuda.current_stream(t0.device).cuda_stream
+			rc = self._lib.b200mvs_estimate_device(self._ctx, arr, len(arr), C.c_float(depthData.dMin), C.c_float(depthData.dMax),
+				int(nGeometricIter), depthData.depthMap.data_ptr(), depthData.normalMap.data_ptr(),
+				depthData.confMap.data_ptr(), depthData.viewsMap.data_ptr(), C.c_void_p(stream),
+				C.byref(self.stats) if sync else None)
+			_lib.check(self._lib, self._ctx, rc, "b200mvs_estimate_device")
+		else:
+			def hmap(a, shape, dtype):
+				if a is None:
+					return np.zeros(shape, dtype)
+				a = np.ascontiguousarray(a, dtype)
+				if a.shape != tuple(shape):
+					raise ValueError("map has the wrong shape")
+				return a
+			depthData.depthMap = hmap(depthData.depthMap, (h, w), np.float32)
+			depthData.normalMap = hmap(depthData.normalMap, (h, w, 3), np.float32)
+			depthData.confMap = hmap(depthData.confMap, (h, w), np.float32)
+			depthData.viewsMap = hmap(depthData.viewsMap, (h, w, 4), np.uint8)
+			rc = self._lib.b200mvs_estimate(self._ctx, arr, len(arr), C.c_float(depthData.dMin), C.c_float(depthData.dMax),
+				int(nGeometricIter), depthData.depthMap.ctypes.data, depthData.normalMap.ctypes.data,
+				depthData.confMap.ctypes.data, depthData.viewsMap.ctypes.data, C.byref(self.stats))
+			_lib.check(self._lib, self._ctx, rc, "b200mvs_estimate")
+		return depthData
+
+	# ---- building blocks on device tensors (used by the parity tests) -----------------------
+	def _dev_views(self, images):
+		arr, keep, dev = _make_views(images)
+		if not dev:
+			raise ValueError("building blocks need device-resident views")
+		return arr, keep
+
+	def ScoreDepthMap(self, images, dMin, dMax, plane4, cost, lowres=None):
+		"""pass A (ScoreDepthMapTmp) on a packed plane field (H, W, 4) = {nx,ny,nz,depth}."""
+		import torch
+		self._set_params()
+		arr, keep = self._dev_views(images)
+		s = torch.cuda.current_stream(plane4.device).cuda_stream
+		rc = self._lib.b200mvs_pm_score(self._ctx, arr, len(arr), C.c_float(dMin), C.c_float(dMax),
+			lowres.data_ptr() if lowres is not None else None, plane4.data_ptr(), cost.data_ptr(), C.c_void_p(s))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_pm_score")
+
+	def SweepDepthMap(self, images, dMin, dMax, plane4, cost, sweep, half=-1, nRandomIters=None, lowres=None):
+		"""pass B: one red-black sweep (both colours, or one if half in {0,1})."""
+		import torch
+		self._set_params()
+		arr, keep = self._dev_views(images)
+		if nRandomIters is None:
+			spi = max(1, OPTDENSE.nSweepsPerIter)
+			nRandomIters = (OPTDENSE.nRandomIters+spi-1)//spi
+		s = torch.cuda.current_stream(plane4.device).cuda_stream
+		rc = self._lib.b200mvs_pm_sweep(self._ctx, arr, len(arr), C.c_float(dMin), C.c_float(dMax),
+			lowres.data_ptr() if lowres is not None else None, int(sweep), int(half), int(nRandomIters),
+			plane4.data_ptr(), cost.data_ptr(), C.c_void_p(s))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_pm_sweep")
+
+
+class DepthMapsData:
+	"""The slice of the reference's DepthMapsData that owns the hot path
+	(libs/MVS/SceneDensify.h:52-93): arrDepthData + EstimateDepthMap(idxImage, nGeometricIter)."""
+
+	def __init__(self, arrDepthData: List[DepthData], device: int = 0):
+		self.arrDepthData = arrDepthData
+		self.pmCUDA = PatchMatchB200(device)
+
+	def EstimateDepthMap(self, idxImage: int, nGeometricIter: int = -1) -> bool:
+		self.pmCUDA.Init(nGeometricIter >= 0)
+		self.pmCUDA.EstimateDepthMap(self.arrDepthData[idxImage], nGeometricIter)
+		return True

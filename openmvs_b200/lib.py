@@ -1,0 +1,89 @@
+"""ctypes binding of include/b200mvs.h.  There is no CPU fallback: if the CUDA library is
+missing or no GPU is present, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_VIEWS = 32
+
+
+class View(C.Structure):
+	"""b200mvs_view"""
+	_fields_ = [("image", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("stride_bytes", C.c_int),
+		("K", C.c_double*9), ("R", C.c_double*9), ("C", C.c_double*3),
+		("depth", C.c_void_p), ("dwidth", C.c_int), ("dheight", C.c_int), ("dstride_bytes", C.c_int),
+		("Kd", C.c_double*9), ("Rd", C.c_double*9), ("Cd", C.c_double*3)]
+
+
+class Params(C.Structure):
+	"""b200mvs_params"""
+	_fields_ = [("nEstimationIters", C.c_int), ("nEstimationGeometricIters", C.c_int), ("nRandomIters", C.c_int),
+		("nSubResolutionLevels", C.c_int),
+		("fNCCThresholdKeep", C.c_float), ("fDescriptorMinMagnitudeThreshold", C.c_float),
+		("fRandomDepthRatio", C.c_float), ("fRandomAngle1Range", C.c_float), ("fRandomAngle2Range", C.c_float),
+		("fRandomSmoothDepth", C.c_float), ("fRandomSmoothNormal", C.c_float), ("fRandomSmoothBonus", C.c_float),
+		("fEstimationGeometricWeight", C.c_float),
+		("nSweepsPerIter", C.c_int), ("nPropagation", C.c_int), ("seed", C.c_uint32)]
+
+
+class Stats(C.Structure):
+	"""b200mvs_stats"""
+	_fields_ = [("ms_total", C.c_double), ("ms_device", C.c_double), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
+		("kernel_launches", C.c_int), ("levels", C.c_int)]
+
+
+# every symbol include/b200mvs.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+	"b200mvs_create", "b200mvs_destroy", "b200mvs_default_params", "b200mvs_set_params", "b200mvs_last_error",
+	"b200mvs_device_count", "b200mvs_estimate", "b200mvs_estimate_device",
+	"b200mvs_pm_pack", "b200mvs_pm_unpack", "b200mvs_pm_score", "b200mvs_pm_sweep", "b200mvs_pm_finalize",
+]
+
+_LIB = None
+
+
+def load(build_if_missing: bool = True):
+	"""Load libb200mvs.so (building it in-tree when stale and nvcc is available)."""
+	global _LIB
+	if _LIB is not None:
+		return _LIB
+	path = _build.LIB_PATH
+	if build_if_missing:
+		try:
+			path = _build.build_extension()
+		except Exception:
+			if not os.path.exists(path):
+				raise
+	if not os.path.exists(path):
+		raise RuntimeError("CUDA extension %s is missing: run __graft_entry__.build() (no CPU fallback exists)" % path)
+	lib = C.CDLL(path)
+	lib.b200mvs_last_error.restype = C.c_char_p
+	lib.b200mvs_last_error.argtypes = [C.c_void_p]
+	lib.b200mvs_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+	lib.b200mvs_destroy.argtypes = [C.c_void_p]
+	lib.b200mvs_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+	lib.b200mvs_default_params.argtypes = [C.POINTER(Params)]
+	F = C.c_float
+	P = C.c_void_p
+	lib.b200mvs_estimate.argtypes = [P, C.POINTER(View), C.c_int, F, F, C.c_int, P, P, P, P, C.POINTER(Stats)]
+	lib.b200mvs_estimate_device.argtypes = [P, C.POINTER(View), C.c_int, F, F, C.c_int, P, P, P, P, P, C.POINTER(Stats)]
+	lib.b200mvs_pm_pack.argtypes = [P, C.c_int, C.c_int, P, P, P, P]
+	lib.b200mvs_pm_unpack.argtypes = [P, C.c_int, C.c_int, P, P, P, P]
+	lib.b200mvs_pm_score.argtypes = [P, C.POINTER(View), C.c_int, F, F, P, P, P, P]
+	lib.b200mvs_pm_sweep.argtypes = [P, C.POINTER(View), C.c_int, F, F, P, C.c_int, C.c_int, C.c_int, P, P, P]
+	lib.b200mvs_pm_finalize.argtypes = [P, C.c_int, C.c_int, F, P, P, P, P, P, P]
+	_LIB = lib
+	return lib
+
+
+class B200MVSError(RuntimeError):
+	pass
+
+
+def check(lib, ctx, rc: int, what: str):
+	if rc != 0:
+		msg = lib.b200mvs_last_error(ctx).decode() if ctx else ""
+		raise B200MVSError("%s failed with status %d: %s" % (what, rc, msg))

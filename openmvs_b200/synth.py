@@ -1,0 +1,116 @@
+"""Seeded synthetic multi-view scenes with analytic ground truth.
+
+A smooth textured height-field z = h(x, y) seen by pinhole cameras placed on a spherical
+cap and looking at the origin.  Images are rendered by exact ray casting (Newton on the
+height function) and an analytic band-limited texture, so depth and normal ground truth
+are exact and there is no resampling blur.  Camera convention is the reference's:
+X_cam = R (X - C), x ~ K X_cam, pixel centres at integer coordinates
+(libs/MVS/Camera.h:331-344).
+
+Pure numpy; deterministic for a given seed (inputs of parity tests are generated once on
+the CPU and fed to both the oracle and the CUDA engine).
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+
+@dataclasses.dataclass
+class View:
+	image: np.ndarray      # (H, W) float32 gray in [0, 1]
+	K: np.ndarray          # (3, 3) float64
+	R: np.ndarray          # (3, 3) float64
+	C: np.ndarray          # (3,) float64
+	depth_gt: np.ndarray   # (H, W) float32
+	normal_gt: np.ndarray  # (H, W, 3) float32 camera space, facing the camera
+
+
+@dataclasses.dataclass
+class Scene:
+	views: list
+	dmin: float
+	dmax: float
+
+	def neighbors(self, ref: int, n: int) -> list:
+		"""indices of the n nearest views (by camera centre) of `ref`"""
+		c = np.stack([v.C for v in self.views])
+		d = np.linalg.norm(c - c[ref], axis=1)
+		order = [int(i) for i in np.argsort(d, kind="stable") if i != ref]
+		return order[:n]
+
+
+def _height(x, y):
+	h = 0.22*np.sin(1.7*x + 0.3)*np.cos(1.3*y - 0.2) + 0.08*np.sin(3.1*x - 1.0)*np.sin(2.7*y + 0.5)
+	hx = 0.22*1.7*np.cos(1.7*x + 0.3)*np.cos(1.3*y - 0.2) + 0.08*3.1*np.cos(3.1*x - 1.0)*np.sin(2.7*y + 0.5)
+	hy = -0.22*1.3*np.sin(1.7*x + 0.3)*np.sin(1.3*y - 0.2) + 0.08*2.7*np.sin(3.1*x - 1.0)*np.cos(2.7*y + 0.5)
+	return h, hx, hy
+
+
+class _Texture:
+	def __init__(self, seed: int, px_per_unit: float, n_waves: int = 20):
+		rng = np.random.RandomState(seed)
+		# wavelengths between 5 and 48 pixels in the image (log-uniform)
+		lam_px = np.exp(rng.uniform(np.log(5.0), np.log(48.0), n_waves))
+		freq = 2*np.pi*px_per_unit/lam_px
+		ang = rng.uniform(0, np.pi, n_waves)
+		self.fx = freq*np.cos(ang)
+		self.fy = freq*np.sin(ang)
+		self.ph = rng.uniform(0, 2*np.pi, n_waves)
+		amp = rng.uniform(0.6, 1.0, n_waves)
+		self.amp = amp/np.sqrt((amp**2).sum()/2.0)  # unit variance of the sum
+
+	def __call__(self, x, y):
+		acc = np.zeros_like(x)
+		for fx, fy, ph, a in zip(self.fx, self.fy, self.ph, self.amp):
+			acc += a*np.sin(fx*x + fy*y + ph)
+		return np.clip(0.5 + 0.17*acc, 0.0, 1.0)
+
+
+def look_at(C, target=np.zeros(3)):
+	z = target - C
+	z = z/np.linalg.norm(z)
+	x = np.cross(np.array([0.0, 1.0, 0.0]), z)
+	x = x/np.linalg.norm(x)
+	y = np.cross(z, x)
+	return np.stack([x, y, z])
+
+
+def make_scene(width: int, height: int, n_views: int, seed: int = 1234, radius: float = 5.5,
+		step_deg: float = 4.0, focal_ratio: float = 0.9, cols: int | None = None) -> Scene:
+	"""n_views cameras on a (rows x cols) angular grid `step_deg` apart, radius `radius`."""
+	if cols is None:
+		cols = int(np.ceil(np.sqrt(n_views*4/3.0))) if n_views > 2 else n_views
+	rows = int(np.ceil(n_views/cols))
+	f = focal_ratio*width
+	K = np.array([[f, 0, (width-1)/2.0], [0, f, (height-1)/2.0], [0, 0, 1.0]])
+	tex = _Texture(seed, px_per_unit=f/radius)
+	views = []
+	ys, xs = np.mgrid[0:height, 0:width].astype(np.float64)
+	for i in range(n_views):
+		r, c = divmod(i, cols)
+		ax = np.deg2rad(step_deg*(c-(cols-1)/2.0))
+		ay = np.deg2rad(step_deg*(r-(rows-1)/2.0))
+		C = radius*np.array([np.sin(ax)*np.cos(ay), np.sin(ay), np.cos(ax)*np.cos(ay)])
+		R = look_at(C)
+		# rays in world space, parameterised so that t == camera-space depth
+		dx = (xs-K[0, 2])/K[0, 0]
+		dy = (ys-K[1, 2])/K[1, 1]
+		D = np.stack([dx, dy, np.ones_like(dx)], -1) @ R  # R^T applied to each row vector
+		t = (0.0-C[2])/D[..., 2]
+		for _ in range(12):
+			px = C[0]+t*D[..., 0]
+			py = C[1]+t*D[..., 1]
+			h, hx, hy = _height(px, py)
+			F = C[2]+t*D[..., 2]-h
+			dF = D[..., 2]-(hx*D[..., 0]+hy*D[..., 1])
+			t = t-F/dF
+		px = C[0]+t*D[..., 0]
+		py = C[1]+t*D[..., 1]
+		h, hx, hy = _height(px, py)
+		nw = np.stack([-hx, -hy, np.ones_like(hx)], -1)
+		nw /= np.linalg.norm(nw, axis=-1, keepdims=True)
+		nc = nw @ R.T
+		img = tex(px, py)
+		views.append(View(img.astype(np.float32), K.copy(), R, C, t.astype(np.float32), nc.astype(np.float32)))
+	return Scene(views, dmin=float(radius-1.5), dmax=float(radius+1.5))

@@ -1,0 +1,147 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE — see oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may
+import this module.  The product package openmvs_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OView(C.Structure):
+	_fields_ = [("image", C.c_void_p), ("width", C.c_int), ("height", C.c_int),
+		("K", C.c_double*9), ("R", C.c_double*9), ("C", C.c_double*3),
+		("depth", C.c_void_p), ("dwidth", C.c_int), ("dheight", C.c_int),
+		("Kd", C.c_double*9), ("Rd", C.c_double*9), ("Cd", C.c_double*3)]
+
+
+class OParams(C.Structure):
+	_fields_ = [("nEstimationIters", C.c_int), ("nEstimationGeometricIters", C.c_int), ("nRandomIters", C.c_int),
+		("fNCCThresholdKeep", C.c_float), ("fDescriptorMinMagnitudeThreshold", C.c_float),
+		("fRandomDepthRatio", C.c_float), ("fRandomAngle1Range", C.c_float), ("fRandomAngle2Range", C.c_float),
+		("fRandomSmoothDepth", C.c_float), ("fRandomSmoothNormal", C.c_float), ("fRandomSmoothBonus", C.c_float),
+		("fEstimationGeometricWeight", C.c_float), ("nSubResolutionLevels", C.c_int),
+		("schedule", C.c_int), ("propagation", C.c_int), ("seed", C.c_uint32), ("threads", C.c_int)]
+
+
+def build(force: bool = False) -> str:
+	so = os.path.join(_HERE, "liboracle.so")
+	srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.cpp", "sgm_oracle.cpp", "oracle.h")]
+	if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
+		subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+	return so
+
+
+def lib():
+	global _LIB
+	if _LIB is None:
+		_LIB = C.CDLL(build())
+		_LIB.oracle_pm_score_pixel.restype = C.c_float
+		_LIB.oracle_interpolate_pixel.restype = C.c_float
+	return _LIB
+
+
+def default_params(**kw) -> OParams:
+	p = OParams()
+	lib().oracle_default_params(C.byref(p))
+	for k, v in kw.items():
+		if not hasattr(p, k):
+			raise AttributeError(k)
+		setattr(p, k, v)
+	return p
+
+
+def _fptr(a):
+	return a.ctypes.data_as(C.c_void_p)
+
+
+def make_views(views, depths=None):
+	"""views: list of objects with .image .K .R .C (reference first); depths: optional list of
+	(depth, K, R, C) or None per view. Returns (ctypes array, keepalive)."""
+	arr = (OView*len(views))()
+	keep = []
+	for i, v in enumerate(views):
+		img = np.ascontiguousarray(v.image, np.float32)
+		keep.append(img)
+		o = arr[i]
+		o.image = _fptr(img); o.width = img.shape[1]; o.height = img.shape[0]
+		o.K[:] = np.asarray(v.K, np.float64).ravel(); o.R[:] = np.asarray(v.R, np.float64).ravel(); o.C[:] = np.asarray(v.C, np.float64).ravel()
+		o.depth = None
+		if depths is not None and depths[i] is not None:
+			d, Kd, Rd, Cd = depths[i]
+			d = np.ascontiguousarray(d, np.float32)
+			keep.append(d)
+			o.depth = _fptr(d); o.dwidth = d.shape[1]; o.dheight = d.shape[0]
+			o.Kd[:] = np.asarray(Kd, np.float64).ravel(); o.Rd[:] = np.asarray(Rd, np.float64).ravel(); o.Cd[:] = np.asarray(Cd, np.float64).ravel()
+	return arr, keep
+
+
+def _state(views, depth, normal):
+	h, w = views[0].image.shape
+	d = np.zeros((h, w), np.float32) if depth is None else np.array(depth, np.float32, copy=True, order="C")
+	n = np.zeros((h, w, 3), np.float32) if normal is None else np.array(normal, np.float32, copy=True, order="C")
+	c = np.zeros((h, w), np.float32)
+	return d, n, c
+
+
+def pm_score(views, prm, dmin, dmax, depth=None, normal=None, lowres=None, depths=None):
+	arr, keep = make_views(views, depths)
+	d, n, c = _state(views, depth, normal)
+	lr = None if lowres is None else np.ascontiguousarray(lowres, np.float32)
+	rc = lib().oracle_pm_score(arr, len(views), C.byref(prm), C.c_float(dmin), C.c_float(dmax),
+		None if lr is None else _fptr(lr), _fptr(d), _fptr(n), _fptr(c))
+	assert rc == 0
+	return d, n, c
+
+
+def pm_iterate(views, prm, dmin, dmax, depth, normal, conf, it, half=-1, lowres=None, depths=None):
+	arr, keep = make_views(views, depths)
+	d = np.array(depth, np.float32, copy=True, order="C")
+	n = np.array(normal, np.float32, copy=True, order="C")
+	c = np.array(conf, np.float32, copy=True, order="C")
+	lr = None if lowres is None else np.ascontiguousarray(lowres, np.float32)
+	rc = lib().oracle_pm_iterate(arr, len(views), C.byref(prm), C.c_float(dmin), C.c_float(dmax),
+		None if lr is None else _fptr(lr), int(it), int(half), _fptr(d), _fptr(n), _fptr(c))
+	assert rc == 0
+	return d, n, c
+
+
+def pm_finalize(depth, normal, conf, keep):
+	d = np.array(depth, np.float32, copy=True, order="C")
+	n = np.array(normal, np.float32, copy=True, order="C")
+	c = np.array(conf, np.float32, copy=True, order="C")
+	lib().oracle_pm_finalize(d.shape[1], d.shape[0], C.c_float(keep), _fptr(d), _fptr(n), _fptr(c))
+	return d, n, c
+
+
+def pm_estimate(views, prm, dmin, dmax, geometric_iter=-1, depth=None, normal=None, depths=None):
+	arr, keep = make_views(views, depths)
+	d, n, c = _state(views, depth, normal)
+	rc = lib().oracle_pm_estimate(arr, len(views), C.byref(prm), C.c_float(dmin), C.c_float(dmax),
+		int(geometric_iter), _fptr(d), _fptr(n), _fptr(c))
+	assert rc == 0
+	return d, n, c
+
+
+def pm_score_pixel(views, prm, dmin, dmax, x, y, depth, normal, close=None, lowres=None, depths=None):
+	arr, keep = make_views(views, depths)
+	nrm = (C.c_float*3)(*[float(v) for v in normal])
+	cl = np.zeros((0, 7), np.float32) if close is None else np.ascontiguousarray(close, np.float32).reshape(-1, 7)
+	vs = np.zeros(len(views)-1, np.float32)
+	lr = None if lowres is None else np.ascontiguousarray(lowres, np.float32)
+	s = lib().oracle_pm_score_pixel(arr, len(views), C.byref(prm), C.c_float(dmin), C.c_float(dmax),
+		None if lr is None else _fptr(lr), int(x), int(y), C.c_float(depth), nrm,
+		_fptr(cl) if len(cl) else None, len(cl), _fptr(vs))
+	return float(s), vs
+
+
+def philox(ctr, key):
+	c = (C.c_uint32*4)(*ctr); k = (C.c_uint32*2)(*key); o = (C.c_uint32*4)()
+	lib().oracle_philox4x32(c, k, o)
+	return [int(v) for v in o]
