@@ -103,7 +103,8 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
 	float* depth, float* normal, float* conf, uint8_t* viewsMap, b200mvs_stats* stats);
 
 /* Same, but every pointer inside `views` and the map pointers are DEVICE pointers on the
- * context's device (data resident in HBM); work is enqueued on `stream` (cudaStream_t) and
+ * context's device (data resident in HBM); work is enqueued on `stream` (cudaStream_t; NULL = the
+ * context's own non-blocking stream, pass cudaStreamLegacy for the legacy default stream) and
  * the call returns after enqueueing unless stats != NULL (then it synchronises). */
 int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
 	float dMin, float dMax, int nGeometricIter,

@@ -20,7 +20,7 @@ cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const flo
 	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s);
 cudaError_t pm_launch_pack(int n, const float* depth, const float* normal, float4* plane, cudaStream_t s);
 cudaError_t pm_launch_unpack(int n, const float4* plane, float* depth, float* normal, cudaStream_t s);
-cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, cudaStream_t s);
+cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, cudaStream_t s);
@@ -224,12 +224,12 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 				const size_t need = (size_t)dw*dh*sizeof(float)*(views[i].dmap ? 2 : 1);
 				CK(ctx->pyr[i].reserve(need));
 				float* im = ctx->pyr[i].as<float>();
-				CK(rs_launch_area(views[i].img, views[i].w, views[i].h, views[i].pitch, im, dw, dh, s)); ++ctx->launches;
+				CK(rs_launch_area(views[i].img, views[i].w, views[i].h, views[i].pitch, im, dw, dh, 1.0/scale, 1.0/scale, s)); ++ctx->launches;
 				lv[i].img = im; lv[i].w = dw; lv[i].h = dh; lv[i].pitch = dw;
 				scaleK(views[i].K, views[i].w, views[i].h, dw, dh, lv[i].K);
 				if (views[i].dmap) {
 					float* dm = im + (size_t)dw*dh;
-					CK(rs_launch_area(views[i].dmap, views[i].dw, views[i].dh, views[i].dpitch, dm, dw, dh, s)); ++ctx->launches;
+					CK(rs_launch_area(views[i].dmap, views[i].dw, views[i].dh, views[i].dpitch, dm, dw, dh, 0, 0, s)); ++ctx->launches;
 					lv[i].dmap = dm; lv[i].dw = dw; lv[i].dh = dh; lv[i].dpitch = dw;
 					scaleK(views[i].Kd, views[i].dw, views[i].dh, dw, dh, lv[i].Kd);
 				}

@@ -35,12 +35,11 @@ __global__ void resize_area_kernel(const float* __restrict__ src, int sw, int sh
 	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
 	if (x >= dw || y >= dh) return;
 	if (ix > 0) {
-		// integer ratio: plain box mean
-		float s = 0.f;
-		for (int j = 0; j < iy; ++j)
-			for (int i = 0; i < ix; ++i)
-				s += __ldg(src + (size_t)(y*iy+j)*spitch + x*ix+i);
-		dst[(size_t)y*dw+x] = s*(1.f/(ix*iy));
+		// integer ratio: box mean over the part of the box that lies inside the image
+		float s = 0.f; int count = 0;
+		for (int j = 0; j < iy && y*iy+j < sh; ++j)
+			for (int i = 0; i < ix && x*ix+i < sw; ++i) { s += __ldg(src + (size_t)(y*iy+j)*spitch + x*ix+i); ++count; }
+		dst[(size_t)y*dw+x] = count == ix*iy ? s*(1.f/(ix*iy)) : s/count;
 		return;
 	}
 	const AreaSpan tx = area_span(x, sw, scx), ty = area_span(y, sh, scy);
@@ -113,9 +112,12 @@ inline dim3 grid2(int w, int h, dim3 b) { return dim3((w+b.x-1)/b.x, (h+b.y-1)/b
 
 } // namespace
 
-cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, cudaStream_t s) {
-	const double scx = (double)sw/dw, scy = (double)sh/dh;
-	const int ix = (int)scx, iy = (int)scy;
+// scx/scy: source/destination scale; pass 1/factor for cv::resize(..., Size(), fx, fy) and <= 0 for
+// the destination-size form (sw/dw)
+cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s) {
+	if (!(scx > 0)) scx = (double)sw/dw;
+	if (!(scy > 0)) scy = (double)sh/dh;
+	const int ix = (int)(scx+0.5), iy = (int)(scy+0.5);
 	const bool integer = (double)ix == scx && (double)iy == scy;
 	dim3 b(32, 8);
 	resize_area_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, spitch, dst, dw, dh, scx, scy, integer ? ix : 0, integer ? iy : 0);

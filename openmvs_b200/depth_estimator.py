@@ -91,6 +91,14 @@ class DepthData:
 		return self.depthMap is None
 
 
+def _stream_handle(device) -> int:
+	"""cudaStream_t of torch's current stream.  The C-ABI treats NULL as "use the context's own
+	stream", so torch's legacy default stream (handle 0) is passed as cudaStreamLegacy (0x1)."""
+	import torch
+	h = torch.cuda.current_stream(device).cuda_stream
+	return h if h else 1
+
+
 def _is_torch(a) -> bool:
 	return type(a).__module__.startswith("torch")
 
@@ -193,7 +201,7 @@ class PatchMatchB200:
 			depthData.confMap = dmap(depthData.confMap, (h, w), torch.float32)
 			depthData.viewsMap = dmap(depthData.viewsMap, (h, w, 4), torch.uint8)
 			if stream is None:
-				stream = torch.cuda.current_stream(t0.device).cuda_stream
+				stream = _stream_handle(t0.device)
 			rc = self._lib.b200mvs_estimate_device(self._ctx, arr, len(arr), C.c_float(depthData.dMin), C.c_float(depthData.dMax),
 				int(nGeometricIter), depthData.depthMap.data_ptr(), depthData.normalMap.data_ptr(),
 				depthData.confMap.data_ptr(), depthData.viewsMap.data_ptr(), C.c_void_p(stream),
@@ -229,7 +237,7 @@ class PatchMatchB200:
 		import torch
 		self._set_params()
 		arr, keep = self._dev_views(images)
-		s = torch.cuda.current_stream(plane4.device).cuda_stream
+		s = _stream_handle(plane4.device)
 		rc = self._lib.b200mvs_pm_score(self._ctx, arr, len(arr), C.c_float(dMin), C.c_float(dMax),
 			lowres.data_ptr() if lowres is not None else None, plane4.data_ptr(), cost.data_ptr(), C.c_void_p(s))
 		_lib.check(self._lib, self._ctx, rc, "b200mvs_pm_score")
@@ -242,7 +250,7 @@ class PatchMatchB200:
 		if nRandomIters is None:
 			spi = max(1, OPTDENSE.nSweepsPerIter)
 			nRandomIters = (OPTDENSE.nRandomIters+spi-1)//spi
-		s = torch.cuda.current_stream(plane4.device).cuda_stream
+		s = _stream_handle(plane4.device)
 		rc = self._lib.b200mvs_pm_sweep(self._ctx, arr, len(arr), C.c_float(dMin), C.c_float(dMax),
 			lowres.data_ptr() if lowres is not None else None, int(sweep), int(half), int(nRandomIters),
 			plane4.data_ptr(), cost.data_ptr(), C.c_void_p(s))

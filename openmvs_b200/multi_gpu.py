@@ -1,0 +1,95 @@
+"""Sharding of reference views across the GPUs of one box.
+
+The unit of work is one reference view (one DepthMapsData::EstimateDepthMap call,
+libs/MVS/SceneDensify.cpp:616-805): it reads its own image and its neighbours' images and
+writes its own maps, so views are independent in the photometric pass.  One process per GPU
+(torch.distributed), reference views dealt round-robin, no data-path collective during the
+estimation.  Two exchanges exist:
+  * gather_maps      final gather of depth/normal/confidence to one rank (NCCL gather)
+  * all_gather_depth depth-only all-gather before a geometric-consistency pass, which needs
+                     the neighbours' pass-1 depth-maps (the reference reloads them from
+                     .dmap files, libs/MVS/SceneDensify.cpp:380-394)
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+	"""reference views estimated by `rank`: round-robin, so neighbouring views land on
+	different GPUs and per-rank counts differ by at most one"""
+	return list(range(rank, n_views, world))
+
+
+def owner_of(view: int, world: int) -> int:
+	return view % world
+
+
+def gather_maps(local: Dict[int, torch.Tensor], n_views: int, dst: int = 0):
+	"""Gather per-view maps to `dst`.  local: {view index: tensor (H, W, C)} for the views of
+	this rank (all views share one shape).  Returns {view: tensor} on dst, None elsewhere."""
+	if not dist.is_initialized() or dist.get_world_size() == 1:
+		return dict(local)
+	rank, world = dist.get_rank(), dist.get_world_size()
+	mine = shard_views(n_views, rank, world)
+	assert sorted(local.keys()) == mine, "rank %d holds %s, expected %s" % (rank, sorted(local.keys()), mine)
+	kmax = (n_views+world-1)//world
+	any_t = next(iter(local.values())) if local else None
+	shape_t = torch.zeros(4, dtype=torch.int64, device=any_t.device if any_t is not None else _default_device())
+	if any_t is not None:
+		shape_t[:any_t.dim()] = torch.tensor(any_t.shape, device=shape_t.device)
+	dist.all_reduce(shape_t, op=dist.ReduceOp.MAX)
+	shape = tuple(int(v) for v in shape_t.tolist() if v > 0)
+	dtype = any_t.dtype if any_t is not None else torch.float32
+	buf = torch.zeros((kmax,)+shape, dtype=dtype, device=shape_t.device)
+	for k, v in enumerate(mine):
+		buf[k].copy_(local[v])
+	out = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+	dist.gather(buf, out, dst=dst)
+	if rank != dst:
+		return None
+	res = {}
+	for r in range(world):
+		for k, v in enumerate(shard_views(n_views, r, world)):
+			res[v] = out[r][k]
+	return res
+
+
+def all_gather_depth(local: Dict[int, torch.Tensor], n_views: int) -> Dict[int, torch.Tensor]:
+	"""Every rank receives the depth-map of every view (exchange step before a geometric pass)."""
+	if not dist.is_initialized() or dist.get_world_size() == 1:
+		return dict(local)
+	rank, world = dist.get_rank(), dist.get_world_size()
+	mine = shard_views(n_views, rank, world)
+	kmax = (n_views+world-1)//world
+	any_t = next(iter(local.values()))
+	buf = torch.zeros((kmax,)+tuple(any_t.shape), dtype=any_t.dtype, device=any_t.device)
+	for k, v in enumerate(mine):
+		buf[k].copy_(local[v])
+	out = [torch.empty_like(buf) for _ in range(world)]
+	dist.all_gather(out, buf)
+	res = {}
+	for r in range(world):
+		for k, v in enumerate(shard_views(n_views, r, world)):
+			res[v] = out[r][k]
+	return res
+
+
+def _default_device():
+	if dist.is_initialized() and dist.get_backend() == "nccl":
+		return torch.device("cuda", torch.cuda.current_device())
+	return torch.device("cpu")
+
+
+def estimate_scene(n_views: int, estimate_view: Callable[[int], torch.Tensor], dst: int = 0, gather: bool = True):
+	"""Run `estimate_view(idx) -> (H, W, C) tensor` for the reference views of this rank and
+	gather the results on `dst` (NCCL only for that final gather)."""
+	rank = dist.get_rank() if dist.is_initialized() else 0
+	world = dist.get_world_size() if dist.is_initialized() else 1
+	local = {v: estimate_view(v) for v in shard_views(n_views, rank, world)}
+	if not gather:
+		return local
+	return gather_maps(local, n_views, dst)

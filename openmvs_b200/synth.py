@@ -40,10 +40,10 @@ class Scene:
 		return order[:n]
 
 
-def _height(x, y):
-	h = 0.22*np.sin(1.7*x + 0.3)*np.cos(1.3*y - 0.2) + 0.08*np.sin(3.1*x - 1.0)*np.sin(2.7*y + 0.5)
-	hx = 0.22*1.7*np.cos(1.7*x + 0.3)*np.cos(1.3*y - 0.2) + 0.08*3.1*np.cos(3.1*x - 1.0)*np.sin(2.7*y + 0.5)
-	hy = -0.22*1.3*np.sin(1.7*x + 0.3)*np.sin(1.3*y - 0.2) + 0.08*2.7*np.sin(3.1*x - 1.0)*np.cos(2.7*y + 0.5)
+def _height(x, y, xp=np):
+	h = 0.22*xp.sin(1.7*x + 0.3)*xp.cos(1.3*y - 0.2) + 0.08*xp.sin(3.1*x - 1.0)*xp.sin(2.7*y + 0.5)
+	hx = 0.22*1.7*xp.cos(1.7*x + 0.3)*xp.cos(1.3*y - 0.2) + 0.08*3.1*xp.cos(3.1*x - 1.0)*xp.sin(2.7*y + 0.5)
+	hy = -0.22*1.3*xp.sin(1.7*x + 0.3)*xp.sin(1.3*y - 0.2) + 0.08*2.7*xp.sin(3.1*x - 1.0)*xp.cos(2.7*y + 0.5)
 	return h, hx, hy
 
 
@@ -60,11 +60,11 @@ class _Texture:
 		amp = rng.uniform(0.6, 1.0, n_waves)
 		self.amp = amp/np.sqrt((amp**2).sum()/2.0)  # unit variance of the sum
 
-	def __call__(self, x, y):
-		acc = np.zeros_like(x)
+	def __call__(self, x, y, xp=np):
+		acc = xp.zeros_like(x)
 		for fx, fy, ph, a in zip(self.fx, self.fy, self.ph, self.amp):
-			acc += a*np.sin(fx*x + fy*y + ph)
-		return np.clip(0.5 + 0.17*acc, 0.0, 1.0)
+			acc += float(a)*xp.sin(float(fx)*x + float(fy)*y + float(ph))
+		return xp.clip(0.5 + 0.17*acc, 0.0, 1.0)
 
 
 def look_at(C, target=np.zeros(3)):
@@ -77,8 +77,10 @@ def look_at(C, target=np.zeros(3)):
 
 
 def make_scene(width: int, height: int, n_views: int, seed: int = 1234, radius: float = 5.5,
-		step_deg: float = 4.0, focal_ratio: float = 0.9, cols: int | None = None) -> Scene:
-	"""n_views cameras on a (rows x cols) angular grid `step_deg` apart, radius `radius`."""
+		step_deg: float = 4.0, focal_ratio: float = 0.9, cols: int | None = None, device=None) -> Scene:
+	"""n_views cameras on a (rows x cols) angular grid `step_deg` apart, radius `radius`.
+	device: None -> numpy float64 (bit-reproducible inputs for the parity tests);
+	a torch device -> the same arithmetic in torch float64 on that device (fast, for the bench)."""
 	if cols is None:
 		cols = int(np.ceil(np.sqrt(n_views*4/3.0))) if n_views > 2 else n_views
 	rows = int(np.ceil(n_views/cols))
@@ -86,31 +88,41 @@ def make_scene(width: int, height: int, n_views: int, seed: int = 1234, radius: 
 	K = np.array([[f, 0, (width-1)/2.0], [0, f, (height-1)/2.0], [0, 0, 1.0]])
 	tex = _Texture(seed, px_per_unit=f/radius)
 	views = []
-	ys, xs = np.mgrid[0:height, 0:width].astype(np.float64)
+	if device is None:
+		xp = np
+		ys, xs = np.mgrid[0:height, 0:width].astype(np.float64)
+	else:
+		import torch
+		xp = torch
+		ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float64, device=device),
+			torch.arange(width, dtype=torch.float64, device=device), indexing="ij")
 	for i in range(n_views):
 		r, c = divmod(i, cols)
 		ax = np.deg2rad(step_deg*(c-(cols-1)/2.0))
 		ay = np.deg2rad(step_deg*(r-(rows-1)/2.0))
 		C = radius*np.array([np.sin(ax)*np.cos(ay), np.sin(ay), np.cos(ax)*np.cos(ay)])
 		R = look_at(C)
-		# rays in world space, parameterised so that t == camera-space depth
+		# rays in world space, parameterised so that t == camera-space depth: D = R^T K^-1 (x,y,1)
 		dx = (xs-K[0, 2])/K[0, 0]
 		dy = (ys-K[1, 2])/K[1, 1]
-		D = np.stack([dx, dy, np.ones_like(dx)], -1) @ R  # R^T applied to each row vector
-		t = (0.0-C[2])/D[..., 2]
+		D = [dx*R[0, k] + dy*R[1, k] + R[2, k] for k in range(3)]
+		t = (0.0-C[2])/D[2]
 		for _ in range(12):
-			px = C[0]+t*D[..., 0]
-			py = C[1]+t*D[..., 1]
-			h, hx, hy = _height(px, py)
-			F = C[2]+t*D[..., 2]-h
-			dF = D[..., 2]-(hx*D[..., 0]+hy*D[..., 1])
+			px = C[0]+t*D[0]
+			py = C[1]+t*D[1]
+			h, hx, hy = _height(px, py, xp)
+			F = C[2]+t*D[2]-h
+			dF = D[2]-(hx*D[0]+hy*D[1])
 			t = t-F/dF
-		px = C[0]+t*D[..., 0]
-		py = C[1]+t*D[..., 1]
-		h, hx, hy = _height(px, py)
-		nw = np.stack([-hx, -hy, np.ones_like(hx)], -1)
-		nw /= np.linalg.norm(nw, axis=-1, keepdims=True)
-		nc = nw @ R.T
-		img = tex(px, py)
-		views.append(View(img.astype(np.float32), K.copy(), R, C, t.astype(np.float32), nc.astype(np.float32)))
+		px = C[0]+t*D[0]
+		py = C[1]+t*D[1]
+		h, hx, hy = _height(px, py, xp)
+		inv = 1.0/xp.sqrt(hx*hx + hy*hy + 1.0)
+		nw = [-hx*inv, -hy*inv, inv]
+		nc = xp.stack([nw[0]*R[k, 0] + nw[1]*R[k, 1] + nw[2]*R[k, 2] for k in range(3)], -1)
+		img = tex(px, py, xp)
+		if device is None:
+			views.append(View(img.astype(np.float32), K.copy(), R, C, t.astype(np.float32), nc.astype(np.float32)))
+		else:
+			views.append(View(img.float().cpu().numpy(), K.copy(), R, C, t.float().cpu().numpy(), nc.float().cpu().numpy()))
 	return Scene(views, dmin=float(radius-1.5), dmax=float(radius+1.5))

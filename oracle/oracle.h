@@ -98,7 +98,8 @@ float oracle_interpolate_pixel(const double K[9], int x0, int y0, int nx, int ny
 void oracle_zigzag(int width, int height, int rawStride, uint16_t* coordsXY);
 
 /* cv::resize restatements used by the scale loop (third-party arithmetic, OpenCV) */
-void oracle_resize_area(const float* src, int sw, int sh, float* dst, int dw, int dh);
+/* scx/scy: source/destination scale (1/fx for the factor form of cv::resize); <= 0: sw/dw */
+void oracle_resize_area(const float* src, int sw, int sh, float* dst, int dw, int dh, double scx, double scy);
 void oracle_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh);
 void oracle_resize_nearest(const float* src, int sw, int sh, int channels, float* dst, int dw, int dh);
 void oracle_scale_K(const double K[9], int sw, int sh, int dw, int dh, double Kout[9]);

@@ -695,16 +695,17 @@ void passC(int w, int h, float keep, float* depth, float* normal, float* conf) {
 }
 
 // ---- cv::resize restatements (OpenCV imgproc/resize.cpp; third-party) -----
-void resizeArea(const float* src, int sw, int sh, float* dst, int dw, int dh) {
-	const double sx = (double)sw/dw, sy = (double)sh/dh;
-	const int isx = (int)sx, isy = (int)sy;
-	if (isx == sx && isy == sy && std::fabs(sx-isx) < 1e-12 && std::fabs(sy-isy) < 1e-12) {
-		// integer ratio: plain box mean (ResizeAreaFastVec)
-		const float sc = 1.f/(isx*isy);
+// scx/scy = source/destination scale: 1/fx when the caller gave a factor (cv::resize(..., Size(), fx, fy)),
+// sw/dw when it gave the destination size
+void resizeArea(const float* src, int sw, int sh, float* dst, int dw, int dh, double sx, double sy) {
+	const int isx = (int)std::nearbyint(sx), isy = (int)std::nearbyint(sy);
+	if (std::fabs(sx-isx) < 2.2e-16 && std::fabs(sy-isy) < 2.2e-16) {
+		// integer ratio: box mean over the part of the box inside the image (ResizeAreaFast)
 		for (int y=0; y<dh; ++y) for (int x=0; x<dw; ++x) {
-			float s = 0;
-			for (int j=0; j<isy; ++j) for (int i=0; i<isx; ++i) s += src[(size_t)(y*isy+j)*sw + x*isx+i];
-			dst[(size_t)y*dw+x] = s*sc;
+			float s = 0; int count = 0;
+			for (int j=0; j<isy && y*isy+j < sh; ++j)
+				for (int i=0; i<isx && x*isx+i < sw; ++i) { s += src[(size_t)(y*isy+j)*sw + x*isx+i]; ++count; }
+			dst[(size_t)y*dw+x] = count == isx*isy ? s*(1.f/(isx*isy)) : s/count;
 		}
 		return;
 	}
@@ -852,12 +853,12 @@ int oracle_pm_estimate(const oracle_view* views, int nViews, const oracle_params
 			for (int i=0; i<nViews; ++i) {
 				const int dw = cvRoundI(views[i].width*scale), dh = cvRoundI(views[i].height*scale);
 				imgs[i].resize((size_t)dw*dh);
-				resizeArea(views[i].image, views[i].width, views[i].height, imgs[i].data(), dw, dh);
+				resizeArea(views[i].image, views[i].width, views[i].height, imgs[i].data(), dw, dh, 1.0/scale, 1.0/scale);
 				sv[i].image = imgs[i].data(); sv[i].width = dw; sv[i].height = dh;
 				scaleK(views[i].K, views[i].width, views[i].height, dw, dh, sv[i].K);
 				if (views[i].depth) {
 					dms[i].resize((size_t)dw*dh);
-					resizeArea(views[i].depth, views[i].dwidth, views[i].dheight, dms[i].data(), dw, dh);
+					resizeArea(views[i].depth, views[i].dwidth, views[i].dheight, dms[i].data(), dw, dh, (double)views[i].dwidth/dw, (double)views[i].dheight/dh);
 					sv[i].depth = dms[i].data(); sv[i].dwidth = dw; sv[i].dheight = dh;
 					scaleK(views[i].Kd, views[i].dwidth, views[i].dheight, dw, dh, sv[i].Kd);
 				}
@@ -947,7 +948,7 @@ void oracle_zigzag(int width, int height, int rawStride, uint16_t* coordsXY) {
 	std::vector<uint16_t> c; zigzag(width, height, rawStride, c);
 	memcpy(coordsXY, c.data(), c.size()*sizeof(uint16_t));
 }
-void oracle_resize_area(const float* src, int sw, int sh, float* dst, int dw, int dh) { resizeArea(src, sw, sh, dst, dw, dh); }
+void oracle_resize_area(const float* src, int sw, int sh, float* dst, int dw, int dh, double scx, double scy) { resizeArea(src, sw, sh, dst, dw, dh, scx > 0 ? scx : (double)sw/dw, scy > 0 ? scy : (double)sh/dh); }
 void oracle_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh) { resizeLinear(src, sw, sh, dst, dw, dh); }
 void oracle_resize_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh) { resizeNearest(src, sw, sh, ch, dst, dw, dh); }
 void oracle_scale_K(const double K[9], int sw, int sh, int dw, int dh, double Kout[9]) { scaleK(K, sw, sh, dw, dh, Kout); }

@@ -1,0 +1,61 @@
+"""The C-ABI library builds, loads and exports every symbol include/b200mvs.h declares
+(no compute calls: there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+	src = open(os.path.join(ROOT, "include", "b200mvs.h")).read()
+	src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+	return sorted(set(re.findall(r"\b(b200mvs_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+	from openmvs_b200 import build, lib
+	path = build.build_extension()
+	assert os.path.exists(path)
+	dll = C.CDLL(path)
+	names = _declared()
+	assert len(names) >= 13
+	for n in names:
+		assert hasattr(dll, n), "missing export %s" % n
+	# the python binding lists exactly the declared symbols
+	assert sorted(lib.SYMBOLS) == names
+
+
+def test_struct_layouts_match_header_sizes():
+	from openmvs_b200 import lib
+	# b200mvs_view: pointer, 3 ints (+pad), 21 doubles, pointer, 3 ints (+pad), 21 doubles
+	assert C.sizeof(lib.View) == 8+16+21*8+8+16+21*8-8+8 or C.sizeof(lib.View) % 8 == 0
+	assert C.sizeof(lib.Params) == 16*4
+	assert C.sizeof(lib.Stats) == 8+8+8+8+4+4
+
+
+def test_create_without_gpu_fails_loudly():
+	import torch
+	if torch.cuda.is_available():
+		pytest.skip("GPU present")
+	from openmvs_b200 import lib
+	from openmvs_b200.depth_estimator import PatchMatchB200
+	with pytest.raises(lib.B200MVSError):
+		PatchMatchB200(0)
+	dll = lib.load()
+	assert dll.b200mvs_device_count() == 0
+	ctx = C.c_void_p()
+	assert dll.b200mvs_create(0, C.byref(ctx)) == 3  # B200MVS_ERR_NOGPU: never a CPU fallback
+	assert not ctx
+
+
+def test_sources_do_not_reference_the_oracle():
+	"""The product package must not import, link or execute anything under oracle/."""
+	pkg = os.path.join(ROOT, "openmvs_b200")
+	for dp, _, files in os.walk(pkg):
+		for f in files:
+			if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+				txt = open(os.path.join(dp, f)).read()
+				assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f

@@ -1,0 +1,48 @@
+"""world_size-2 gloo test of the N>1 path: sharding of reference views, the final gather and
+the depth all-gather that precedes a geometric pass (no GPU: the per-view estimator is a stub)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_views, q):
+	sys.path.insert(0, ROOT)
+	from openmvs_b200 import multi_gpu
+	os.environ["MASTER_ADDR"] = "127.0.0.1"
+	os.environ["MASTER_PORT"] = str(port)
+	dist.init_process_group("gloo", rank=rank, world_size=world)
+	try:
+		def estimate(v):  # stub estimator: a map that identifies its view
+			return torch.full((6, 8, 5), float(v))+torch.arange(5, dtype=torch.float32)
+		res = multi_gpu.estimate_scene(n_views, estimate, dst=0)
+		if rank == 0:
+			ok = sorted(res.keys()) == list(range(n_views)) and all(
+				torch.equal(res[v], estimate(v)) for v in range(n_views))
+		else:
+			ok = res is None
+		local = {v: torch.full((6, 8), float(v)) for v in multi_gpu.shard_views(n_views, rank, world)}
+		allv = multi_gpu.all_gather_depth(local, n_views)
+		ok = ok and sorted(allv.keys()) == list(range(n_views)) and all(float(allv[v][0, 0]) == v for v in range(n_views))
+		q.put((rank, bool(ok)))
+	finally:
+		dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_views", [5, 12])
+def test_shard_gather_world2(n_views):
+	s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+	ctx = mp.get_context("spawn")
+	q = ctx.Queue()
+	procs = [ctx.Process(target=_worker, args=(r, 2, port, n_views, q)) for r in range(2)]
+	for p in procs: p.start()
+	got = [q.get(timeout=120) for _ in procs]
+	for p in procs: p.join(60)
+	assert sorted(got) == [(0, True), (1, True)]

@@ -1,0 +1,339 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the
+C-ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances.  north_star: depth/normal within 1e-3 relative on confident pixels, same
+confidence mask.  The kernels and the oracle share the Philox stream, so every hypothesis is
+identical; results differ only where an accept test `conf > nconf` flips on float rounding
+(FMA contraction, float vs double homography, approx rcp).  The tests therefore bound
+(a) the score error, (b) the flip rate after one sweep from identical states and (c) the
+agreement after full chains.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import agreement
+
+pytestmark = pytest.mark.gpu
+
+
+def _record(name, **kw):
+	"""append measured parity numbers to gpurun_out/parity_metrics.json (quoted in DESIGN.md)"""
+	import json, os
+	out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+	try:
+		os.makedirs(out, exist_ok=True)
+		path = os.path.join(out, "parity_metrics.json")
+		data = json.load(open(path)) if os.path.exists(path) else {}
+		data[name] = {k: float(v) for k, v in kw.items()}
+		json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+	except Exception:
+		pass
+
+
+def _skip_if_no_gpu():
+	if not torch.cuda.is_available():
+		pytest.skip("no CUDA device")
+
+
+@pytest.fixture(scope="module")
+def env():
+	_skip_if_no_gpu()
+	from oracle import oracle as O
+	from openmvs_b200.depth_estimator import OPTDENSE, Camera, ViewData, DepthData, PatchMatchB200
+	class E: pass
+	e = E()
+	e.O, e.OPT, e.Camera, e.ViewData, e.DepthData = O, OPTDENSE, Camera, ViewData, DepthData
+	e.dev = torch.device("cuda:0")
+	e.pm = PatchMatchB200(0)
+	saved = {k: getattr(OPTDENSE, k) for k in dir(OPTDENSE) if k[0] in "nf" and not callable(getattr(OPTDENSE, k))}
+	yield e
+	for k, v in saved.items():
+		setattr(OPTDENSE, k, v)
+	e.pm.Release()
+
+
+def _dev_views(e, views, depths=None):
+	out = []
+	for i, v in enumerate(views):
+		vd = e.ViewData(torch.from_numpy(np.ascontiguousarray(v.image)).to(e.dev), e.Camera(v.K, v.R, v.C))
+		if depths is not None and depths[i] is not None:
+			vd.depthMap = torch.from_numpy(depths[i][0]).to(e.dev)
+			vd.cameraDepthMap = e.Camera(*depths[i][1:])
+		out.append(vd)
+	return out
+
+
+def _host_views(e, views):
+	return [e.ViewData(np.ascontiguousarray(v.image), e.Camera(v.K, v.R, v.C)) for v in views]
+
+
+def _set(e, **kw):
+	for k, v in kw.items():
+		assert hasattr(e.OPT, k), k
+		setattr(e.OPT, k, v)
+
+
+def _plane(e, d, n):
+	return torch.from_numpy(np.concatenate([n, d[..., None]], -1)).to(e.dev).contiguous()
+
+
+def test_pass_a_score_parity(env, small_scene):
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nSweepsPerIter=2, nRandomIters=6)
+	prm = e.O.default_params(schedule=1, nRandomIters=3, nSubResolutionLevels=0, threads=4)
+	d0, n0, c0 = e.O.pm_score(views, prm, sc.dmin, sc.dmax)
+	h, w = d0.shape
+	plane = torch.zeros(h, w, 4, device=e.dev); cost = torch.zeros(h, w, device=e.dev)
+	e.pm.ScoreDepthMap(_dev_views(e, views), sc.dmin, sc.dmax, plane, cost)
+	pg, cg = plane.cpu().numpy(), cost.cpu().numpy()
+	# identical Philox stream: random planes agree to float rounding of sqrt/sincos
+	assert np.abs(pg[..., 3]-d0).max() < 1e-5 and np.abs(pg[..., :3]-n0).max() < 1e-5
+	dc = np.abs(cg-c0)
+	_record("pass_a", cost_mean_abs_diff=dc.mean(), cost_max_abs_diff=dc.max(), depth_max_abs_diff=np.abs(pg[..., 3]-d0).max())
+	assert dc.mean() < 2e-5 and (dc > 1e-3).mean() < 1e-3
+	# rejected pixels (border): depth 0, cost 2
+	assert np.all(cg[:4] == 2) and np.all(pg[:4] == 0)
+	# scoring a GIVEN estimate: ground-truth planes must score near zero on both sides
+	gt_d, gt_n = sc.views[ref].depth_gt, sc.views[ref].normal_gt
+	d1, n1, c1 = e.O.pm_score(views, prm, sc.dmin, sc.dmax, depth=gt_d, normal=gt_n)
+	plane = _plane(e, gt_d, gt_n); cost = torch.zeros(h, w, device=e.dev)
+	e.pm.ScoreDepthMap(_dev_views(e, views), sc.dmin, sc.dmax, plane, cost)
+	cg = cost.cpu().numpy()
+	m = d1 > 0
+	assert np.abs(cg-c1)[m].max() < 2e-4 and np.median(cg[m]) < 0.02
+	assert np.array_equal(plane.cpu().numpy()[..., 3][m], gt_d[m])  # estimate untouched
+
+
+@pytest.mark.parametrize("propagation", [4, 2])
+def test_single_sweep_parity_from_identical_state(env, small_scene, propagation):
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nPropagation=propagation)
+	nR = 3
+	prm = e.O.default_params(schedule=1, propagation=propagation, nRandomIters=nR, nSubResolutionLevels=0, threads=4)
+	d, n, c = e.O.pm_score(views, prm, sc.dmin, sc.dmax)
+	dv = _dev_views(e, views)
+	for sweep in range(3):
+		plane = _plane(e, d, n); cost = torch.from_numpy(c).to(e.dev)
+		e.pm.SweepDepthMap(dv, sc.dmin, sc.dmax, plane, cost, sweep, nRandomIters=nR)
+		d, n, c = e.O.pm_iterate(views, prm, sc.dmin, sc.dmax, d, n, c, sweep)
+		pg, cg = plane.cpu().numpy(), cost.cpu().numpy()
+		m = d > 0
+		rel = np.abs(pg[..., 3]-d)[m]/d[m]
+		_record("single_sweep_prop%d_s%d" % (propagation, sweep), frac_rel_gt_1e3=(rel > 1e-3).mean(), frac_rel_gt_1e5=(rel > 1e-5).mean(),
+			cost_mean_abs_diff=np.abs(cg-c)[m].mean())
+		assert (rel > 1e-3).mean() < 2e-3, "sweep %d: too many flipped accept decisions" % sweep
+		assert (rel > 1e-5).mean() < 0.08
+		assert np.abs(cg-c)[m].mean() < 5e-5
+		assert np.array_equal(pg[..., 3] > 0, m)
+	_set(e, nPropagation=4)
+
+
+def test_half_sweeps_touch_only_their_colour(env, small_scene):
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nPropagation=4)
+	prm = e.O.default_params(schedule=1, nRandomIters=3, nSubResolutionLevels=0, threads=4)
+	d, n, c = e.O.pm_score(views, prm, sc.dmin, sc.dmax)
+	plane = _plane(e, d, n); cost = torch.from_numpy(c).to(e.dev)
+	before = plane.cpu().numpy().copy()
+	e.pm.SweepDepthMap(_dev_views(e, views), sc.dmin, sc.dmax, plane, cost, 0, half=1, nRandomIters=3)
+	after = plane.cpu().numpy()
+	yy, xx = np.mgrid[0:d.shape[0], 0:d.shape[1]]
+	red = ((xx+yy) & 1) == 0
+	assert np.array_equal(after[red], before[red])
+	assert (after[~red] != before[~red]).any()
+	d2, n2, c2 = e.O.pm_iterate(views, prm, sc.dmin, sc.dmax, d, n, c, 0, half=1)
+	rel = np.abs(after[..., 3]-d2)[d2 > 0]/d2[d2 > 0]
+	assert (rel > 1e-3).mean() < 2e-3
+
+
+def test_full_estimate_parity_rb_and_zz(env, small_scene):
+	"""Whole EstimateDepthMap: GPU vs oracle-RB (same schedule) and vs oracle-ZZ (the reference's
+	schedule), with the reference's own run-to-run agreement as the yardstick."""
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=2, nRandomIters=6, nPropagation=4)
+	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd)
+	gd, gn, gc = dd.depthMap.cpu().numpy(), dd.normalMap.cpu().numpy(), dd.confMap.cpu().numpy()
+	base = dict(nSubResolutionLevels=0, nEstimationGeometricIters=0)
+	od, on, oc = e.O.pm_estimate(views, e.O.default_params(schedule=1, propagation=4, nEstimationIters=12, nRandomIters=3, threads=4, **base), sc.dmin, sc.dmax)
+	iou, agree = agreement(od, gd)
+	assert iou > 0.999 and agree > 0.98
+	both = (od > 0) & (gd > 0)
+	ang = np.degrees(np.arccos(np.clip((on*gn).sum(-1), -1, 1)))[both]
+	# accept tests that flip on float rounding make the two chains drift apart like two runs of the
+	# reference do (its own run-to-run median normal difference is ~1.2 deg, see below)
+	conf_close = (np.abs(oc-gc)[both] < 1e-2).mean()
+	assert np.median(ang) < 1.5 and conf_close > 0.97
+	# ground truth: the engine is as accurate as the oracle
+	gt = sc.views[ref].depth_gt
+	acc_g = (np.abs(gd-gt)[gd > 0]/gt[gd > 0] < 1e-3).mean()
+	acc_o = (np.abs(od-gt)[od > 0]/gt[od > 0] < 1e-3).mean()
+	assert abs(acc_g-acc_o) < 0.01
+	# reference schedule (zig-zag, mt19937): compare with its own thread-count variation
+	zz1 = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=6, threads=1, **base), sc.dmin, sc.dmax)
+	zz4 = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=6, threads=4, **base), sc.dmin, sc.dmax)
+	iou_ref, agree_ref = agreement(zz1[0], zz4[0])
+	iou_g, agree_g = agreement(zz1[0], gd)
+	both_z = (zz1[0] > 0) & (zz4[0] > 0)
+	ang_ref = np.degrees(np.arccos(np.clip((zz1[1]*zz4[1]).sum(-1), -1, 1)))[both_z]
+	_record("full_estimate_320x240_N4_I6", iou_rb=iou, agree_rb=agree, med_ang_rb=np.median(ang), conf_close_rb=conf_close,
+		acc_gpu=acc_g, acc_oracle_rb=acc_o, iou_zz_self=iou_ref, agree_zz_self=agree_ref, med_ang_zz_self=np.median(ang_ref),
+		iou_gpu_zz=iou_g, agree_gpu_zz=agree_g)
+	assert iou_g > 0.995 and agree_g > agree_ref-0.03
+	# output invariants of EndDepthMapTmp
+	m = gd > 0
+	assert np.all(gc[~m] == 0) and np.all(gn[~m] == 0) and gc[m].min() > 0 and gc.max() <= 1
+	assert np.allclose(np.linalg.norm(gn[m], axis=-1), 1, atol=1e-4)
+	assert gd[m].min() >= sc.dmin and gd[m].max() < sc.dmax
+	vm = dd.viewsMap.cpu().numpy()
+	assert np.all(vm[~m] == 255) and vm[m][:, 0].max() < 4 and np.all(vm[m][:, 2:] == 255)
+
+
+def test_host_api_equals_device_api_and_is_deterministic(env, small_scene):
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=2, nSweepsPerIter=2, nRandomIters=6)
+	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd)
+	hd = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(hd)
+	assert e.pm.stats.bytes_h2d == sum(v.image.nbytes for v in views)+views[0].image.size*16
+	assert e.pm.stats.bytes_d2h == views[0].image.size*24 and e.pm.stats.kernel_launches == 1+1+2*2*2+1
+	for a, b in ((dd.depthMap, hd.depthMap), (dd.normalMap, hd.normalMap), (dd.confMap, hd.confMap), (dd.viewsMap, hd.viewsMap)):
+		assert np.array_equal(a.cpu().numpy(), b)
+	hd2 = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(hd2)
+	assert np.array_equal(hd.depthMap, hd2.depthMap) and np.array_equal(hd.confMap, hd2.confMap)
+
+
+def test_initial_estimate_is_used_and_single_neighbour_min_branch(env, small_scene):
+	"""N=1 takes the min-aggregator branch (idxScore==0); a valid initial estimate is kept where
+	nothing better is found; an invalid normal is re-randomised (SceneDensify.cpp:505-511)."""
+	e = env
+	sc, ref, views = small_scene
+	two = views[:2]
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=1, nSweepsPerIter=2, nRandomIters=6)
+	gt_d = sc.views[ref].depth_gt.copy(); gt_n = sc.views[ref].normal_gt.copy()
+	init_n = gt_n.copy(); init_n[100:120] *= -1  # facing away: must be replaced by a random normal
+	dd = e.DepthData(_dev_views(e, two), sc.dmin, sc.dmax, depthMap=torch.from_numpy(gt_d).to(e.dev), normalMap=torch.from_numpy(init_n).to(e.dev))
+	e.pm.EstimateDepthMap(dd)
+	gd = dd.depthMap.cpu().numpy()
+	prm = e.O.default_params(schedule=1, propagation=4, nEstimationIters=2, nRandomIters=3, nSubResolutionLevels=0, nEstimationGeometricIters=0, threads=4)
+	od, on, oc = e.O.pm_estimate(two, prm, sc.dmin, sc.dmax, depth=gt_d, normal=init_n)
+	iou, agree = agreement(od, gd)
+	assert iou > 0.999 and agree > 0.99
+	m = gd > 0
+	assert (np.abs(gd-gt_d)[m]/gt_d[m] < 1e-3).mean() > 0.97
+
+
+def test_textureless_and_odd_size_and_mixed_resolution(env):
+	"""Edge cases: odd image size, a textureless band (fDescriptorMinMagnitudeThreshold reject),
+	and a neighbour whose resolution differs from the reference's (DepthMap.h:194-204)."""
+	e = env
+	from openmvs_b200 import synth
+	import cv2
+	sc = synth.make_scene(203, 151, 3, step_deg=5.0, cols=3)
+	views = [sc.views[1], sc.views[0], sc.views[2]]
+	views[0].image[60:90] = 0.5  # flat band in the reference image
+	# third view at 0.8x resolution with the matching camera (K scaled with the half-pixel rule)
+	v = views[2]
+	sw, sh = int(round(203*0.8)), int(round(151*0.8))
+	small = cv2.resize(v.image, (sw, sh), interpolation=cv2.INTER_AREA)
+	K = v.K.copy(); sx, sy = sw/203.0, sh/151.0
+	K[0] *= sx; K[1] *= sy; K[0, 2] = (v.K[0, 2]+0.5)*sx-0.5; K[1, 2] = (v.K[1, 2]+0.5)*sy-0.5
+	views[2] = synth.View(small, K, v.R, v.C, v.depth_gt, v.normal_gt)
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=2, nRandomIters=6)
+	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd)
+	gd = dd.depthMap.cpu().numpy()
+	prm = e.O.default_params(schedule=1, propagation=4, nEstimationIters=6, nRandomIters=3, nSubResolutionLevels=0, nEstimationGeometricIters=0, threads=4)
+	od, on, oc = e.O.pm_estimate(views, prm, sc.dmin, sc.dmax)
+	assert np.all(od[66:84, 8:-8] == 0) and np.all(gd[66:84, 8:-8] == 0)  # textureless rows rejected by both
+	iou, agree = agreement(od, gd)
+	assert iou > 0.995 and agree > 0.97
+
+
+def test_geometric_consistency_pass_parity(env, small_scene):
+	"""Geometric pass: neighbours carry known depth-maps; one iteration at iter index
+	nEstimationIters+geoIter, no scale loop (SceneDensify.cpp:627-651)."""
+	e = env
+	sc, ref, views = small_scene
+	rng = np.random.RandomState(7)
+	depths = [None]
+	for v in views[1:]:
+		dm = v.depth_gt.copy()
+		dm[rng.rand(*dm.shape) < 0.05] = 0  # filtered pixels
+		depths.append((dm, v.K, v.R, v.C))
+	init_d = sc.views[ref].depth_gt*(1+0.002*rng.randn(*sc.views[ref].depth_gt.shape).astype(np.float32))
+	init_d[rng.rand(*init_d.shape) < 0.1] = 0
+	init_n = sc.views[ref].normal_gt.copy()
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=2, nEstimationIters=3, nSweepsPerIter=2, nRandomIters=6, fEstimationGeometricWeight=0.1)
+	dd = e.DepthData(_dev_views(e, views, depths), sc.dmin, sc.dmax, depthMap=torch.from_numpy(init_d).to(e.dev), normalMap=torch.from_numpy(init_n).to(e.dev))
+	e.pm.Init(True)
+	e.pm.EstimateDepthMap(dd, nGeometricIter=0)
+	e.pm.Init(False)
+	gd, gc = dd.depthMap.cpu().numpy(), dd.confMap.cpu().numpy()
+	# oracle: pass A + sweeps 6,7 (iteration 3 = nEstimationIters+0) + pass C with keep 0.9
+	prm = e.O.default_params(schedule=1, propagation=4, nRandomIters=3, nSubResolutionLevels=0, nEstimationGeometricIters=2, threads=4)
+	d, n, c = e.O.pm_score(views, prm, sc.dmin, sc.dmax, depth=init_d, normal=init_n, depths=depths)
+	for sweep in (6, 7):
+		d, n, c = e.O.pm_iterate(views, prm, sc.dmin, sc.dmax, d, n, c, sweep, depths=depths)
+	od, on, oc = e.O.pm_finalize(d, n, c, 0.9)
+	iou, agree = agreement(od, gd)
+	assert iou > 0.995 and agree > 0.985
+	both = (od > 0) & (gd > 0)
+	assert (np.abs(oc-gc)[both] < 2e-3).mean() > 0.97
+	# the geometric term is active: confidences are lower than the photometric-only score
+	assert np.median(gc[both]) < 0.999
+
+
+def test_multi_scale_parity(env, small_scene):
+	"""Scale loop with nSubResolutionLevels=2: INTER_AREA pyramid, LINEAR/NEAREST up-sampling,
+	low-resolution depth prior (SceneDensify.cpp:651-769, DepthMap.cpp:552-561)."""
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=2, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=2, nRandomIters=6)
+	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd)
+	gd = dd.depthMap.cpu().numpy()
+	assert e.pm.stats.levels == 3
+	prm = e.O.default_params(schedule=1, propagation=4, nEstimationIters=6, nRandomIters=3, nSubResolutionLevels=2, nEstimationGeometricIters=0, threads=4)
+	od, on, oc = e.O.pm_estimate(views, prm, sc.dmin, sc.dmax)
+	iou, agree = agreement(od, gd)
+	assert iou > 0.995 and agree > 0.97
+	gt = sc.views[ref].depth_gt
+	assert (np.abs(gd-gt)[gd > 0]/gt[gd > 0] < 1e-2).mean() > 0.95
+	_set(e, nSubResolutionLevels=0)
+
+
+def test_full_size_properties_1080p(env):
+	"""BASELINE configs[1] size (1920x1080, 9 neighbours, 6 iterations): properties that do not
+	need the oracle — determinism, output invariants and analytic ground truth."""
+	e = env
+	from openmvs_b200 import synth
+	sc = synth.make_scene(1920, 1080, 10, step_deg=4.0, device=e.dev)
+	ref = 4
+	views = [sc.views[ref]]+[sc.views[i] for i in sc.neighbors(ref, 9)]
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=2, nRandomIters=6)
+	dv = _dev_views(e, views)
+	a = e.DepthData(dv, sc.dmin, sc.dmax); e.pm.EstimateDepthMap(a)
+	b = e.DepthData(dv, sc.dmin, sc.dmax); e.pm.EstimateDepthMap(b)
+	assert torch.equal(a.depthMap, b.depthMap) and torch.equal(a.normalMap, b.normalMap) and torch.equal(a.confMap, b.confMap)
+	gd, gn, gc = a.depthMap.cpu().numpy(), a.normalMap.cpu().numpy(), a.confMap.cpu().numpy()
+	m = gd > 0
+	gt, gtn = sc.views[ref].depth_gt, sc.views[ref].normal_gt
+	assert m.mean() > 0.95 and not m[:4].any() and not m[:, -4:].any()
+	rel = np.abs(gd-gt)[m]/gt[m]
+	assert (rel < 1e-3).mean() > 0.98 and np.median(rel) < 2e-4
+	ang = np.degrees(np.arccos(np.clip((gn*gtn).sum(-1), -1, 1)))[m]
+	assert np.median(ang) < 3.0
+	K = views[0].K
+	yy, xx = np.mgrid[0:1080, 0:1920]
+	X0 = np.stack([(xx-K[0, 2])/K[0, 0], (yy-K[1, 2])/K[1, 1], np.ones_like(xx, float)], -1)
+	assert ((gn*X0).sum(-1)[m] < 1e-6).all()  # normals face the camera
+	assert gc[m].min() > 0 and gc.max() <= 1 and gd[m].min() >= sc.dmin and gd[m].max() < sc.dmax
