@@ -234,8 +234,13 @@ def main():
 		if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 		return float(ms.item()), ret
 
+	if os.environ.get("BENCH_DEBUG"):
+		for tag in ("cold", "warm"):
+			dd0 = DepthData([ViewData(d_imgs[5], cams[5])]+[ViewData(d_imgs[i], cams[i]) for i in nbrs[5]], scene.dmin, scene.dmax)
+			pm.EstimateDepthMap(dd0, sync=True)
+			print("debug %s: view 5 device %.2f ms, sweep avg %.3f ms" % (tag, pm.stats.ms_device, pm.stats.ms_sweep_kernels/max(1, pm.stats.sweep_launches)), file=sys.stderr)
 	sampler = ClockSampler(local_rank)
-	if rank == 0: sampler.start()
+	if rank == 0 and not os.environ.get("BENCH_NO_SMI"): sampler.start()
 	launches[0] = 0
 	ms_res, _ = timed(step_resident, args.steps, args.warmup)
 	n_launch = launches[0]*args.steps//(args.steps+args.warmup)
@@ -246,21 +251,16 @@ def main():
 	e2e = mpix_step/(ms_e2e/args.steps/1e3)
 
 	# ---- roofline of the dominant kernel: one red-black half-sweep, timed live --------------------
+	# CUDA events are recorded by the engine around every pm_sweep_kernel launch of one more (untimed)
+	# resident EstimateDepthMap call, on the stream the kernels are launched on (b200mvs_stats)
 	r = 5
-	views = [ViewData(d_imgs[r], cams[r])]+[ViewData(d_imgs[i], cams[i]) for i in nbrs[r]]
-	plane = torch.zeros(h, w, 4, device=dev); cost = torch.zeros(h, w, device=dev)
-	pm.ScoreDepthMap(views, scene.dmin, scene.dmax, plane, cost)
-	for s in range(4):
-		pm.SweepDepthMap(views, scene.dmin, scene.dmax, plane, cost, s)
-	torch.cuda.synchronize()
-	reps = 6
-	evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-	for k, (a, b) in enumerate(evs):
-		a.record()
-		pm.SweepDepthMap(views, scene.dmin, scene.dmax, plane, cost, 4+k//2, half=k & 1)
-		b.record()
-	torch.cuda.synchronize()
-	k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+	m = d_maps[r]
+	m["depth"].zero_(); m["normal"].zero_()
+	dd = DepthData([ViewData(d_imgs[r], cams[r])]+[ViewData(d_imgs[i], cams[i]) for i in nbrs[r]], scene.dmin, scene.dmax,
+		depthMap=m["depth"], normalMap=m["normal"], confMap=m["conf"], viewsMap=m["views"])
+	pm.EstimateDepthMap(dd, sync=True)
+	k_ms = pm.stats.ms_sweep_kernels/max(1, pm.stats.sweep_launches)
+	sweep_share = pm.stats.ms_sweep_kernels/max(1e-9, pm.stats.ms_device)
 	bytes_launch = w*h*(20+10+4*(N_NEIGH+1))
 	peaks = {}
 	try:
@@ -271,9 +271,9 @@ def main():
 	achieved = bytes_launch/(k_ms*1e-3)/1e9
 	nR = (OPTDENSE.nRandomIters+OPTDENSE.nSweepsPerIter-1)//OPTDENSE.nSweepsPerIter
 	samples_launch = (w*h/2)*(4+nR)*N_NEIGH*25
-	roof = {"kernel": "pm_sweep_kernel<false> (one red-black half-sweep)", "bound": "hbm", "achieved": achieved, "peak": peak,
+	roof = {"kernel": "pm_sweep_kernel<1,false,true> (one red-black half-sweep)", "bound": "hbm", "achieved": achieved, "peak": peak,
 		"unit": "GB/s", "frac": achieved/peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-		"launch_ms": k_ms, "algorithmic_bytes_per_launch": bytes_launch,
+		"launch_ms": k_ms, "launches_timed": int(pm.stats.sweep_launches), "share_of_step": sweep_share, "algorithmic_bytes_per_launch": bytes_launch,
 		"secondary": {"bound": "issue/L1 (gather stencil, AI ~ 280 flop/B)", "bilinear_samples_per_launch": samples_launch,
 			"gsamples_per_s": samples_launch/(k_ms*1e-3)/1e9}}
 	traffic_file = os.path.join(ROOT, "profiles", "sweep_traffic.json")

@@ -80,6 +80,9 @@ typedef struct {
 	uint64_t bytes_h2d, bytes_d2h;
 	int kernel_launches;
 	int levels;
+	double ms_sweep_kernels; /* summed device time of the red-black half-sweep launches (CUDA events) */
+	int sweep_launches;
+	int reserved;
 } b200mvs_stats;
 
 /* ---- lifetime (PatchMatchCUDA ctor / Init / Release, PatchMatchCUDA.cpp:60-117) ---- */

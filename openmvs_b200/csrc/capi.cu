@@ -13,9 +13,11 @@
 #include <vector>
 #include <chrono>
 #include <algorithm>
+#include <cstdlib>
 
-cudaError_t pm_launch_score(const PMParams& P, bool geom, cudaStream_t s);
-cudaError_t pm_launch_sweep(const PMParams& P, bool geom, cudaStream_t s);
+cudaError_t pm_launch_score(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s);
+cudaError_t pm_launch_sweep(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s);
+cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s);
 cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
 	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s);
 cudaError_t pm_launch_pack(int n, const float* depth, const float* normal, float4* plane, cudaStream_t s);
@@ -74,6 +76,7 @@ inline float d2r(float d) { return d*(3.14159265358979323846f/180.f); }
 // a view whose image (and optional depth-map) pointers are device pointers, pitch in floats
 struct DView {
 	const float* img; int w, h, pitch;
+	const void* tex; int tpitch;             // tap-fetch layout of img (set by prepare_tex)
 	double K[9], R[9], C[3];
 	const float* dmap; int dw, dh, dpitch;
 	double Kd[9], Rd[9], Cd[3];
@@ -93,6 +96,11 @@ struct b200mvs_ctx {
 	DevBuf plane, cost, best, prior, lowPlane;
 	DevBuf dDepth, dNormal, dConf, dViews;    // level scratch / staging of the maps (host API)
 	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
+	std::vector<DevBuf> tex;                  // neighbour images in the tap-fetch layout
+	int layout = 1;                           // 1 plain float rows, 2 row pairs (B200MVS_LAYOUT overrides)
+	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
+	std::vector<cudaEvent_t> sweepEv;         // event pairs around the sweep launches (stats only)
+	int nSweepEv = 0; bool timeSweeps = false;
 	int launches = 0;
 };
 
@@ -147,6 +155,7 @@ void build_params(const b200mvs_params& o, const DView* v, int nViews, float dMi
 		for (int k=0;k<9;++k) V.A[k] = (float)A[k];
 		for (int k=0;k<3;++k) V.Hm[k] = (float)Hm[k];
 		V.img = v[i].img; V.w = v[i].w; V.h = v[i].h; V.pitch = v[i].pitch;
+		V.tex = v[i].tex; V.tpitch = v[i].tpitch;
 		V.dmap = v[i].dmap; V.dw = v[i].dw; V.dh = v[i].dh; V.dpitch = v[i].dpitch;
 		if (v[i].dmap) {
 			geom = true;
@@ -186,6 +195,34 @@ void to_dview(const b200mvs_view& s, const float* img, int pitch, const float* d
 }
 
 inline int cvRoundI(double v) { return (int)std::nearbyint(v); }
+
+// store the neighbour images of one level in the tap-fetch layout of the kernels
+int prepare_tex(b200mvs_ctx* ctx, DView* v, int nViews, cudaStream_t s) {
+	if ((int)ctx->tex.size() < nViews) ctx->tex.resize(nViews);
+	v[0].tex = v[0].img; v[0].tpitch = v[0].pitch;
+	for (int i = 1; i < nViews; ++i) {
+		if (ctx->layout == 1) { v[i].tex = v[i].img; v[i].tpitch = v[i].pitch; continue; }
+		CK(ctx->tex[i].reserve((size_t)v[i].w*v[i].h*sizeof(float)*ctx->layout));
+		CK(pm_launch_relayout(v[i].img, v[i].w, v[i].h, v[i].pitch, ctx->tex[i].p, ctx->layout, s)); ++ctx->launches;
+		v[i].tex = ctx->tex[i].p; v[i].tpitch = v[i].w;
+	}
+	return B200MVS_OK;
+}
+
+int launch_sweep_timed(b200mvs_ctx* ctx, const PMParams& P, bool geom, cudaStream_t s) {
+	if (ctx->timeSweeps) {
+		while ((int)ctx->sweepEv.size() < 2*(ctx->nSweepEv+1)) {
+			cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->sweepEv.push_back(e);
+		}
+		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv], s));
+	}
+	CK(pm_launch_sweep(P, ctx->layout, geom, ctx->wsmem, s)); ++ctx->launches;
+	if (ctx->timeSweeps) {
+		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv+1], s));
+		++ctx->nSweepEv;
+	}
+	return B200MVS_OK;
+}
 
 // The whole EstimateDepthMap on device-resident views.  d_depth/d_normal hold the initial
 // estimate (full resolution) and receive the result together with d_conf / d_views.
@@ -236,6 +273,7 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 			}
 		}
 		const int w = lv[0].w, h = lv[0].h;
+		{ const int rc = prepare_tex(ctx, lv.data(), nViews, s); if (rc) return rc; }
 		const float* lowres = nullptr;
 		if (sc != totalScale) {
 			// depth LINEAR / normal NEAREST up-sampling of the coarser level; the up-sampled
@@ -255,13 +293,13 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 		PMParams P; bool geom;
 		build_params(o, lv.data(), nViews, dMin, dMax, lowres, plane, cost, best, P, geom);
 		P.nRandomIters = nR;
-		CK(pm_launch_score(P, geom, s)); ++ctx->launches;
+		CK(pm_launch_score(P, ctx->layout, geom, ctx->wsmem, s)); ++ctx->launches;
 		for (int it = iterBegin; it < iterEnd; ++it) {
 			for (int k = 0; k < spi; ++k) {
 				P.sweep = it*spi+k;
 				for (int colour = 0; colour < 2; ++colour) {
 					P.colour = colour;
-					CK(pm_launch_sweep(P, geom, s)); ++ctx->launches;
+					{ const int rc = launch_sweep_timed(ctx, P, geom, s); if (rc) return rc; }
 				}
 			}
 		}
@@ -308,6 +346,8 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 	b200mvs_ctx* c = new b200mvs_ctx();
 	c->device = device;
 	b200mvs_default_params(&c->prm);
+	if (const char* e = getenv("B200MVS_LAYOUT")) { const int l = atoi(e); if (l == 1 || l == 2) c->layout = l; }
+	if (const char* e = getenv("B200MVS_WSMEM")) c->wsmem = atoi(e) != 0;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
 		delete c;
@@ -323,6 +363,8 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto& b: c->imgs) b.release();
 	for (auto& b: c->dmaps) b.release();
 	for (auto& b: c->pyr) b.release();
+	for (auto& b: c->tex) b.release();
+	for (auto e: c->sweepEv) cudaEventDestroy(e);
 	c->plane.release(); c->cost.release(); c->best.release(); c->prior.release(); c->lowPlane.release();
 	c->dDepth.release(); c->dNormal.release(); c->dConf.release(); c->dViews.release(); c->mapD.release(); c->mapN.release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -357,7 +399,7 @@ int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nVi
 		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
 			views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
 	const auto t0 = std::chrono::steady_clock::now();
-	ctx->launches = 0;
+	ctx->launches = 0; ctx->nSweepEv = 0; ctx->timeSweeps = stats != nullptr;
 	if (stats) CK(cudaEventRecord(ctx->ev0, s));
 	rc = estimate_on_device(ctx, dv.data(), nViews, dMin, dMax, nGeometricIter, depth, normal, conf, (uint32_t*)viewsMap, s);
 	if (rc) return rc;
@@ -370,6 +412,8 @@ int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nVi
 		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
 		stats->kernel_launches = ctx->launches;
 		stats->levels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
+		for (int k = 0; k < ctx->nSweepEv; ++k) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->sweepEv[2*k], ctx->sweepEv[2*k+1])); stats->ms_sweep_kernels += t; }
+		stats->sweep_launches = ctx->nSweepEv;
 	}
 	return B200MVS_OK;
 }
@@ -410,7 +454,7 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	CK(cudaMemcpyAsync(dD.p, depth, P0*sizeof(float), cudaMemcpyHostToDevice, s));
 	CK(cudaMemcpyAsync(dN.p, normal, P0*3*sizeof(float), cudaMemcpyHostToDevice, s));
 	h2d += P0*16;
-	ctx->launches = 0;
+	ctx->launches = 0; ctx->nSweepEv = 0; ctx->timeSweeps = stats != nullptr;
 	CK(cudaEventRecord(ctx->ev0, s));
 	rc = estimate_on_device(ctx, dv.data(), nViews, dMin, dMax, nGeometricIter, dD.as<float>(), dN.as<float>(),
 		ctx->dConf.as<float>(), ctx->dViews.as<uint32_t>(), s);
@@ -430,6 +474,8 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 		stats->bytes_h2d = h2d; stats->bytes_d2h = d2h;
 		stats->kernel_launches = ctx->launches;
 		stats->levels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
+		for (int k = 0; k < ctx->nSweepEv; ++k) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->sweepEv[2*k], ctx->sweepEv[2*k+1])); stats->ms_sweep_kernels += t; }
+		stats->sweep_launches = ctx->nSweepEv;
 	}
 	return B200MVS_OK;
 }
@@ -448,7 +494,7 @@ int b200mvs_pm_unpack(b200mvs_ctx* ctx, int width, int height, const float* plan
 	return B200MVS_OK;
 }
 static int block_params(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax, const float* lowres,
-	float* plane4, float* cost, PMParams& P, bool& geom)
+	float* plane4, float* cost, cudaStream_t s, PMParams& P, bool& geom)
 {
 	int rc = check_views(ctx, views, nViews);
 	if (rc) return rc;
@@ -457,6 +503,7 @@ static int block_params(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
 	for (int i = 0; i < nViews; ++i)
 		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
 			views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
+	{ const int rc2 = prepare_tex(ctx, dv.data(), nViews, s); if (rc2) return rc2; }
 	build_params(ctx->prm, dv.data(), nViews, dMin, dMax, lowres, (float4*)plane4, cost, nullptr, P, geom);
 	return B200MVS_OK;
 }
@@ -464,24 +511,28 @@ int b200mvs_pm_score(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	const float* lowres, float* plane4, float* cost, void* stream)
 {
 	PMParams P; bool geom;
-	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, P, geom);
-	if (rc) return rc;
+	if (!ctx) return B200MVS_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
-	CK(pm_launch_score(P, geom, stream ? (cudaStream_t)stream : ctx->stream));
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, s, P, geom);
+	if (rc) return rc;
+	CK(pm_launch_score(P, ctx->layout, geom, ctx->wsmem, s));
 	return B200MVS_OK;
 }
 int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
 	const float* lowres, int sweep, int half, int nRandomIters, float* plane4, float* cost, void* stream)
 {
 	PMParams P; bool geom;
-	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, P, geom);
-	if (rc) return rc;
+	if (!ctx) return B200MVS_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, s, P, geom);
+	if (rc) return rc;
 	P.sweep = sweep; P.nRandomIters = nRandomIters;
 	for (int colour = 0; colour < 2; ++colour) {
 		if (half >= 0 && half != colour) continue;
 		P.colour = colour;
-		CK(pm_launch_sweep(P, geom, stream ? (cudaStream_t)stream : ctx->stream));
+		CK(pm_launch_sweep(P, ctx->layout, geom, ctx->wsmem, s));
 	}
 	return B200MVS_OK;
 }

@@ -12,7 +12,8 @@
 struct PMView {
 	float A[9];
 	float Hm[3];
-	const float* img; int w, h, pitch;       // pitch in floats
+	const float* img; int w, h, pitch;       // plain float image, pitch in floats
+	const void* tex; int tpitch;             // the image in the tap-fetch layout (pm_kernels.cu fetch_bilinear), pitch in texels
 	const float* dmap; int dw, dh, dpitch;   // known depth-map (geometric pass) or null
 	float Tl[9], Tm[3], Tr[9], Tn[3];
 };

@@ -20,29 +20,45 @@ namespace {
 constexpr int BLOCK_X = 32;  // lanes: 32 same-colour pixels = 64-pixel span
 constexpr int BLOCK_Y = 8;
 
-struct Patch {
+constexpr int NTHREADS = BLOCK_X*BLOCK_Y;
+
+// bilateral weights of the 5x5 reference patch (WeightedPatchFix<25>, DepthMap.h:145-155).
+// WS=false: all 50 values in registers; WS=true: in shared memory as float2{w,tw}[tap][thread]
+// (conflict-free LDS.64), which frees ~50 registers per thread for occupancy.
+template <bool WS> struct PatchT;
+template <> struct PatchT<false> {
 	float w[PM_TEXELS];
 	float tw[PM_TEXELS];
 	float sumW, normSq0;
+	__device__ __forceinline__ void set(int k, float a, float b) { w[k] = a; tw[k] = b; }
+	__device__ __forceinline__ float2 get(int k) const { return make_float2(w[k], tw[k]); }
+};
+template <> struct PatchT<true> {
+	float2* s; // &smem[threadIndex]; tap k at s[k*NTHREADS]
+	float sumW, normSq0;
+	__device__ __forceinline__ void set(int k, float a, float b) { s[k*NTHREADS] = make_float2(a, b); }
+	__device__ __forceinline__ float2 get(int k) const { return s[k*NTHREADS]; }
 };
 
 // FillPixelPatch + GetWeight (DepthMap.cpp:422-462, DepthMap.h:403-412)
-__device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pitch, int x, int y, Patch& p) {
+template <bool WS>
+__device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pitch, int x, int y, PatchT<WS>& p) {
 	const float sigmaColor = -1.f/(2.f*0.1f*0.1f);
 	const float sigmaSpatial = -1.f/(2.f*9.f);
 	const float center = __ldg(img + (size_t)y*pitch + x);
 	float acc = 0.f, sumW = 0.f;
+	float w[PM_TEXELS], I[PM_TEXELS];
 	#pragma unroll
 	for (int i = 0; i < 5; ++i) {
 		#pragma unroll
 		for (int j = 0; j < 5; ++j) {
 			const int dy = 2*i-PM_HALF, dx = 2*j-PM_HALF;
-			const float I = __ldg(img + (size_t)(y+dy)*pitch + (x+dx));
-			const float dI = I-center;
+			const float v = __ldg(img + (size_t)(y+dy)*pitch + (x+dx));
+			const float dI = v-center;
 			const float wgt = expf(dI*dI*sigmaColor + float(dx*dx+dy*dy)*sigmaSpatial);
-			p.w[i*5+j] = wgt;
-			p.tw[i*5+j] = I;
-			acc += I*wgt;
+			w[i*5+j] = wgt;
+			I[i*5+j] = v;
+			acc += v*wgt;
 			sumW += wgt;
 		}
 	}
@@ -50,9 +66,10 @@ __device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pi
 	float nsq = 0.f;
 	#pragma unroll
 	for (int k = 0; k < PM_TEXELS; ++k) {
-		const float t = p.tw[k]-tm;
-		p.tw[k] = p.w[k]*t;
-		nsq += p.tw[k]*t;
+		const float t = I[k]-tm;
+		const float tw = w[k]*t;
+		nsq += tw*t;
+		p.set(k, w[k], tw);
 	}
 	p.sumW = sumW;
 	p.normSq0 = nsq;
@@ -92,9 +109,38 @@ __device__ __forceinline__ bool sample_depth_masked(const float* __restrict__ im
 	return true;
 }
 
+// Bilinear fetch of one warped tap.  LAYOUT selects how the neighbour image is stored in HBM:
+//   1: plain float rows                       4 x LDG.32 per tap
+//   2: row pairs  float2{I(y,x), I(y+1,x)}    2 x LDG.64 per tap (second at +8 B)
+// (measured and dropped, DESIGN.md §6: float4 quads with one LDG.128 per tap, texture gather TLD4,
+//  and a TLD4/LDG split across views — all slower than these two on B200)
+template <int LAYOUT>
+__device__ __forceinline__ float fetch_bilinear(const void* __restrict__ tex, int pitch, unsigned idx, float ax, float ay) {
+	float v00, v10, v01, v11;
+	// address = tex + idx*sizeof(texel) as one IMAD.WIDE.U32
+	unsigned long long addr;
+	asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"((unsigned)(4*LAYOUT)), "l"((unsigned long long)tex));
+	if (LAYOUT == 1) {
+		const float* r0 = (const float*)addr;
+		v00 = __ldg(r0); v10 = __ldg(r0+1); v01 = __ldg(r0+pitch); v11 = __ldg(r0+pitch+1);
+	} else {
+		const float2* r0 = (const float2*)addr;
+		const float2 a = __ldg(r0), b = __ldg(r0+1);
+		v00 = a.x; v01 = a.y; v10 = b.x; v11 = b.y;
+	}
+	const float top = fmaf(ax, v10-v00, v00);
+	const float bot = fmaf(ax, v11-v01, v01);
+	return fmaf(ay, bot-top, top);
+}
+
 // ScorePixelImage (DepthMap.cpp:465-564) for one neighbour view.
-template <bool GEOM>
-__device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, const Patch& pt,
+// The reference rejects a hypothesis as soon as one warped tap leaves the neighbour image
+// (1-pixel border).  A homography maps the convex patch quad onto the convex quad of its
+// projected corners as long as the depth Z keeps its sign, so "all 25 taps inside" is decided
+// once from the 4 corner taps; the tap loop itself is then branch-free and test-free, and the
+// loads of a whole tap row are in flight together.  Rejected lanes run the loop on texel (1,1).
+template <int LAYOUT, bool GEOM, bool WS>
+__device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, const PatchT<WS>& pt,
 	float fx, float fy, float X0x, float X0y, const Hyp& h, float priorF, float priorD)
 {
 	// H = A + Hm (n^T Kref^-1)/(n.X0 d); columns 0/1 and the centre point H*(x,y,1)
@@ -107,10 +153,29 @@ __device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, 
 	float bx = fmaf(-4.f, c0x+c1x, xc), by = fmaf(-4.f, c0y+c1y, yc), bz = fmaf(-4.f, c0z+c1z, zc);
 	c0x *= 2.f; c0y *= 2.f; c0z *= 2.f; c1x *= 2.f; c1y *= 2.f; c1z *= 2.f;
 	const float xmax = float(V.w-2), ymax = float(V.h-2);
-	const float* __restrict__ img = V.img;
-	const int pitch = V.pitch;
+	bool ok;
+	{
+		// the four corner taps (0,0) (4,0) (0,4) (4,4)
+		const float x1 = fmaf(4.f, c0x, bx), y1 = fmaf(4.f, c0y, by), z1 = fmaf(4.f, c0z, bz);
+		const float x2 = fmaf(4.f, c1x, bx), y2 = fmaf(4.f, c1y, by), z2 = fmaf(4.f, c1z, bz);
+		const float x3 = fmaf(4.f, c1x, x1), y3 = fmaf(4.f, c1y, y1), z3 = fmaf(4.f, c1z, z1);
+		const float zmin = fminf(fminf(bz, z1), fminf(z2, z3)), zmax = fmaxf(fmaxf(bz, z1), fmaxf(z2, z3));
+		const float i0 = fast_rcp(bz), i1 = fast_rcp(z1), i2 = fast_rcp(z2), i3 = fast_rcp(z3);
+		const float pxmin = fminf(fminf(bx*i0, x1*i1), fminf(x2*i2, x3*i3)), pxmax = fmaxf(fmaxf(bx*i0, x1*i1), fmaxf(x2*i2, x3*i3));
+		const float pymin = fminf(fminf(by*i0, y1*i1), fminf(y2*i2, y3*i3)), pymax = fmaxf(fmaxf(by*i0, y1*i1), fmaxf(y2*i2, y3*i3));
+		ok = (zmin > 0.f || zmax < 0.f) && pxmin >= 1.f && pymin >= 1.f && pxmax <= xmax && pymax <= ymax;
+		// NaN anywhere makes a comparison false (fminf/fmaxf drop NaNs, so test them explicitly)
+		ok = ok && (bx*i0 == bx*i0) && (x1*i1 == x1*i1) && (x2*i2 == x2*i2) && (x3*i3 == x3*i3)
+		        && (by*i0 == by*i0) && (y1*i1 == y1*i1) && (y2*i2 == y2*i2) && (y3*i3 == y3*i3);
+	}
+	if (!__any_sync(__activemask(), ok))
+		return P.thRobust;
+	if (!ok) { bx = by = bz = 1.f; c0x = c0y = c0z = c1x = c1y = c1z = 0.f; }
+	const void* tex = V.tex;
+	int pitch = V.tpitch;
+	// keep the per-view constants in registers (otherwise re-read from the constant bank per tap)
+	asm volatile("" : "+r"(pitch), "+l"(tex));
 	float sum = 0.f, sumSq = 0.f, num = 0.f;
-	bool bad = false;
 	#pragma unroll
 	for (int i = 0; i < 5; ++i) {
 		float X = bx, Y = by, Z = bz;
@@ -118,27 +183,21 @@ __device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, 
 		for (int j = 0; j < 5; ++j) {
 			const float iz = fast_rcp(Z);
 			const float px = X*iz, py = Y*iz;
-			const bool in = px >= 1.f && py >= 1.f && px <= xmax && py <= ymax;
-			bad |= !in;
-			float v = 0.f;
-			if (in) {
-				const int lx = (int)px, ly = (int)py;
-				const float ax = px-(float)lx, ay = py-(float)ly;
-				const float* r0 = img + (size_t)ly*pitch + lx;
-				const float v00 = __ldg(r0), v10 = __ldg(r0+1), v01 = __ldg(r0+pitch), v11 = __ldg(r0+pitch+1);
-				const float ax1 = 1.f-ax, ay1 = 1.f-ay;
-				v = (v00*ax1 + v10*ax)*ay1 + (v01*ax1 + v11*ax)*ay;
-			}
-			const float vw = v*pt.w[i*5+j];
+			const int lx = __float2int_rz(px), ly = __float2int_rz(py);
+			const float flx = (float)lx, fly = (float)ly;
+			const float ax = px-flx, ay = py-fly;
+			const unsigned idx = (unsigned)(ly*pitch + lx);
+			const float v = fetch_bilinear<LAYOUT>(tex, pitch, idx, ax, ay);
+			const float2 wk = pt.get(i*5+j);
+			const float vw = v*wk.x;
 			sum += vw;
 			sumSq = fmaf(v, vw, sumSq);
-			num = fmaf(v, pt.tw[i*5+j], num);
+			num = fmaf(v, wk.y, num);
 			X += c0x; Y += c0y; Z += c0z;
 		}
 		bx += c1x; by += c1y; bz += c1z;
-		if (__all_sync(__activemask(), bad))
-			break;
 	}
+	const bool bad = !ok;
 	if (bad)
 		return P.thRobust;
 	const float normSq1 = sumSq - sum*sum/pt.sumW;
@@ -182,15 +241,15 @@ __device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, 
 }
 
 // ScorePixel (DepthMap.cpp:567-626): MINMEAN over the views; also reports the two best views
-template <bool GEOM>
-__device__ __forceinline__ float score_pixel(const PMParams& P, const Patch& pt,
+template <int LAYOUT, bool GEOM, bool WS>
+__device__ __forceinline__ float score_pixel(const PMParams& P, const PatchT<WS>& pt,
 	float fx, float fy, float X0x, float X0y, const Hyp& h, float priorF, float priorD, uint32_t& best)
 {
 	float s0 = CUDART_INF_F, s1 = CUDART_INF_F;
 	int i0 = 255, i1 = 255;
 	#pragma unroll 1
 	for (int v = 0; v < P.nViews; ++v) {
-		const float s = score_view<GEOM>(P, P.views[v], pt, fx, fy, X0x, X0y, h, priorF, priorD);
+		const float s = score_view<LAYOUT, GEOM, WS>(P, P.views[v], pt, fx, fy, X0x, X0y, h, priorF, priorD);
 		if (s < s0) { s1 = s0; i1 = i0; s0 = s; i0 = v; }
 		else if (s < s1) { s1 = s; i1 = v; }
 	}
@@ -271,17 +330,19 @@ __device__ __forceinline__ void correct_normal(float3& n, float X0x, float X0y) 
 
 // ------------------------------------------------------------------------------------
 // pass A: score the initial estimate of every pixel (random where invalid)
-template <bool GEOM>
-__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, 2)
+template <int LAYOUT, bool GEOM, bool WS>
+__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, WS ? 3 : 2)
 pm_score_kernel(const __grid_constant__ PMParams P)
 {
+	extern __shared__ float2 smemW[];
 	const int x = blockIdx.x*BLOCK_X + threadIdx.x;
 	const int y = blockIdx.y*BLOCK_Y + threadIdx.y;
 	if (x >= P.W || y >= P.H)
 		return;
 	const size_t idx = (size_t)y*P.W + x;
 	const bool inside = x >= PM_HALF && y >= PM_HALF && x < P.W-PM_HALF && y < P.H-PM_HALF;
-	Patch pt;
+	PatchT<WS> pt;
+	if constexpr (WS) pt.s = smemW + threadIdx.y*BLOCK_X + threadIdx.x;
 	float priorD = 0.f, priorF = 0.f;
 	bool ok = inside;
 	if (inside) {
@@ -316,7 +377,7 @@ pm_score_kernel(const __grid_constant__ PMParams P)
 	Hyp h;
 	make_hyp(P, X0x, X0y, d, n, cl, false, h);
 	uint32_t best;
-	const float c = score_pixel<GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, best);
+	const float c = score_pixel<LAYOUT, GEOM, WS>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, best);
 	P.plane[idx] = make_float4(n.x, n.y, n.z, d);
 	P.cost[idx] = c;
 	if (P.bestViews) P.bestViews[idx] = best;
@@ -324,17 +385,19 @@ pm_score_kernel(const __grid_constant__ PMParams P)
 
 // ------------------------------------------------------------------------------------
 // pass B: one red-black half-sweep
-template <bool GEOM>
-__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, 2)
+template <int LAYOUT, bool GEOM, bool WS>
+__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, WS ? 3 : 2)
 pm_sweep_kernel(const __grid_constant__ PMParams P)
 {
+	extern __shared__ float2 smemW[];
 	const int y = blockIdx.y*BLOCK_Y + threadIdx.y;
 	const int x = blockIdx.x*(2*BLOCK_X) + 2*threadIdx.x + ((y+P.colour)&1);
 	if (x < PM_HALF || y < PM_HALF || x >= P.W-PM_HALF || y >= P.H-PM_HALF)
 		return;
 	const int W = P.W, H = P.H;
 	const size_t idx = (size_t)y*W + x;
-	Patch pt;
+	PatchT<WS> pt;
+	if constexpr (WS) pt.s = smemW + threadIdx.y*BLOCK_X + threadIdx.x;
 	fill_patch(P.img0, P.pitch0, x, y, pt);
 	float priorD = 0.f, priorF = 0.f;
 	if (P.lowres)
@@ -380,29 +443,37 @@ pm_sweep_kernel(const __grid_constant__ PMParams P)
 	const int nProp = P.propagation;
 	const uint2 key = make_uint2(P.seed, 0xB200C0DEu);
 	const uint32_t phase = 1u + (uint32_t)P.sweep;
-	// refinement state machine (DepthMap.cpp:800-852)
+	// refinement state machine (DepthMap.cpp:800-852).  Lanes in restart mode spend their random
+	// tries in the same steps in which refine-mode lanes spend their perturbation tries; every try
+	// has its own Philox slot (restart try k: slot k, refinement try k: slot nR+k), so the result
+	// does not depend on the step at which a lane executes it.
 	int mode = 0;               // 0 undecided, 1 restart (fully random), 2 refine, 3 done
 	bool useClose = true;
 	unsigned idxScale = 0;
 	float scaleRange = 1.f, depthRange = 0.f, pa = 0.f, pb = 0.f;
+	int nRestart = 0, nRefine = 0; // tries spent
 	const int nSteps = 4 + 2*nR;
 	#pragma unroll 1
 	for (int step = 0; step < nSteps; ++step) {
-		if (step == 4 || (mode == 1 && step >= 4 && conf < P.thConfRand)) {
+		if (step == 4 || (mode == 1 && step > 4 && conf < P.thConfRand)) {
 			// RefineIters: choose the perturbation scale from the current score
-			if (mode == 0 || mode == 1) {
-				bool toRefine = true;
-				if (conf <= P.thConfSmall) idxScale = 2;
-				else if (conf <= P.thConfBig) idxScale = 1;
-				else if (conf >= P.thConfRand && mode == 0) { mode = 1; useClose = false; toRefine = false; }
-				if (toRefine) {
-					mode = 2;
-					scaleRange = pow2neg(idxScale);
-					depthRange = depth*P.depthRatio;
-					pa = atan2f(normal.y, normal.x);
-					pb = acosf(normal.z);
-				}
+			bool toRefine = true;
+			if (conf <= P.thConfSmall) idxScale = 2;
+			else if (conf <= P.thConfBig) idxScale = 1;
+			else if (conf >= P.thConfRand && mode == 0) { mode = 1; useClose = false; toRefine = false; }
+			if (toRefine) {
+				mode = 2;
+				scaleRange = pow2neg(idxScale);
+				depthRange = depth*P.depthRatio;
+				pa = atan2f(normal.y, normal.x);
+				pb = acosf(normal.z);
 			}
+		}
+		if (step >= 4) {
+			if (mode == 1 && nRestart >= nR) mode = 3; // all random tries failed: no refinement this sweep
+			const bool work = (mode == 1) || (mode == 2 && nRefine < nR);
+			if (!__any_sync(__activemask(), work))
+				break;
 		}
 		bool have = false, isRefine = false;
 		float hd = 0.f, na = 0.f, nb = 0.f; float3 hn = make_float3(0.f, 0.f, 1.f);
@@ -431,27 +502,25 @@ pm_sweep_kernel(const __grid_constant__ PMParams P)
 					have = true;
 				}
 			}
-		} else if (step < 4+nR) {
-			if (mode == 1) {
-				// completely random plane (DepthMap.cpp:810-825)
-				const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)(step-4), 0u), key);
-				const float s = P.dMinSqr + (P.dMaxSqr-P.dMinSqr)*u32_to_unit(r.x);
-				hd = s*s;
-				hn = random_normal(u32_to_unit(r.y), u32_to_unit(r.z), X0x, X0y);
-				have = true;
-			}
-		} else {
-			if (mode == 2) {
-				// perturb around the current estimate (DepthMap.cpp:832-851)
-				const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)(step-4), 0u), key);
-				hd = depth + depthRange*scaleRange*(2.f*u32_to_unit(r.x)-1.f);
-				if (P.dMin <= hd && hd < P.dMax) {
-					na = pa + P.angle1Range*scaleRange*(2.f*u32_to_unit(r.y)-1.f);
-					nb = pb + P.angle2Range*scaleRange*(2.f*u32_to_unit(r.z)-1.f);
-					hn = dir2normal(na, nb);
-					have = hn.x*X0x + hn.y*X0y + hn.z < 0.f;
-					isRefine = true;
-				}
+		} else if (mode == 1) {
+			// completely random plane (DepthMap.cpp:810-825)
+			const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)nRestart, 0u), key);
+			++nRestart;
+			const float s = P.dMinSqr + (P.dMaxSqr-P.dMinSqr)*u32_to_unit(r.x);
+			hd = s*s;
+			hn = random_normal(u32_to_unit(r.y), u32_to_unit(r.z), X0x, X0y);
+			have = true;
+		} else if (mode == 2 && nRefine < nR) {
+			// perturb around the current estimate (DepthMap.cpp:832-851)
+			const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)(nR+nRefine), 0u), key);
+			++nRefine;
+			hd = depth + depthRange*scaleRange*(2.f*u32_to_unit(r.x)-1.f);
+			if (P.dMin <= hd && hd < P.dMax) {
+				na = pa + P.angle1Range*scaleRange*(2.f*u32_to_unit(r.y)-1.f);
+				nb = pb + P.angle2Range*scaleRange*(2.f*u32_to_unit(r.z)-1.f);
+				hn = dir2normal(na, nb);
+				have = hn.x*X0x + hn.y*X0y + hn.z < 0.f;
+				isRefine = true;
 			}
 		}
 		if (!__any_sync(__activemask(), have))
@@ -460,7 +529,7 @@ pm_sweep_kernel(const __grid_constant__ PMParams P)
 			Hyp h;
 			make_hyp(P, X0x, X0y, hd, hn, cl, useClose, h);
 			uint32_t bv;
-			const float nconf = score_pixel<GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
+			const float nconf = score_pixel<LAYOUT, GEOM, WS>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
 			if (conf > nconf) {
 				conf = nconf; depth = hd; normal = hn; bestViews = bv;
 				if (isRefine) {
@@ -470,8 +539,6 @@ pm_sweep_kernel(const __grid_constant__ PMParams P)
 				}
 			}
 		}
-		if (mode == 1 && step == 4+nR-1 && !(conf < P.thConfRand))
-			mode = 3; // all random tries failed: no refinement this sweep
 	}
 	P.plane[idx] = make_float4(normal.x, normal.y, normal.z, depth);
 	P.cost[idx] = conf;
@@ -499,6 +566,12 @@ __global__ void pm_finalize_kernel(int n, float keep, const float4* __restrict__
 	if (viewsMap) viewsMap[i] = bv;
 }
 
+__global__ void pm_pairs_kernel(const float* __restrict__ src, int w, int h, int spitch, float2* __restrict__ dst) {
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= w || y >= h) return;
+	const int y1 = min(y+1, h-1);
+	dst[(size_t)y*w+x] = make_float2(src[(size_t)y*spitch+x], src[(size_t)y1*spitch+x]);
+}
 __global__ void pm_pack_kernel(int n, const float* __restrict__ depth, const float* __restrict__ normal, float4* __restrict__ plane) {
 	const int i = blockIdx.x*blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -512,19 +585,46 @@ __global__ void pm_unpack_kernel(int n, const float4* __restrict__ plane, float*
 	normal[3*(size_t)i] = p.x; normal[3*(size_t)i+1] = p.y; normal[3*(size_t)i+2] = p.z;
 }
 
-} // namespace
-
 // ---- host launchers ---------------------------------------------------------------------
-cudaError_t pm_launch_score(const PMParams& P, bool geom, cudaStream_t s) {
-	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+BLOCK_X-1)/BLOCK_X, (P.H+BLOCK_Y-1)/BLOCK_Y);
-	if (geom) pm_score_kernel<true><<<grid, block, 0, s>>>(P);
-	else pm_score_kernel<false><<<grid, block, 0, s>>>(P);
+template <int LAYOUT, bool GEOM, bool WS>
+cudaError_t launch_one(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P) {
+	const size_t smem = WS ? (size_t)PM_TEXELS*NTHREADS*sizeof(float2) : 0;
+	auto* k = sweep ? pm_sweep_kernel<LAYOUT, GEOM, WS> : pm_score_kernel<LAYOUT, GEOM, WS>;
+	if (WS) {
+		static bool done[2] = {false, false};
+		if (!done[sweep]) {
+			cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) return e;
+			done[sweep] = true;
+		}
+	}
+	k<<<grid, block, smem, s>>>(P);
 	return cudaGetLastError();
 }
-cudaError_t pm_launch_sweep(const PMParams& P, bool geom, cudaStream_t s) {
+template <int LAYOUT>
+cudaError_t launch_layout(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, bool geom, bool ws) {
+	if (geom) return ws ? launch_one<LAYOUT, true, true>(sweep, grid, block, s, P) : launch_one<LAYOUT, true, false>(sweep, grid, block, s, P);
+	return ws ? launch_one<LAYOUT, false, true>(sweep, grid, block, s, P) : launch_one<LAYOUT, false, false>(sweep, grid, block, s, P);
+}
+cudaError_t launch_any(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, int layout, bool geom, bool ws) {
+	if (layout == 2) return launch_layout<2>(sweep, grid, block, s, P, geom, ws);
+	return launch_layout<1>(sweep, grid, block, s, P, geom, ws);
+}
+
+} // namespace
+
+cudaError_t pm_launch_score(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s) {
+	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+BLOCK_X-1)/BLOCK_X, (P.H+BLOCK_Y-1)/BLOCK_Y);
+	return launch_any(false, grid, block, s, P, layout, geom, ws);
+}
+cudaError_t pm_launch_sweep(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s) {
 	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+2*BLOCK_X-1)/(2*BLOCK_X), (P.H+BLOCK_Y-1)/BLOCK_Y);
-	if (geom) pm_sweep_kernel<true><<<grid, block, 0, s>>>(P);
-	else pm_sweep_kernel<false><<<grid, block, 0, s>>>(P);
+	return launch_any(true, grid, block, s, P, layout, geom, ws);
+}
+// re-layout of a neighbour image for the tap fetch (see fetch_bilinear)
+cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s) {
+	dim3 block(32, 8), grid((w+31)/32, (h+7)/8);
+	if (layout == 2) pm_pairs_kernel<<<grid, block, 0, s>>>(src, w, h, spitch, (float2*)dst);
 	return cudaGetLastError();
 }
 cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
