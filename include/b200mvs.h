@@ -130,6 +130,43 @@ int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 int b200mvs_pm_finalize(b200mvs_ctx* ctx, int width, int height, float keepThreshold,
 	const float* plane4, const float* cost, float* depth, float* normal, float* conf, void* stream);
 
+/* ---- SemiGlobalMatcher::Match(leftImage, rightImage, disparityMap, costMap) replacement -------
+ * (libs/MVS/SemiGlobalMatcher.cpp:863-1302; WZNCC 7x7 cost, 8-path aggregation with per-pixel
+ * disparity ranges, winner-takes-all).  Images are rectified: left/right gray float (sRGB->linear,
+ * SemiGlobalMatcher.cpp:580-581) and the left colour image (BGR, 3 x uint8), all width x height.
+ * `pixels` is the reference's PixelMap over the valid region (width-6) x (height-6):
+ * idx = offset of the pixel's first cost in the ragged volume, [dmin,dmax) its disparity range
+ * (dmin >= dmax: invalid pixel, skipped; PixelData, SemiGlobalMatcher.h:78-81).  numCosts = total
+ * number of (pixel, disparity) entries.  Outputs over the valid region: disparity (int16) and the
+ * summed path cost (uint16, 65535 for invalid pixels). */
+typedef struct {
+	uint64_t idx;
+	int16_t dmin, dmax;
+	int32_t reserved;
+} b200mvs_sgm_pixel;
+
+typedef struct {
+	int P1;            /* 3  (SemiGlobalMatcher ctor defaults, SemiGlobalMatcher.h:149) */
+	int P2;            /* 4  */
+	float P2alpha;     /* 14 */
+	float P2beta;      /* 38 */
+} b200mvs_sgm_params;
+
+void b200mvs_sgm_default_params(b200mvs_sgm_params* p);
+
+/* HOST buffers */
+int b200mvs_sgm_match(b200mvs_ctx* ctx, const float* leftGray, const uint8_t* leftBGR, const float* rightGray,
+	int width, int height, const b200mvs_sgm_pixel* pixels, uint64_t numCosts, const b200mvs_sgm_params* prm,
+	int16_t* disparity, uint16_t* cost, b200mvs_stats* stats);
+
+/* DEVICE pointers.  stages: bit 0 compute the cost volume, bit 1 aggregate the 8 paths, bit 2
+ * winner-takes-all.  costs (uint8) / accums (uint16) hold numCosts entries; pass NULL to use the
+ * context's scratch, or buffers to inspect / supply the volumes (parity tests feed the oracle's cost
+ * volume into the aggregation). */
+int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint8_t* leftBGR, const float* rightGray,
+	int width, int height, const b200mvs_sgm_pixel* pixels, uint64_t numCosts, const b200mvs_sgm_params* prm,
+	int stages, uint8_t* costs, uint16_t* accums, int16_t* disparity, uint16_t* cost, void* stream, b200mvs_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

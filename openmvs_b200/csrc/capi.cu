@@ -22,6 +22,21 @@ cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const flo
 	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s);
 cudaError_t pm_launch_pack(int n, const float* depth, const float* normal, float4* plane, cudaStream_t s);
 cudaError_t pm_launch_unpack(int n, const float4* plane, float* depth, float* normal, cudaStream_t s);
+struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
+struct SGMParams {
+	const float* lgray; const uchar3* lbgr; const float* rgray;
+	int w, h, vw, vh;
+	const SGMPixel* px;
+	uint8_t* costs; uint16_t* accums;
+	int P1;
+	uint16_t P2s[256];
+	int maxNumDisp;
+};
+cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out, cudaStream_t s);
+cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
+cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
+cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
+int sgm_max_disparities();
 cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s);
@@ -97,6 +112,7 @@ struct b200mvs_ctx {
 	DevBuf dDepth, dNormal, dConf, dViews;    // level scratch / staging of the maps (host API)
 	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
 	std::vector<DevBuf> tex;                  // neighbour images in the tap-fetch layout
+	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgDisp, sgCost, sgMax; // SGM staging / scratch
 	int layout = 1;                           // 1 plain float rows, 2 row pairs (B200MVS_LAYOUT overrides)
 	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
 	std::vector<cudaEvent_t> sweepEv;         // event pairs around the sweep launches (stats only)
@@ -365,6 +381,8 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto& b: c->pyr) b.release();
 	for (auto& b: c->tex) b.release();
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
+	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release();
+	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
 	c->plane.release(); c->cost.release(); c->best.release(); c->prior.release(); c->lowPlane.release();
 	c->dDepth.release(); c->dNormal.release(); c->dConf.release(); c->dViews.release(); c->mapD.release(); c->mapN.release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -543,6 +561,103 @@ int b200mvs_pm_finalize(b200mvs_ctx* ctx, int width, int height, float keep, con
 	CK(cudaSetDevice(ctx->device));
 	CK(pm_launch_finalize(width*height, keep, (const float4*)plane4, cost, nullptr, depth, normal, conf, nullptr,
 		stream ? (cudaStream_t)stream : ctx->stream));
+	return B200MVS_OK;
+}
+
+// ---- SGM --------------------------------------------------------------------------------------
+void b200mvs_sgm_default_params(b200mvs_sgm_params* p) { p->P1 = 3; p->P2 = 4; p->P2alpha = 14.f; p->P2beta = 38.f; }
+
+int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint8_t* leftBGR, const float* rightGray,
+	int width, int height, const b200mvs_sgm_pixel* pixels, uint64_t numCosts, const b200mvs_sgm_params* prm,
+	int stages, uint8_t* costs, uint16_t* accums, int16_t* disparity, uint16_t* cost, void* stream, b200mvs_stats* stats)
+{
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!leftGray || !leftBGR || !rightGray || !pixels || width <= 6 || height <= 6 || numCosts == 0)
+		return fail(ctx, B200MVS_ERR_ARG, "sgm: null image/pixel map or image too small");
+	if ((stages & 4) && (!disparity || !cost))
+		return fail(ctx, B200MVS_ERR_ARG, "sgm: null output map");
+	b200mvs_sgm_params def; b200mvs_sgm_default_params(&def);
+	if (!prm) prm = &def;
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	static_assert(sizeof(b200mvs_sgm_pixel) == sizeof(SGMPixel), "pixel record layout");
+	SGMParams P; memset(&P, 0, sizeof(P));
+	P.lgray = leftGray; P.lbgr = (const uchar3*)leftBGR; P.rgray = rightGray;
+	P.w = width; P.h = height; P.vw = width-6; P.vh = height-6;
+	P.px = (const SGMPixel*)pixels;
+	P.P1 = prm->P1;
+	int minP2 = 1<<30;
+	for (int i = 0; i < 256; ++i) {
+		// GenerateP2s (libs/MVS/SemiGlobalMatcher.cpp:518-524)
+		P.P2s[i] = (uint16_t)(int)std::floor(prm->P2*(1.f+prm->P2alpha*std::exp(-float(i)*float(i)/(2.f*prm->P2beta*prm->P2beta)))+.5f);
+		minP2 = std::min(minP2, (int)P.P2s[i]);
+	}
+	if (prm->P1 < 0 || prm->P1 > minP2)
+		return fail(ctx, B200MVS_ERR_ARG, "sgm: needs 0 <= P1 <= min(P2s)");
+	if (!costs) { CK(ctx->sgCosts.reserve(numCosts)); costs = ctx->sgCosts.as<uint8_t>(); }
+	if (!accums) { CK(ctx->sgAccums.reserve(numCosts*sizeof(uint16_t))); accums = ctx->sgAccums.as<uint16_t>(); }
+	P.costs = costs; P.accums = accums;
+	const auto t0 = std::chrono::steady_clock::now();
+	ctx->launches = 0;
+	if (stats) CK(cudaEventRecord(ctx->ev0, s));
+	if (stages & 2) {
+		// the warp-per-scanline kernel keeps one line of at most sgm_max_disparities() values
+		CK(ctx->sgMax.reserve(sizeof(int)));
+		CK(sgm_launch_maxdisp(P.px, P.vw*P.vh, ctx->sgMax.as<int>(), s)); ++ctx->launches;
+		int m = 0;
+		CK(cudaMemcpyAsync(&m, ctx->sgMax.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		if (m > sgm_max_disparities())
+			return fail(ctx, B200MVS_ERR_ARG, "sgm: more than 256 disparities per pixel");
+		P.maxNumDisp = m;
+	}
+	if (stages & 1) { CK(sgm_launch_cost(P, s)); ++ctx->launches; }
+	if (stages & 2) {
+		CK(cudaMemsetAsync(accums, 0, numCosts*sizeof(uint16_t), s));
+		for (int dir = 0; dir < 8; ++dir) { CK(sgm_launch_aggregate(P, dir, s)); ++ctx->launches; }
+	}
+	if (stages & 4) { CK(sgm_launch_wta(P, disparity, cost, s)); ++ctx->launches; }
+	if (stats) {
+		CK(cudaEventRecord(ctx->ev1, s));
+		CK(cudaStreamSynchronize(s));
+		float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		memset(stats, 0, sizeof(*stats));
+		stats->ms_device = ms;
+		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
+		stats->kernel_launches = ctx->launches; stats->levels = 1;
+	}
+	return B200MVS_OK;
+}
+
+int b200mvs_sgm_match(b200mvs_ctx* ctx, const float* leftGray, const uint8_t* leftBGR, const float* rightGray,
+	int width, int height, const b200mvs_sgm_pixel* pixels, uint64_t numCosts, const b200mvs_sgm_params* prm,
+	int16_t* disparity, uint16_t* cost, b200mvs_stats* stats)
+{
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!leftGray || !leftBGR || !rightGray || !pixels || !disparity || !cost || width <= 6 || height <= 6)
+		return fail(ctx, B200MVS_ERR_ARG, "sgm: null pointer or image too small");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	const auto t0 = std::chrono::steady_clock::now();
+	const size_t n = (size_t)width*height, nv = (size_t)(width-6)*(height-6);
+	CK(ctx->sgL.reserve(n*4)); CK(ctx->sgR.reserve(n*4)); CK(ctx->sgC.reserve(n*3)); CK(ctx->sgPx.reserve(nv*sizeof(SGMPixel)));
+	CK(ctx->sgDisp.reserve(nv*2)); CK(ctx->sgCost.reserve(nv*2));
+	CK(cudaMemcpyAsync(ctx->sgL.p, leftGray, n*4, cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(ctx->sgR.p, rightGray, n*4, cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(ctx->sgC.p, leftBGR, n*3, cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(ctx->sgPx.p, pixels, nv*sizeof(SGMPixel), cudaMemcpyHostToDevice, s));
+	b200mvs_stats st;
+	int rc = b200mvs_sgm_match_device(ctx, ctx->sgL.as<float>(), ctx->sgC.as<uint8_t>(), ctx->sgR.as<float>(), width, height,
+		(const b200mvs_sgm_pixel*)ctx->sgPx.p, numCosts, prm, 7, nullptr, nullptr, ctx->sgDisp.as<int16_t>(), ctx->sgCost.as<uint16_t>(), s, &st);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(disparity, ctx->sgDisp.p, nv*2, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(cost, ctx->sgCost.p, nv*2, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	if (stats) {
+		*stats = st;
+		stats->bytes_h2d = n*11+nv*sizeof(SGMPixel); stats->bytes_d2h = nv*4;
+		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
+	}
 	return B200MVS_OK;
 }
 

@@ -1,0 +1,262 @@
+// sgm_kernels.cu — SGM pair matcher kernels for sm_100a.
+//
+// Behaviour follows SemiGlobalMatcher::Match(left, right, disparityMap, costMap)
+// (libs/MVS/SemiGlobalMatcher.cpp:863-1302, SGM_SIMILARITY_WZNCC, 8 paths):
+//   sgm_cost_kernel       WZNCC 7x7 cost, bilateral weights from the colour image -> uint8   :875-985
+//   sgm_aggregate_kernel  one warp per scanline, disparities across lanes; the previous line
+//                         lives in shared memory so that ragged per-pixel ranges [dmin,dmax)
+//                         (tSGM) can be intersected and shifted freely                       :1003-1201
+//   sgm_wta_kernel        first arg-min of the summed path costs                            :1272-1301
+// The cost volume is ragged: pixel p owns costs[p.idx .. p.idx + (dmax-dmin)) (PixelData,
+// libs/MVS/SemiGlobalMatcher.h:78-81); it is uint8, the path sum uint16 — HBM-bound integer work.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
+
+struct SGMParams {
+	const float* lgray; const uchar3* lbgr; const float* rgray;
+	int w, h, vw, vh;           // image size, valid-region size (w-6, h-6)
+	const SGMPixel* px;
+	uint8_t* costs; uint16_t* accums;
+	int P1;
+	uint16_t P2s[256];
+	int maxNumDisp;
+};
+
+namespace {
+
+constexpr int HW = 3, NT = 49;
+constexpr int COST_THREADS = 128;
+
+// ---- (1) cost ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(COST_THREADS)
+sgm_cost_kernel(const __grid_constant__ SGMParams P)
+{
+	extern __shared__ float2 sw[]; // {weight, tempWeight}[tap][thread]
+	const int col = blockIdx.x*COST_THREADS + threadIdx.x;
+	const int r = blockIdx.y;
+	if (col >= P.vw) return;
+	const SGMPixel p = P.px[(size_t)r*P.vw + col];
+	if (!(p.dmin < p.dmax)) return;
+	const int ux = col+HW, uy = r+HW;
+	const float sigmaColor = -1.f/(2.f*(0.3f*255)*(0.3f*255));
+	const float sigmaSpatial = -1.f/(2.f*(0.4f*7)*(0.4f*7));
+	float2* w = sw + threadIdx.x;
+	const uchar3 cc = P.lbgr[(size_t)uy*P.w + ux];
+	float acc = 0.f, sumW = 0.f;
+	#pragma unroll 1
+	for (int i = -HW; i <= HW; ++i) {
+		#pragma unroll
+		for (int j = -HW; j <= HW; ++j) {
+			const size_t o = (size_t)(uy+i)*P.w + (ux+j);
+			const uchar3 pc = P.lbgr[o];
+			const int d0 = abs((int)pc.x-(int)cc.x), d1 = abs((int)pc.y-(int)cc.y), d2 = abs((int)pc.z-(int)cc.z);
+			const float wgt = expf(float(d0*d0+d1*d1+d2*d2)*sigmaColor + float(j*j+i*i)*sigmaSpatial);
+			const float g = __ldg(P.lgray + o);
+			w[((i+HW)*7+(j+HW))*COST_THREADS] = make_float2(wgt, g);
+			acc += g*wgt;
+			sumW += wgt;
+		}
+	}
+	const float tm = acc/sumW;
+	float normSq0 = 0.f;
+	#pragma unroll 7
+	for (int n = 0; n < NT; ++n) {
+		float2 e = w[n*COST_THREADS];
+		const float t = e.y-tm;
+		e.y = e.x*t;
+		normSq0 += e.y*t;
+		w[n*COST_THREADS] = e;
+	}
+	uint8_t* costs = P.costs + p.idx;
+	const float eps = 1e-3f;
+	#pragma unroll 1
+	for (int d = p.dmin; d < p.dmax; ++d) {
+		const int x0 = ux-HW+d;
+		if (x0 < 0 || x0+2*HW >= P.w) { *costs++ = 255; continue; }
+		const float* rp = P.rgray + (size_t)(uy-HW)*P.w + x0;
+		float sum = 0.f, sumSq = 0.f, nom = 0.f;
+		#pragma unroll
+		for (int i = 0; i < 7; ++i) {
+			#pragma unroll
+			for (int j = 0; j < 7; ++j) {
+				const float f = __ldg(rp + i*P.w + j);
+				const float2 e = w[(i*7+j)*COST_THREADS];
+				const float fw = f*e.x;
+				sum += fw;
+				sumSq = fmaf(f, fw, sumSq);
+				nom = fmaf(f, e.y, nom);
+			}
+		}
+		const float normSq1 = sumSq - sum*sum/sumW;
+		const float ncc = nom/sqrtf(normSq0*normSq1+eps);
+		*costs++ = ncc <= 0.f ? (uint8_t)255 : (uint8_t)(int)floorf((1.f-fminf(ncc, 1.f))*255.f+.5f);
+	}
+}
+
+// ---- (2) path aggregation ------------------------------------------------------------------
+constexpr int AGG_WARPS = 4;
+constexpr int MAXD = 256;        // disparities per pixel supported by the warp-per-scanline kernel
+constexpr int LPAD = 8;
+
+// start pixel and step of scanline `k` of direction `dir` (order of SemiGlobalMatcher.cpp:1084-1199)
+__device__ __forceinline__ bool path_start(int dir, int k, int W, int H, int& x, int& y, int& dx, int& dy) {
+	switch (dir) {
+	case 0: if (k >= W) return false; x = k; y = 0; dx = 0; dy = 1; return true;        // width-down
+	case 1: if (k >= H) return false; x = 0; y = k; dx = 1; dy = 0; return true;        // height-right
+	case 2: if (k >= W) return false; x = k; y = H-1; dx = 0; dy = -1; return true;     // width-up
+	case 3: if (k >= H) return false; x = W-1; y = k; dx = -1; dy = 0; return true;     // height-left
+	case 4: dx = 1; dy = 1;                                                             // right-down
+		if (k < W) { x = k; y = 0; return true; } k -= W; if (k >= H-1) return false; x = 0; y = k+1; return true;
+	case 5: dx = -1; dy = 1;                                                            // left-down
+		if (k < W-1) { x = k; y = 0; return true; } k -= W-1; if (k >= H) return false; x = W-1; y = k; return true;
+	case 6: dx = 1; dy = -1;                                                            // right-up
+		if (k < W-1) { x = k+1; y = H-1; return true; } k -= W-1; if (k >= H) return false; x = 0; y = k; return true;
+	default: dx = -1; dy = -1;                                                          // left-up
+		if (k < W) { x = k; y = H-1; return true; } k -= W; if (k >= H-1) return false; x = W-1; y = k; return true;
+	}
+}
+
+__global__ void __launch_bounds__(AGG_WARPS*32)
+sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
+{
+	__shared__ uint16_t lines[AGG_WARPS][2][MAXD+2*LPAD];
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
+	const int k = blockIdx.x*AGG_WARPS + warp;
+	int x, y, dx, dy;
+	if (!path_start(dir, k, P.vw, P.vh, x, y, dx, dy))
+		return;
+	int cur = 0;
+	int pmin = 0, pmax = 0;     // previous range (empty at the start of a scanline)
+	float Ip = 0.5f;
+	// the pixel record and intensity of the next step are fetched one step ahead (the chain is
+	// latency bound: one dependent step per pixel of the scanline)
+	SGMPixel pn = P.px[(size_t)y*P.vw + x];
+	float In = __ldg(P.lgray + (size_t)y*P.w + x);
+	for (; x >= 0 && y >= 0 && x < P.vw && y < P.vh; x += dx, y += dy) {
+		const SGMPixel p = pn;
+		// NB: the reference reads the intensity at the valid-region coordinates (no half-window offset)
+		const float I = In;
+		{
+			const int nx = x+dx, ny = y+dy;
+			if (nx >= 0 && ny >= 0 && nx < P.vw && ny < P.vh) {
+				pn = P.px[(size_t)ny*P.vw + nx];
+				In = __ldg(P.lgray + (size_t)ny*P.w + nx);
+			}
+		}
+		if (!(p.dmin < p.dmax))
+			continue;
+		const int P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
+		Ip = I;
+		const uint16_t* Lp = lines[warp][cur] + LPAD;
+		uint16_t* Ls = lines[warp][cur^1] + LPAD;
+		const int imin = max(pmin, (int)p.dmin), imax = min(pmax, (int)p.dmax);
+		const int num = p.dmax-p.dmin;
+		const uint8_t* costs = P.costs + p.idx;
+		uint16_t* accums = P.accums + p.idx;
+		if (imin >= imax) {
+			for (int kk = lane; kk < num; kk += 32) {
+				const uint16_t L = (uint16_t)(costs[kk]+P2);
+				Ls[kk] = L;
+				accums[kk] = (uint16_t)(accums[kk]+L);
+			}
+		} else {
+			// min of the previous line over the intersection
+			unsigned m = 0xFFFFu;
+			for (int d = imin+lane; d < imax; d += 32)
+				m = min(m, (unsigned)Lp[d-pmin]);
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+			const int minLp = (int)m;
+			for (int kk = lane; kk < num; kk += 32) {
+				const int d = p.dmin+kk;
+				// candidates exist only inside the intersection [imin, imax)
+				int best = minLp+P2;                                      // some dp with |dp-d| > 1 ... see below
+				// the reference takes min over dp in the intersection of Lp(dp)+{0,P1,P2}; because
+				// P1 <= P2 this equals min(Lp(d), Lp(d+-1)+P1, min_{|dp-d|>1} Lp(dp)+P2) and the last
+				// term may be replaced by minLp+P2 only if the arg-min is not one of d-1,d,d+1 —
+				// otherwise the cheaper 0/P1 penalty of that very element wins anyway.  When the
+				// intersection holds nothing but d-1,d,d+1 the P2 term does not exist:
+				const bool hasFar = (imin < d-1) || (imax > d+2);
+				if (!hasFar) best = 0x7FFFFFFF;
+				if (d >= imin && d < imax) best = min(best, (int)Lp[d-pmin]);
+				if (d-1 >= imin && d-1 < imax) best = min(best, (int)Lp[d-1-pmin]+P.P1);
+				if (d+1 >= imin && d+1 < imax) best = min(best, (int)Lp[d+1-pmin]+P.P1);
+				const uint16_t L = (uint16_t)(costs[kk]+best-minLp);
+				Ls[kk] = L;
+				accums[kk] = (uint16_t)(accums[kk]+L);
+			}
+		}
+		__syncwarp();
+		pmin = p.dmin; pmax = p.dmax;
+		cur ^= 1;
+	}
+}
+
+// ---- (3) winner takes all ------------------------------------------------------------------------
+__global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int16_t* __restrict__ disparity, uint16_t* __restrict__ cost)
+{
+	const int gw = (blockIdx.x*blockDim.x + threadIdx.x)>>5, lane = threadIdx.x&31;
+	if (gw >= P.vw*P.vh) return;
+	const SGMPixel p = P.px[gw];
+	if (!(p.dmin < p.dmax)) {
+		if (lane == 0) { disparity[gw] = p.dmin; cost[gw] = 0xFFFFu; }
+		return;
+	}
+	const uint16_t* a = P.accums + p.idx;
+	unsigned best = 0xFFFFFFFFu; // (value << 16) | index: the minimum is the first arg-min
+	for (int k = lane; k < p.dmax-p.dmin; k += 32)
+		best = min(best, ((unsigned)a[k]<<16) | (unsigned)k);
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+	if (lane == 0) { disparity[gw] = (int16_t)(p.dmin+(int)(best&0xFFFFu)); cost[gw] = (uint16_t)(best>>16); }
+}
+
+// largest disparity count over the valid pixels
+__global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* __restrict__ out) {
+	int m = 0;
+	for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		const SGMPixel p = px[i];
+		if (p.dmin < p.dmax) m = max(m, p.dmax-p.dmin);
+	}
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+	if ((threadIdx.x&31) == 0) atomicMax(out, m);
+}
+
+} // namespace
+
+cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out, cudaStream_t s) {
+	cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int), s);
+	if (e != cudaSuccess) return e;
+	sgm_maxdisp_kernel<<<148*4, 256, 0, s>>>(px, n, out);
+	return cudaGetLastError();
+}
+cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s) {
+	const size_t smem = (size_t)NT*COST_THREADS*sizeof(float2);
+	static bool done = false;
+	if (!done) {
+		cudaError_t e = cudaFuncSetAttribute(sgm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		done = true;
+	}
+	dim3 grid((P.vw+COST_THREADS-1)/COST_THREADS, P.vh);
+	sgm_cost_kernel<<<grid, COST_THREADS, smem, s>>>(P);
+	return cudaGetLastError();
+}
+int sgm_max_disparities() { return MAXD; }
+cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s) {
+	const int W = P.vw, H = P.vh;
+	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
+	sgm_aggregate_kernel<<<(paths+AGG_WARPS-1)/AGG_WARPS, AGG_WARPS*32, 0, s>>>(P, dir);
+	return cudaGetLastError();
+}
+cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
+	const long long threads = (long long)P.vw*P.vh*32;
+	sgm_wta_kernel<<<(unsigned)((threads+255)/256), 256, 0, s>>>(P, disparity, cost);
+	return cudaGetLastError();
+}

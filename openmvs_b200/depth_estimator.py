@@ -269,3 +269,65 @@ class DepthMapsData:
 		self.pmCUDA.Init(nGeometricIter >= 0)
 		self.pmCUDA.EstimateDepthMap(self.arrDepthData[idxImage], nGeometricIter)
 		return True
+
+
+class SemiGlobalMatcher:
+	"""The pair matcher of the reference's STEREO::SemiGlobalMatcher
+	(libs/MVS/SemiGlobalMatcher.h:61-203): Match(left, right) -> (disparityMap, costMap) over the
+	valid region, with the ctor parameters P1, P2, P2alpha, P2beta (defaults 3, 4, 14, 38)."""
+	NO_DISP = 32767
+	NO_ACCUMCOST = 65535
+
+	def __init__(self, P1: int = 3, P2: int = 4, P2alpha: float = 14.0, P2beta: float = 38.0, device: int = 0):
+		self._lib = _lib.load()
+		self._ctx = C.c_void_p()
+		rc = self._lib.b200mvs_create(int(device), C.byref(self._ctx))
+		if rc != 0:
+			raise _lib.B200MVSError("b200mvs_create(device=%d) failed with status %d (no GPU => no fallback)" % (device, rc))
+		self.prm = _lib.SgmParams(int(P1), int(P2), float(P2alpha), float(P2beta))
+		self.stats = _lib.Stats()
+
+	def Release(self):
+		if self._ctx:
+			self._lib.b200mvs_destroy(self._ctx)
+			self._ctx = C.c_void_p()
+
+	def __del__(self):
+		try:
+			self.Release()
+		except Exception:
+			pass
+
+	def Match(self, leftGray, leftColor, rightGray, imagePixels, numCosts: int):
+		"""Host path: numpy images (gray float32 HxW, colour uint8 HxWx3 BGR) and the PixelMap
+		(structured array from synth.sgm_pixel_map or any {u8 idx, i2 dmin, i2 dmax, i4} records)."""
+		lg = np.ascontiguousarray(leftGray, np.float32); rg = np.ascontiguousarray(rightGray, np.float32)
+		lc = np.ascontiguousarray(leftColor, np.uint8)
+		h, w = lg.shape
+		if rg.shape != (h, w) or lc.shape != (h, w, 3):
+			raise ValueError("left/right/colour images must share one size")
+		px = np.ascontiguousarray(imagePixels)
+		if px.itemsize != 16 or px.size != (w-6)*(h-6):
+			raise ValueError("PixelMap must hold (w-6)*(h-6) 16-byte records")
+		disp = np.zeros((h-6, w-6), np.int16); cost = np.zeros((h-6, w-6), np.uint16)
+		rc = self._lib.b200mvs_sgm_match(self._ctx, lg.ctypes.data, lc.ctypes.data, rg.ctypes.data, w, h, px.ctypes.data,
+			C.c_uint64(numCosts), C.byref(self.prm), disp.ctypes.data, cost.ctypes.data, C.byref(self.stats))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_sgm_match")
+		return disp, cost
+
+	def MatchDevice(self, leftGray, leftColor, rightGray, imagePixels, numCosts: int, stages: int = 7, costs=None, accums=None, sync: bool = True):
+		"""Device-resident path on torch CUDA tensors; costs (uint8) / accums (uint16 viewed as int16)
+		are optional in/out volumes of numCosts entries.  Returns (disparity, cost) int16 tensors
+		(cost holds the uint16 bit pattern)."""
+		import torch
+		h, w = leftGray.shape
+		dev = leftGray.device
+		disp = torch.zeros((h-6, w-6), dtype=torch.int16, device=dev)
+		cost = torch.zeros((h-6, w-6), dtype=torch.int16, device=dev)
+		s = _stream_handle(dev)
+		rc = self._lib.b200mvs_sgm_match_device(self._ctx, leftGray.data_ptr(), leftColor.data_ptr(), rightGray.data_ptr(), w, h,
+			imagePixels.data_ptr(), C.c_uint64(numCosts), C.byref(self.prm), int(stages),
+			costs.data_ptr() if costs is not None else None, accums.data_ptr() if accums is not None else None,
+			disp.data_ptr(), cost.data_ptr(), C.c_void_p(s), C.byref(self.stats) if sync else None)
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_sgm_match_device")
+		return disp, cost

@@ -36,11 +36,17 @@ class Stats(C.Structure):
 		("ms_sweep_kernels", C.c_double), ("sweep_launches", C.c_int), ("reserved", C.c_int)]
 
 
+class SgmParams(C.Structure):
+	"""b200mvs_sgm_params"""
+	_fields_ = [("P1", C.c_int), ("P2", C.c_int), ("P2alpha", C.c_float), ("P2beta", C.c_float)]
+
+
 # every symbol include/b200mvs.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
 	"b200mvs_create", "b200mvs_destroy", "b200mvs_default_params", "b200mvs_set_params", "b200mvs_last_error",
 	"b200mvs_device_count", "b200mvs_estimate", "b200mvs_estimate_device",
 	"b200mvs_pm_pack", "b200mvs_pm_unpack", "b200mvs_pm_score", "b200mvs_pm_sweep", "b200mvs_pm_finalize",
+	"b200mvs_sgm_default_params", "b200mvs_sgm_match", "b200mvs_sgm_match_device",
 ]
 
 _LIB = None
@@ -76,6 +82,9 @@ def load(build_if_missing: bool = True):
 	lib.b200mvs_pm_score.argtypes = [P, C.POINTER(View), C.c_int, F, F, P, P, P, P]
 	lib.b200mvs_pm_sweep.argtypes = [P, C.POINTER(View), C.c_int, F, F, P, C.c_int, C.c_int, C.c_int, P, P, P]
 	lib.b200mvs_pm_finalize.argtypes = [P, C.c_int, C.c_int, F, P, P, P, P, P, P]
+	lib.b200mvs_sgm_default_params.argtypes = [C.POINTER(SgmParams)]
+	lib.b200mvs_sgm_match.argtypes = [P, P, P, P, C.c_int, C.c_int, P, C.c_uint64, C.POINTER(SgmParams), P, P, C.POINTER(Stats)]
+	lib.b200mvs_sgm_match_device.argtypes = [P, P, P, P, C.c_int, C.c_int, P, C.c_uint64, C.POINTER(SgmParams), C.c_int, P, P, P, P, P, C.POINTER(Stats)]
 	_LIB = lib
 	return lib
 

@@ -126,3 +126,35 @@ def make_scene(width: int, height: int, n_views: int, seed: int = 1234, radius: 
 		else:
 			views.append(View(img.float().cpu().numpy(), K.copy(), R, C, t.float().cpu().numpy(), nc.float().cpu().numpy()))
 	return Scene(views, dmin=float(radius-1.5), dmax=float(radius+1.5))
+
+
+def make_stereo_pair(width: int, height: int, seed: int = 7, d0: float = 12.0, amp: float = 6.0):
+	"""Rectified synthetic pair for the SGM path: left(x, y) = right(x + d(x, y), y) with a smooth
+	analytic disparity d = d0 + amp*sin(.)cos(.) (the reference's convention: the cost of
+	disparity d compares left x with right x+d, libs/MVS/SemiGlobalMatcher.cpp:960).
+	Returns left gray float32, left BGR uint8, right gray float32, ground-truth disparity."""
+	tex = _Texture(seed, px_per_unit=1.0)
+	tex_c = [_Texture(seed+11+k, px_per_unit=1.0, n_waves=6) for k in range(3)]
+	ys, xs = np.mgrid[0:height, 0:width].astype(np.float64)
+	d = d0 + amp*np.sin(2*np.pi*xs/(0.9*width)+0.4)*np.cos(2*np.pi*ys/(1.3*height)-0.3)
+	left = tex(xs+d, ys)
+	right = tex(xs, ys)
+	bgr = np.stack([np.clip(0.8*left+0.2*t(xs+d, ys), 0, 1) for t in tex_c], -1)
+	return left.astype(np.float32), np.rint(bgr*255).astype(np.uint8), right.astype(np.float32), d.astype(np.float32)
+
+
+def sgm_pixel_map(width: int, height: int, dmin, dmax, invalid=None):
+	"""PixelMap of the valid region (width-6) x (height-6): per-pixel [dmin, dmax) (scalars or
+	arrays), idx = running offset into the ragged cost volume (SemiGlobalMatcher.cpp:660-667).
+	Returns (structured array {idx u8, dmin i2, dmax i2, reserved i4}, numCosts)."""
+	vw, vh = width-6, height-6
+	lo = np.broadcast_to(np.asarray(dmin, np.int16), (vh, vw)).copy()
+	hi = np.broadcast_to(np.asarray(dmax, np.int16), (vh, vw)).copy()
+	if invalid is not None:
+		lo[invalid] = np.iinfo(np.int16).max
+		hi[invalid] = np.iinfo(np.int16).max
+	num = np.maximum(hi.astype(np.int64)-lo.astype(np.int64), 0).ravel()
+	px = np.zeros(vh*vw, dtype=np.dtype([("idx", "<u8"), ("dmin", "<i2"), ("dmax", "<i2"), ("reserved", "<i4")]))
+	px["idx"] = np.concatenate([[0], np.cumsum(num)[:-1]])
+	px["dmin"] = lo.ravel(); px["dmax"] = hi.ravel()
+	return px, int(num.sum())

@@ -107,8 +107,15 @@ void oracle_scale_K(const double K[9], int sw, int sh, int dw, int dh, double Ko
 /* ---- SGM (SemiGlobalMatcher::Match, libs/MVS/SemiGlobalMatcher.cpp:863-1302) ---- */
 typedef struct {
 	uint64_t idx;      /* offset of the first cost of this pixel in the ragged volume */
-	int16_t dmin, dmax;/* disparity range [dmin, dmax); invalid pixel: dmin == NO_DISP */
+	int16_t dmin, dmax;/* disparity range [dmin, dmax); invalid pixel: dmin >= dmax */
+	int32_t reserved;
 } oracle_sgm_pixel;
+
+void oracle_sgm_p2s(uint16_t P2, float alpha, float beta, uint16_t out[256]);
+/* stage & 7: 1 costs, 2 + aggregation, 3 + WTA; stage & 8: costs[] is supplied, skip stage 1 */
+int oracle_sgm_match(const float* leftGray, const uint8_t* leftBGR, const float* rightGray, int width, int height,
+	const oracle_sgm_pixel* pixels, uint64_t numCosts, uint16_t P1, uint16_t P2, float P2alpha, float P2beta, int stage,
+	uint8_t* costs, uint16_t* accums, int16_t* disparity, uint16_t* cost);
 
 #ifdef __cplusplus
 }

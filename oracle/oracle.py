@@ -145,3 +145,25 @@ def philox(ctr, key):
 	c = (C.c_uint32*4)(*ctr); k = (C.c_uint32*2)(*key); o = (C.c_uint32*4)()
 	lib().oracle_philox4x32(c, k, o)
 	return [int(v) for v in o]
+
+
+def sgm_match(left_gray, left_bgr, right_gray, pixels, num_costs, P1=3, P2=4, alpha=14.0, beta=38.0, stage=3, costs=None):
+	"""-> (costs u8, accums u16, disparity i16, cost u16); costs given => skip the cost stage"""
+	lg = np.ascontiguousarray(left_gray, np.float32); rg = np.ascontiguousarray(right_gray, np.float32)
+	lc = np.ascontiguousarray(left_bgr, np.uint8)
+	h, w = lg.shape
+	px = np.ascontiguousarray(pixels)
+	assert px.itemsize == 16 and px.size == (w-6)*(h-6)
+	st = int(stage)
+	if costs is None:
+		c = np.zeros(num_costs, np.uint8)
+	else:
+		c = np.array(costs, np.uint8, copy=True); st |= 8
+	a = np.zeros(num_costs, np.uint16)
+	disp = np.zeros((h-6, w-6), np.int16); cost = np.zeros((h-6, w-6), np.uint16)
+	f = lib().oracle_sgm_match
+	f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint16, C.c_uint16,
+		C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+	rc = f(_fptr(lg), _fptr(lc), _fptr(rg), w, h, _fptr(px), num_costs, P1, P2, alpha, beta, st, _fptr(c), _fptr(a), _fptr(disp), _fptr(cost))
+	assert rc == 0
+	return c, a, disp, cost

@@ -1,0 +1,107 @@
+"""GPU parity of the SGM pair matcher against the oracle (run with -m gpu).
+Integer stages (8-path aggregation, WTA) must be bit-exact; the WZNCC cost is a float
+rounded to uint8 and may differ by one level on a small fraction of entries."""
+import numpy as np
+import pytest
+import torch
+
+from openmvs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sgm():
+	if not torch.cuda.is_available():
+		pytest.skip("no CUDA device")
+	from oracle import oracle as O
+	from openmvs_b200.depth_estimator import SemiGlobalMatcher
+	m = SemiGlobalMatcher()
+	yield m, O
+	m.Release()
+
+
+def _dev(a):
+	return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _px_dev(px):
+	return torch.from_numpy(px.view(np.uint8).reshape(-1, 16).copy()).cuda()
+
+
+def test_cost_volume_parity(sgm):
+	m, O = sgm
+	w, h = 240, 136
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	px, n = synth.sgm_pixel_map(w, h, -4, 28)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n, stage=1)
+	costs = torch.zeros(n, dtype=torch.uint8, device="cuda")
+	m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=1, costs=costs)
+	g = costs.cpu().numpy().astype(np.int32)
+	diff = np.abs(g-c.astype(np.int32))
+	assert diff.max() <= 1 and (diff > 0).mean() < 5e-3
+	assert np.array_equal(g == 255, c == 255) or ((g == 255) != (c == 255)).mean() < 1e-4
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_aggregation_and_wta_bit_exact(sgm, ragged):
+	m, O = sgm
+	w, h = 200, 120
+	rng = np.random.RandomState(11)
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	vw, vh = w-6, h-6
+	if ragged:
+		# tSGM-like ragged ranges around the true disparity, with invalid pixels and range jumps
+		base = np.rint(d[3:-3, 3:-3]).astype(np.int16)
+		lo = base-rng.randint(2, 9, (vh, vw)).astype(np.int16)
+		hi = base+rng.randint(2, 40, (vh, vw)).astype(np.int16)
+		hi[10:14] = lo[10:14]+256   # the widest range the kernel supports
+		px, n = synth.sgm_pixel_map(w, h, lo, hi, rng.rand(vh, vw) < 0.07)
+	else:
+		px, n = synth.sgm_pixel_map(w, h, 0, 64)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n)
+	accums = torch.zeros(n, dtype=torch.int16, device="cuda")
+	gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(c), accums=accums)
+	assert np.array_equal(accums.cpu().numpy().view(np.uint16), a)
+	assert np.array_equal(gd.cpu().numpy(), disp)
+	assert np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
+
+
+def test_host_api_full_match_and_errors(sgm):
+	m, O = sgm
+	w, h = 200, 120
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	px, n = synth.sgm_pixel_map(w, h, 0, 32)
+	gd, gc = m.Match(lg, lc, rg, px, n)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n)
+	# end to end the two pipelines differ only through the +-1 cost roundings
+	assert (gd != disp).mean() < 0.01
+	gt = d[3:-3, 3:-3]
+	assert (np.abs(gd-gt)[5:-5, 5:-40] <= 1).mean() > 0.97
+	assert m.stats.kernel_launches == 1+1+8+1 and m.stats.bytes_d2h == (w-6)*(h-6)*4
+	# more than 256 disparities per pixel is refused loudly
+	from openmvs_b200 import lib
+	px2, n2 = synth.sgm_pixel_map(w, h, 0, 300)
+	with pytest.raises(lib.B200MVSError):
+		m.Match(lg, lc, rg, px2, n2)
+	# same input twice -> identical output
+	gd2, gc2 = m.Match(lg, lc, rg, px, n)
+	assert np.array_equal(gd, gd2) and np.array_equal(gc, gc2)
+
+
+def test_full_size_sgm_properties_1080p(sgm):
+	"""BASELINE configs[2] size: 1920x1080 pair, fixed range D=128 (the non-tSGM branch,
+	SemiGlobalMatcher.cpp:643-669): determinism and ground-truth disparity."""
+	m, O = sgm
+	w, h = 1920, 1080
+	lg, lc, rg, d = synth.make_stereo_pair(w, h, d0=40.0, amp=25.0)
+	px, n = synth.sgm_pixel_map(w, h, 0, 128)
+	args = (_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n)
+	gd, gc = m.MatchDevice(*args)
+	ms = m.stats.ms_device
+	gd2, gc2 = m.MatchDevice(*args)
+	assert torch.equal(gd, gd2) and torch.equal(gc, gc2)
+	gt = d[3:-3, 3:-3]
+	err = np.abs(gd.cpu().numpy()-gt)[8:-8, 8:-140]
+	assert (err <= 1).mean() > 0.97
+	print("sgm 1080p D=128: %.2f ms device" % ms)
