@@ -99,6 +99,7 @@ sgm_cost_kernel(const __grid_constant__ SGMParams P)
 constexpr int AGG_WARPS = 4;
 constexpr int MAXD = 256;        // disparities per pixel supported by the warp-per-scanline kernel
 constexpr int LPAD = 8;
+constexpr int AGG_PD = 2;        // prefetch distance (steps) of the scanline pipeline
 
 // start pixel and step of scanline `k` of direction `dir` (order of SemiGlobalMatcher.cpp:1084-1199)
 __device__ __forceinline__ bool path_start(int dir, int k, int W, int H, int& x, int& y, int& dx, int& dy) {
@@ -118,6 +119,10 @@ __device__ __forceinline__ bool path_start(int dir, int k, int W, int H, int& x,
 	}
 }
 
+// One warp walks one scanline; lane l owns disparities l, l+32, ... (NPL per lane) of every pixel.
+// The scanline is a chain of dependent steps, so it is software-pipelined: the pixel record of
+// step t+PD+1 and the cost / accumulator values of step t+PD are in flight while step t computes.
+template <int NPL, int PD>
 __global__ void __launch_bounds__(AGG_WARPS*32)
 sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 {
@@ -130,68 +135,111 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 	int cur = 0;
 	int pmin = 0, pmax = 0;     // previous range (empty at the start of a scanline)
 	float Ip = 0.5f;
-	// the pixel record and intensity of the next step are fetched one step ahead (the chain is
-	// latency bound: one dependent step per pixel of the scanline)
-	SGMPixel pn = P.px[(size_t)y*P.vw + x];
-	float In = __ldg(P.lgray + (size_t)y*P.w + x);
-	for (; x >= 0 && y >= 0 && x < P.vw && y < P.vh; x += dx, y += dy) {
-		const SGMPixel p = pn;
-		// NB: the reference reads the intensity at the valid-region coordinates (no half-window offset)
-		const float I = In;
+	auto inside = [&](int xx, int yy) { return xx >= 0 && yy >= 0 && xx < P.vw && yy < P.vh; };
+	SGMPixel none; none.idx = 0; none.dmin = 0; none.dmax = 0; none.pad = 0;
+	// pipeline registers: pr[i] / Ir[i] = record and intensity of pixel t+i (i <= PD),
+	// c[i] / a[i] = its costs and accumulators (i < PD)
+	SGMPixel pr[PD+1]; float Ir[PD+1];
+	uint8_t c[PD][NPL]; uint16_t a[PD][NPL];
+	#pragma unroll
+	for (int i = 0; i <= PD; ++i) {
+		pr[i] = none; Ir[i] = 0.f;
+		const int xx = x+i*dx, yy = y+i*dy;
+		if (inside(xx, yy)) { pr[i] = P.px[(size_t)yy*P.vw + xx]; Ir[i] = __ldg(P.lgray + (size_t)yy*P.w + xx); }
+	}
+	#pragma unroll
+	for (int i = 0; i < PD; ++i) {
+		#pragma unroll
+		for (int j = 0; j < NPL; ++j) {
+			const int kk = lane+32*j;
+			const bool v = kk < pr[i].dmax-pr[i].dmin;
+			c[i][j] = v ? P.costs[pr[i].idx+kk] : 0; a[i][j] = v ? P.accums[pr[i].idx+kk] : 0;
+		}
+	}
+	for (; inside(x, y); x += dx, y += dy) {
+		// stage A: pixel record PD+1 steps ahead
+		SGMPixel pnew = none; float Inew = 0.f;
 		{
-			const int nx = x+dx, ny = y+dy;
-			if (nx >= 0 && ny >= 0 && nx < P.vw && ny < P.vh) {
-				pn = P.px[(size_t)ny*P.vw + nx];
-				In = __ldg(P.lgray + (size_t)ny*P.w + nx);
-			}
+			const int xx = x+(PD+1)*dx, yy = y+(PD+1)*dy;
+			if (inside(xx, yy)) { pnew = P.px[(size_t)yy*P.vw + xx]; Inew = __ldg(P.lgray + (size_t)yy*P.w + xx); }
 		}
-		if (!(p.dmin < p.dmax))
-			continue;
-		const int P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
-		Ip = I;
-		const uint16_t* Lp = lines[warp][cur] + LPAD;
-		uint16_t* Ls = lines[warp][cur^1] + LPAD;
-		const int imin = max(pmin, (int)p.dmin), imax = min(pmax, (int)p.dmax);
-		const int num = p.dmax-p.dmin;
-		const uint8_t* costs = P.costs + p.idx;
-		uint16_t* accums = P.accums + p.idx;
-		if (imin >= imax) {
-			for (int kk = lane; kk < num; kk += 32) {
-				const uint16_t L = (uint16_t)(costs[kk]+P2);
-				Ls[kk] = L;
-				accums[kk] = (uint16_t)(accums[kk]+L);
+		// stage B: costs and accumulators PD steps ahead
+		uint8_t cn[NPL]; uint16_t an[NPL];
+		#pragma unroll
+		for (int j = 0; j < NPL; ++j) {
+			const int kk = lane+32*j;
+			const bool v = kk < pr[PD].dmax-pr[PD].dmin;
+			cn[j] = v ? P.costs[pr[PD].idx+kk] : 0; an[j] = v ? P.accums[pr[PD].idx+kk] : 0;
+		}
+		uint8_t* c0 = c[0]; uint16_t* a0 = a[0];
+		const float I0 = Ir[0];
+		const SGMPixel p0 = pr[0];
+		// stage C: this pixel
+		const SGMPixel p = p0;
+		if (p.dmin < p.dmax) {
+			// NB: the reference reads the intensity at the valid-region coordinates (no half-window offset)
+			const float I = I0;
+			const int P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
+			Ip = I;
+			const uint16_t* Lp = lines[warp][cur] + LPAD;
+			uint16_t* Ls = lines[warp][cur^1] + LPAD;
+			const int imin = max(pmin, (int)p.dmin), imax = min(pmax, (int)p.dmax);
+			const int num = p.dmax-p.dmin;
+			uint16_t* accums = P.accums + p.idx;
+			if (imin >= imax) {
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int kk = lane+32*j;
+					if (kk < num) {
+						const uint16_t L = (uint16_t)(c0[j]+P2);
+						Ls[kk] = L;
+						accums[kk] = (uint16_t)(a0[j]+L);
+					}
+				}
+			} else {
+				// min of the previous line over the intersection
+				unsigned m = 0xFFFFu;
+				for (int d = imin+lane; d < imax; d += 32)
+					m = min(m, (unsigned)Lp[d-pmin]);
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+					m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+				const int minLp = (int)m;
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int kk = lane+32*j;
+					if (kk < num) {
+						const int d = p.dmin+kk;
+						// The reference takes min over dp in the intersection I of Lp(dp)+{0 | P1 | P2}.
+						// Because P1 <= P2 this is min(Lp(d), Lp(d+-1)+P1, minLp+P2): if the arg-min of Lp
+						// is one of d-1,d,d+1 its cheaper 0/P1 term wins anyway.  The P2 term only exists
+						// when I holds a dp with |dp-d| > 1.
+						const bool hasFar = (imin < d-1) || (imax > d+2);
+						int best = hasFar ? minLp+P2 : 0x7FFFFFFF;
+						if (d >= imin && d < imax) best = min(best, (int)Lp[d-pmin]);
+						if (d-1 >= imin && d-1 < imax) best = min(best, (int)Lp[d-1-pmin]+P.P1);
+						if (d+1 >= imin && d+1 < imax) best = min(best, (int)Lp[d+1-pmin]+P.P1);
+						const uint16_t L = (uint16_t)(c0[j]+best-minLp);
+						Ls[kk] = L;
+						accums[kk] = (uint16_t)(a0[j]+L);
+					}
+				}
 			}
-		} else {
-			// min of the previous line over the intersection
-			unsigned m = 0xFFFFu;
-			for (int d = imin+lane; d < imax; d += 32)
-				m = min(m, (unsigned)Lp[d-pmin]);
+			__syncwarp();
+			pmin = p.dmin; pmax = p.dmax;
+			cur ^= 1;
+		}
+		// advance the pipeline
+		#pragma unroll
+		for (int i = 0; i < PD; ++i) { pr[i] = pr[i+1]; Ir[i] = Ir[i+1]; }
+		pr[PD] = pnew; Ir[PD] = Inew;
+		#pragma unroll
+		for (int i = 0; i+1 < PD; ++i) {
 			#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-				m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-			const int minLp = (int)m;
-			for (int kk = lane; kk < num; kk += 32) {
-				const int d = p.dmin+kk;
-				// candidates exist only inside the intersection [imin, imax)
-				int best = minLp+P2;                                      // some dp with |dp-d| > 1 ... see below
-				// the reference takes min over dp in the intersection of Lp(dp)+{0,P1,P2}; because
-				// P1 <= P2 this equals min(Lp(d), Lp(d+-1)+P1, min_{|dp-d|>1} Lp(dp)+P2) and the last
-				// term may be replaced by minLp+P2 only if the arg-min is not one of d-1,d,d+1 —
-				// otherwise the cheaper 0/P1 penalty of that very element wins anyway.  When the
-				// intersection holds nothing but d-1,d,d+1 the P2 term does not exist:
-				const bool hasFar = (imin < d-1) || (imax > d+2);
-				if (!hasFar) best = 0x7FFFFFFF;
-				if (d >= imin && d < imax) best = min(best, (int)Lp[d-pmin]);
-				if (d-1 >= imin && d-1 < imax) best = min(best, (int)Lp[d-1-pmin]+P.P1);
-				if (d+1 >= imin && d+1 < imax) best = min(best, (int)Lp[d+1-pmin]+P.P1);
-				const uint16_t L = (uint16_t)(costs[kk]+best-minLp);
-				Ls[kk] = L;
-				accums[kk] = (uint16_t)(accums[kk]+L);
-			}
+			for (int j = 0; j < NPL; ++j) { c[i][j] = c[i+1][j]; a[i][j] = a[i+1][j]; }
 		}
-		__syncwarp();
-		pmin = p.dmin; pmax = p.dmax;
-		cur ^= 1;
+		#pragma unroll
+		for (int j = 0; j < NPL; ++j) { c[PD-1][j] = cn[j]; a[PD-1][j] = an[j]; }
 	}
 }
 
@@ -252,7 +300,12 @@ int sgm_max_disparities() { return MAXD; }
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s) {
 	const int W = P.vw, H = P.vh;
 	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
-	sgm_aggregate_kernel<<<(paths+AGG_WARPS-1)/AGG_WARPS, AGG_WARPS*32, 0, s>>>(P, dir);
+	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
+	const int npl = (P.maxNumDisp+31)/32;
+	if (npl <= 1) sgm_aggregate_kernel<1, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+	else if (npl <= 2) sgm_aggregate_kernel<2, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+	else if (npl <= 4) sgm_aggregate_kernel<4, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+	else sgm_aggregate_kernel<8, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
 	return cudaGetLastError();
 }
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
