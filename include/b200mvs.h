@@ -82,7 +82,7 @@ typedef struct {
 	int levels;
 	double ms_sweep_kernels; /* summed device time of the red-black half-sweep launches (CUDA events) */
 	int sweep_launches;
-	int reserved;
+	int tma_active;          /* 1: the sweep kernels staged the reference tile with TMA (cp.async.bulk.tensor) */
 } b200mvs_stats;
 
 /* ---- lifetime (PatchMatchCUDA ctor / Init / Release, PatchMatchCUDA.cpp:60-117) ---- */

@@ -6,6 +6,7 @@
 // no host synchronisation between kernels.
 #include "../../include/b200mvs.h"
 #include "pm_common.cuh"
+#include <cuda.h>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -16,7 +17,8 @@
 #include <cstdlib>
 
 cudaError_t pm_launch_score(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s);
-cudaError_t pm_launch_sweep(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s);
+cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, int layout, bool geom, bool ws, cudaStream_t s);
+void pm_tma_box(int* w, int* h);
 cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s);
 cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
 	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s);
@@ -115,6 +117,10 @@ struct b200mvs_ctx {
 	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgDisp, sgCost, sgMax; // SGM staging / scratch
 	int layout = 1;                           // 1 plain float rows, 2 row pairs (B200MVS_LAYOUT overrides)
 	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
+	bool tma = true;                          // reference tile staged by TMA (B200MVS_TMA=0: plain loads)
+	DevBuf refPad;                            // 16-byte aligned copy of a reference image whose pitch TMA cannot address
+	CUtensorMap tmapRef;                      // descriptor of the current level's reference image
+	bool tmapValid = false;
 	std::vector<cudaEvent_t> sweepEv;         // event pairs around the sweep launches (stats only)
 	int nSweepEv = 0; bool timeSweeps = false;
 	int launches = 0;
@@ -225,6 +231,45 @@ int prepare_tex(b200mvs_ctx* ctx, DView* v, int nViews, cudaStream_t s) {
 	return B200MVS_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+	static EncodeTiledFn fn = nullptr; static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void* p = nullptr; cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+			fn = (EncodeTiledFn)p;
+	}
+	return fn;
+}
+
+// TMA descriptor of the reference image of one level: 2-D float tensor {W, H}, box = the tile a CTA
+// of the sweep kernel stages (72 x 16).  TMA needs a 16-byte aligned base and row pitch; an image that
+// does not satisfy this (odd width, cv::Mat ROI) is first copied to an aligned scratch image.
+int prepare_ref_tmap(b200mvs_ctx* ctx, const DView& ref, cudaStream_t s) {
+	ctx->tmapValid = false;
+	EncodeTiledFn enc = ctx->tma ? encode_tiled_fn() : nullptr;
+	if (!enc) return B200MVS_OK;
+	const float* base = ref.img; size_t pitchB = (size_t)ref.pitch*4;
+	if (((uintptr_t)base & 15) || (pitchB & 15)) {
+		pitchB = (((size_t)ref.w*4)+15)&~(size_t)15;
+		CK(ctx->refPad.reserve(pitchB*ref.h));
+		CK(cudaMemcpy2DAsync(ctx->refPad.p, pitchB, ref.img, (size_t)ref.pitch*4, (size_t)ref.w*4, ref.h, cudaMemcpyDeviceToDevice, s));
+		base = ctx->refPad.as<float>();
+	}
+	int bw, bh; pm_tma_box(&bw, &bh);
+	const cuuint64_t dims[2] = {(cuuint64_t)ref.w, (cuuint64_t)ref.h};
+	const cuuint64_t strides[1] = {(cuuint64_t)pitchB};
+	const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+	const cuuint32_t estr[2] = {1, 1};
+	const CUresult r = enc(&ctx->tmapRef, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	ctx->tmapValid = (r == CUDA_SUCCESS);
+	return B200MVS_OK;
+}
+
 int launch_sweep_timed(b200mvs_ctx* ctx, const PMParams& P, bool geom, cudaStream_t s) {
 	if (ctx->timeSweeps) {
 		while ((int)ctx->sweepEv.size() < 2*(ctx->nSweepEv+1)) {
@@ -232,7 +277,7 @@ int launch_sweep_timed(b200mvs_ctx* ctx, const PMParams& P, bool geom, cudaStrea
 		}
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv], s));
 	}
-	CK(pm_launch_sweep(P, ctx->layout, geom, ctx->wsmem, s)); ++ctx->launches;
+	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout, geom, ctx->wsmem, s)); ++ctx->launches;
 	if (ctx->timeSweeps) {
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv+1], s));
 		++ctx->nSweepEv;
@@ -290,6 +335,7 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 		}
 		const int w = lv[0].w, h = lv[0].h;
 		{ const int rc = prepare_tex(ctx, lv.data(), nViews, s); if (rc) return rc; }
+		{ const int rc = prepare_ref_tmap(ctx, lv[0], s); if (rc) return rc; }
 		const float* lowres = nullptr;
 		if (sc != totalScale) {
 			// depth LINEAR / normal NEAREST up-sampling of the coarser level; the up-sampled
@@ -309,6 +355,7 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 		PMParams P; bool geom;
 		build_params(o, lv.data(), nViews, dMin, dMax, lowres, plane, cost, best, P, geom);
 		P.nRandomIters = nR;
+		P.tma = ctx->tmapValid ? 1 : 0;
 		CK(pm_launch_score(P, ctx->layout, geom, ctx->wsmem, s)); ++ctx->launches;
 		for (int it = iterBegin; it < iterEnd; ++it) {
 			for (int k = 0; k < spi; ++k) {
@@ -364,6 +411,7 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 	b200mvs_default_params(&c->prm);
 	if (const char* e = getenv("B200MVS_LAYOUT")) { const int l = atoi(e); if (l == 1 || l == 2) c->layout = l; }
 	if (const char* e = getenv("B200MVS_WSMEM")) c->wsmem = atoi(e) != 0;
+	if (const char* e = getenv("B200MVS_TMA")) c->tma = atoi(e) != 0;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
 		delete c;
@@ -380,6 +428,7 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto& b: c->dmaps) b.release();
 	for (auto& b: c->pyr) b.release();
 	for (auto& b: c->tex) b.release();
+	c->refPad.release();
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
 	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release();
 	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
@@ -432,6 +481,7 @@ int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nVi
 		stats->levels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
 		for (int k = 0; k < ctx->nSweepEv; ++k) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->sweepEv[2*k], ctx->sweepEv[2*k+1])); stats->ms_sweep_kernels += t; }
 		stats->sweep_launches = ctx->nSweepEv;
+		stats->tma_active = ctx->tmapValid ? 1 : 0;
 	}
 	return B200MVS_OK;
 }
@@ -494,6 +544,7 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 		stats->levels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
 		for (int k = 0; k < ctx->nSweepEv; ++k) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->sweepEv[2*k], ctx->sweepEv[2*k+1])); stats->ms_sweep_kernels += t; }
 		stats->sweep_launches = ctx->nSweepEv;
+		stats->tma_active = ctx->tmapValid ? 1 : 0;
 	}
 	return B200MVS_OK;
 }
@@ -522,7 +573,9 @@ static int block_params(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
 		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
 			views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
 	{ const int rc2 = prepare_tex(ctx, dv.data(), nViews, s); if (rc2) return rc2; }
+	{ const int rc2 = prepare_ref_tmap(ctx, dv[0], s); if (rc2) return rc2; }
 	build_params(ctx->prm, dv.data(), nViews, dMin, dMax, lowres, (float4*)plane4, cost, nullptr, P, geom);
+	P.tma = ctx->tmapValid ? 1 : 0;
 	return B200MVS_OK;
 }
 int b200mvs_pm_score(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
@@ -550,7 +603,7 @@ int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	for (int colour = 0; colour < 2; ++colour) {
 		if (half >= 0 && half != colour) continue;
 		P.colour = colour;
-		CK(pm_launch_sweep(P, ctx->layout, geom, ctx->wsmem, s));
+		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout, geom, ctx->wsmem, s));
 	}
 	return B200MVS_OK;
 }

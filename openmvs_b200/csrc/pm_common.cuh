@@ -29,6 +29,7 @@ struct PMParams {
 	float depthRatio, angle1Range, angle2Range, geomWeight;
 	int nRandomIters, propagation;
 	int sweep, colour;
+	int tma;                                 // reference tile staged by TMA (tensor map passed beside the params)
 	uint32_t seed;
 	const float* lowres;                     // low-resolution depth prior or null
 	float4* plane; float* cost; uint32_t* bestViews;

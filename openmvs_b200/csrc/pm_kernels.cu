@@ -14,6 +14,8 @@
 // All four 4-neighbours belong to the other colour, so in-place updates are race-free.
 #include "pm_common.cuh"
 #include <math_constants.h>
+#include <cstring>
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace {
 
@@ -41,6 +43,73 @@ template <> struct PatchT<true> {
 };
 
 // FillPixelPatch + GetWeight (DepthMap.cpp:422-462, DepthMap.h:403-412)
+// ---- TMA staging of the reference tile ---------------------------------------------------------
+// A CTA of the sweep kernel covers 64 x 8 pixels; their 9x9 patches need a (64+8) x (8+8) float tile
+// of the reference image.  One elected thread issues a cp.async.bulk.tensor.2d (TMA) into shared
+// memory and everybody waits on the mbarrier; out-of-image parts of the box are zero-filled by the
+// TMA unit (those pixels are rejected by the patch-inside test anyway).
+constexpr int TILE_W = 2*BLOCK_X+2*PM_HALF;   // 72 floats = 288 B (multiple of 16 B)
+constexpr int TILE_H = BLOCK_Y+2*PM_HALF;     // 16 rows
+constexpr int TILE_BYTES = TILE_W*TILE_H*4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+		:: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// FillPixelPatch + GetWeight from the staged tile; (lx, ly) = pixel position inside the tile
+template <bool WS>
+__device__ __forceinline__ void fill_patch_tile(const float* __restrict__ tile, int lx, int ly, PatchT<WS>& p) {
+	const float sigmaColor = -1.f/(2.f*0.1f*0.1f);
+	const float sigmaSpatial = -1.f/(2.f*9.f);
+	const float center = tile[ly*TILE_W + lx];
+	float acc = 0.f, sumW = 0.f;
+	float w[PM_TEXELS], I[PM_TEXELS];
+	#pragma unroll
+	for (int i = 0; i < 5; ++i) {
+		#pragma unroll
+		for (int j = 0; j < 5; ++j) {
+			const int dy = 2*i-PM_HALF, dx = 2*j-PM_HALF;
+			const float v = tile[(ly+dy)*TILE_W + (lx+dx)];
+			const float dI = v-center;
+			const float wgt = expf(dI*dI*sigmaColor + float(dx*dx+dy*dy)*sigmaSpatial);
+			w[i*5+j] = wgt;
+			I[i*5+j] = v;
+			acc += v*wgt;
+			sumW += wgt;
+		}
+	}
+	const float tm = acc/sumW;
+	float nsq = 0.f;
+	#pragma unroll
+	for (int k = 0; k < PM_TEXELS; ++k) {
+		const float t = I[k]-tm;
+		const float tw = w[k]*t;
+		nsq += tw*t;
+		p.set(k, w[k], tw);
+	}
+	p.sumW = sumW;
+	p.normSq0 = nsq;
+}
+
 template <bool WS>
 __device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pitch, int x, int y, PatchT<WS>& p) {
 	const float sigmaColor = -1.f/(2.f*0.1f*0.1f);
@@ -387,9 +456,26 @@ pm_score_kernel(const __grid_constant__ PMParams P)
 // pass B: one red-black half-sweep
 template <int LAYOUT, bool GEOM, bool WS>
 __global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, WS ? 3 : 2)
-pm_sweep_kernel(const __grid_constant__ PMParams P)
+pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUtensorMap tmapRef)
 {
-	extern __shared__ float2 smemW[];
+	extern __shared__ __align__(128) unsigned char smemRaw[];
+	// [ patch weights (WS) | reference tile | mbarrier ]
+	float2* smemW = (float2*)smemRaw;
+	float* tile = (float*)(smemRaw + (WS ? PM_TEXELS*NTHREADS*sizeof(float2) : 0));
+	uint64_t* bar = (uint64_t*)(tile + TILE_W*TILE_H);
+	const int tid = threadIdx.y*BLOCK_X + threadIdx.x;
+	if (P.tma) {
+		if (tid == 0) {
+			mbar_init(bar, 1);
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // make the init visible to the async proxy
+		}
+		__syncthreads();
+		if (tid == 0) {
+			mbar_expect_tx(bar, TILE_BYTES);
+			tma_load_2d(tile, &tmapRef, (int)blockIdx.x*(2*BLOCK_X)-PM_HALF, (int)blockIdx.y*BLOCK_Y-PM_HALF, bar);
+		}
+		mbar_wait(bar, 0);
+	}
 	const int y = blockIdx.y*BLOCK_Y + threadIdx.y;
 	const int x = blockIdx.x*(2*BLOCK_X) + 2*threadIdx.x + ((y+P.colour)&1);
 	if (x < PM_HALF || y < PM_HALF || x >= P.W-PM_HALF || y >= P.H-PM_HALF)
@@ -397,8 +483,11 @@ pm_sweep_kernel(const __grid_constant__ PMParams P)
 	const int W = P.W, H = P.H;
 	const size_t idx = (size_t)y*W + x;
 	PatchT<WS> pt;
-	if constexpr (WS) pt.s = smemW + threadIdx.y*BLOCK_X + threadIdx.x;
-	fill_patch(P.img0, P.pitch0, x, y, pt);
+	if constexpr (WS) pt.s = smemW + tid;
+	if (P.tma)
+		fill_patch_tile(tile, 2*(int)threadIdx.x + ((y+P.colour)&1) + PM_HALF, (int)threadIdx.y + PM_HALF, pt);
+	else
+		fill_patch(P.img0, P.pitch0, x, y, pt);
 	float priorD = 0.f, priorF = 0.f;
 	if (P.lowres)
 		priorD = fmaxf(__ldg(P.lowres + idx), 0.f);
@@ -587,40 +676,53 @@ __global__ void pm_unpack_kernel(int n, const float4* __restrict__ plane, float*
 
 // ---- host launchers ---------------------------------------------------------------------
 template <int LAYOUT, bool GEOM, bool WS>
-cudaError_t launch_one(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P) {
-	const size_t smem = WS ? (size_t)PM_TEXELS*NTHREADS*sizeof(float2) : 0;
-	auto* k = sweep ? pm_sweep_kernel<LAYOUT, GEOM, WS> : pm_score_kernel<LAYOUT, GEOM, WS>;
-	if (WS) {
-		static bool done[2] = {false, false};
-		if (!done[sweep]) {
-			cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_one(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap) {
+	const size_t wbytes = WS ? (size_t)PM_TEXELS*NTHREADS*sizeof(float2) : 0;
+	if (sweep) {
+		const size_t smem = wbytes + TILE_BYTES + 16;
+		static bool done = false;
+		if (!done) {
+			cudaError_t e = cudaFuncSetAttribute(pm_sweep_kernel<LAYOUT, GEOM, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) return e;
-			done[sweep] = true;
+			done = true;
 		}
+		pm_sweep_kernel<LAYOUT, GEOM, WS><<<grid, block, smem, s>>>(P, tmap);
+	} else {
+		static bool done = false;
+		if (WS && !done) {
+			cudaError_t e = cudaFuncSetAttribute(pm_score_kernel<LAYOUT, GEOM, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
+			if (e != cudaSuccess) return e;
+			done = true;
+		}
+		pm_score_kernel<LAYOUT, GEOM, WS><<<grid, block, wbytes, s>>>(P);
 	}
-	k<<<grid, block, smem, s>>>(P);
 	return cudaGetLastError();
 }
 template <int LAYOUT>
-cudaError_t launch_layout(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, bool geom, bool ws) {
-	if (geom) return ws ? launch_one<LAYOUT, true, true>(sweep, grid, block, s, P) : launch_one<LAYOUT, true, false>(sweep, grid, block, s, P);
-	return ws ? launch_one<LAYOUT, false, true>(sweep, grid, block, s, P) : launch_one<LAYOUT, false, false>(sweep, grid, block, s, P);
+cudaError_t launch_layout(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap, bool geom, bool ws) {
+	if (geom) return ws ? launch_one<LAYOUT, true, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, true, false>(sweep, grid, block, s, P, tmap);
+	return ws ? launch_one<LAYOUT, false, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, false, false>(sweep, grid, block, s, P, tmap);
 }
-cudaError_t launch_any(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, int layout, bool geom, bool ws) {
-	if (layout == 2) return launch_layout<2>(sweep, grid, block, s, P, geom, ws);
-	return launch_layout<1>(sweep, grid, block, s, P, geom, ws);
+cudaError_t launch_any(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap, int layout, bool geom, bool ws) {
+	if (layout == 2) return launch_layout<2>(sweep, grid, block, s, P, tmap, geom, ws);
+	return launch_layout<1>(sweep, grid, block, s, P, tmap, geom, ws);
 }
 
 } // namespace
 
 cudaError_t pm_launch_score(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s) {
 	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+BLOCK_X-1)/BLOCK_X, (P.H+BLOCK_Y-1)/BLOCK_Y);
-	return launch_any(false, grid, block, s, P, layout, geom, ws);
+	CUtensorMap none; memset(&none, 0, sizeof(none));
+	return launch_any(false, grid, block, s, P, none, layout, geom, ws);
 }
-cudaError_t pm_launch_sweep(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s) {
+// tmapRef: TMA descriptor of the reference image with box {72, 16} (pm_tma_box), or null (P.tma must be 0)
+cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, int layout, bool geom, bool ws, cudaStream_t s) {
 	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+2*BLOCK_X-1)/(2*BLOCK_X), (P.H+BLOCK_Y-1)/BLOCK_Y);
-	return launch_any(true, grid, block, s, P, layout, geom, ws);
+	CUtensorMap map; memset(&map, 0, sizeof(map));
+	if (tmapRef) memcpy(&map, tmapRef, sizeof(map));
+	return launch_any(true, grid, block, s, P, map, layout, geom, ws);
 }
+void pm_tma_box(int* w, int* h) { *w = TILE_W; *h = TILE_H; }
 // re-layout of a neighbour image for the tap fetch (see fetch_bilinear)
 cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s) {
 	dim3 block(32, 8), grid((w+31)/32, (h+7)/8);

@@ -33,7 +33,7 @@ class Stats(C.Structure):
 	"""b200mvs_stats"""
 	_fields_ = [("ms_total", C.c_double), ("ms_device", C.c_double), ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64),
 		("kernel_launches", C.c_int), ("levels", C.c_int),
-		("ms_sweep_kernels", C.c_double), ("sweep_launches", C.c_int), ("reserved", C.c_int)]
+		("ms_sweep_kernels", C.c_double), ("sweep_launches", C.c_int), ("tma_active", C.c_int)]
 
 
 class SgmParams(C.Structure):

@@ -205,6 +205,7 @@ def test_host_api_equals_device_api_and_is_deterministic(env, small_scene):
 	assert e.pm.stats.bytes_h2d == sum(v.image.nbytes for v in views)+views[0].image.size*16
 	assert e.pm.stats.bytes_d2h == views[0].image.size*24 and e.pm.stats.sweep_launches == 2*2*2
 	assert e.pm.stats.kernel_launches >= 1+1+2*2*2+1 and e.pm.stats.ms_sweep_kernels > 0
+	assert e.pm.stats.tma_active == 1  # reference tile staged by cp.async.bulk.tensor (UTMALDG)
 	for a, b in ((dd.depthMap, hd.depthMap), (dd.normalMap, hd.normalMap), (dd.confMap, hd.confMap), (dd.viewsMap, hd.viewsMap)):
 		assert np.array_equal(a.cpu().numpy(), b)
 	hd2 = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
@@ -260,6 +261,7 @@ def test_textureless_and_odd_size_and_mixed_resolution(env):
 	od, on, oc = e.O.pm_estimate(views, prm, sc.dmin, sc.dmax)
 	assert np.all(od[66:84, 8:-8] == 0) and np.all(gd[66:84, 8:-8] == 0)  # textureless rows rejected by both
 	iou, agree = agreement(od, gd)
+	assert e.pm.stats.tma_active == 1  # odd width: the reference image is re-pitched for the TMA descriptor
 	_record("edge_cases_203x151_N2", iou=iou, agree=agree)
 	assert iou > 0.995 and agree > 0.95
 
