@@ -167,6 +167,17 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	int width, int height, const b200mvs_sgm_pixel* pixels, uint64_t numCosts, const b200mvs_sgm_params* prm,
 	int stages, uint8_t* costs, uint16_t* accums, int16_t* disparity, uint16_t* cost, void* stream, b200mvs_stats* stats);
 
+/* ConsistencyCrossCheck(l2r, r2l, thCross) (SemiGlobalMatcher.cpp:1449-1489), DEVICE pointers, l2r in place:
+ * a left disparity survives if the right disparity it points to is valid and |ld + rd| <= thCross. */
+int b200mvs_sgm_cross_check_device(b200mvs_ctx* ctx, int16_t* l2r, const int16_t* r2l, int width, int height,
+	int thCross, void* stream);
+
+/* RefineDisparityMap (SemiGlobalMatcher.cpp:1693-1811) with SUBPIXEL_LC_BLEND: sub-pixel offset from the
+ * accumulated costs around the winner, result stored as round(disparity * subpixelSteps).  DEVICE pointers;
+ * accums = NULL uses the accumulated costs of the last match on this context. */
+int b200mvs_sgm_refine_device(b200mvs_ctx* ctx, const b200mvs_sgm_pixel* pixels, const uint16_t* accums,
+	int16_t* disparity, int nPixels, int subpixelSteps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,8 @@ cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
+cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
+cudaError_t sgm_launch_refine(const SGMPixel* px, const uint16_t* accums, int16_t* disparity, int n, int steps, cudaStream_t s);
 cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s);
@@ -711,6 +713,25 @@ int b200mvs_sgm_match(b200mvs_ctx* ctx, const float* leftGray, const uint8_t* le
 		stats->bytes_h2d = n*11+nv*sizeof(SGMPixel); stats->bytes_d2h = nv*4;
 		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
 	}
+	return B200MVS_OK;
+}
+
+int b200mvs_sgm_cross_check_device(b200mvs_ctx* ctx, int16_t* l2r, const int16_t* r2l, int width, int height, int thCross, void* stream) {
+	if (!ctx || !l2r || !r2l || width <= 0 || height <= 0 || thCross < 0) return B200MVS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(sgm_launch_cross_check(l2r, r2l, width, height, thCross, stream ? (cudaStream_t)stream : ctx->stream));
+	return B200MVS_OK;
+}
+
+int b200mvs_sgm_refine_device(b200mvs_ctx* ctx, const b200mvs_sgm_pixel* pixels, const uint16_t* accums, int16_t* disparity,
+	int nPixels, int subpixelSteps, void* stream)
+{
+	if (!ctx || !pixels || !disparity || nPixels <= 0) return B200MVS_ERR_ARG;
+	if (!accums) accums = ctx->sgAccums.as<uint16_t>(); // the accumulated costs of the last match on this context
+	if (!accums) return fail(ctx, B200MVS_ERR_ARG, "sgm refine: no accumulated costs");
+	if (subpixelSteps <= 1) return B200MVS_OK;
+	CK(cudaSetDevice(ctx->device));
+	CK(sgm_launch_refine((const SGMPixel*)pixels, accums, disparity, nPixels, subpixelSteps, stream ? (cudaStream_t)stream : ctx->stream));
 	return B200MVS_OK;
 }
 

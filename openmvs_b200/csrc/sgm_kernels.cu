@@ -263,6 +263,55 @@ __global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int16_t* __r
 	if (lane == 0) { disparity[gw] = (int16_t)(p.dmin+(int)(best&0xFFFFu)); cost[gw] = (uint16_t)(best>>16); }
 }
 
+// ConsistencyCrossCheck (SemiGlobalMatcher.cpp:1449-1489): every pixel reads r2l and writes only
+// its own l2r entry, so the in-place update is race-free
+__global__ void sgm_cross_check_kernel(int16_t* __restrict__ l2r, const int16_t* __restrict__ r2l, int w, int h, int th) {
+	const int c = blockIdx.x*blockDim.x + threadIdx.x, r = blockIdx.y;
+	if (c >= w) return;
+	const int16_t ld = l2r[(size_t)r*w+c];
+	if (ld == 32767) return;
+	const int vx = c+ld;
+	int16_t out = ld;
+	if (vx < 0 || vx >= w) out = 32767;
+	else {
+		const int16_t rd = r2l[(size_t)r*w+vx];
+		if (rd == 32767 || abs((int)ld+(int)rd) > th) out = 32767;
+	}
+	l2r[(size_t)r*w+c] = out;
+}
+
+// RefineDisparityMap with SUBPIXEL_LC_BLEND (SemiGlobalMatcher.cpp:1693-1811)
+__global__ void sgm_refine_kernel(const SGMPixel* __restrict__ px, const uint16_t* __restrict__ accums, int16_t* __restrict__ disparity, int n, int steps) {
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const SGMPixel p = px[i];
+	if (p.dmax-p.dmin < 2) return;
+	const int16_t d = disparity[i];
+	if (d == 32767) return;
+	const uint16_t* a = accums + p.idx;
+	const int k = d-p.dmin;
+	float disp = (float)d;
+	auto semi = [](uint16_t primary, uint16_t other) { return other == 0 ? 0.f : 0.5f*((float)primary/(float)other); };
+	if (d == p.dmin) disp += semi(a[k], a[k+1]);
+	else if (d+1 == p.dmax) disp -= semi(a[k], a[k-1]);
+	else {
+		const uint16_t prev = a[k-1], center = a[k], next = a[k+1];
+		float off;
+		if (prev == center) off = center == next ? 0.f : semi(center, next);
+		else if (center == next) off = -semi(center, prev);
+		else {
+			const uint16_t ld = (uint16_t)(prev-center), rd = (uint16_t)(next-center);
+			float x, mult;
+			if (ld < rd) { x = (float)ld/(float)rd; mult = 1.f; } else { x = (float)rd/(float)ld; mult = -1.f; }
+			const float cosine = 1.f-cosf(x*(float)(3.14159265358979323846/3.0));
+			const float factor = 1.195f-cosf(x*(float)(3.14159265358979323846/2.3));
+			off = (cosine*factor + (x*0.5f)*(1.f-factor) - 0.5f)*mult;
+		}
+		disp += off;
+	}
+	disparity[i] = (int16_t)(int)floorf(disp*steps+.5f);
+}
+
 // largest disparity count over the valid pixels
 __global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* __restrict__ out) {
 	int m = 0;
@@ -311,5 +360,14 @@ cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s) {
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
 	const long long threads = (long long)P.vw*P.vh*32;
 	sgm_wta_kernel<<<(unsigned)((threads+255)/256), 256, 0, s>>>(P, disparity, cost);
+	return cudaGetLastError();
+}
+
+cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s) {
+	sgm_cross_check_kernel<<<dim3((w+255)/256, h), 256, 0, s>>>(l2r, r2l, w, h, th);
+	return cudaGetLastError();
+}
+cudaError_t sgm_launch_refine(const SGMPixel* px, const uint16_t* accums, int16_t* disparity, int n, int steps, cudaStream_t s) {
+	sgm_refine_kernel<<<(n+255)/256, 256, 0, s>>>(px, accums, disparity, n, steps);
 	return cudaGetLastError();
 }

@@ -331,3 +331,17 @@ class SemiGlobalMatcher:
 			disp.data_ptr(), cost.data_ptr(), C.c_void_p(s), C.byref(self.stats) if sync else None)
 		_lib.check(self._lib, self._ctx, rc, "b200mvs_sgm_match_device")
 		return disp, cost
+
+	def ConsistencyCrossCheck(self, l2r, r2l, thCross: int = 1):
+		"""SemiGlobalMatcher::ConsistencyCrossCheck on int16 CUDA tensors; l2r is modified in place."""
+		h, w = l2r.shape
+		rc = self._lib.b200mvs_sgm_cross_check_device(self._ctx, l2r.data_ptr(), r2l.data_ptr(), w, h, int(thCross), C.c_void_p(_stream_handle(l2r.device)))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_sgm_cross_check_device")
+		return l2r
+
+	def RefineDisparityMap(self, disparityMap, imagePixels, accums=None, subpixelSteps: int = 4):
+		"""SemiGlobalMatcher::RefineDisparityMap (LC-blend) on CUDA tensors; disparityMap in place."""
+		rc = self._lib.b200mvs_sgm_refine_device(self._ctx, imagePixels.data_ptr(), accums.data_ptr() if accums is not None else None,
+			disparityMap.data_ptr(), disparityMap.numel(), int(subpixelSteps), C.c_void_p(_stream_handle(disparityMap.device)))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_sgm_refine_device")
+		return disparityMap

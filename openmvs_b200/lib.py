@@ -47,6 +47,7 @@ SYMBOLS = [
 	"b200mvs_device_count", "b200mvs_estimate", "b200mvs_estimate_device",
 	"b200mvs_pm_pack", "b200mvs_pm_unpack", "b200mvs_pm_score", "b200mvs_pm_sweep", "b200mvs_pm_finalize",
 	"b200mvs_sgm_default_params", "b200mvs_sgm_match", "b200mvs_sgm_match_device",
+	"b200mvs_sgm_cross_check_device", "b200mvs_sgm_refine_device",
 ]
 
 _LIB = None
@@ -85,6 +86,8 @@ def load(build_if_missing: bool = True):
 	lib.b200mvs_sgm_default_params.argtypes = [C.POINTER(SgmParams)]
 	lib.b200mvs_sgm_match.argtypes = [P, P, P, P, C.c_int, C.c_int, P, C.c_uint64, C.POINTER(SgmParams), P, P, C.POINTER(Stats)]
 	lib.b200mvs_sgm_match_device.argtypes = [P, P, P, P, C.c_int, C.c_int, P, C.c_uint64, C.POINTER(SgmParams), C.c_int, P, P, P, P, P, C.POINTER(Stats)]
+	lib.b200mvs_sgm_cross_check_device.argtypes = [P, P, P, C.c_int, C.c_int, C.c_int, P]
+	lib.b200mvs_sgm_refine_device.argtypes = [P, P, P, P, C.c_int, C.c_int, P]
 	_LIB = lib
 	return lib
 

@@ -117,6 +117,9 @@ int oracle_sgm_match(const float* leftGray, const uint8_t* leftBGR, const float*
 	const oracle_sgm_pixel* pixels, uint64_t numCosts, uint16_t P1, uint16_t P2, float P2alpha, float P2beta, int stage,
 	uint8_t* costs, uint16_t* accums, int16_t* disparity, uint16_t* cost);
 
+void oracle_sgm_cross_check(int16_t* l2r, const int16_t* r2l, int width, int height, int thCross);
+void oracle_sgm_refine(const oracle_sgm_pixel* pixels, const uint16_t* accums, int16_t* disparity, int nPixels, int subpixelSteps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,3 +167,16 @@ def sgm_match(left_gray, left_bgr, right_gray, pixels, num_costs, P1=3, P2=4, al
 	rc = f(_fptr(lg), _fptr(lc), _fptr(rg), w, h, _fptr(px), num_costs, P1, P2, alpha, beta, st, _fptr(c), _fptr(a), _fptr(disp), _fptr(cost))
 	assert rc == 0
 	return c, a, disp, cost
+
+
+def sgm_cross_check(l2r, r2l, th=1):
+	a = np.array(l2r, np.int16, copy=True, order="C"); b = np.ascontiguousarray(r2l, np.int16)
+	lib().oracle_sgm_cross_check(_fptr(a), _fptr(b), a.shape[1], a.shape[0], int(th))
+	return a
+
+
+def sgm_refine(pixels, accums, disparity, steps=4):
+	d = np.array(disparity, np.int16, copy=True, order="C")
+	px = np.ascontiguousarray(pixels); a = np.ascontiguousarray(accums, np.uint16)
+	lib().oracle_sgm_refine(_fptr(px), _fptr(a), _fptr(d), d.size, int(steps))
+	return d

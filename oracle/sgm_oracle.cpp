@@ -207,4 +207,55 @@ int oracle_sgm_match(const float* leftGray, const uint8_t* leftBGR, const float*
 	return 0;
 }
 
+// ConsistencyCrossCheck (SemiGlobalMatcher.cpp:1449-1489): l2r is modified in place
+void oracle_sgm_cross_check(int16_t* l2r, const int16_t* r2l, int width, int height, int thCross) {
+	for (int r=0; r<height; ++r) for (int c=0; c<width; ++c) {
+		int16_t& ld = l2r[(size_t)r*width+c];
+		if (ld == NO_DISP) continue;
+		const int vx = c+ld;
+		if (vx < 0 || vx >= width) { ld = NO_DISP; continue; }
+		const int16_t rd = r2l[(size_t)r*width+vx];
+		if (rd == NO_DISP) { ld = NO_DISP; continue; }
+		if (std::abs(ld+rd) > thCross) ld = NO_DISP;
+	}
+}
+
+// RefineDisparityMap, SUBPIXEL_LC_BLEND (SemiGlobalMatcher.cpp:1693-1811)
+void oracle_sgm_refine(const oracle_sgm_pixel* pixels, const uint16_t* accums, int16_t* disparity, int nPixels, int subpixelSteps) {
+	if (subpixelSteps <= 1) return;
+	typedef float real;
+	const real PI = 3.14159265358979323846f;
+	auto linear = [](real x) { return x/real(2); };
+	auto cosine = [&](real x) { return real(1)-std::cos(x*(real)(3.14159265358979323846/3.0)); };
+	auto lcBlend = [&](real x) { const real factor = real(1.195)-std::cos(x*(real)(3.14159265358979323846/2.3)); return cosine(x)*factor + linear(x)*(real(1)-factor); };
+	auto semi = [](uint16_t primary, uint16_t other) { return other == 0 ? real(0) : real(0.5)*((real)primary/(real)other); };
+	(void)PI;
+	for (int i=0; i<nPixels; ++i) {
+		const oracle_sgm_pixel& p = pixels[i];
+		if (p.dmax-p.dmin < 2) continue;
+		int16_t& d = disparity[i];
+		if (d == NO_DISP) continue;
+		const uint16_t* a = accums+p.idx;
+		const int k = d-p.dmin;
+		real disp = (real)d;
+		if (d == p.dmin) disp += semi(a[k], a[k+1]);
+		else if (d+1 == p.dmax) disp -= semi(a[k], a[k-1]);
+		else {
+			const uint16_t prev = a[k-1], center = a[k], next = a[k+1];
+			real off;
+			if (prev == center) off = center == next ? real(0) : semi(center, next);
+			else if (center == next) off = -semi(center, prev);
+			else {
+				const uint16_t ld = (uint16_t)(prev-center), rd = (uint16_t)(next-center);
+				real x, mult;
+				if (ld < rd) { x = (real)ld/(real)rd; mult = real(1); }
+				else { x = (real)rd/(real)ld; mult = real(-1); }
+				off = (lcBlend(x)-real(0.5))*mult;
+			}
+			disp += off;
+		}
+		d = (int16_t)round2int(disp*subpixelSteps);
+	}
+}
+
 } // extern "C"

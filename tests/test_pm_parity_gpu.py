@@ -346,3 +346,34 @@ def test_full_size_properties_1080p(env):
 	X0 = np.stack([(xx-K[0, 2])/K[0, 0], (yy-K[1, 2])/K[1, 1], np.ones_like(xx, float)], -1)
 	assert ((gn*X0).sum(-1)[m] < 1e-6).all()  # normals face the camera
 	assert gc[m].min() > 0 and gc.max() <= 1 and gd[m].min() >= sc.dmin and gd[m].max() < sc.dmax
+
+
+def test_high_resolution_geometric_pass_properties(env):
+	"""BASELINE configs[4] size (4032x3024) with a geometric-consistency second pass: pixel indices
+	beyond 2^23, determinism, output invariants and analytic ground truth."""
+	e = env
+	from openmvs_b200 import synth
+	w, h = 4032, 3024
+	sc = synth.make_scene(w, h, 4, step_deg=4.0, cols=2, device=e.dev)
+	ref = 0
+	views = [sc.views[ref]]+[sc.views[i] for i in sc.neighbors(ref, 3)]
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=1, nEstimationIters=2, nSweepsPerIter=2, nRandomIters=6)
+	dv = _dev_views(e, views)
+	a = e.DepthData(dv, sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(a)                       # photometric pass (keep threshold x1.333)
+	d1 = a.depthMap.clone()
+	# second pass: neighbours carry their depth-maps (ground truth stands in for their pass-1 result)
+	depths = [None]+[(v.depth_gt, v.K, v.R, v.C) for v in views[1:]]
+	dvg = _dev_views(e, views, depths)
+	g1 = e.DepthData(dvg, sc.dmin, sc.dmax, depthMap=a.depthMap.clone(), normalMap=a.normalMap.clone())
+	g2 = e.DepthData(dvg, sc.dmin, sc.dmax, depthMap=a.depthMap.clone(), normalMap=a.normalMap.clone())
+	e.pm.Init(True); e.pm.EstimateDepthMap(g1, nGeometricIter=0); e.pm.EstimateDepthMap(g2, nGeometricIter=0); e.pm.Init(False)
+	assert torch.equal(g1.depthMap, g2.depthMap) and torch.equal(g1.confMap, g2.confMap)
+	gd, gc = g1.depthMap.cpu().numpy(), g1.confMap.cpu().numpy()
+	gt = sc.views[ref].depth_gt
+	m = gd > 0
+	rel = np.abs(gd-gt)[m]/gt[m]
+	_record("high_res_4032x3024_geo", valid=m.mean(), acc_1e3=(rel < 1e-3).mean(), med_rel=np.median(rel), valid_pass1=(d1 > 0).float().mean().item())
+	assert m.mean() > 0.9 and (rel < 1e-3).mean() > 0.9 and np.median(rel) < 3e-4
+	assert not m[:4].any() and not m[-4:].any() and gc[m].min() > 0 and gc.max() <= 1
+	_set(e, nEstimationGeometricIters=0)

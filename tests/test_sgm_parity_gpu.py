@@ -105,3 +105,29 @@ def test_full_size_sgm_properties_1080p(sgm):
 	err = np.abs(gd.cpu().numpy()-gt)[8:-8, 8:-140]
 	assert (err <= 1).mean() > 0.97
 	print("sgm 1080p D=128: %.2f ms device" % ms)
+
+
+def test_cross_check_and_subpixel_refinement_parity(sgm):
+	"""ConsistencyCrossCheck (exact) and RefineDisparityMap / LC-blend (float -> quarter-pixel integer)."""
+	m, O = sgm
+	w, h = 200, 120
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	px, n = synth.sgm_pixel_map(w, h, 0, 32)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n)
+	# right-to-left map of the same pair: swap the roles, negative disparities
+	pxr, nr = synth.sgm_pixel_map(w, h, -32, 0)
+	bgr_r = np.repeat(np.rint(rg*255).astype(np.uint8)[..., None], 3, -1)
+	cr, ar, dispr, costr = O.sgm_match(rg, bgr_r, lg, pxr, nr)
+	rng = np.random.RandomState(2)
+	disp_in = disp.copy(); disp_in[rng.rand(*disp.shape) < 0.05] = 32767
+	want = O.sgm_cross_check(disp_in, dispr, 1)
+	got = m.ConsistencyCrossCheck(_dev(disp_in), _dev(dispr), 1).cpu().numpy()
+	assert np.array_equal(got, want)
+	assert 0.3 < (want != 32767).mean() < 0.999
+	# sub-pixel refinement on the oracle's accumulated costs
+	want = O.sgm_refine(px, a, disp_in, 4)
+	got = m.RefineDisparityMap(_dev(disp_in), _px_dev(px), accums=_dev(a.view(np.int16)), subpixelSteps=4).cpu().numpy()
+	diff = np.abs(got.astype(np.int32)-want.astype(np.int32))
+	assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+	valid = want != 32767
+	assert np.abs(want[valid]/4.0-disp_in[valid]).max() <= 0.5+1e-6  # the offset stays within half a pixel
