@@ -134,6 +134,7 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 		return;
 	int cur = 0;
 	int pmin = 0, pmax = 0;     // previous range (empty at the start of a scanline)
+	unsigned minPrev = 0xFFFFu; // minimum of the previous line over its whole range
 	float Ip = 0.5f;
 	auto inside = [&](int xx, int yy) { return xx >= 0 && yy >= 0 && xx < P.vw && yy < P.vh; };
 	SGMPixel none; none.idx = 0; none.dmin = 0; none.dmax = 0; none.pad = 0;
@@ -186,18 +187,37 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 			const int imin = max(pmin, (int)p.dmin), imax = min(pmax, (int)p.dmax);
 			const int num = p.dmax-p.dmin;
 			uint16_t* accums = P.accums + p.idx;
+			unsigned Lnew[NPL];
 			if (imin >= imax) {
 				#pragma unroll
 				for (int j = 0; j < NPL; ++j) {
 					const int kk = lane+32*j;
+					Lnew[j] = 0xFFFFu;
 					if (kk < num) {
-						const uint16_t L = (uint16_t)(c0[j]+P2);
-						Ls[kk] = L;
-						accums[kk] = (uint16_t)(a0[j]+L);
+						Lnew[j] = (unsigned)(c0[j]+P2);
+						Ls[kk] = (uint16_t)Lnew[j];
+						accums[kk] = (uint16_t)(a0[j]+Lnew[j]);
+					}
+				}
+			} else if (p.dmin == pmin && p.dmax == pmax && num >= 4) {
+				// fast path: same range as the previous pixel of the scanline (always, for fixed ranges).
+				// The line is padded with 0xFFFF on both sides, so d-1 / d+1 need no range test, and
+				// the minimum of the previous line was reduced when it was written.
+				const int minLp = (int)minPrev;
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int kk = lane+32*j;
+					Lnew[j] = 0xFFFFu;
+					if (kk < num) {
+						const int l0 = Lp[kk], lm = Lp[kk-1], lp1 = Lp[kk+1];
+						const int best = min(min(l0, min(lm, lp1)+P.P1), minLp+P2);
+						Lnew[j] = (unsigned)(c0[j]+best-minLp);
+						Ls[kk] = (uint16_t)Lnew[j];
+						accums[kk] = (uint16_t)(a0[j]+Lnew[j]);
 					}
 				}
 			} else {
-				// min of the previous line over the intersection
+				// general (ragged) path: min of the previous line over the intersection
 				unsigned m = 0xFFFFu;
 				for (int d = imin+lane; d < imax; d += 32)
 					m = min(m, (unsigned)Lp[d-pmin]);
@@ -208,6 +228,7 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 				#pragma unroll
 				for (int j = 0; j < NPL; ++j) {
 					const int kk = lane+32*j;
+					Lnew[j] = 0xFFFFu;
 					if (kk < num) {
 						const int d = p.dmin+kk;
 						// The reference takes min over dp in the intersection I of Lp(dp)+{0 | P1 | P2}.
@@ -219,12 +240,21 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 						if (d >= imin && d < imax) best = min(best, (int)Lp[d-pmin]);
 						if (d-1 >= imin && d-1 < imax) best = min(best, (int)Lp[d-1-pmin]+P.P1);
 						if (d+1 >= imin && d+1 < imax) best = min(best, (int)Lp[d+1-pmin]+P.P1);
-						const uint16_t L = (uint16_t)(c0[j]+best-minLp);
-						Ls[kk] = L;
-						accums[kk] = (uint16_t)(a0[j]+L);
+						Lnew[j] = (unsigned)(c0[j]+best-minLp);
+						Ls[kk] = (uint16_t)Lnew[j];
+						accums[kk] = (uint16_t)(a0[j]+Lnew[j]);
 					}
 				}
 			}
+			// sentinels around the new line and its minimum, for the next step's fast path
+			if (lane == 0) { Ls[-1] = 0xFFFFu; Ls[num] = 0xFFFFu; }
+			unsigned mn = Lnew[0];
+			#pragma unroll
+			for (int j = 1; j < NPL; ++j) mn = min(mn, Lnew[j]);
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+			minPrev = mn;
 			__syncwarp();
 			pmin = p.dmin; pmax = p.dmax;
 			cur ^= 1;
