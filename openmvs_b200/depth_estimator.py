@@ -90,6 +90,24 @@ class DepthData:
 	def IsEmpty(self) -> bool:
 		return self.depthMap is None
 
+	def Save(self, fileName: str, IDs=None, imageFileName: str = "image.jpg") -> bool:
+		"""DepthData::Save (libs/MVS/DepthMap.cpp:237-251): write depth/normal/conf/views as a .dmap file."""
+		from . import dmap_io
+		tonp = lambda a: None if a is None else (a.detach().cpu().numpy() if _is_torch(a) else np.asarray(a))
+		ref = self.images[0]
+		h, w = tonp(self.depthMap).shape
+		ids = list(IDs) if IDs is not None else list(range(len(self.images)))
+		return dmap_io.ExportDepthDataRaw(fileName, imageFileName, ids, (w, h), ref.camera.K, ref.camera.R, ref.camera.C,
+			self.dMin, self.dMax, tonp(self.depthMap), tonp(self.normalMap), tonp(self.confMap), tonp(self.viewsMap))
+
+	def Load(self, fileName: str, flags: int = 15) -> bool:
+		"""DepthData::Load: read the maps and the depth range back from a .dmap file."""
+		from . import dmap_io
+		d = dmap_io.ImportDepthDataRaw(fileName, flags)
+		self.depthMap, self.normalMap, self.confMap, self.viewsMap = d["depthMap"], d["normalMap"], d["confMap"], d["viewsMap"]
+		self.dMin, self.dMax = d["dMin"], d["dMax"]
+		return True
+
 
 def _stream_handle(device) -> int:
 	"""cudaStream_t of torch's current stream.  The C-ABI treats NULL as "use the context's own

@@ -50,3 +50,18 @@ def test_shard_assignment_is_a_partition():
 		flat = sorted(i for p in parts for i in p)
 		assert flat == list(range(n))
 		assert max(len(p) for p in parts)-min(len(p) for p in parts) <= 1
+
+
+def test_depthdata_save_load_round_trip(tmp_path):
+	K = np.array([[100.0, 0, 31.5], [0, 100.0, 23.5], [0, 0, 1]])
+	cam = Camera(K, np.eye(3), np.zeros(3))
+	img = np.zeros((48, 64), np.float32)
+	rng = np.random.RandomState(2)
+	dd = DepthData([ViewData(img, cam), ViewData(img, cam)], 1.0, 9.0, depthMap=rng.rand(48, 64).astype(np.float32),
+		normalMap=rng.rand(48, 64, 3).astype(np.float32), confMap=rng.rand(48, 64).astype(np.float32),
+		viewsMap=rng.randint(0, 255, (48, 64, 4)).astype(np.uint8))
+	p = str(tmp_path/"depth0000.dmap")
+	assert dd.Save(p, IDs=[4, 2])
+	back = DepthData([ViewData(img, cam), ViewData(img, cam)], 0.0, 0.0)
+	assert back.Load(p) and np.array_equal(back.depthMap, dd.depthMap) and np.array_equal(back.viewsMap, dd.viewsMap)
+	assert (back.dMin, back.dMax) == (1.0, 9.0)
