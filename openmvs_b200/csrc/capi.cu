@@ -37,6 +37,7 @@ struct SGMParams {
 cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out, cudaStream_t s);
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
+cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
@@ -654,22 +655,29 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	P.costs = costs; P.accums = accums;
 	const auto t0 = std::chrono::steady_clock::now();
 	ctx->launches = 0;
+	int st6[6] = {0, 0, 0, 0, 0, 0}; bool uniform = false;
 	if (stats) CK(cudaEventRecord(ctx->ev0, s));
 	if (stages & 2) {
 		// the warp-per-scanline kernel keeps one line of at most sgm_max_disparities() values
-		CK(ctx->sgMax.reserve(sizeof(int)));
-		CK(sgm_launch_maxdisp(P.px, P.vw*P.vh, ctx->sgMax.as<int>(), s)); ++ctx->launches;
-		int m = 0;
-		CK(cudaMemcpyAsync(&m, ctx->sgMax.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+		CK(ctx->sgMax.reserve(6*sizeof(int)));
+		CK(sgm_launch_maxdisp(P.px, P.vw*P.vh, ctx->sgMax.as<int>(), s)); ctx->launches += 2;
+		CK(cudaMemcpyAsync(st6, ctx->sgMax.p, 6*sizeof(int), cudaMemcpyDeviceToHost, s));
 		CK(cudaStreamSynchronize(s));
-		if (m > sgm_max_disparities())
+		if (st6[0] > sgm_max_disparities())
 			return fail(ctx, B200MVS_ERR_ARG, "sgm: more than 256 disparities per pixel");
-		P.maxNumDisp = m;
+		P.maxNumDisp = st6[0];
+		// one global range (the non-tSGM branch): packed, shared-memory-free aggregation kernel
+		uniform = st6[0] >= 4 && st6[1] == st6[2] && st6[3] == st6[4] && (st6[0] & 3) == 0 && st6[5] == 0
+			&& !getenv("B200MVS_SGM_GENERAL");
 	}
 	if (stages & 1) { CK(sgm_launch_cost(P, s)); ++ctx->launches; }
 	if (stages & 2) {
 		CK(cudaMemsetAsync(accums, 0, numCosts*sizeof(uint16_t), s));
-		for (int dir = 0; dir < 8; ++dir) { CK(sgm_launch_aggregate(P, dir, s)); ++ctx->launches; }
+		for (int dir = 0; dir < 8; ++dir) {
+			if (uniform) CK(sgm_launch_aggregate_uniform(P, dir, st6[1], st6[0], s));
+			else CK(sgm_launch_aggregate(P, dir, s));
+			++ctx->launches;
+		}
 	}
 	if (stages & 4) { CK(sgm_launch_wta(P, disparity, cost, s)); ++ctx->launches; }
 	if (stats) {

@@ -11,6 +11,7 @@
 // libs/MVS/SemiGlobalMatcher.h:78-81); it is uint8, the path sum uint16 — HBM-bound integer work.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
 
@@ -71,27 +72,48 @@ sgm_cost_kernel(const __grid_constant__ SGMParams P)
 	}
 	uint8_t* costs = P.costs + p.idx;
 	const float eps = 1e-3f;
+	// four disparities per pass over the 7x7 taps: one LDS of a tap's weights and ten loads of a right
+	// image row serve 4 x 7 products.  Columns are clamped for the loads; windows that leave the right
+	// image are overwritten with 255 afterwards (SemiGlobalMatcher.cpp:959-963).
+	constexpr int DCH = 4;
 	#pragma unroll 1
-	for (int d = p.dmin; d < p.dmax; ++d) {
+	for (int d = p.dmin; d < p.dmax; d += DCH) {
 		const int x0 = ux-HW+d;
-		if (x0 < 0 || x0+2*HW >= P.w) { *costs++ = 255; continue; }
-		const float* rp = P.rgray + (size_t)(uy-HW)*P.w + x0;
-		float sum = 0.f, sumSq = 0.f, nom = 0.f;
+		float sum[DCH], sumSq[DCH], nom[DCH];
+		#pragma unroll
+		for (int q = 0; q < DCH; ++q) { sum[q] = 0.f; sumSq[q] = 0.f; nom[q] = 0.f; }
+		int col[2*HW+DCH];
+		#pragma unroll
+		for (int t = 0; t < 2*HW+DCH; ++t) col[t] = min(max(x0+t, 0), P.w-1);
 		#pragma unroll
 		for (int i = 0; i < 7; ++i) {
+			const float* rp = P.rgray + (size_t)(uy-HW+i)*P.w;
+			float f[2*HW+DCH];
+			#pragma unroll
+			for (int t = 0; t < 2*HW+DCH; ++t) f[t] = __ldg(rp + col[t]);
 			#pragma unroll
 			for (int j = 0; j < 7; ++j) {
-				const float f = __ldg(rp + i*P.w + j);
 				const float2 e = w[(i*7+j)*COST_THREADS];
-				const float fw = f*e.x;
-				sum += fw;
-				sumSq = fmaf(f, fw, sumSq);
-				nom = fmaf(f, e.y, nom);
+				#pragma unroll
+				for (int q = 0; q < DCH; ++q) {
+					const float fv = f[j+q];
+					const float fw = fv*e.x;
+					sum[q] += fw;
+					sumSq[q] = fmaf(fv, fw, sumSq[q]);
+					nom[q] = fmaf(fv, e.y, nom[q]);
+				}
 			}
 		}
-		const float normSq1 = sumSq - sum*sum/sumW;
-		const float ncc = nom/sqrtf(normSq0*normSq1+eps);
-		*costs++ = ncc <= 0.f ? (uint8_t)255 : (uint8_t)(int)floorf((1.f-fminf(ncc, 1.f))*255.f+.5f);
+		#pragma unroll
+		for (int q = 0; q < DCH; ++q) {
+			if (d+q < p.dmax) {
+				const float normSq1 = sumSq[q] - sum[q]*sum[q]/sumW;
+				const float ncc = nom[q]/sqrtf(normSq0*normSq1+eps);
+				uint8_t cst = ncc <= 0.f ? (uint8_t)255 : (uint8_t)(int)floorf((1.f-fminf(ncc, 1.f))*255.f+.5f);
+				if (x0+q < 0 || x0+q+2*HW >= P.w) cst = 255;
+				costs[d-p.dmin+q] = cst;
+			}
+		}
 	}
 }
 
@@ -99,7 +121,10 @@ sgm_cost_kernel(const __grid_constant__ SGMParams P)
 constexpr int AGG_WARPS = 4;
 constexpr int MAXD = 256;        // disparities per pixel supported by the warp-per-scanline kernel
 constexpr int LPAD = 8;
-constexpr int AGG_PD = 2;        // prefetch distance (steps) of the scanline pipeline
+constexpr int AGG_PD = 2;        // prefetch distance (steps) of the scanline pipeline (general kernel)
+#ifndef AGG_PD_UNIFORM
+#define AGG_PD_UNIFORM 4          // the packed uniform kernel keeps only 3 registers per stage in flight
+#endif
 
 // start pixel and step of scanline `k` of direction `dir` (order of SemiGlobalMatcher.cpp:1084-1199)
 __device__ __forceinline__ bool path_start(int dir, int k, int W, int H, int& x, int& y, int& dx, int& dy) {
@@ -273,6 +298,122 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 	}
 }
 
+// Uniform-range variant (the reference's non-tSGM branch gives every pixel one global range,
+// SemiGlobalMatcher.cpp:643-669): all valid pixels share [dmin, dmax), the count is a multiple of 4 and
+// every pixel's slice of the volume is 4-aligned.  Lane l owns the NPL consecutive disparities
+// [l*NPL, l*NPL+NPL): its costs are one packed 32-bit (NPL=4) or 64-bit (NPL=8) load, its accumulators one
+// 64/128-bit load and store, d-1 / d+1 live in the lane's own registers except at the two ends (one
+// shuffle each), and the line never touches shared memory.
+template <int NPL> struct Pack;
+template <> struct Pack<4> { typedef uint32_t C; typedef uint2 A; };
+template <> struct Pack<8> { typedef uint2 C; typedef uint4 A; };
+
+template <int NPL, int PD>
+__global__ void __launch_bounds__(AGG_WARPS*32)
+sgm_aggregate_uniform_kernel(const __grid_constant__ SGMParams P, int dir, int dmin, int num)
+{
+	typedef typename Pack<NPL>::C CW;
+	typedef typename Pack<NPL>::A AW;
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
+	const int k = blockIdx.x*AGG_WARPS + warp;
+	int x, y, dx, dy;
+	if (!path_start(dir, k, P.vw, P.vh, x, y, dx, dy))
+		return;
+	const bool active = lane*NPL < num;   // num % 4 == 0 and NPL in {4, 8}: a lane is all in or all out ...
+	const int nval = min(NPL, max(0, num-lane*NPL)); // ... except with NPL = 8 and num % 8 == 4
+	auto inside = [&](int xx, int yy) { return xx >= 0 && yy >= 0 && xx < P.vw && yy < P.vh; };
+	auto valid = [&](const SGMPixel& p) { return p.dmin < p.dmax; };
+	SGMPixel none; none.idx = 0; none.dmin = 0; none.dmax = 0; none.pad = 0;
+	SGMPixel pr[PD+1]; float Ir[PD+1];
+	CW c[PD]; AW a[PD];
+	auto loadC = [&](const SGMPixel& p) -> CW {
+		CW v; memset(&v, 0, sizeof(v));
+		if (active && valid(p)) {
+			const uint32_t* src = (const uint32_t*)(P.costs + p.idx) + lane*(NPL/4);
+			if (NPL == 4) { uint32_t t = src[0]; memcpy(&v, &t, 4); }
+			else { uint2 t; t.x = src[0]; t.y = nval > 4 ? src[1] : 0u; memcpy(&v, &t, 8); }
+		}
+		return v;
+	};
+	auto loadA = [&](const SGMPixel& p) -> AW {
+		AW v; memset(&v, 0, sizeof(v));
+		if (active && valid(p)) {
+			const uint2* src = (const uint2*)(P.accums + p.idx) + lane*(NPL/4);
+			if (NPL == 4) { uint2 t = src[0]; memcpy(&v, &t, 8); }
+			else { uint4 t; const uint2 lo = src[0]; t.x = lo.x; t.y = lo.y; t.z = t.w = 0u; if (nval > 4) { const uint2 hi = src[1]; t.z = hi.x; t.w = hi.y; } memcpy(&v, &t, 16); }
+		}
+		return v;
+	};
+	#pragma unroll
+	for (int i = 0; i <= PD; ++i) {
+		pr[i] = none; Ir[i] = 0.f;
+		const int xx = x+i*dx, yy = y+i*dy;
+		if (inside(xx, yy)) { pr[i] = P.px[(size_t)yy*P.vw + xx]; Ir[i] = __ldg(P.lgray + (size_t)yy*P.w + xx); }
+	}
+	#pragma unroll
+	for (int i = 0; i < PD; ++i) { c[i] = loadC(pr[i]); a[i] = loadA(pr[i]); }
+	unsigned Lp[NPL];
+	#pragma unroll
+	for (int j = 0; j < NPL; ++j) Lp[j] = 0xFFFFu;
+	unsigned minLp = 0xFFFFu;
+	bool havePrev = false;
+	float Ip = 0.5f;
+	for (; inside(x, y); x += dx, y += dy) {
+		SGMPixel pnew = none; float Inew = 0.f;
+		{
+			const int xx = x+(PD+1)*dx, yy = y+(PD+1)*dy;
+			if (inside(xx, yy)) { pnew = P.px[(size_t)yy*P.vw + xx]; Inew = __ldg(P.lgray + (size_t)yy*P.w + xx); }
+		}
+		const CW cn = loadC(pr[PD]);
+		const AW an = loadA(pr[PD]);
+		const SGMPixel p = pr[0];
+		if (valid(p)) {
+			const float I = Ir[0];
+			const int P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
+			Ip = I;
+			uint8_t cb[NPL]; uint16_t ab[NPL];
+			memcpy(cb, &c[0], NPL); memcpy(ab, &a[0], 2*NPL);
+			unsigned Ln[NPL];
+			if (!havePrev) {
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) Ln[j] = j < nval ? (unsigned)(cb[j]+P2) : 0xFFFFu;
+			} else {
+				const unsigned below = __shfl_up_sync(0xFFFFFFFFu, Lp[NPL-1], 1);
+				const unsigned above = __shfl_down_sync(0xFFFFFFFFu, Lp[0], 1);
+				const int far = (int)minLp+P2;
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int lm = j > 0 ? (int)Lp[j-1] : (lane > 0 ? (int)below : 0xFFFF);
+					const int lq = j < NPL-1 ? (int)Lp[j+1] : (lane < 31 ? (int)above : 0xFFFF);
+					const int best = min(min((int)Lp[j], min(lm, lq)+P.P1), far);
+					Ln[j] = j < nval ? (unsigned)((int)cb[j]+best-(int)minLp) : 0xFFFFu;
+				}
+			}
+			if (active) {
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) ab[j] = (uint16_t)(ab[j]+(j < nval ? Ln[j] : 0u));
+				uint2* dst = (uint2*)(P.accums + p.idx) + lane*(NPL/4);
+				uint2 w0; memcpy(&w0, ab, 8); dst[0] = w0;
+				if (NPL == 8 && nval > 4) { uint2 w1; memcpy(&w1, ab+4, 8); dst[1] = w1; }
+			}
+			unsigned mn = Ln[0];
+			#pragma unroll
+			for (int j = 0; j < NPL; ++j) { Lp[j] = Ln[j]; mn = min(mn, Ln[j]); }
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+			minLp = mn;
+			havePrev = true;
+		}
+		#pragma unroll
+		for (int i = 0; i < PD; ++i) { pr[i] = pr[i+1]; Ir[i] = Ir[i+1]; }
+		pr[PD] = pnew; Ir[PD] = Inew;
+		#pragma unroll
+		for (int i = 0; i+1 < PD; ++i) { c[i] = c[i+1]; a[i] = a[i+1]; }
+		c[PD-1] = cn; a[PD-1] = an;
+	}
+}
+
 // ---- (3) winner takes all ------------------------------------------------------------------------
 __global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int16_t* __restrict__ disparity, uint16_t* __restrict__ cost)
 {
@@ -342,25 +483,48 @@ __global__ void sgm_refine_kernel(const SGMPixel* __restrict__ px, const uint16_
 	disparity[i] = (int16_t)(int)floorf(disp*steps+.5f);
 }
 
-// largest disparity count over the valid pixels
+// statistics of the pixel map: out[0] = largest disparity count, out[1]/out[2] = min/max of dmin,
+// out[3]/out[4] = min/max of dmax over the valid pixels, out[5] = OR of (idx & 3)
 __global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* __restrict__ out) {
-	int m = 0;
+	int m = 0, lo0 = 0x7FFFFFFF, hi0 = -0x7FFFFFFF, lo1 = 0x7FFFFFFF, hi1 = -0x7FFFFFFF, al = 0;
 	for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
 		const SGMPixel p = px[i];
-		if (p.dmin < p.dmax) m = max(m, p.dmax-p.dmin);
+		if (p.dmin < p.dmax) {
+			m = max(m, p.dmax-p.dmin);
+			lo0 = min(lo0, (int)p.dmin); hi0 = max(hi0, (int)p.dmin);
+			lo1 = min(lo1, (int)p.dmax); hi1 = max(hi1, (int)p.dmax);
+			al |= (int)(p.idx & 3ull);
+		}
 	}
 	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
+	for (int o = 16; o > 0; o >>= 1) {
 		m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-	if ((threadIdx.x&31) == 0) atomicMax(out, m);
+		lo0 = min(lo0, __shfl_xor_sync(0xFFFFFFFFu, lo0, o)); hi0 = max(hi0, __shfl_xor_sync(0xFFFFFFFFu, hi0, o));
+		lo1 = min(lo1, __shfl_xor_sync(0xFFFFFFFFu, lo1, o)); hi1 = max(hi1, __shfl_xor_sync(0xFFFFFFFFu, hi1, o));
+		al |= __shfl_xor_sync(0xFFFFFFFFu, al, o);
+	}
+	if ((threadIdx.x&31) == 0) {
+		atomicMax(out, m); atomicMin(out+1, lo0); atomicMax(out+2, hi0); atomicMin(out+3, lo1); atomicMax(out+4, hi1); atomicOr(out+5, al);
+	}
+}
+__global__ void sgm_stats_init_kernel(int* out) {
+	out[0] = 0; out[1] = 0x7FFFFFFF; out[2] = -0x7FFFFFFF; out[3] = 0x7FFFFFFF; out[4] = -0x7FFFFFFF; out[5] = 0;
 }
 
 } // namespace
 
-cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out, cudaStream_t s) {
-	cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int), s);
-	if (e != cudaSuccess) return e;
-	sgm_maxdisp_kernel<<<148*4, 256, 0, s>>>(px, n, out);
+cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out6, cudaStream_t s) {
+	sgm_stats_init_kernel<<<1, 1, 0, s>>>(out6);
+	sgm_maxdisp_kernel<<<148*4, 256, 0, s>>>(px, n, out6);
+	return cudaGetLastError();
+}
+// uniform-range fast path: every valid pixel has the range [dmin, dmin+num), num % 4 == 0, 4-aligned slices
+cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s) {
+	const int W = P.vw, H = P.vh;
+	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
+	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
+	if (num <= 128) sgm_aggregate_uniform_kernel<4, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
+	else sgm_aggregate_uniform_kernel<8, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
 	return cudaGetLastError();
 }
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s) {

@@ -78,7 +78,7 @@ def test_host_api_full_match_and_errors(sgm):
 	assert (gd != disp).mean() < 0.01
 	gt = d[3:-3, 3:-3]
 	assert (np.abs(gd-gt)[5:-5, 5:-40] <= 1).mean() > 0.97
-	assert m.stats.kernel_launches == 1+1+8+1 and m.stats.bytes_d2h == (w-6)*(h-6)*4
+	assert m.stats.kernel_launches == 2+1+8+1 and m.stats.bytes_d2h == (w-6)*(h-6)*4
 	# more than 256 disparities per pixel is refused loudly
 	from openmvs_b200 import lib
 	px2, n2 = synth.sgm_pixel_map(w, h, 0, 300)
@@ -131,3 +131,20 @@ def test_cross_check_and_subpixel_refinement_parity(sgm):
 	assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 	valid = want != 32767
 	assert np.abs(want[valid]/4.0-disp_in[valid]).max() <= 0.5+1e-6  # the offset stays within half a pixel
+
+
+@pytest.mark.parametrize("num", [4, 36, 128, 132, 256])
+def test_uniform_range_fast_path_bit_exact(sgm, num):
+	"""One global disparity range (the non-tSGM branch): the packed, shared-memory-free aggregation
+	kernel (lane-contiguous disparities) against the oracle, with some invalid pixels."""
+	m, O = sgm
+	w, h = 150, 90
+	rng = np.random.RandomState(num)
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	px, n = synth.sgm_pixel_map(w, h, -7, -7+num, rng.rand(h-6, w-6) < 0.05)
+	costs = rng.randint(0, 256, n).astype(np.uint8)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n, costs=costs)
+	accums = torch.zeros(n, dtype=torch.int16, device="cuda")
+	gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
+	assert np.array_equal(accums.cpu().numpy().view(np.uint16), a)
+	assert np.array_equal(gd.cpu().numpy(), disp) and np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
