@@ -9,11 +9,14 @@ With N GPUs every rank estimates its own 12-view shard (weak scaling; reference 
 independent, no data-path collective) and the maps are gathered on rank 0 over NCCL inside
 the timed region.
 
-  value      device-resident throughput: images already in HBM, CUDA events on the launching
-             stream, barrier + synchronize on both sides, max over ranks.
-  e2e        the same work through the reference-facing call (b200mvs_estimate with HOST
-             buffers, pinned): per reference view the H2D copy of its 10 images + initial
-             maps and the D2H read of depth/normal/conf/views are inside the timed region.
+  value      device-resident throughput: images already in HBM, reference views alternating
+             between two contexts on two CUDA streams (joined back into the timing stream), CUDA
+             events, barrier + synchronize on both sides, max over ranks.
+  e2e        the same work through the reference-facing call with HOST buffers (pinned):
+             b200mvs_estimate_async + b200mvs_sync on two contexts used alternately, so that the
+             copies of one reference view overlap the kernels of the other; per reference view
+             the H2D copy of its 10 images + initial maps and the D2H read of
+             depth/normal/conf/views are inside the timed region.
   roofline   dominant kernel (pm_sweep_kernel, one red-black half-sweep), timed live with CUDA
              events; algorithmic bytes per launch = (20 B plane+cost read for every pixel +
              20 B written for the active half + 4(N+1) B of images) per pixel.
@@ -191,14 +194,27 @@ def main():
 		views=pin((h, w, 4), torch.uint8)) for _ in range(N_VIEWS)]
 	launches = [0]
 
+	pm2 = PatchMatchB200(local_rank)
+	pms = [pm, pm2]
+	streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+
 	def step_resident():
+		# reference views alternate between two contexts on two CUDA streams, so that the ramp-down of one
+		# view's kernels overlaps the start of the next view's (same two-context scheme as the e2e path)
+		main = torch.cuda.current_stream(dev)
+		for st in streams:
+			st.wait_stream(main)
 		for r in range(N_VIEWS):
-			m = d_maps[r]
-			m["depth"].zero_(); m["normal"].zero_()  # depth 0 => random initialisation on device
-			dd = DepthData([ViewData(d_imgs[r], cams[r])]+[ViewData(d_imgs[i], cams[i]) for i in nbrs[r]], scene.dmin, scene.dmax,
-				depthMap=m["depth"], normalMap=m["normal"], confMap=m["conf"], viewsMap=m["views"])
-			pm.EstimateDepthMap(dd, sync=False)
+			k = r & 1
+			with torch.cuda.stream(streams[k]):
+				m = d_maps[r]
+				m["depth"].zero_(); m["normal"].zero_()  # depth 0 => random initialisation on device
+				dd = DepthData([ViewData(d_imgs[r], cams[r])]+[ViewData(d_imgs[i], cams[i]) for i in nbrs[r]], scene.dmin, scene.dmax,
+					depthMap=m["depth"], normalMap=m["normal"], confMap=m["conf"], viewsMap=m["views"])
+				pms[k].EstimateDepthMap(dd, sync=False)
 			launches[0] += 1+1+ITERS*OPTDENSE.nSweepsPerIter*2+1
+		for st in streams:
+			main.wait_stream(st)
 		if world > 1:
 			# final gather of depth+normal+conf of this rank's views on rank 0 (NCCL)
 			packed = {v: torch.cat([d_maps[k]["depth"][..., None], d_maps[k]["normal"], d_maps[k]["conf"][..., None]], -1)
@@ -206,14 +222,23 @@ def main():
 			multi_gpu.gather_maps(packed, N_VIEWS*world, dst=0)
 
 	def step_e2e():
+		# two contexts used alternately (b200mvs_estimate_async / b200mvs_sync): the H2D/D2H copies of one
+		# reference view overlap the kernels of the other, like the reference's two worker threads around the seam
 		h2d = d2h = 0
+		busy = [False, False]
 		for r in range(N_VIEWS):
+			k = r & 1
+			if busy[k]:
+				pms[k].Wait(); h2d += pms[k].stats.bytes_h2d; d2h += pms[k].stats.bytes_d2h
 			m = h_maps[r]
-			m["depth"][:] = 0; m["normal"][:] = 0
+			m["depth"][:] = 0  # depth 0 => random initialisation (the normal is ignored then)
 			dd = DepthData([ViewData(h_imgs[r], cams[r])]+[ViewData(h_imgs[i], cams[i]) for i in nbrs[r]], scene.dmin, scene.dmax,
 				depthMap=m["depth"], normalMap=m["normal"], confMap=m["conf"], viewsMap=m["views"])
-			pm.EstimateDepthMap(dd)
-			h2d += pm.stats.bytes_h2d; d2h += pm.stats.bytes_d2h
+			pms[k].EstimateDepthMap(dd, sync=False)
+			busy[k] = True
+		for k in range(2):
+			if busy[k]:
+				pms[k].Wait(); h2d += pms[k].stats.bytes_h2d; d2h += pms[k].stats.bytes_d2h
 		return h2d, d2h
 
 	def timed(fn, steps, warmup):

@@ -105,6 +105,16 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
 	float dMin, float dMax, int nGeometricIter,
 	float* depth, float* normal, float* conf, uint8_t* viewsMap, b200mvs_stats* stats);
 
+/* Asynchronous form of b200mvs_estimate: enqueues the H2D copies, the kernels and the D2H copies on the
+ * context's stream and returns; host buffers (pinned for real overlap) must stay valid until
+ * b200mvs_sync(ctx, stats) returns.  Two contexts used alternately overlap the copies of one reference view
+ * with the kernels of the other — what the reference's two worker threads do around the seam
+ * (SceneDensify.cpp:1893-1899, 2036-2059). */
+int b200mvs_estimate_async(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
+	float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf, uint8_t* viewsMap);
+int b200mvs_sync(b200mvs_ctx* ctx, b200mvs_stats* stats);
+
 /* Same, but every pointer inside `views` and the map pointers are DEVICE pointers on the
  * context's device (data resident in HBM); work is enqueued on `stream` (cudaStream_t; NULL = the
  * context's own non-blocking stream, pass cudaStreamLegacy for the legacy default stream) and

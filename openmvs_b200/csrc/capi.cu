@@ -127,6 +127,9 @@ struct b200mvs_ctx {
 	std::vector<cudaEvent_t> sweepEv;         // event pairs around the sweep launches (stats only)
 	int nSweepEv = 0; bool timeSweeps = false;
 	int launches = 0;
+	// state of an enqueued b200mvs_estimate_async call
+	bool pending = false; uint64_t pendH2D = 0, pendD2H = 0; int pendLevels = 1;
+	std::chrono::steady_clock::time_point t0;
 };
 
 namespace {
@@ -489,8 +492,8 @@ int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nVi
 	return B200MVS_OK;
 }
 
-int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax, int nGeometricIter,
-	float* depth, float* normal, float* conf, uint8_t* viewsMap, b200mvs_stats* stats)
+int b200mvs_estimate_async(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf, uint8_t* viewsMap)
 {
 	int rc = check_views(ctx, views, nViews);
 	if (rc) return rc;
@@ -498,7 +501,7 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 		return fail(ctx, B200MVS_ERR_ARG, "null map pointer or invalid depth range");
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = ctx->stream;
-	const auto t0 = std::chrono::steady_clock::now();
+	ctx->t0 = std::chrono::steady_clock::now();
 	if ((int)ctx->imgs.size() < nViews) { ctx->imgs.resize(nViews); ctx->dmaps.resize(nViews); }
 	std::vector<DView> dv(nViews);
 	uint64_t h2d = 0, d2h = 0;
@@ -525,7 +528,7 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	CK(cudaMemcpyAsync(dD.p, depth, P0*sizeof(float), cudaMemcpyHostToDevice, s));
 	CK(cudaMemcpyAsync(dN.p, normal, P0*3*sizeof(float), cudaMemcpyHostToDevice, s));
 	h2d += P0*16;
-	ctx->launches = 0; ctx->nSweepEv = 0; ctx->timeSweeps = stats != nullptr;
+	ctx->launches = 0; ctx->nSweepEv = 0; ctx->timeSweeps = true;
 	CK(cudaEventRecord(ctx->ev0, s));
 	rc = estimate_on_device(ctx, dv.data(), nViews, dMin, dMax, nGeometricIter, dD.as<float>(), dN.as<float>(),
 		ctx->dConf.as<float>(), ctx->dViews.as<uint32_t>(), s);
@@ -536,20 +539,39 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	CK(cudaMemcpyAsync(conf, ctx->dConf.p, P0*sizeof(float), cudaMemcpyDeviceToHost, s));
 	d2h += P0*20;
 	if (viewsMap) { CK(cudaMemcpyAsync(viewsMap, ctx->dViews.p, P0*4, cudaMemcpyDeviceToHost, s)); d2h += P0*4; }
-	CK(cudaStreamSynchronize(s));
-	if (stats) {
-		float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-		memset(stats, 0, sizeof(*stats));
-		stats->ms_device = ms;
-		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
-		stats->bytes_h2d = h2d; stats->bytes_d2h = d2h;
-		stats->kernel_launches = ctx->launches;
-		stats->levels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
-		for (int k = 0; k < ctx->nSweepEv; ++k) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->sweepEv[2*k], ctx->sweepEv[2*k+1])); stats->ms_sweep_kernels += t; }
-		stats->sweep_launches = ctx->nSweepEv;
-		stats->tma_active = ctx->tmapValid ? 1 : 0;
-	}
+	ctx->pendH2D = h2d; ctx->pendD2H = d2h; ctx->pendLevels = (nGeometricIter < 0 ? ctx->prm.nSubResolutionLevels : 0)+1;
+	ctx->pending = true;
 	return B200MVS_OK;
+}
+
+int b200mvs_sync(b200mvs_ctx* ctx, b200mvs_stats* stats) {
+	if (!ctx) return B200MVS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		if (ctx->pending) {
+			float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+			stats->ms_device = ms;
+			stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-ctx->t0).count();
+			stats->bytes_h2d = ctx->pendH2D; stats->bytes_d2h = ctx->pendD2H;
+			stats->kernel_launches = ctx->launches;
+			stats->levels = ctx->pendLevels;
+			for (int k = 0; k < ctx->nSweepEv; ++k) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->sweepEv[2*k], ctx->sweepEv[2*k+1])); stats->ms_sweep_kernels += t; }
+			stats->sweep_launches = ctx->nSweepEv;
+			stats->tma_active = ctx->tmapValid ? 1 : 0;
+		}
+	}
+	ctx->pending = false;
+	return B200MVS_OK;
+}
+
+int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf, uint8_t* viewsMap, b200mvs_stats* stats)
+{
+	const int rc = b200mvs_estimate_async(ctx, views, nViews, dMin, dMax, nGeometricIter, depth, normal, conf, viewsMap);
+	if (rc) return rc;
+	return b200mvs_sync(ctx, stats);
 }
 
 // ---- building blocks ----------------------------------------------------------------------

@@ -237,11 +237,25 @@ class PatchMatchB200:
 			depthData.normalMap = hmap(depthData.normalMap, (h, w, 3), np.float32)
 			depthData.confMap = hmap(depthData.confMap, (h, w), np.float32)
 			depthData.viewsMap = hmap(depthData.viewsMap, (h, w, 4), np.uint8)
-			rc = self._lib.b200mvs_estimate(self._ctx, arr, len(arr), C.c_float(depthData.dMin), C.c_float(depthData.dMax),
-				int(nGeometricIter), depthData.depthMap.ctypes.data, depthData.normalMap.ctypes.data,
-				depthData.confMap.ctypes.data, depthData.viewsMap.ctypes.data, C.byref(self.stats))
-			_lib.check(self._lib, self._ctx, rc, "b200mvs_estimate")
+			if sync:
+				rc = self._lib.b200mvs_estimate(self._ctx, arr, len(arr), C.c_float(depthData.dMin), C.c_float(depthData.dMax),
+					int(nGeometricIter), depthData.depthMap.ctypes.data, depthData.normalMap.ctypes.data,
+					depthData.confMap.ctypes.data, depthData.viewsMap.ctypes.data, C.byref(self.stats))
+				_lib.check(self._lib, self._ctx, rc, "b200mvs_estimate")
+			else:
+				# asynchronous host path: the caller keeps depthData alive and calls Wait() before reading the maps
+				rc = self._lib.b200mvs_estimate_async(self._ctx, arr, len(arr), C.c_float(depthData.dMin), C.c_float(depthData.dMax),
+					int(nGeometricIter), depthData.depthMap.ctypes.data, depthData.normalMap.ctypes.data,
+					depthData.confMap.ctypes.data, depthData.viewsMap.ctypes.data)
+				_lib.check(self._lib, self._ctx, rc, "b200mvs_estimate_async")
+				self._inflight = (depthData, keep)
 		return depthData
+
+	def Wait(self):
+		"""b200mvs_sync: wait for an EstimateDepthMap(..., sync=False) on host buffers and fetch its stats."""
+		rc = self._lib.b200mvs_sync(self._ctx, C.byref(self.stats))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_sync")
+		self._inflight = None
 
 	# ---- building blocks on device tensors (used by the parity tests) -----------------------
 	def _dev_views(self, images):

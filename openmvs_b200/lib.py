@@ -44,7 +44,7 @@ class SgmParams(C.Structure):
 # every symbol include/b200mvs.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
 	"b200mvs_create", "b200mvs_destroy", "b200mvs_default_params", "b200mvs_set_params", "b200mvs_last_error",
-	"b200mvs_device_count", "b200mvs_estimate", "b200mvs_estimate_device",
+	"b200mvs_device_count", "b200mvs_estimate", "b200mvs_estimate_device", "b200mvs_estimate_async", "b200mvs_sync",
 	"b200mvs_pm_pack", "b200mvs_pm_unpack", "b200mvs_pm_score", "b200mvs_pm_sweep", "b200mvs_pm_finalize",
 	"b200mvs_sgm_default_params", "b200mvs_sgm_match", "b200mvs_sgm_match_device",
 	"b200mvs_sgm_cross_check_device", "b200mvs_sgm_refine_device",
@@ -77,6 +77,8 @@ def load(build_if_missing: bool = True):
 	F = C.c_float
 	P = C.c_void_p
 	lib.b200mvs_estimate.argtypes = [P, C.POINTER(View), C.c_int, F, F, C.c_int, P, P, P, P, C.POINTER(Stats)]
+	lib.b200mvs_estimate_async.argtypes = [P, C.POINTER(View), C.c_int, F, F, C.c_int, P, P, P, P]
+	lib.b200mvs_sync.argtypes = [P, C.POINTER(Stats)]
 	lib.b200mvs_estimate_device.argtypes = [P, C.POINTER(View), C.c_int, F, F, C.c_int, P, P, P, P, P, C.POINTER(Stats)]
 	lib.b200mvs_pm_pack.argtypes = [P, C.c_int, C.c_int, P, P, P, P]
 	lib.b200mvs_pm_unpack.argtypes = [P, C.c_int, C.c_int, P, P, P, P]

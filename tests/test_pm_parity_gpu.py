@@ -211,6 +211,12 @@ def test_host_api_equals_device_api_and_is_deterministic(env, small_scene):
 	hd2 = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
 	e.pm.EstimateDepthMap(hd2)
 	assert np.array_equal(hd.depthMap, hd2.depthMap) and np.array_equal(hd.confMap, hd2.confMap)
+	# asynchronous host path (b200mvs_estimate_async + b200mvs_sync) gives the same maps and stats
+	hd3 = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(hd3, sync=False)
+	e.pm.Wait()
+	assert np.array_equal(hd.depthMap, hd3.depthMap) and np.array_equal(hd.normalMap, hd3.normalMap) and np.array_equal(hd.viewsMap, hd3.viewsMap)
+	assert e.pm.stats.sweep_launches == 2*2*2 and e.pm.stats.bytes_d2h == views[0].image.size*24
 
 
 def test_initial_estimate_is_used_and_single_neighbour_min_branch(env, small_scene):
