@@ -115,6 +115,21 @@ int b200mvs_estimate_async(b200mvs_ctx* ctx, const b200mvs_view* views, int nVie
 	float* depth, float* normal, float* conf, uint8_t* viewsMap);
 int b200mvs_sync(b200mvs_ctx* ctx, b200mvs_stats* stats);
 
+/* One reference-view job of a batch: the arguments of b200mvs_estimate */
+typedef struct {
+	const b200mvs_view* views; int nViews;
+	float dMin, dMax; int nGeometricIter;
+	float* depth; float* normal; float* conf; uint8_t* viewsMap;
+	int status;            /* out: status code of this job */
+} b200mvs_job;
+
+/* Batch form for per-reference-view parallelism inside ONE process: jobs are dealt round-robin over the
+ * given contexts (one per GPU of the box, or two on one GPU for copy/compute overlap) through
+ * b200mvs_estimate_async, each context is drained with b200mvs_sync before it is reused.  Reference views
+ * are independent (SceneDensify.cpp:2036-2059 estimates them one by one), so there is no data-path
+ * collective.  Returns the first non-zero job status (all jobs are attempted). */
+int b200mvs_estimate_batch(b200mvs_ctx** ctxs, int nCtx, b200mvs_job* jobs, int nJobs);
+
 /* Same, but every pointer inside `views` and the map pointers are DEVICE pointers on the
  * context's device (data resident in HBM); work is enqueued on `stream` (cudaStream_t; NULL = the
  * context's own non-blocking stream, pass cudaStreamLegacy for the legacy default stream) and

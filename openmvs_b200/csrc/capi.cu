@@ -574,6 +574,30 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	return b200mvs_sync(ctx, stats);
 }
 
+int b200mvs_estimate_batch(b200mvs_ctx** ctxs, int nCtx, b200mvs_job* jobs, int nJobs) {
+	if (!ctxs || nCtx <= 0 || (!jobs && nJobs > 0) || nJobs < 0) return B200MVS_ERR_ARG;
+	for (int k = 0; k < nCtx; ++k) if (!ctxs[k]) return B200MVS_ERR_ARG;
+	int first = B200MVS_OK;
+	std::vector<int> inflight(nCtx, -1); // job running on each context
+	auto drain = [&](int k) {
+		if (inflight[k] < 0) return;
+		const int rc = b200mvs_sync(ctxs[k], nullptr);
+		if (rc && !jobs[inflight[k]].status) jobs[inflight[k]].status = rc;
+		if (jobs[inflight[k]].status && !first) first = jobs[inflight[k]].status;
+		inflight[k] = -1;
+	};
+	for (int j = 0; j < nJobs; ++j) {
+		const int k = j % nCtx;
+		drain(k);
+		b200mvs_job& J = jobs[j];
+		J.status = b200mvs_estimate_async(ctxs[k], J.views, J.nViews, J.dMin, J.dMax, J.nGeometricIter, J.depth, J.normal, J.conf, J.viewsMap);
+		if (J.status) { if (!first) first = J.status; continue; }
+		inflight[k] = j;
+	}
+	for (int k = 0; k < nCtx; ++k) drain(k);
+	return first;
+}
+
 // ---- building blocks ----------------------------------------------------------------------
 int b200mvs_pm_pack(b200mvs_ctx* ctx, int width, int height, const float* depth, const float* normal, float* plane4, void* stream) {
 	if (!ctx || !depth || !normal || !plane4) return B200MVS_ERR_ARG;

@@ -289,6 +289,34 @@ class PatchMatchB200:
 		_lib.check(self._lib, self._ctx, rc, "b200mvs_pm_sweep")
 
 
+def EstimateDepthMapsBatch(arrDepthData: List[DepthData], engines: List["PatchMatchB200"], nGeometricIter: int = -1):
+	"""b200mvs_estimate_batch: estimate every DepthData (host buffers) with the given engines — one per GPU of
+	the box, or two on one GPU — dealt round-robin inside this process."""
+	lib = engines[0]._lib
+	for e in engines:
+		e._set_params()
+	jobs = (_lib.Job*len(arrDepthData))()
+	keep = []
+	for j, dd in enumerate(arrDepthData):
+		arr, k, dev = _make_views(dd.images)
+		if dev:
+			raise ValueError("the batch call takes host buffers")
+		h, w = dd.images[0].image.shape
+		dd.depthMap = np.zeros((h, w), np.float32) if dd.depthMap is None else np.ascontiguousarray(dd.depthMap, np.float32)
+		dd.normalMap = np.zeros((h, w, 3), np.float32) if dd.normalMap is None else np.ascontiguousarray(dd.normalMap, np.float32)
+		dd.confMap = np.zeros((h, w), np.float32); dd.viewsMap = np.zeros((h, w, 4), np.uint8)
+		keep.append((arr, k))
+		J = jobs[j]
+		J.views = arr; J.nViews = len(arr); J.dMin = dd.dMin; J.dMax = dd.dMax; J.nGeometricIter = int(nGeometricIter)
+		J.depth = dd.depthMap.ctypes.data; J.normal = dd.normalMap.ctypes.data; J.conf = dd.confMap.ctypes.data; J.viewsMap = dd.viewsMap.ctypes.data
+	ctxs = (C.c_void_p*len(engines))(*[e._ctx for e in engines])
+	rc = lib.b200mvs_estimate_batch(ctxs, len(engines), jobs, len(arrDepthData))
+	if rc != 0:
+		bad = [j for j in range(len(arrDepthData)) if jobs[j].status]
+		raise _lib.B200MVSError("b200mvs_estimate_batch: jobs %s failed with status %d" % (bad, rc))
+	return arrDepthData
+
+
 class DepthMapsData:
 	"""The slice of the reference's DepthMapsData that owns the hot path
 	(libs/MVS/SceneDensify.h:52-93): arrDepthData + EstimateDepthMap(idxImage, nGeometricIter)."""

@@ -383,3 +383,22 @@ def test_high_resolution_geometric_pass_properties(env):
 	assert m.mean() > 0.9 and (rel < 1e-3).mean() > 0.9 and np.median(rel) < 3e-4
 	assert not m[:4].any() and not m[-4:].any() and gc[m].min() > 0 and gc.max() <= 1
 	_set(e, nEstimationGeometricIters=0)
+
+
+def test_batch_call_over_two_contexts_equals_single_calls(env, small_scene):
+	"""b200mvs_estimate_batch deals reference views over contexts (here two on one GPU); every job
+	must equal the synchronous single call."""
+	e = env
+	from openmvs_b200.depth_estimator import EstimateDepthMapsBatch, PatchMatchB200
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=1, nSweepsPerIter=2, nRandomIters=6)
+	orders = [[0, 1, 2, 3, 4], [1, 0, 2, 3], [2, 1, 3], [3, 2, 4, 0], [4, 3, 2]]
+	jobs = [e.DepthData(_host_views(e, [views[i] for i in o]), sc.dmin, sc.dmax) for o in orders]
+	singles = [e.DepthData(_host_views(e, [views[i] for i in o]), sc.dmin, sc.dmax) for o in orders]
+	for s in singles:
+		e.pm.EstimateDepthMap(s)
+	pm2 = PatchMatchB200(0)
+	EstimateDepthMapsBatch(jobs, [e.pm, pm2])
+	pm2.Release()
+	for a, b in zip(jobs, singles):
+		assert np.array_equal(a.depthMap, b.depthMap) and np.array_equal(a.confMap, b.confMap) and np.array_equal(a.viewsMap, b.viewsMap)
