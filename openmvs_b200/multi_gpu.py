@@ -93,3 +93,57 @@ def estimate_scene(n_views: int, estimate_view: Callable[[int], torch.Tensor], d
 	if not gather:
 		return local
 	return gather_maps(local, n_views, dst)
+
+
+def compute_depth_maps(n_views: int, estimate: Callable, n_geometric_iters: int = 0, dst: int = 0, gather: bool = True):
+	"""The estimation part of Scene::ComputeDepthMaps (libs/MVS/SceneDensify.cpp:1754-1953) over the ranks:
+
+	  pass 1            every rank estimates its reference views photometrically (nGeometricIter = -1)
+	  geometric pass g  one exchange step — all-gather of the depth-maps of the previous pass, because a
+	                    reference view needs its neighbours' depth-maps (the reference reloads their .dmap
+	                    files, SceneDensify.cpp:380-394) — then every rank re-estimates its views with
+	                    nGeometricIter = g, initialised from its own previous result
+
+	estimate(view, nGeometricIter, previous, depths) -> dict(depth=(H,W), normal=(H,W,3), conf=(H,W)) of tensors;
+	`previous` is this view's result of the pass before (None in pass 1), `depths` the gathered
+	{view: depth} of all views (None in pass 1).  Returns {view: (H,W,5) depth|normal|conf} on `dst`."""
+	rank = dist.get_rank() if dist.is_initialized() else 0
+	world = dist.get_world_size() if dist.is_initialized() else 1
+	mine = shard_views(n_views, rank, world)
+	local = {v: estimate(v, -1, None, None) for v in mine}
+	for g in range(n_geometric_iters):
+		depths = all_gather_depth({v: local[v]["depth"] for v in mine}, n_views) if mine or world > 1 else {}
+		local = {v: estimate(v, g, local[v], depths) for v in mine}
+	packed = {v: torch.cat([m["depth"][..., None], m["normal"], m["conf"][..., None]], -1) for v, m in local.items()}
+	if not gather:
+		return packed
+	return gather_maps(packed, n_views, dst)
+
+
+class SceneEstimator:
+	"""estimate() callable for compute_depth_maps on one GPU: images resident in HBM, one PatchMatchB200.
+	views: list of objects with .image (numpy HxW float32) .K .R .C; neighbors: list of index lists."""
+
+	def __init__(self, views, neighbors, dmin: float, dmax: float, device=None):
+		from .depth_estimator import Camera, PatchMatchB200
+		self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+		self.pm = PatchMatchB200(self.dev.index or 0)
+		self.cams = [Camera(v.K, v.R, v.C) for v in views]
+		self.imgs = [torch.from_numpy(v.image).to(self.dev) for v in views]
+		self.neighbors = neighbors
+		self.dmin, self.dmax = dmin, dmax
+
+	def __call__(self, v: int, nGeometricIter: int, previous, depths):
+		from .depth_estimator import DepthData, ViewData
+		images = [ViewData(self.imgs[v], self.cams[v])]
+		for i in self.neighbors[v]:
+			vd = ViewData(self.imgs[i], self.cams[i])
+			if depths is not None:
+				vd.depthMap = depths[i].to(self.dev).contiguous(); vd.cameraDepthMap = self.cams[i]
+			images.append(vd)
+		dd = DepthData(images, self.dmin, self.dmax)
+		if previous is not None:
+			dd.depthMap = previous["depth"].clone(); dd.normalMap = previous["normal"].clone()
+		self.pm.Init(nGeometricIter >= 0)
+		self.pm.EstimateDepthMap(dd, nGeometricIter)
+		return dict(depth=dd.depthMap, normal=dd.normalMap, conf=dd.confMap)

@@ -59,3 +59,16 @@ def test_sources_do_not_reference_the_oracle():
 			if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
 				txt = open(os.path.join(dp, f)).read()
 				assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_null_context_and_bad_arguments_return_status_codes():
+	"""Error behaviour at the boundary: status codes, never a crash or exit()."""
+	from openmvs_b200 import lib
+	dll = lib.load()
+	assert dll.b200mvs_set_params(None, None) == 1
+	assert dll.b200mvs_destroy(None) == 1
+	assert dll.b200mvs_estimate(None, None, 0, C.c_float(1), C.c_float(2), -1, None, None, None, None, None) == 1
+	assert dll.b200mvs_sync(None, None) == 1
+	assert dll.b200mvs_estimate_batch(None, 0, None, 0) == 1
+	assert dll.b200mvs_sgm_match(None, None, None, None, 0, 0, None, C.c_uint64(0), None, None, None, None) == 1
+	assert dll.b200mvs_last_error(None) == b"null context"

@@ -31,6 +31,19 @@ def _worker(rank, world, port, n_views, q):
 		local = {v: torch.full((6, 8), float(v)) for v in multi_gpu.shard_views(n_views, rank, world)}
 		allv = multi_gpu.all_gather_depth(local, n_views)
 		ok = ok and sorted(allv.keys()) == list(range(n_views)) and all(float(allv[v][0, 0]) == v for v in range(n_views))
+		# pass 1 + two geometric passes: every geometric pass must see ALL views' depth-maps of the pass before
+		seen = []
+		def est(v, g, previous, depths):
+			if g >= 0:
+				seen.append((v, g, previous is not None, sorted(depths.keys()) == list(range(n_views)),
+					all(float(depths[u][0, 0]) == 100*(g)+u for u in range(n_views))))
+			val = 100.0*(g+1)+v
+			return dict(depth=torch.full((6, 8), val), normal=torch.zeros(6, 8, 3), conf=torch.ones(6, 8))
+		res = multi_gpu.compute_depth_maps(n_views, est, n_geometric_iters=2, dst=0)
+		mine = multi_gpu.shard_views(n_views, rank, world)
+		ok = ok and len(seen) == 2*len(mine) and all(s[2] and s[3] and s[4] for s in seen)
+		if rank == 0:
+			ok = ok and all(float(res[v][0, 0, 0]) == 200.0+v for v in range(n_views))
 		q.put((rank, bool(ok)))
 	finally:
 		dist.destroy_process_group()
