@@ -405,3 +405,27 @@ class SemiGlobalMatcher:
 			disparityMap.data_ptr(), disparityMap.numel(), int(subpixelSteps), C.c_void_p(_stream_handle(disparityMap.device)))
 		_lib.check(self._lib, self._ctx, rc, "b200mvs_sgm_refine_device")
 		return disparityMap
+
+	def MatchPairDevice(self, leftGray, leftColor, rightGray, rightColor, minDisp: int, maxDisp: int, thCross: int = 1, subpixelSteps: int = 4):
+		"""The per-level body of SemiGlobalMatcher::Match(scene, ...) for one global range (non-tSGM branch,
+		libs/MVS/SemiGlobalMatcher.cpp:643-725) on CUDA tensors: right->left match with the range [minDisp, maxDisp),
+		left->right match with the mirrored range, cross-check of the left map, sub-pixel refinement.
+		Returns (leftDisparity * subpixelSteps, rightDisparity) as int16 tensors (NO_DISP = 32767)."""
+		import torch
+		h, w = leftGray.shape
+		nv = (w-6)*(h-6)
+		num = int(maxDisp-minDisp)
+		def pixel_map(lo, hi):
+			px = np.zeros(nv, dtype=np.dtype([("idx", "<u8"), ("dmin", "<i2"), ("dmax", "<i2"), ("reserved", "<i4")]))
+			px["idx"] = np.arange(nv, dtype=np.uint64)*np.uint64(num); px["dmin"] = lo; px["dmax"] = hi
+			return torch.from_numpy(px.view(np.uint8).reshape(-1, 16).copy()).to(leftGray.device)
+		# Match(rightDataLevel, leftDataLevel): the right image plays "left" with range [minDisp, maxDisp)
+		pxr = pixel_map(minDisp, maxDisp)
+		rdisp, _ = self.MatchDevice(rightGray, rightColor, leftGray, pxr, nv*num)
+		# ranges are mirrored for the left->right match (SemiGlobalMatcher.cpp:677-682)
+		pxl = pixel_map(-maxDisp, -minDisp)
+		ldisp, _ = self.MatchDevice(leftGray, leftColor, rightGray, pxl, nv*num)
+		self.ConsistencyCrossCheck(ldisp, rdisp, thCross)
+		self.RefineDisparityMap(ldisp, pxl, None, subpixelSteps)  # accumulated costs of the last (left) match
+		torch.cuda.current_stream(leftGray.device).synchronize()
+		return ldisp, rdisp

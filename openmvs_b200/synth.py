@@ -128,7 +128,7 @@ def make_scene(width: int, height: int, n_views: int, seed: int = 1234, radius: 
 	return Scene(views, dmin=float(radius-1.5), dmax=float(radius+1.5))
 
 
-def make_stereo_pair(width: int, height: int, seed: int = 7, d0: float = 12.0, amp: float = 6.0):
+def make_stereo_pair(width: int, height: int, seed: int = 7, d0: float = 12.0, amp: float = 6.0, right_color: bool = False):
 	"""Rectified synthetic pair for the SGM path: left(x, y) = right(x + d(x, y), y) with a smooth
 	analytic disparity d = d0 + amp*sin(.)cos(.) (the reference's convention: the cost of
 	disparity d compares left x with right x+d, libs/MVS/SemiGlobalMatcher.cpp:960).
@@ -140,7 +140,11 @@ def make_stereo_pair(width: int, height: int, seed: int = 7, d0: float = 12.0, a
 	left = tex(xs+d, ys)
 	right = tex(xs, ys)
 	bgr = np.stack([np.clip(0.8*left+0.2*t(xs+d, ys), 0, 1) for t in tex_c], -1)
-	return left.astype(np.float32), np.rint(bgr*255).astype(np.uint8), right.astype(np.float32), d.astype(np.float32)
+	out = (left.astype(np.float32), np.rint(bgr*255).astype(np.uint8), right.astype(np.float32), d.astype(np.float32))
+	if right_color:  # + right BGR uint8
+		bgr_r = np.stack([np.clip(0.8*right+0.2*t(xs, ys), 0, 1) for t in tex_c], -1)
+		out = out+(np.rint(bgr_r*255).astype(np.uint8),)
+	return out
 
 
 def sgm_pixel_map(width: int, height: int, dmin, dmax, invalid=None):

@@ -148,3 +148,26 @@ def test_uniform_range_fast_path_bit_exact(sgm, num):
 	gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
 	assert np.array_equal(accums.cpu().numpy().view(np.uint16), a)
 	assert np.array_equal(gd.cpu().numpy(), disp) and np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
+
+
+def test_pair_pipeline_matches_oracle_and_ground_truth(sgm):
+	"""Right->left match, left->right match with mirrored ranges, cross-check, quarter-pixel refinement
+	(the non-tSGM level body, SemiGlobalMatcher.cpp:643-725) against the same chain of oracle calls."""
+	m, O = sgm
+	w, h = 240, 136
+	lg, lc, rg, d, rc = synth.make_stereo_pair(w, h, right_color=True)
+	# left(x) = right(x + d): the left->right disparity is +d, the right->left one about -d
+	ld, rd = m.MatchPairDevice(_dev(lg), _dev(lc), _dev(rg), _dev(rc), -32, 0)
+	ld, rd = ld.cpu().numpy(), rd.cpu().numpy()
+	pxr, n = synth.sgm_pixel_map(w, h, -32, 0)
+	cr, ar, odr, _ = O.sgm_match(rg, rc, lg, pxr, n)
+	pxl, n = synth.sgm_pixel_map(w, h, 0, 32)
+	cl, al, odl, _ = O.sgm_match(lg, lc, rg, pxl, n)
+	want = O.sgm_refine(pxl, al, O.sgm_cross_check(odl, odr, 1), 4)
+	assert (rd != odr).mean() < 0.01
+	both = (ld != 32767) & (want != 32767)
+	assert ((ld != 32767) != (want != 32767)).mean() < 0.02
+	assert (np.abs(ld.astype(np.int32)-want.astype(np.int32))[both] > 1).mean() < 0.02
+	gt = d[3:-3, 3:-3]
+	err = np.abs(ld[both]/4.0-gt[both])
+	assert both.mean() > 0.75 and np.median(err) < 0.2 and (err < 0.5).mean() > 0.9
