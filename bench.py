@@ -301,6 +301,15 @@ def main():
 		"launch_ms": k_ms, "launches_timed": int(pm.stats.sweep_launches), "share_of_step": sweep_share, "algorithmic_bytes_per_launch": bytes_launch,
 		"secondary": {"bound": "issue/L1 (gather stencil, AI ~ 280 flop/B)", "bilinear_samples_per_launch": samples_launch,
 			"gsamples_per_s": samples_launch/(k_ms*1e-3)/1e9}}
+	# the honest bound of this kernel is the L1 LSU data pipe: quote its utilisation from the committed ncu capture
+	try:
+		for line in open(os.path.join(ROOT, "profiles", "ncu_pm_sweep_r01.txt")):
+			if line.startswith("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"):
+				roof["secondary"]["l1_lsu_data_pipe_pct_of_peak_ncu"] = float(line.split()[1])
+			if line.startswith("smsp__issue_active.avg.pct_of_peak_sustained_active"):
+				roof["secondary"]["issue_slots_busy_pct_ncu"] = float(line.split()[1])
+	except Exception:
+		pass
 	traffic_file = os.path.join(ROOT, "profiles", "sweep_traffic.json")
 	if os.path.exists(traffic_file):
 		try:

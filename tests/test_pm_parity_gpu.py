@@ -425,3 +425,32 @@ def test_scene_pipeline_with_geometric_passes(env, small_scene):
 		# the geometric passes keep the surface and only drop pixels (keep threshold 0.9 instead of 1.2)
 		assert m2.mean() > 0.8 and m2.mean() <= m1.mean()+1e-6 and acc2 >= acc1-0.01 and acc2 > 0.95
 	_set(e, nEstimationGeometricIters=0)
+
+
+def test_strided_images_host_and_device(env, small_scene):
+	"""cv::Mat ROIs: rows with a pitch larger than the width, on the host path (cudaMemcpy2D) and on the
+	device path (kernel pitch + re-pitched TMA source when the pitch is not 16-byte aligned)."""
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=1, nSweepsPerIter=2, nRandomIters=6)
+	base = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(base)
+	h, w = views[0].image.shape
+	# host: every image embedded in a wider buffer (pitch = (w+7)*4 bytes, not a multiple of 16)
+	wide = [np.zeros((h, w+7), np.float32) for _ in views]
+	strided = []
+	for buf, v in zip(wide, views):
+		buf[:, :w] = v.image
+		strided.append(e.ViewData(buf[:, :w], e.Camera(v.K, v.R, v.C)))
+	assert strided[0].image.strides[0] == (w+7)*4
+	hd = e.DepthData(strided, sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(hd)
+	assert np.array_equal(hd.depthMap, base.depthMap) and np.array_equal(hd.confMap, base.confMap)
+	# device: the same with torch tensors sliced out of wider allocations
+	dwide = [torch.from_numpy(b).to(e.dev) for b in wide]
+	dviews = [e.ViewData(b[:, :w], e.Camera(v.K, v.R, v.C)) for b, v in zip(dwide, views)]
+	assert dviews[0].image.stride(0) == w+7
+	dd = e.DepthData(dviews, sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd)
+	assert e.pm.stats.tma_active == 1
+	assert np.array_equal(dd.depthMap.cpu().numpy(), base.depthMap) and np.array_equal(dd.confMap.cpu().numpy(), base.confMap)
