@@ -311,6 +311,11 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 		CK(ctx->prior.reserve(P0*sizeof(float)));
 		CK(ctx->lowPlane.reserve((size_t)(W/2+2)*(H/2+2)*sizeof(float4)));
 		if ((int)ctx->pyr.size() < nViews) ctx->pyr.resize(nViews);
+		// level 1 is the largest pyramid level: size the buffers once, so that no level re-allocates mid-stream
+		for (int i = 0; i < nViews; ++i) {
+			const size_t dw = (size_t)cvRoundI(views[i].w*0.5), dh = (size_t)cvRoundI(views[i].h*0.5);
+			CK(ctx->pyr[i].reserve(dw*dh*sizeof(float)*(views[i].dmap ? 2 : 1)));
+		}
 	}
 	float4* plane = ctx->plane.as<float4>();
 	float* cost = ctx->cost.as<float>();
@@ -430,6 +435,7 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 int b200mvs_destroy(b200mvs_ctx* c) {
 	if (!c) return B200MVS_ERR_ARG;
 	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream); // an enqueued asynchronous call may still use the buffers
 	for (auto& b: c->imgs) b.release();
 	for (auto& b: c->dmaps) b.release();
 	for (auto& b: c->pyr) b.release();

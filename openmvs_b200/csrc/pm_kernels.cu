@@ -680,19 +680,22 @@ cudaError_t launch_one(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const 
 	const size_t wbytes = WS ? (size_t)PM_TEXELS*NTHREADS*sizeof(float2) : 0;
 	if (sweep) {
 		const size_t smem = wbytes + TILE_BYTES + 16;
-		static bool done = false;
-		if (!done) {
+		// the attribute is per device: one flag per device of the process (several contexts / GPUs)
+		static bool done[64] = {};
+		int dev = 0; cudaGetDevice(&dev); dev &= 63;
+		if (!done[dev]) {
 			cudaError_t e = cudaFuncSetAttribute(pm_sweep_kernel<LAYOUT, GEOM, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) return e;
-			done = true;
+			done[dev] = true;
 		}
 		pm_sweep_kernel<LAYOUT, GEOM, WS><<<grid, block, smem, s>>>(P, tmap);
 	} else {
-		static bool done = false;
-		if (WS && !done) {
+		static bool done[64] = {};
+		int dev = 0; cudaGetDevice(&dev); dev &= 63;
+		if (WS && !done[dev]) {
 			cudaError_t e = cudaFuncSetAttribute(pm_score_kernel<LAYOUT, GEOM, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
 			if (e != cudaSuccess) return e;
-			done = true;
+			done[dev] = true;
 		}
 		pm_score_kernel<LAYOUT, GEOM, WS><<<grid, block, wbytes, s>>>(P);
 	}

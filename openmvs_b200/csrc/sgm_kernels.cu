@@ -529,11 +529,12 @@ cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, 
 }
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s) {
 	const size_t smem = (size_t)NT*COST_THREADS*sizeof(float2);
-	static bool done = false;
-	if (!done) {
+	static bool done[64] = {}; // per device
+	int dev = 0; cudaGetDevice(&dev); dev &= 63;
+	if (!done[dev]) {
 		cudaError_t e = cudaFuncSetAttribute(sgm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
-		done = true;
+		done[dev] = true;
 	}
 	dim3 grid((P.vw+COST_THREADS-1)/COST_THREADS, P.vh);
 	sgm_cost_kernel<<<grid, COST_THREADS, smem, s>>>(P);

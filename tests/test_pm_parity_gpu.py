@@ -454,3 +454,23 @@ def test_strided_images_host_and_device(env, small_scene):
 	e.pm.EstimateDepthMap(dd)
 	assert e.pm.stats.tma_active == 1
 	assert np.array_equal(dd.depthMap.cpu().numpy(), base.depthMap) and np.array_equal(dd.confMap.cpu().numpy(), base.confMap)
+
+
+def test_batch_call_over_two_gpus_in_one_process(env, small_scene):
+	"""b200mvs_estimate_batch with one context per GPU (needs 2 devices; skipped on a 1-GPU box)."""
+	e = env
+	if torch.cuda.device_count() < 2:
+		pytest.skip("needs 2 GPUs")
+	from openmvs_b200.depth_estimator import EstimateDepthMapsBatch, PatchMatchB200
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=1, nSweepsPerIter=2, nRandomIters=6)
+	orders = [[0, 1, 2, 3, 4], [1, 0, 2, 3], [2, 1, 3], [3, 2, 4, 0]]
+	jobs = [e.DepthData(_host_views(e, [views[i] for i in o]), sc.dmin, sc.dmax) for o in orders]
+	singles = [e.DepthData(_host_views(e, [views[i] for i in o]), sc.dmin, sc.dmax) for o in orders]
+	for s in singles:
+		e.pm.EstimateDepthMap(s)
+	pm1 = PatchMatchB200(1)
+	EstimateDepthMapsBatch(jobs, [e.pm, pm1])
+	pm1.Release()
+	for a, b in zip(jobs, singles):
+		assert np.array_equal(a.depthMap, b.depthMap) and np.array_equal(a.confMap, b.confMap)
