@@ -191,7 +191,13 @@ __device__ __forceinline__ float fetch_bilinear(const void* __restrict__ tex, in
 	asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"((unsigned)(4*LAYOUT)), "l"((unsigned long long)tex));
 	if (LAYOUT == 1) {
 		const float* r0 = (const float*)addr;
-		v00 = __ldg(r0); v10 = __ldg(r0+1); v01 = __ldg(r0+pitch); v11 = __ldg(r0+pitch+1);
+		// L1 evict-last: the warped footprints of successive hypotheses and of the CTA's other rows overlap,
+		// keeping them in L1 against the streaming plane/cost traffic is worth 2.5 % (2.73 -> 2.66 ms)
+		const float* r1 = r0+pitch;
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v00) : "l"(r0));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v10) : "l"(r0));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v01) : "l"(r1));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v11) : "l"(r1));
 	} else {
 		const float2* r0 = (const float2*)addr;
 		const float2 a = __ldg(r0), b = __ldg(r0+1);
