@@ -136,7 +136,10 @@ def main():
 	rank = int(os.environ.get("RANK", "0"))
 	world = int(os.environ.get("WORLD_SIZE", "1"))
 	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-	threads = os.cpu_count() or 1
+	try:
+		threads = len(os.sched_getaffinity(0)) or 1
+	except Exception:
+		threads = os.cpu_count() or 1
 
 	if args.impl == "reference":
 		# the reference's own CPU implementation of the path: the oracle port (the reference cannot
