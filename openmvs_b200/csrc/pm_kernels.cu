@@ -9,9 +9,11 @@
 // Schedule: red-black.  One thread owns one pixel of the active colour; a warp owns 32
 // same-colour pixels of one image row (64-pixel span), so the homography-warped taps of
 // the 32 lanes fall on 2-3 cache lines of two neighbour-image rows.  The bilateral
-// weights of the 5x5 reference patch live in registers for the whole sweep (computed once
-// per pixel from a TMA-staged reference tile) and are reused by every hypothesis x view.
+// weights of the 5x5 reference patch are computed once per pixel and sweep from a reference
+// tile that TMA stages into shared memory, kept in shared memory as float2{w, tw}[tap][thread]
+// (80 registers per thread, 24 warps per SM) and reused by every hypothesis x view.
 // All four 4-neighbours belong to the other colour, so in-place updates are race-free.
+// Measured design history and the variants that were dropped: DESIGN.md section 5.1.
 #include "pm_common.cuh"
 #include <math_constants.h>
 #include <cstring>
@@ -42,7 +44,6 @@ template <> struct PatchT<true> {
 	__device__ __forceinline__ float2 get(int k) const { return s[k*NTHREADS]; }
 };
 
-// FillPixelPatch + GetWeight (DepthMap.cpp:422-462, DepthMap.h:403-412)
 // ---- TMA staging of the reference tile ---------------------------------------------------------
 // A CTA of the sweep kernel covers 64 x 8 pixels; their 9x9 patches need a (64+8) x (8+8) float tile
 // of the reference image.  One elected thread issues a cp.async.bulk.tensor.2d (TMA) into shared
@@ -110,6 +111,8 @@ __device__ __forceinline__ void fill_patch_tile(const float* __restrict__ tile, 
 	p.normSq0 = nsq;
 }
 
+// FillPixelPatch + GetWeight (DepthMap.cpp:422-462, DepthMap.h:403-412) from global memory (pass A, and
+// the sweep when no TMA descriptor is available)
 template <bool WS>
 __device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pitch, int x, int y, PatchT<WS>& p) {
 	const float sigmaColor = -1.f/(2.f*0.1f*0.1f);
