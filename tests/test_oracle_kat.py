@@ -222,3 +222,120 @@ def test_rb_is_deterministic_and_thread_independent(tiny_scene):
 	b = O.pm_estimate(views, O.default_params(threads=4, **base), sc.dmin, sc.dmax)
 	for x, y in zip(a, b):
 		assert np.array_equal(x, y)
+
+
+def _patch_stats(img, x, y):
+	"""FillPixelPatch in numpy (DepthMap.cpp:422-462): weights, weighted mean, normSq0"""
+	taps = [(i, j) for i in range(-4, 5, 2) for j in range(-4, 5, 2)]
+	I = np.array([img[y+i, x+j] for i, j in taps], np.float64)
+	w = np.exp(-(I-img[y, x])**2/(2*0.1**2)-np.array([i*i+j*j for i, j in taps])/(2*3.0**2))
+	tm = (I*w).sum()/w.sum()
+	return w, I, tm, float((w*(I-tm)**2).sum())
+
+
+def test_low_resolution_prior_blend_known_answer(small_scene):
+	"""score' = (1-f) score + f min(|d0-d|/d0, 0.5) with f = exp(-normSq0/0.02) (DepthMap.cpp:552-561);
+	normSq0 is recomputed here in numpy, which also pins FillPixelPatch."""
+	sc, ref, views = small_scene
+	prm = O.default_params(nSubResolutionLevels=0)
+	gt_d, gt_n = sc.views[ref].depth_gt, sc.views[ref].normal_gt
+	h, w = gt_d.shape
+	rng = np.random.RandomState(9)
+	checked = 0
+	for _ in range(12):
+		x, y = int(rng.randint(30, 290)), int(rng.randint(30, 210))
+		_, _, _, nsq = _patch_stats(views[0].image.astype(np.float64), x, y)
+		f = np.exp(-nsq/0.02)
+		d = float(gt_d[y, x])*1.002
+		s0, v0 = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d, gt_n[y, x])
+		for d0 in (d, d*1.25, d*3.0):
+			prior = np.zeros((h, w), np.float32); prior[y, x] = d0
+			s1, v1 = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d, gt_n[y, x], lowres=prior)
+			want = (1-f)*v0 + f*min(abs(d0-d)/d0, 0.5)
+			assert np.allclose(v1, np.minimum(want, 2.0), atol=2e-5)
+			checked += 1
+	assert checked == 36
+
+
+def test_geometric_consistency_term_known_answers(small_scene):
+	"""score += 0.1 min(sqrt(dist (dist+2)), 4) (DepthMap.cpp:535-551): consistent neighbour depth-maps add
+	almost nothing, depth-maps without a similar depth add the full 0.1*4, a shifted hypothesis adds the
+	analytic reprojection distance."""
+	sc, ref, views = small_scene
+	prm = O.default_params(nSubResolutionLevels=0, nEstimationGeometricIters=2)
+	gt_d, gt_n = sc.views[ref].depth_gt, sc.views[ref].normal_gt
+	good = [None]+[(v.depth_gt, v.K, v.R, v.C) for v in views[1:]]
+	empty = [None]+[(np.zeros_like(v.depth_gt), v.K, v.R, v.C) for v in views[1:]]
+	rng = np.random.RandomState(4)
+	for _ in range(10):
+		x, y = int(rng.randint(40, 280)), int(rng.randint(40, 200))
+		d, n = float(gt_d[y, x]), gt_n[y, x]
+		s0, v0 = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d, n)
+		s1, v1 = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d, n, depths=good)
+		s2, v2 = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d, n, depths=empty)
+		assert np.all(v1-v0 >= -1e-6) and np.all(v1-v0 < 0.02)       # consistent: distance ~ 0
+		assert np.allclose(v2-v0, 0.4, atol=1e-5)                     # no similar depth: consistency = 4
+		# hypothesis 2 % in front of the surface: the neighbour's surface point re-projects off the pixel
+		d2 = d*0.98
+		sb, vb = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d2, n)
+		sg, vg = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d2, n, depths=good)
+		K0, R0, C0 = views[0].K, views[0].R, views[0].C
+		X = R0.T @ (np.array([(x-K0[0, 2])/K0[0, 0], (y-K0[1, 2])/K0[1, 1], 1.0])*d2) + C0
+		for k, v in enumerate(views[1:]):
+			p1 = v.K @ (v.R @ (X-v.C)); z1 = p1[2]; u1 = p1[:2]/z1
+			# depth of the neighbour's surface at u1 (bilinear on its ground truth), similar within 3 %
+			lx, ly = int(u1[0]), int(u1[1]); ax, ay = u1[0]-lx, u1[1]-ly
+			g = v.depth_gt
+			dn = (g[ly, lx]*(1-ax)+g[ly, lx+1]*ax)*(1-ay)+(g[ly+1, lx]*(1-ax)+g[ly+1, lx+1]*ax)*ay
+			if abs(z1-dn)/z1 >= 0.03:
+				assert abs((vg[k]-vb[k])-0.4) < 1e-4
+				continue
+			Xb = v.R.T @ (np.linalg.inv(v.K) @ np.array([u1[0]*dn, u1[1]*dn, dn])) + v.C
+			pb = K0 @ (R0 @ (Xb-C0)); ub = pb[:2]/pb[2]
+			dist = np.hypot(x-ub[0], y-ub[1])
+			want = 0.1*min(np.sqrt(dist*(dist+2)), 4.0)
+			assert abs((vg[k]-vb[k])-want) < 5e-3
+
+
+def test_score_pixel_image_against_textbook_homography(small_scene):
+	"""ScorePixelImage (DepthMap.cpp:465-564) against an independent float64 evaluation: the textbook
+	plane-induced homography K1 (R + t n^T / (n.X)) K0^-1, bilinear taps and the weighted NCC
+	1 - num / sqrt(normSq0 normSq1) with the bilateral weights of FillPixelPatch."""
+	sc, ref, views = small_scene
+	prm = O.default_params(nSubResolutionLevels=0)
+	gt_d, gt_n = sc.views[ref].depth_gt, sc.views[ref].normal_gt
+	img0 = views[0].image.astype(np.float64)
+	K0, R0, C0 = views[0].K, views[0].R, views[0].C
+	rng = np.random.RandomState(12)
+	n_checked = 0
+	for _ in range(15):
+		x, y = int(rng.randint(40, 280)), int(rng.randint(40, 200))
+		d = float(gt_d[y, x])*(1+0.01*rng.randn())
+		n = gt_n[y, x].astype(np.float64)+0.05*rng.randn(3); n /= np.linalg.norm(n)
+		s, vs = O.pm_score_pixel(views, prm, sc.dmin, sc.dmax, x, y, d, n.astype(np.float32))
+		w, I, tm, nsq0 = _patch_stats(img0, x, y)
+		X0 = np.array([(x-K0[0, 2])/K0[0, 0], (y-K0[1, 2])/K0[1, 1], 1.0])
+		c = float(n @ X0)*d
+		for k, v in enumerate(views[1:]):
+			Rrel = v.R @ R0.T; t = v.R @ (C0-v.C)
+			Hm = v.K @ (Rrel + np.outer(t, n)/c) @ np.linalg.inv(K0)
+			img1 = v.image.astype(np.float64)
+			vals, inside = [], True
+			for i in range(-4, 5, 2):
+				for j in range(-4, 5, 2):
+					p = Hm @ np.array([x+j, y+i, 1.0]); px, py = p[0]/p[2], p[1]/p[2]
+					if not (1 <= px <= img1.shape[1]-2 and 1 <= py <= img1.shape[0]-2):
+						inside = False; break
+					lx, ly = int(px), int(py); ax, ay = px-lx, py-ly
+					vals.append((img1[ly, lx]*(1-ax)+img1[ly, lx+1]*ax)*(1-ay)+(img1[ly+1, lx]*(1-ax)+img1[ly+1, lx+1]*ax)*ay)
+				if not inside: break
+			if not inside:
+				assert vs[k] == pytest.approx(1.2)
+				continue
+			f = np.array(vals)
+			sumw, sumsq, num = (f*w).sum(), (f*f*w).sum(), (f*w*(I-tm)).sum()
+			nsq1 = sumsq-sumw**2/w.sum()
+			ncc = np.clip(num/np.sqrt(nsq0*nsq1), -1, 1)
+			assert abs(vs[k]-(1-ncc)) < 2e-4
+			n_checked += 1
+	assert n_checked > 40
