@@ -474,3 +474,32 @@ def test_batch_call_over_two_gpus_in_one_process(env, small_scene):
 	pm1.Release()
 	for a, b in zip(jobs, singles):
 		assert np.array_equal(a.depthMap, b.depthMap) and np.array_equal(a.confMap, b.confMap)
+
+
+def test_baseline_config0_two_view_640x480(env):
+	"""BASELINE configs[0]: 2-view synthetic pinhole pair 640x480, PatchMatch 3 iterations — the reference's
+	own CPU-runnable case (one neighbour: min-aggregator branch).  Engine vs the oracle on the reference's
+	zig-zag schedule, with the oracle's thread-count variation as the yardstick, and vs the RB oracle."""
+	e = env
+	from openmvs_b200 import synth
+	sc = synth.make_scene(640, 480, 2, step_deg=5.0, cols=2)
+	views = [sc.views[0], sc.views[1]]
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=4, nRandomIters=6)
+	dd = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd)
+	gd = dd.depthMap
+	base = dict(nSubResolutionLevels=0, nEstimationGeometricIters=0)
+	# same schedule: 3 iterations x 4 sweeps, ceil(6/4) = 2 refinements per sweep
+	od, on, oc = e.O.pm_estimate(views, e.O.default_params(schedule=1, propagation=4, nEstimationIters=12, nRandomIters=2, threads=8, **base), sc.dmin, sc.dmax)
+	iou, agree = agreement(od, gd)
+	assert iou > 0.999 and agree > 0.97
+	zz1 = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=3, threads=1, **base), sc.dmin, sc.dmax)
+	zz8 = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=3, threads=8, **base), sc.dmin, sc.dmax)
+	iou_ref, agree_ref = agreement(zz1[0], zz8[0])
+	iou_g, agree_g = agreement(zz1[0], gd)
+	gt = sc.views[0].depth_gt
+	acc_g = (np.abs(gd-gt)[gd > 0]/gt[gd > 0] < 1e-3).mean()
+	acc_z = (np.abs(zz1[0]-gt)[zz1[0] > 0]/gt[zz1[0] > 0] < 1e-3).mean()
+	_record("config0_640x480_N1_I3", iou_rb=iou, agree_rb=agree, iou_zz_self=iou_ref, agree_zz_self=agree_ref, iou_gpu_zz=iou_g, agree_gpu_zz=agree_g, acc_gpu=acc_g, acc_zz=acc_z)
+	assert iou_g > 0.99 and agree_g > agree_ref-0.08 and acc_g > acc_z-0.05
+	_set(e, nSweepsPerIter=2)
