@@ -9,6 +9,9 @@
 // MVS::DepthData (libs/MVS/DepthMap.h:157-271: images[i].image (cv::Mat-backed Image32F),
 // images[i].camera.{K,R,C}, images[i].depthMap, images[i].cameraDepthMap, depthMap, normalMap,
 // confMap, viewsMap, dMin, dMax) and against the minimal mock used by tests/test_cpp_adapter.py.
+// Three more members forward the per-view post-processing that follows the estimation
+// (DepthMapsData::RemoveSmallSegments / GapInterpolation / FilterDepthMap,
+// libs/MVS/SceneDensify.cpp:810-1299) to the same context.
 // Nothing here computes: it marshals pointers and OPTDENSE values into the C structs.
 #pragma once
 #include "b200mvs.h"
@@ -72,6 +75,50 @@ public:
 		check(b200mvs_estimate(ctx_, views.data(), n, depthData.dMin, depthData.dMax, geom_ ? nGeometricIter : -1,
 			depthData.depthMap.template ptr<float>(), depthData.normalMap.template ptr<float>(),
 			depthData.confMap.template ptr<float>(), depthData.viewsMap.template ptr<uint8_t>(), stats), "b200mvs_estimate");
+	}
+
+	// DepthMapsData::RemoveSmallSegments(DepthData&) (SceneDensify.cpp:810-900); the OPTDENSE values are
+	// passed raw (fDepthDiffThreshold, nSpeckleSize), maps are processed in place
+	template <typename DEPTHDATA>
+	void RemoveSmallSegments(DEPTHDATA& depthData, float fDepthDiffThreshold, unsigned nSpeckleSize) {
+		if (!ctx_) throw std::runtime_error("PatchMatchB200 used after Release()");
+		check(b200mvs_remove_small_segments(ctx_, depthData.depthMap.template ptr<float>(),
+			depthData.normalMap.empty() ? nullptr : depthData.normalMap.template ptr<float>(),
+			depthData.confMap.empty() ? nullptr : depthData.confMap.template ptr<float>(),
+			depthData.depthMap.cols, depthData.depthMap.rows, fDepthDiffThreshold, nSpeckleSize, nullptr), "b200mvs_remove_small_segments");
+	}
+	// DepthMapsData::GapInterpolation(DepthData&) (SceneDensify.cpp:904-1045)
+	template <typename DEPTHDATA>
+	void GapInterpolation(DEPTHDATA& depthData, float fDepthDiffThreshold, unsigned nIpolGapSize) {
+		if (!ctx_) throw std::runtime_error("PatchMatchB200 used after Release()");
+		check(b200mvs_gap_interpolation(ctx_, depthData.depthMap.template ptr<float>(),
+			depthData.normalMap.empty() ? nullptr : depthData.normalMap.template ptr<float>(),
+			depthData.confMap.empty() ? nullptr : depthData.confMap.template ptr<float>(),
+			depthData.depthMap.cols, depthData.depthMap.rows, fDepthDiffThreshold, nIpolGapSize, nullptr), "b200mvs_gap_interpolation");
+	}
+	// DepthMapsData::FilterDepthMap(depthDataRef, idxNeighbors, bAdjust) (SceneDensify.cpp:1050-1299): `neighbors` are the
+	// DepthData of the valid neighbour views (arrDepthData[depthDataRef.neighbors[idx].ID]); newDepthMap / newConfMap are
+	// what the reference saves as filtered.dmap / filtered.cmap.  Returns false when the map can not be filtered.
+	template <typename DEPTHDATA, typename DMAP, typename CMAP>
+	bool FilterDepthMap(DEPTHDATA& depthDataRef, const std::vector<DEPTHDATA*>& neighbors, const b200mvs_filter_params& prm,
+		DMAP& newDepthMap, CMAP& newConfMap) {
+		if (!ctx_) throw std::runtime_error("PatchMatchB200 used after Release()");
+		std::vector<b200mvs_dmap> maps(neighbors.size()+1);
+		for (size_t i = 0; i < maps.size(); ++i) {
+			DEPTHDATA& d = i ? *neighbors[i-1] : depthDataRef;
+			b200mvs_dmap& o = maps[i];
+			o.depth = d.depthMap.template ptr<float>();
+			o.conf = d.confMap.empty() ? nullptr : d.confMap.template ptr<float>();
+			o.width = d.depthMap.cols; o.height = d.depthMap.rows;
+			const auto& cam = d.images[0].camera;
+			copy9(cam.K.val, o.K); copy9(cam.R.val, o.R); copy3(cam.C.ptr(), o.C);
+		}
+		newDepthMap.create(maps[0].height, maps[0].width);
+		newConfMap.create(maps[0].height, maps[0].width);
+		int filtered = 0;
+		check(b200mvs_filter_depth_map(ctx_, &maps[0], maps.data()+1, (int)neighbors.size(), &prm, depthDataRef.dMin, depthDataRef.dMax,
+			newDepthMap.template ptr<float>(), newConfMap.template ptr<float>(), &filtered, nullptr), "b200mvs_filter_depth_map");
+		return filtered != 0;
 	}
 
 private:

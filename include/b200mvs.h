@@ -203,6 +203,60 @@ int b200mvs_sgm_cross_check_device(b200mvs_ctx* ctx, int16_t* l2r, const int16_t
 int b200mvs_sgm_refine_device(b200mvs_ctx* ctx, const b200mvs_sgm_pixel* pixels, const uint16_t* accums,
 	int16_t* disparity, int nPixels, int subpixelSteps, void* stream);
 
+/* ---- depth-map post-processing after the estimation -----------------
+ * DepthMapsData::FilterDepthMap / RemoveSmallSegments / GapInterpolation
+ * (libs/MVS/SceneDensify.cpp:1050-1299, 810-900, 904-1045).  Maps are contiguous row-major float
+ * (cv::Mat-backed DepthMap / ConfidenceMap / NormalMap).  The OPTDENSE values are passed raw; the
+ * per-function multipliers (x1.2 / x0.8, x0.7, x2.5) are applied inside, as in the reference. */
+#define B200MVS_MAX_FILTER_VIEWS 16 /* the reference uses at most numMaxNeighbors = 8 (SceneDensify.cpp:2152) */
+
+/* an estimated depth-map with the camera it was estimated in (DepthData: depthMap, confMap,
+ * images.First().camera) */
+typedef struct {
+	const float* depth;   /* width x height */
+	const float* conf;    /* width x height; may be NULL for neighbours when bAdjust = 0 */
+	int width, height;
+	double K[9], R[9], C[3];
+} b200mvs_dmap;
+
+typedef struct {
+	int nMinViews;              /* min(OPTDENSE::nMinViewsFilter = 2, nCalibratedImages-1) */
+	int nMinViewsAdjust;        /* min(OPTDENSE::nMinViewsFilterAdjust = 1, nCalibratedImages-1) */
+	float fDepthDiffThreshold;  /* OPTDENSE::fDepthDiffThreshold = 0.01 */
+	int bAdjust;                /* OPTDENSE::bFilterAdjust = 1 */
+} b200mvs_filter_params;
+
+void b200mvs_filter_default_params(b200mvs_filter_params* p);
+
+/* FilterDepthMap(depthDataRef, idxNeighbors, bAdjust): z-buffered projection of the nNbrs neighbour
+ * depth-maps into the reference view, then per pixel either the confidence-weighted average of the
+ * agreeing depths (bAdjust) or a keep/discard vote.  HOST buffers; outDepth/outConf are the
+ * "filtered.dmap"/"filtered.cmap" maps the reference saves.  *filtered (nullable) receives 0 when the
+ * map can not be filtered (nNbrs < nMinViews or < nMinViewsAdjust; outputs untouched), else 1. */
+int b200mvs_filter_depth_map(b200mvs_ctx* ctx, const b200mvs_dmap* ref, const b200mvs_dmap* nbrs, int nNbrs,
+	const b200mvs_filter_params* prm, float dMin, float dMax, float* outDepth, float* outConf, int* filtered,
+	b200mvs_stats* stats);
+/* Same with DEVICE pointers inside ref/nbrs and for the outputs (outputs must not alias the inputs).
+ * projDepth / projConf (nullable, nNbrs x height x width) receive the projected neighbour maps. */
+int b200mvs_filter_depth_map_device(b200mvs_ctx* ctx, const b200mvs_dmap* ref, const b200mvs_dmap* nbrs, int nNbrs,
+	const b200mvs_filter_params* prm, float dMin, float dMax, float* outDepth, float* outConf,
+	float* projDepth, float* projConf, int* filtered, void* stream);
+
+/* RemoveSmallSegments(depthData): zero every 4-connected segment of similar depths
+ * (threshold fDepthDiffThreshold*0.7) smaller than nSpeckleSize pixels; in place; normal / conf nullable. */
+int b200mvs_remove_small_segments(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nSpeckleSize, b200mvs_stats* stats);
+int b200mvs_remove_small_segments_device(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nSpeckleSize, void* stream);
+
+/* GapInterpolation(depthData): fill row gaps, then column gaps, of at most nIpolGapSize invalid pixels
+ * between two similar depths (threshold fDepthDiffThreshold*2.5) by linear interpolation of the depth and
+ * of the normal's direction angles; confidence = min of the two ends; in place; normal / conf nullable. */
+int b200mvs_gap_interpolation(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nIpolGapSize, b200mvs_stats* stats);
+int b200mvs_gap_interpolation_device(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nIpolGapSize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

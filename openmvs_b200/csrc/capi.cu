@@ -37,11 +37,23 @@ struct SGMParams {
 cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out, cudaStream_t s);
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
-cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s);
+cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
 cudaError_t sgm_launch_refine(const SGMPixel* px, const uint16_t* accums, int16_t* disparity, int n, int steps, cudaStream_t s);
+#define FLT_MAX_NBR 16
+struct FltView { const float* depth; const float* conf; int w, h; double fx, fy, cx, cy; double R[9], C[3]; };
+struct FltParams {
+	FltView ref; FltView nbr[FLT_MAX_NBR];
+	int N, nMinViews, nMinViewsAdjust;
+	float thDepthDiff, thStrict, dMin, dMax;
+	unsigned long long* zbuf; float* outDepth; float* outConf;
+};
+cudaError_t flt_launch_filter(const FltParams& P, int maxNbrPixels, bool adjust, cudaStream_t s);
+cudaError_t flt_launch_resolve(const unsigned long long* z, const float* nbrConf, size_t np, float* depth, float* conf, cudaStream_t s);
+cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, int H, float th, unsigned speckle, int* labels, int* sizes, cudaStream_t s);
+cudaError_t gap_launch(float* depth, float* normal, float* conf, float* tDepth, float* tNormal, float* tConf, int W, int H, float th, int gap, cudaStream_t s);
 cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s);
@@ -118,6 +130,8 @@ struct b200mvs_ctx {
 	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
 	std::vector<DevBuf> tex;                  // neighbour images in the tap-fetch layout
 	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgDisp, sgCost, sgMax; // SGM staging / scratch
+	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
+	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
 	int layout = 1;                           // 1 plain float rows, 2 row pairs (B200MVS_LAYOUT overrides)
 	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
 	bool tma = true;                          // reference tile staged by TMA (B200MVS_TMA=0: plain loads)
@@ -444,6 +458,8 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
 	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release();
 	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
+	c->fltZ.release(); c->fltIn.release(); c->fltOutD.release(); c->fltOutC.release();
+	c->ppA.release(); c->ppB.release(); c->ppD.release(); c->ppN.release(); c->ppC.release();
 	c->plane.release(); c->cost.release(); c->best.release(); c->prior.release(); c->lowPlane.release();
 	c->dDepth.release(); c->dNormal.release(); c->dConf.release(); c->dViews.release(); c->mapD.release(); c->mapN.release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -707,7 +723,7 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	P.costs = costs; P.accums = accums;
 	const auto t0 = std::chrono::steady_clock::now();
 	ctx->launches = 0;
-	int st6[6] = {0, 0, 0, 0, 0, 0}; bool uniform = false;
+	int st6[6] = {0, 0, 0, 0, 0, 0}; bool uniform = false, ring = false;
 	if (stats) CK(cudaEventRecord(ctx->ev0, s));
 	if (stages & 2) {
 		// the warp-per-scanline kernel keeps one line of at most sgm_max_disparities() values
@@ -719,14 +735,17 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 			return fail(ctx, B200MVS_ERR_ARG, "sgm: more than 256 disparities per pixel");
 		P.maxNumDisp = st6[0];
 		// one global range (the non-tSGM branch): packed, shared-memory-free aggregation kernel
-		uniform = st6[0] >= 4 && st6[1] == st6[2] && st6[3] == st6[4] && (st6[0] & 3) == 0 && st6[5] == 0
+		uniform = st6[0] >= 4 && st6[1] == st6[2] && st6[3] == st6[4] && (st6[0] & 3) == 0 && (st6[5] & 3) == 0
 			&& !getenv("B200MVS_SGM_GENERAL");
+		// every slice 16-byte aligned: bulk-copy ring kernel (B200MVS_SGM_RING=0 keeps the register-pipelined one)
+		const char* re = getenv("B200MVS_SGM_RING");
+		ring = uniform && (st6[0] & 15) == 0 && st6[5] == 0 && !((uintptr_t)P.costs & 15) && !((uintptr_t)P.accums & 15) && !(re && atoi(re) == 0);
 	}
 	if (stages & 1) { CK(sgm_launch_cost(P, s)); ++ctx->launches; }
 	if (stages & 2) {
 		CK(cudaMemsetAsync(accums, 0, numCosts*sizeof(uint16_t), s));
 		for (int dir = 0; dir < 8; ++dir) {
-			if (uniform) CK(sgm_launch_aggregate_uniform(P, dir, st6[1], st6[0], s));
+			if (uniform) CK(sgm_launch_aggregate_uniform(P, dir, st6[1], st6[0], ring, s));
 			else CK(sgm_launch_aggregate(P, dir, s));
 			++ctx->launches;
 		}
@@ -793,6 +812,193 @@ int b200mvs_sgm_refine_device(b200mvs_ctx* ctx, const b200mvs_sgm_pixel* pixels,
 	CK(cudaSetDevice(ctx->device));
 	CK(sgm_launch_refine((const SGMPixel*)pixels, accums, disparity, nPixels, subpixelSteps, stream ? (cudaStream_t)stream : ctx->stream));
 	return B200MVS_OK;
+}
+
+// ---- depth-map post-processing (SceneDensify.cpp:810-1299) ----
+
+void b200mvs_filter_default_params(b200mvs_filter_params* p) {
+	p->nMinViews = 2; p->nMinViewsAdjust = 1; p->fDepthDiffThreshold = 0.01f; p->bAdjust = 1;
+}
+
+static void flt_view(const b200mvs_dmap& m, const float* depth, const float* conf, FltView& v) {
+	v.depth = depth; v.conf = conf; v.w = m.width; v.h = m.height;
+	v.fx = m.K[0]; v.fy = m.K[4]; v.cx = m.K[2]; v.cy = m.K[5];
+	memcpy(v.R, m.R, sizeof(v.R)); memcpy(v.C, m.C, sizeof(v.C));
+}
+
+static int flt_check(b200mvs_ctx* ctx, const b200mvs_dmap* ref, const b200mvs_dmap* nbrs, int nNbrs, const b200mvs_filter_params* prm,
+	const float* outDepth, const float* outConf)
+{
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!ref || !prm || !outDepth || !outConf || nNbrs < 0 || (nNbrs > 0 && !nbrs))
+		return fail(ctx, B200MVS_ERR_ARG, "filter: null pointer");
+	if (nNbrs > B200MVS_MAX_FILTER_VIEWS) return fail(ctx, B200MVS_ERR_ARG, "filter: too many neighbour depth-maps");
+	if (!ref->depth || !ref->conf || ref->width <= 0 || ref->height <= 0 || (size_t)ref->width*ref->height >= 0xFFFFFFFFull)
+		return fail(ctx, B200MVS_ERR_ARG, "filter: invalid reference depth-map");
+	if (prm->nMinViews < 1 || prm->nMinViewsAdjust < 0 || !(prm->fDepthDiffThreshold > 0))
+		return fail(ctx, B200MVS_ERR_ARG, "filter: invalid parameter block"); // nMinViewsFilter > 0 is asserted by the reference (:1057)
+	for (int i = 0; i < nNbrs; ++i) {
+		const b200mvs_dmap& m = nbrs[i];
+		if (!m.depth || (prm->bAdjust && !m.conf) || m.width <= 0 || m.height <= 0 || (size_t)m.width*m.height >= 0xFFFFFFFFull)
+			return fail(ctx, B200MVS_ERR_ARG, "filter: invalid neighbour depth-map");
+	}
+	return B200MVS_OK;
+}
+
+int b200mvs_filter_depth_map_device(b200mvs_ctx* ctx, const b200mvs_dmap* ref, const b200mvs_dmap* nbrs, int nNbrs,
+	const b200mvs_filter_params* prm, float dMin, float dMax, float* outDepth, float* outConf,
+	float* projDepth, float* projConf, int* filtered, void* stream)
+{
+	int rc = flt_check(ctx, ref, nbrs, nNbrs, prm, outDepth, outConf);
+	if (rc) return rc;
+	if (nNbrs < prm->nMinViews || nNbrs < prm->nMinViewsAdjust) { // "can not be filtered" (:1060-1063)
+		if (filtered) *filtered = 0;
+		return B200MVS_OK;
+	}
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	const size_t np = (size_t)ref->width*ref->height;
+	CK(ctx->fltZ.reserve(np*8*(size_t)nNbrs));
+	FltParams P;
+	memset(&P, 0, sizeof(P));
+	flt_view(*ref, ref->depth, ref->conf, P.ref);
+	int maxPix = 0;
+	for (int i = 0; i < nNbrs; ++i) {
+		flt_view(nbrs[i], nbrs[i].depth, nbrs[i].conf, P.nbr[i]);
+		maxPix = std::max(maxPix, nbrs[i].width*nbrs[i].height);
+	}
+	P.N = nNbrs; P.nMinViews = prm->nMinViews; P.nMinViewsAdjust = prm->nMinViewsAdjust;
+	P.thDepthDiff = prm->fDepthDiffThreshold*1.2f; P.thStrict = prm->fDepthDiffThreshold*0.8f;
+	P.dMin = dMin; P.dMax = dMax;
+	P.zbuf = ctx->fltZ.as<unsigned long long>(); P.outDepth = outDepth; P.outConf = outConf;
+	CK(flt_launch_filter(P, maxPix, prm->bAdjust != 0, s));
+	ctx->launches = 2;
+	if (projDepth) {
+		for (int i = 0; i < nNbrs; ++i)
+			CK(flt_launch_resolve(P.zbuf+np*i, nbrs[i].conf, np, projDepth+np*i, projConf ? projConf+np*i : nullptr, s));
+		ctx->launches += nNbrs;
+	}
+	if (filtered) *filtered = 1;
+	return B200MVS_OK;
+}
+
+int b200mvs_filter_depth_map(b200mvs_ctx* ctx, const b200mvs_dmap* ref, const b200mvs_dmap* nbrs, int nNbrs,
+	const b200mvs_filter_params* prm, float dMin, float dMax, float* outDepth, float* outConf, int* filtered, b200mvs_stats* stats)
+{
+	int rc = flt_check(ctx, ref, nbrs, nNbrs, prm, outDepth, outConf);
+	if (rc) return rc;
+	if (nNbrs < prm->nMinViews || nNbrs < prm->nMinViewsAdjust) { if (filtered) *filtered = 0; return B200MVS_OK; }
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	const auto t0 = std::chrono::steady_clock::now();
+	// stage every map once: [ref depth | ref conf | nbr0 depth | nbr0 conf | ...]
+	size_t total = 0;
+	for (int i = -1; i < nNbrs; ++i) { const b200mvs_dmap& m = i < 0 ? *ref : nbrs[i]; total += (size_t)m.width*m.height*2; }
+	const size_t np = (size_t)ref->width*ref->height;
+	CK(ctx->fltIn.reserve(total*4)); CK(ctx->fltOutD.reserve(np*4)); CK(ctx->fltOutC.reserve(np*4));
+	std::vector<b200mvs_dmap> dv(nNbrs+1);
+	float* p = ctx->fltIn.as<float>();
+	uint64_t h2d = 0;
+	for (int i = -1; i < nNbrs; ++i) {
+		const b200mvs_dmap& m = i < 0 ? *ref : nbrs[i];
+		const size_t n = (size_t)m.width*m.height;
+		b200mvs_dmap& d = dv[i+1];
+		d = m;
+		CK(cudaMemcpyAsync(p, m.depth, n*4, cudaMemcpyHostToDevice, s)); d.depth = p; p += n; h2d += n*4;
+		d.conf = nullptr;
+		if (m.conf) { CK(cudaMemcpyAsync(p, m.conf, n*4, cudaMemcpyHostToDevice, s)); d.conf = p; h2d += n*4; }
+		p += n;
+	}
+	CK(cudaEventRecord(ctx->ev0, s));
+	rc = b200mvs_filter_depth_map_device(ctx, &dv[0], dv.data()+1, nNbrs, prm, dMin, dMax, ctx->fltOutD.as<float>(), ctx->fltOutC.as<float>(),
+		nullptr, nullptr, filtered, s);
+	if (rc) return rc;
+	CK(cudaEventRecord(ctx->ev1, s));
+	CK(cudaMemcpyAsync(outDepth, ctx->fltOutD.p, np*4, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(outConf, ctx->fltOutC.p, np*4, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+		stats->ms_device = ms; stats->bytes_h2d = h2d; stats->bytes_d2h = np*8; stats->kernel_launches = ctx->launches; stats->levels = 1;
+		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
+	}
+	return B200MVS_OK;
+}
+
+int b200mvs_remove_small_segments_device(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nSpeckleSize, void* stream)
+{
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!depth || width <= 0 || height <= 0 || (size_t)width*height > 0x7FFFFFFFull || !(fDepthDiffThreshold > 0))
+		return fail(ctx, B200MVS_ERR_ARG, "remove_small_segments: invalid argument");
+	CK(cudaSetDevice(ctx->device));
+	const size_t n = (size_t)width*height;
+	CK(ctx->ppA.reserve(n*4)); CK(ctx->ppB.reserve(n*4));
+	CK(seg_launch_remove(depth, normal, conf, width, height, fDepthDiffThreshold*0.7f, nSpeckleSize, ctx->ppA.as<int>(), ctx->ppB.as<int>(),
+		stream ? (cudaStream_t)stream : ctx->stream));
+	ctx->launches = 4;
+	return B200MVS_OK;
+}
+
+int b200mvs_gap_interpolation_device(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nIpolGapSize, void* stream)
+{
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!depth || width <= 0 || height <= 0 || (size_t)width*height > 0x7FFFFFFFull/3 || !(fDepthDiffThreshold > 0))
+		return fail(ctx, B200MVS_ERR_ARG, "gap_interpolation: invalid argument");
+	CK(cudaSetDevice(ctx->device));
+	const size_t n = (size_t)width*height;
+	CK(ctx->ppA.reserve(n*4)); CK(ctx->ppB.reserve(n*4)); CK(ctx->ppN.reserve(n*12));
+	const int gap = (int)std::min<unsigned>(nIpolGapSize, (unsigned)std::max(width, height));
+	CK(gap_launch(depth, normal, conf, ctx->ppA.as<float>(), ctx->ppN.as<float>(), ctx->ppB.as<float>(), width, height,
+		fDepthDiffThreshold*2.5f, gap, stream ? (cudaStream_t)stream : ctx->stream));
+	ctx->launches = 2;
+	return B200MVS_OK;
+}
+
+// host form of the two in-place passes: stage, run, copy back
+static int pp_host(b200mvs_ctx* ctx, int which, float* depth, float* normal, float* conf, int width, int height, float th, unsigned arg, b200mvs_stats* stats) {
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!depth || width <= 0 || height <= 0) return fail(ctx, B200MVS_ERR_ARG, "post-processing: invalid argument");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = ctx->stream;
+	const auto t0 = std::chrono::steady_clock::now();
+	const size_t n = (size_t)width*height;
+	CK(ctx->ppD.reserve(n*4+n*12)); CK(ctx->ppC.reserve(n*4));
+	float* dD = ctx->ppD.as<float>(); float* dN = normal ? dD+n : nullptr; float* dC = conf ? ctx->ppC.as<float>() : nullptr;
+	CK(cudaMemcpyAsync(dD, depth, n*4, cudaMemcpyHostToDevice, s));
+	if (normal) CK(cudaMemcpyAsync(dN, normal, n*12, cudaMemcpyHostToDevice, s));
+	if (conf) CK(cudaMemcpyAsync(dC, conf, n*4, cudaMemcpyHostToDevice, s));
+	CK(cudaEventRecord(ctx->ev0, s));
+	const int rc = which == 0 ? b200mvs_remove_small_segments_device(ctx, dD, dN, dC, width, height, th, arg, s)
+		: b200mvs_gap_interpolation_device(ctx, dD, dN, dC, width, height, th, arg, s);
+	if (rc) return rc;
+	CK(cudaEventRecord(ctx->ev1, s));
+	CK(cudaMemcpyAsync(depth, dD, n*4, cudaMemcpyDeviceToHost, s));
+	if (normal) CK(cudaMemcpyAsync(normal, dN, n*12, cudaMemcpyDeviceToHost, s));
+	if (conf) CK(cudaMemcpyAsync(conf, dC, n*4, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+		const uint64_t b = n*4+(normal ? n*12 : 0)+(conf ? n*4 : 0);
+		stats->ms_device = ms; stats->bytes_h2d = b; stats->bytes_d2h = b; stats->kernel_launches = ctx->launches; stats->levels = 1;
+		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
+	}
+	return B200MVS_OK;
+}
+
+int b200mvs_remove_small_segments(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nSpeckleSize, b200mvs_stats* stats)
+{
+	return pp_host(ctx, 0, depth, normal, conf, width, height, fDepthDiffThreshold, nSpeckleSize, stats);
+}
+
+int b200mvs_gap_interpolation(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
+	float fDepthDiffThreshold, unsigned nIpolGapSize, b200mvs_stats* stats)
+{
+	return pp_host(ctx, 1, depth, normal, conf, width, height, fDepthDiffThreshold, nIpolGapSize, stats);
 }
 
 } // extern "C"

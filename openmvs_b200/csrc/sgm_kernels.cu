@@ -246,9 +246,7 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 				unsigned m = 0xFFFFu;
 				for (int d = imin+lane; d < imax; d += 32)
 					m = min(m, (unsigned)Lp[d-pmin]);
-				#pragma unroll
-				for (int o = 16; o > 0; o >>= 1)
-					m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+				m = __reduce_min_sync(0xFFFFFFFFu, m); // redux.sync: one instruction instead of a 5-shuffle chain
 				const int minLp = (int)m;
 				#pragma unroll
 				for (int j = 0; j < NPL; ++j) {
@@ -276,9 +274,7 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 			unsigned mn = Lnew[0];
 			#pragma unroll
 			for (int j = 1; j < NPL; ++j) mn = min(mn, Lnew[j]);
-			#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-				mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+			mn = __reduce_min_sync(0xFFFFFFFFu, mn); // redux.sync: one instruction instead of a 5-shuffle chain
 			minPrev = mn;
 			__syncwarp();
 			pmin = p.dmin; pmax = p.dmax;
@@ -399,9 +395,7 @@ sgm_aggregate_uniform_kernel(const __grid_constant__ SGMParams P, int dir, int d
 			unsigned mn = Ln[0];
 			#pragma unroll
 			for (int j = 0; j < NPL; ++j) { Lp[j] = Ln[j]; mn = min(mn, Ln[j]); }
-			#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-				mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+			mn = __reduce_min_sync(0xFFFFFFFFu, mn); // redux.sync: one instruction instead of a 5-shuffle chain
 			minLp = mn;
 			havePrev = true;
 		}
@@ -411,6 +405,166 @@ sgm_aggregate_uniform_kernel(const __grid_constant__ SGMParams P, int dir, int d
 		#pragma unroll
 		for (int i = 0; i+1 < PD; ++i) { c[i] = c[i+1]; a[i] = a[i+1]; }
 		c[PD-1] = cn; a[PD-1] = an;
+	}
+}
+
+// Uniform-range variant with a bulk-copy ring (cp.async.bulk + mbarrier) — the default on sm_100a when every
+// slice of the volume is 16-byte aligned (num % 16 == 0, idx % 16 == 0).
+// A scanline is a chain of dependent steps, so its bandwidth is set by the bytes it keeps in flight.  Registers
+// limit the kernel above to PD = 4 steps (about 1.5 KB per warp); here every warp owns a ring of 2E stages in
+// shared memory.  The steps are grouped in epochs of E: while epoch e is computed, the copies of epoch e+1
+// are in flight, and when epoch e is done its E stages are refilled for epoch e+2 — lane l < E reads the
+// pixel record of "its" step, posts the expected byte count on that stage's mbarrier and issues the two bulk
+// copies (num cost bytes + 2*num accumulator bytes) itself, so no lane ever waits for another lane's address.
+// 1.5 E stages = 9 KB (num = 128, E = 16) per warp are in flight on average without holding a register.
+// The consumer side reads the record (one broadcast LDS.128), waits on the stage's mbarrier, reads its
+// packed costs / accumulators from the stage (LDS.32 / LDS.64), one step ahead of the arithmetic.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, unsigned parity) {
+	unsigned ok;
+	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+		: "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int NPL, int E>
+__global__ void __launch_bounds__(AGG_WARPS*32)
+sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, int dmin, int num)
+{
+	typedef typename Pack<NPL>::C CW;
+	typedef typename Pack<NPL>::A AW;
+	constexpr int RING = 2*E;
+	static_assert(RING <= 32, "one lane per stage");
+	extern __shared__ __align__(128) unsigned char ring_smem[];
+	const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
+	const int k = blockIdx.x*AGG_WARPS + warp;
+	int x0, y0, dx, dy;
+	if (!path_start(dir, k, P.vw, P.vh, x0, y0, dx, dy))
+		return;
+	// steps until the scanline leaves the valid region
+	int n = 0x7FFFFFFF;
+	if (dx > 0) n = min(n, P.vw-x0); else if (dx < 0) n = min(n, x0+1);
+	if (dy > 0) n = min(n, P.vh-y0); else if (dy < 0) n = min(n, y0+1);
+	const unsigned stageBytes = 3u*(unsigned)num;                       // costs | accumulators
+	const unsigned warpBytes = RING*(stageBytes+16u+8u);
+	unsigned char* base = ring_smem + (size_t)warp*warpBytes;
+	unsigned char* stages = base;                                        // RING x stageBytes (16-byte aligned: num % 16 == 0)
+	uint4* recs = (uint4*)(base + RING*stageBytes);                      // RING x {idx lo, idx hi, intensity, valid | parity << 1}
+	uint64_t* bars = (uint64_t*)(base + RING*(stageBytes+16u));          // RING mbarriers
+	if (lane < RING)
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(bars+lane)) : "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // the init is visible to the async proxy
+	__syncwarp();
+	const bool active = lane*NPL < num;
+	const int nval = min(NPL, max(0, num-lane*NPL));
+	unsigned phase = 0;                                                  // bit h: completions so far (mod 2) of this lane's stage in half h
+	// producer: lane l < E owns step e*E+l of epoch e, stage (e & 1)*E + l
+	auto issue_epoch = [&](int e) {
+		if (lane < E) {
+			const int t = e*E+lane, h = e&1, slot = h*E+lane;
+			uint4 r = make_uint4(0u, 0u, 0u, 0u);
+			if (t < n) {
+				const int xx = x0+t*dx, yy = y0+t*dy;
+				const SGMPixel p = P.px[(size_t)yy*P.vw + xx];
+				r.z = __float_as_uint(__ldg(P.lgray + (size_t)yy*P.w + xx));
+				if (p.dmin < p.dmax) {
+					r.x = (unsigned)p.idx; r.y = (unsigned)(p.idx>>32);
+					r.w = 1u | (((phase>>h)&1u)<<1);
+					phase ^= 1u<<h;
+					const uint32_t bar = smem_addr(bars+slot), dst = smem_addr(stages+(size_t)slot*stageBytes);
+					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(stageBytes) : "memory");
+					bulk_load(dst, P.costs+p.idx, (unsigned)num, bar);
+					bulk_load(dst+(unsigned)num, P.accums+p.idx, 2u*(unsigned)num, bar);
+				}
+			}
+			recs[slot] = r;
+		}
+		__syncwarp();
+	};
+	// consumer: record, wait, packed loads of step t
+	auto fetch = [&](int t, uint4& r, CW& c, AW& a) {
+		const int slot = t & (RING-1);
+		r = recs[slot];
+		memset(&c, 0, sizeof(c)); memset(&a, 0, sizeof(a));
+		if (r.w & 1u) {
+			const uint32_t bar = smem_addr(bars+slot);
+			while (!mbar_try_wait(bar, (r.w>>1)&1u)) {}
+			if (active) {
+				const unsigned char* st = stages+(size_t)slot*stageBytes;
+				const uint32_t* cs = (const uint32_t*)st + lane*(NPL/4);
+				const uint2* as = (const uint2*)(st+num) + lane*(NPL/4);
+				if (NPL == 4) { uint32_t v = cs[0]; memcpy(&c, &v, 4); uint2 w = as[0]; memcpy(&a, &w, 8); }
+				else {
+					uint2 v; v.x = cs[0]; v.y = nval > 4 ? cs[1] : 0u; memcpy(&c, &v, 8);
+					uint4 w; const uint2 lo = as[0]; w.x = lo.x; w.y = lo.y; w.z = w.w = 0u;
+					if (nval > 4) { const uint2 hi = as[1]; w.z = hi.x; w.w = hi.y; }
+					memcpy(&a, &w, 16);
+				}
+			}
+		}
+	};
+	issue_epoch(0);
+	issue_epoch(1);
+	unsigned Lp[NPL];
+	#pragma unroll
+	for (int j = 0; j < NPL; ++j) Lp[j] = 0xFFFFu;
+	unsigned minLp = 0xFFFFu;
+	bool havePrev = false;
+	float Ip = 0.5f;
+	uint4 rec; CW c; AW a;
+	fetch(0, rec, c, a);
+	#pragma unroll 1
+	for (int t = 0; t < n; ++t) {
+		if (t > 0 && (t & (E-1)) == 0) {
+			// epoch t/E-1 is consumed (its last stage was read into registers one step ago): refill its stages
+			__syncwarp();
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			issue_epoch(t/E+1);
+		}
+		uint4 recN = make_uint4(0u, 0u, 0u, 0u); CW cN; AW aN;
+		memset(&cN, 0, sizeof(cN)); memset(&aN, 0, sizeof(aN));
+		if (t+1 < n) fetch(t+1, recN, cN, aN);
+		if (rec.w & 1u) {
+			const float I = __uint_as_float(rec.z);
+			const int P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
+			Ip = I;
+			uint8_t cb[NPL]; uint16_t ab[NPL];
+			memcpy(cb, &c, NPL); memcpy(ab, &a, 2*NPL);
+			unsigned Ln[NPL];
+			if (!havePrev) {
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) Ln[j] = j < nval ? (unsigned)(cb[j]+P2) : 0xFFFFu;
+			} else {
+				const unsigned below = __shfl_up_sync(0xFFFFFFFFu, Lp[NPL-1], 1);
+				const unsigned above = __shfl_down_sync(0xFFFFFFFFu, Lp[0], 1);
+				const int far = (int)minLp+P2;
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int lm = j > 0 ? (int)Lp[j-1] : (lane > 0 ? (int)below : 0xFFFF);
+					const int lq = j < NPL-1 ? (int)Lp[j+1] : (lane < 31 ? (int)above : 0xFFFF);
+					const int best = min(min((int)Lp[j], min(lm, lq)+P.P1), far);
+					Ln[j] = j < nval ? (unsigned)((int)cb[j]+best-(int)minLp) : 0xFFFFu;
+				}
+			}
+			if (active) {
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) ab[j] = (uint16_t)(ab[j]+(j < nval ? Ln[j] : 0u));
+				const unsigned long long idx = (unsigned long long)rec.x | ((unsigned long long)rec.y<<32);
+				uint2* dst = (uint2*)(P.accums + idx) + lane*(NPL/4);
+				uint2 w0; memcpy(&w0, ab, 8); dst[0] = w0;
+				if (NPL == 8 && nval > 4) { uint2 w1; memcpy(&w1, ab+4, 8); dst[1] = w1; }
+			}
+			unsigned mn = Ln[0];
+			#pragma unroll
+			for (int j = 0; j < NPL; ++j) { Lp[j] = Ln[j]; mn = min(mn, Ln[j]); }
+			minLp = __reduce_min_sync(0xFFFFFFFFu, mn);
+			havePrev = true;
+		}
+		rec = recN; c = cN; a = aN;
 	}
 }
 
@@ -428,9 +582,7 @@ __global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int16_t* __r
 	unsigned best = 0xFFFFFFFFu; // (value << 16) | index: the minimum is the first arg-min
 	for (int k = lane; k < p.dmax-p.dmin; k += 32)
 		best = min(best, ((unsigned)a[k]<<16) | (unsigned)k);
-	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+	best = __reduce_min_sync(0xFFFFFFFFu, best); // redux.sync: one instruction instead of a 5-shuffle chain
 	if (lane == 0) { disparity[gw] = (int16_t)(p.dmin+(int)(best&0xFFFFu)); cost[gw] = (uint16_t)(best>>16); }
 }
 
@@ -484,7 +636,7 @@ __global__ void sgm_refine_kernel(const SGMPixel* __restrict__ px, const uint16_
 }
 
 // statistics of the pixel map: out[0] = largest disparity count, out[1]/out[2] = min/max of dmin,
-// out[3]/out[4] = min/max of dmax over the valid pixels, out[5] = OR of (idx & 3)
+// out[3]/out[4] = min/max of dmax over the valid pixels, out[5] = OR of (idx & 15)
 __global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* __restrict__ out) {
 	int m = 0, lo0 = 0x7FFFFFFF, hi0 = -0x7FFFFFFF, lo1 = 0x7FFFFFFF, hi1 = -0x7FFFFFFF, al = 0;
 	for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
@@ -493,7 +645,7 @@ __global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* 
 			m = max(m, p.dmax-p.dmin);
 			lo0 = min(lo0, (int)p.dmin); hi0 = max(hi0, (int)p.dmin);
 			lo1 = min(lo1, (int)p.dmax); hi1 = max(hi1, (int)p.dmax);
-			al |= (int)(p.idx & 3ull);
+			al |= (int)(p.idx & 15ull);
 		}
 	}
 	#pragma unroll
@@ -518,11 +670,27 @@ cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out6, cudaStream_
 	sgm_maxdisp_kernel<<<148*4, 256, 0, s>>>(px, n, out6);
 	return cudaGetLastError();
 }
-// uniform-range fast path: every valid pixel has the range [dmin, dmin+num), num % 4 == 0, 4-aligned slices
-cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s) {
+// uniform-range fast path: every valid pixel has the range [dmin, dmin+num), num % 4 == 0, 4-aligned slices;
+// ring: slices are 16-byte aligned (num % 16 == 0, idx % 16 == 0, aligned base pointers) -> bulk-copy ring kernel
+template <int NPL, int E>
+static cudaError_t launch_ring(const SGMParams& P, int dir, int dmin, int num, int grid, cudaStream_t s) {
+	const size_t smem = (size_t)AGG_WARPS*2*E*(3*(size_t)num+24);
+	static bool done[64] = {}; // per device
+	int dev = 0; cudaGetDevice(&dev); dev &= 63;
+	if (!done[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(sgm_aggregate_uniform_ring_kernel<NPL, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2*E*AGG_WARPS*(3*(NPL*32)+24));
+		if (e != cudaSuccess) return e;
+		done[dev] = true;
+	}
+	sgm_aggregate_uniform_ring_kernel<NPL, E><<<grid, AGG_WARPS*32, smem, s>>>(P, dir, dmin, num);
+	return cudaGetLastError();
+}
+cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s) {
 	const int W = P.vw, H = P.vh;
 	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
 	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
+	if (ring && (num & 15) == 0)
+		return num <= 128 ? launch_ring<4, 16>(P, dir, dmin, num, grid, s) : launch_ring<8, 8>(P, dir, dmin, num, grid, s);
 	if (num <= 128) sgm_aggregate_uniform_kernel<4, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
 	else sgm_aggregate_uniform_kernel<8, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
 	return cudaGetLastError();

@@ -9,6 +9,7 @@ read like tests of the reference:
   PatchMatchB200      the PatchMatchCUDA seam       libs/MVS/PatchMatchCUDA.inl:78-131
                       (ctor(device), Init(bGeomConsistency), Release(), EstimateDepthMap(DepthData&))
   DepthMapsData       EstimateDepthMap(idxImage, nGeometricIter)   libs/MVS/SceneDensify.cpp:616-805
+                      FilterDepthMap / RemoveSmallSegments / GapInterpolation   libs/MVS/SceneDensify.cpp:810-1299
 
 Everything here is plumbing above the C-ABI (include/b200mvs.h); the arithmetic runs in the
 CUDA kernels of openmvs_b200/csrc.  numpy arrays take the host path (H2D/D2H inside the
@@ -42,6 +43,13 @@ class OPTDENSE:
 	fRandomSmoothDepth = 0.02
 	fRandomSmoothNormal = 13.0
 	fRandomSmoothBonus = 0.93
+	# depth-map post-processing (FilterDepthMap / RemoveSmallSegments / GapInterpolation)
+	nMinViewsFilter = 2
+	nMinViewsFilterAdjust = 1
+	bFilterAdjust = True
+	fDepthDiffThreshold = 0.01
+	nSpeckleSize = 100
+	nIpolGapSize = 7
 	# engine schedule (not in the reference): red-black sweeps per reference iteration
 	nSweepsPerIter = 2
 	nPropagation = 4
@@ -318,17 +326,104 @@ def EstimateDepthMapsBatch(arrDepthData: List[DepthData], engines: List["PatchMa
 
 
 class DepthMapsData:
-	"""The slice of the reference's DepthMapsData that owns the hot path
-	(libs/MVS/SceneDensify.h:52-93): arrDepthData + EstimateDepthMap(idxImage, nGeometricIter)."""
+	"""The slice of the reference's DepthMapsData around the hot path (libs/MVS/SceneDensify.h:52-93):
+	arrDepthData + EstimateDepthMap(idxImage, nGeometricIter), and the per-view post-processing that
+	follows it: RemoveSmallSegments, GapInterpolation, FilterDepthMap (SceneDensify.cpp:810-1299)."""
 
-	def __init__(self, arrDepthData: List[DepthData], device: int = 0):
+	def __init__(self, arrDepthData: List[DepthData], device: int = 0, nCalibratedImages: Optional[int] = None):
 		self.arrDepthData = arrDepthData
 		self.pmCUDA = PatchMatchB200(device)
+		self.nCalibratedImages = len(arrDepthData) if nCalibratedImages is None else int(nCalibratedImages)
+		self.stats = _lib.Stats()
 
 	def EstimateDepthMap(self, idxImage: int, nGeometricIter: int = -1) -> bool:
 		self.pmCUDA.Init(nGeometricIter >= 0)
 		self.pmCUDA.EstimateDepthMap(self.arrDepthData[idxImage], nGeometricIter)
 		return True
+
+	@staticmethod
+	def _ptr(a):
+		return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+	@staticmethod
+	def _dmap(o: "_lib.DMap", depthData: DepthData, need_conf: bool, keep: list):
+		cam = depthData.images[0].camera
+		d, c = depthData.depthMap, depthData.confMap
+		if not _is_torch(d):
+			d = np.ascontiguousarray(d, np.float32)
+			c = None if c is None else np.ascontiguousarray(c, np.float32)
+		elif not d.is_contiguous() or (c is not None and not c.is_contiguous()):
+			raise ValueError("depth/confidence maps must be contiguous")
+		if need_conf and c is None:
+			raise ValueError("FilterDepthMap needs the confidence map of every view")
+		keep += [d, c]
+		o.depth = DepthMapsData._ptr(d); o.conf = DepthMapsData._ptr(c) if c is not None else None
+		o.height, o.width = int(d.shape[0]), int(d.shape[1])
+		o.K[:] = np.asarray(cam.K, np.float64).ravel(); o.R[:] = np.asarray(cam.R, np.float64).ravel(); o.C[:] = np.asarray(cam.C, np.float64).ravel()
+		return d
+
+	def FilterDepthMap(self, depthDataRef: DepthData, neighbors: List[DepthData], bAdjust: Optional[bool] = None, projected: bool = False):
+		"""DepthMapsData::FilterDepthMap(depthDataRef, idxNeighbors, bAdjust) (SceneDensify.cpp:1050-1299).
+		`neighbors` are the DepthData of the (at most 8, SceneDensify.cpp:2152) neighbour views whose depth-maps are valid.
+		Returns (newDepthMap, newConfMap) — what the reference saves as filtered.dmap / filtered.cmap — or None when the map
+		can not be filtered; with projected=True also the N projected neighbour depth and confidence maps (device path)."""
+		lib, ctx = self.pmCUDA._lib, self.pmCUDA._ctx
+		bAdjust = OPTDENSE.bFilterAdjust if bAdjust is None else bool(bAdjust)
+		prm = _lib.FilterParams(min(OPTDENSE.nMinViewsFilter, self.nCalibratedImages-1),
+			min(OPTDENSE.nMinViewsFilterAdjust, self.nCalibratedImages-1), OPTDENSE.fDepthDiffThreshold, int(bAdjust))
+		arr = (_lib.DMap*(len(neighbors)+1))()
+		keep: list = []
+		dref = self._dmap(arr[0], depthDataRef, True, keep)
+		for i, nb in enumerate(neighbors):
+			self._dmap(arr[i+1], nb, bAdjust, keep)
+		nbrs = C.cast(C.byref(arr, C.sizeof(_lib.DMap)), C.POINTER(_lib.DMap))
+		ok = C.c_int(0)
+		if _is_torch(dref):
+			import torch
+			od = torch.empty_like(dref); oc = torch.empty_like(dref)
+			pd = pc = None
+			if projected:
+				pd = torch.empty((max(len(neighbors), 1),)+tuple(dref.shape), dtype=torch.float32, device=dref.device)
+				pc = torch.zeros_like(pd)
+			rc = lib.b200mvs_filter_depth_map_device(ctx, C.byref(arr[0]), nbrs, len(neighbors), C.byref(prm), depthDataRef.dMin, depthDataRef.dMax,
+				od.data_ptr(), oc.data_ptr(), pd.data_ptr() if projected else None, pc.data_ptr() if projected and bAdjust else None,
+				C.byref(ok), C.c_void_p(_stream_handle(dref.device)))
+			_lib.check(lib, ctx, rc, "b200mvs_filter_depth_map_device")
+			if not ok.value:
+				return None
+			return (od, oc, pd, pc) if projected else (od, oc)
+		od = np.empty_like(dref); oc = np.empty_like(dref)
+		rc = lib.b200mvs_filter_depth_map(ctx, C.byref(arr[0]), nbrs, len(neighbors), C.byref(prm), depthDataRef.dMin, depthDataRef.dMax,
+			od.ctypes.data, oc.ctypes.data, C.byref(ok), C.byref(self.stats))
+		_lib.check(lib, ctx, rc, "b200mvs_filter_depth_map")
+		return (od, oc) if ok.value else None
+
+	def _post(self, name: str, depthData: DepthData, arg: int) -> bool:
+		lib, ctx = self.pmCUDA._lib, self.pmCUDA._ctx
+		d, n, c = depthData.depthMap, depthData.normalMap, depthData.confMap
+		h, w = int(d.shape[0]), int(d.shape[1])
+		if _is_torch(d):
+			for a in (d, n, c):
+				if a is not None and not a.is_contiguous():
+					raise ValueError("maps must be contiguous")
+			rc = getattr(lib, name+"_device")(ctx, d.data_ptr(), n.data_ptr() if n is not None else None, c.data_ptr() if c is not None else None,
+				w, h, OPTDENSE.fDepthDiffThreshold, int(arg), C.c_void_p(_stream_handle(d.device)))
+		else:
+			for a in (d, n, c):
+				if a is not None and not (a.flags.c_contiguous and a.dtype == np.float32):
+					raise ValueError("maps must be contiguous float32 arrays (processed in place)")
+			rc = getattr(lib, name)(ctx, d.ctypes.data, n.ctypes.data if n is not None else None, c.ctypes.data if c is not None else None,
+				w, h, OPTDENSE.fDepthDiffThreshold, int(arg), C.byref(self.stats))
+		_lib.check(lib, ctx, rc, name)
+		return True
+
+	def RemoveSmallSegments(self, depthData: DepthData) -> bool:
+		"""DepthMapsData::RemoveSmallSegments (SceneDensify.cpp:810-900), depthData's maps in place."""
+		return self._post("b200mvs_remove_small_segments", depthData, OPTDENSE.nSpeckleSize)
+
+	def GapInterpolation(self, depthData: DepthData) -> bool:
+		"""DepthMapsData::GapInterpolation (SceneDensify.cpp:904-1045), depthData's maps in place."""
+		return self._post("b200mvs_gap_interpolation", depthData, OPTDENSE.nIpolGapSize)
 
 
 class SemiGlobalMatcher:

@@ -47,6 +47,19 @@ class SgmParams(C.Structure):
 	_fields_ = [("P1", C.c_int), ("P2", C.c_int), ("P2alpha", C.c_float), ("P2beta", C.c_float)]
 
 
+class DMap(C.Structure):
+	"""b200mvs_dmap"""
+	_fields_ = [("depth", C.c_void_p), ("conf", C.c_void_p), ("width", C.c_int), ("height", C.c_int),
+		("K", C.c_double*9), ("R", C.c_double*9), ("C", C.c_double*3)]
+
+
+class FilterParams(C.Structure):
+	"""b200mvs_filter_params"""
+	_fields_ = [("nMinViews", C.c_int), ("nMinViewsAdjust", C.c_int), ("fDepthDiffThreshold", C.c_float), ("bAdjust", C.c_int)]
+
+
+MAX_FILTER_VIEWS = 16
+
 # every symbol include/b200mvs.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
 	"b200mvs_create", "b200mvs_destroy", "b200mvs_default_params", "b200mvs_set_params", "b200mvs_last_error",
@@ -54,6 +67,9 @@ SYMBOLS = [
 	"b200mvs_pm_pack", "b200mvs_pm_unpack", "b200mvs_pm_score", "b200mvs_pm_sweep", "b200mvs_pm_finalize",
 	"b200mvs_sgm_default_params", "b200mvs_sgm_match", "b200mvs_sgm_match_device",
 	"b200mvs_sgm_cross_check_device", "b200mvs_sgm_refine_device",
+	"b200mvs_filter_default_params", "b200mvs_filter_depth_map", "b200mvs_filter_depth_map_device",
+	"b200mvs_remove_small_segments", "b200mvs_remove_small_segments_device",
+	"b200mvs_gap_interpolation", "b200mvs_gap_interpolation_device",
 ]
 
 _LIB = None
@@ -97,6 +113,15 @@ def load(build_if_missing: bool = True):
 	lib.b200mvs_sgm_match_device.argtypes = [P, P, P, P, C.c_int, C.c_int, P, C.c_uint64, C.POINTER(SgmParams), C.c_int, P, P, P, P, P, C.POINTER(Stats)]
 	lib.b200mvs_sgm_cross_check_device.argtypes = [P, P, P, C.c_int, C.c_int, C.c_int, P]
 	lib.b200mvs_sgm_refine_device.argtypes = [P, P, P, P, C.c_int, C.c_int, P]
+	lib.b200mvs_filter_default_params.argtypes = [C.POINTER(FilterParams)]
+	lib.b200mvs_filter_depth_map.argtypes = [P, C.POINTER(DMap), C.POINTER(DMap), C.c_int, C.POINTER(FilterParams), F, F, P, P,
+		C.POINTER(C.c_int), C.POINTER(Stats)]
+	lib.b200mvs_filter_depth_map_device.argtypes = [P, C.POINTER(DMap), C.POINTER(DMap), C.c_int, C.POINTER(FilterParams), F, F, P, P, P, P,
+		C.POINTER(C.c_int), P]
+	lib.b200mvs_remove_small_segments.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, C.POINTER(Stats)]
+	lib.b200mvs_remove_small_segments_device.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, P]
+	lib.b200mvs_gap_interpolation.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, C.POINTER(Stats)]
+	lib.b200mvs_gap_interpolation_device.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, P]
 	_LIB = lib
 	return lib
 

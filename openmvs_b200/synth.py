@@ -162,3 +162,21 @@ def sgm_pixel_map(width: int, height: int, dmin, dmax, invalid=None):
 	px["idx"] = np.concatenate([[0], np.cumsum(num)[:-1]])
 	px["dmin"] = lo.ravel(); px["dmax"] = hi.ravel()
 	return px, int(num.sum())
+
+
+def make_noisy_dmaps(scene: Scene, seed: int = 7, noise: float = 0.002, outliers: float = 0.03, holes: float = 0.05):
+	"""Per view (depth, conf) float32 maps as an estimator would leave them: ground-truth depth with
+	relative Gaussian noise, a fraction of gross outliers (x U(0.7, 1.3)), a fraction of rejected pixels
+	(depth 0, conf 0), confidence U(0.1, 1).  Inputs of the FilterDepthMap parity tests."""
+	rng = np.random.RandomState(seed)
+	out = []
+	for v in scene.views:
+		h, w = v.depth_gt.shape
+		d = v.depth_gt.astype(np.float64)*(1.0+noise*rng.randn(h, w))
+		o = rng.rand(h, w) < outliers
+		d[o] *= rng.uniform(0.7, 1.3, int(o.sum()))
+		c = rng.uniform(0.1, 1.0, (h, w))
+		z = rng.rand(h, w) < holes
+		d[z] = 0; c[z] = 0
+		out.append((d.astype(np.float32), c.astype(np.float32)))
+	return out

@@ -120,6 +120,26 @@ int oracle_sgm_match(const float* leftGray, const uint8_t* leftBGR, const float*
 void oracle_sgm_cross_check(int16_t* l2r, const int16_t* r2l, int width, int height, int thCross);
 void oracle_sgm_refine(const oracle_sgm_pixel* pixels, const uint16_t* accums, int16_t* disparity, int nPixels, int subpixelSteps);
 
+/* ---- depth-map post-processing (libs/MVS/SceneDensify.cpp:810-1299) ---- */
+/* one estimated depth-map with its camera (DepthData of a view: depthMap, confMap, images[0].camera) */
+typedef struct {
+	const float* depth; const float* conf; /* conf may be NULL when unused (bAdjust = 0 neighbours) */
+	int width, height;
+	double K[9], R[9], C[3];
+} oracle_dmap;
+
+/* z-buffered forward projection of a neighbour depth-map into the reference view (4-pixel splat) */
+void oracle_filter_project(const oracle_dmap* ref, const oracle_dmap* nbr, float* projDepth, float* projConf /*nullable*/);
+/* DepthMapsData::FilterDepthMap; nMinViews / nMinViewsAdjust already min(..., nCalibratedImages-1).
+ * returns 0 when the map can not be filtered (too few neighbours). projected: nullable, N x H x W */
+int oracle_filter_depth_map(const oracle_dmap* ref, const oracle_dmap* nbrs, int nNbrs, int nMinViews, int nMinViewsAdjust,
+	float fDepthDiffThreshold, int bAdjust, float dMin, float dMax, float* outDepth, float* outConf, float* projected);
+/* DepthMapsData::RemoveSmallSegments; th = fDepthDiffThreshold*0.7; normal/conf nullable; in place */
+void oracle_remove_small_segments(float* depth, float* normal, float* conf, int width, int height, float th, unsigned speckle);
+int oracle_count_asymmetric_edges(const float* depth, int width, int height, float th);
+/* DepthMapsData::GapInterpolation; th = fDepthDiffThreshold*2.5; normal/conf nullable; in place */
+void oracle_gap_interpolation(float* depth, float* normal, float* conf, int width, int height, float th, unsigned gap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ class OParams(C.Structure):
 
 def build(force: bool = False) -> str:
 	so = os.path.join(_HERE, "liboracle.so")
-	srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.cpp", "sgm_oracle.cpp", "oracle.h")]
+	srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.cpp", "sgm_oracle.cpp", "filter_oracle.cpp", "oracle.h")]
 	if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
 		subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
 	return so
@@ -180,3 +180,67 @@ def sgm_refine(pixels, accums, disparity, steps=4):
 	px = np.ascontiguousarray(pixels); a = np.ascontiguousarray(accums, np.uint16)
 	lib().oracle_sgm_refine(_fptr(px), _fptr(a), _fptr(d), d.size, int(steps))
 	return d
+
+
+# ---- depth-map post-processing (filter_oracle.cpp) ----
+class ODMap(C.Structure):
+	_fields_ = [("depth", C.c_void_p), ("conf", C.c_void_p), ("width", C.c_int), ("height", C.c_int),
+		("K", C.c_double*9), ("R", C.c_double*9), ("C", C.c_double*3)]
+
+
+def make_dmaps(maps):
+	"""maps: list of (depth HxW, conf HxW or None, K, R, C) -> (ctypes array, keepalive)"""
+	arr = (ODMap*len(maps))()
+	keep = []
+	for i, (d, c, K, R, Cc) in enumerate(maps):
+		d = np.ascontiguousarray(d, np.float32); keep.append(d)
+		o = arr[i]
+		o.depth = _fptr(d); o.conf = None
+		if c is not None:
+			c = np.ascontiguousarray(c, np.float32); keep.append(c); o.conf = _fptr(c)
+		o.width = d.shape[1]; o.height = d.shape[0]
+		o.K[:] = np.asarray(K, np.float64).ravel(); o.R[:] = np.asarray(R, np.float64).ravel(); o.C[:] = np.asarray(Cc, np.float64).ravel()
+	return arr, keep
+
+
+def filter_project(ref, nbr, with_conf=True):
+	arr, keep = make_dmaps([ref, nbr])
+	h, w = arr[0].height, arr[0].width
+	pd = np.zeros((h, w), np.float32); pc = np.zeros((h, w), np.float32)
+	lib().oracle_filter_project(C.byref(arr[0]), C.byref(arr[1]), _fptr(pd), _fptr(pc) if with_conf else None)
+	return pd, pc
+
+
+def filter_depth_map(ref, nbrs, nMinViews=2, nMinViewsAdjust=1, fDepthDiffThreshold=0.01, bAdjust=True, dmin=0.0, dmax=1e30):
+	"""ref / nbrs: (depth, conf, K, R, C).  -> (ok, depth, conf, projected N x H x W)"""
+	arr, keep = make_dmaps([ref]+list(nbrs))
+	h, w = arr[0].height, arr[0].width
+	od = np.zeros((h, w), np.float32); oc = np.zeros((h, w), np.float32)
+	proj = np.zeros((max(len(nbrs), 1), h, w), np.float32)
+	nb = C.cast(C.byref(arr, C.sizeof(ODMap)), C.POINTER(ODMap))
+	ok = lib().oracle_filter_depth_map(C.byref(arr[0]), nb, len(nbrs), int(nMinViews), int(nMinViewsAdjust),
+		C.c_float(fDepthDiffThreshold), int(bool(bAdjust)), C.c_float(dmin), C.c_float(dmax), _fptr(od), _fptr(oc), _fptr(proj))
+	return bool(ok), od, oc, proj
+
+
+def remove_small_segments(depth, normal=None, conf=None, th=0.007, speckle=100):
+	d = np.array(depth, np.float32, copy=True, order="C")
+	n = None if normal is None else np.array(normal, np.float32, copy=True, order="C")
+	c = None if conf is None else np.array(conf, np.float32, copy=True, order="C")
+	lib().oracle_remove_small_segments(_fptr(d), None if n is None else _fptr(n), None if c is None else _fptr(c),
+		d.shape[1], d.shape[0], C.c_float(th), C.c_uint(speckle))
+	return d, n, c
+
+
+def count_asymmetric_edges(depth, th=0.007):
+	d = np.ascontiguousarray(depth, np.float32)
+	return int(lib().oracle_count_asymmetric_edges(_fptr(d), d.shape[1], d.shape[0], C.c_float(th)))
+
+
+def gap_interpolation(depth, normal=None, conf=None, th=0.025, gap=7):
+	d = np.array(depth, np.float32, copy=True, order="C")
+	n = None if normal is None else np.array(normal, np.float32, copy=True, order="C")
+	c = None if conf is None else np.array(conf, np.float32, copy=True, order="C")
+	lib().oracle_gap_interpolation(_fptr(d), None if n is None else _fptr(n), None if c is None else _fptr(c),
+		d.shape[1], d.shape[0], C.c_float(th), C.c_uint(gap))
+	return d, n, c

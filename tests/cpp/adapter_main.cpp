@@ -49,6 +49,17 @@ int main(int argc, char** argv) {
 		b200mvs_stats st;
 		pm.EstimateDepthMap(dd, opt, 0, &st);
 		printf("adapter: %dx%d, %d launches, %.2f ms device\n", hdr[1], hdr[2], st.kernel_launches, st.ms_device);
+		if (argc > 4 && !strcmp(argv[4], "post")) {
+			// the post-processing members: speckles, gaps, then the filter with the map as its own two neighbours
+			pm.RemoveSmallSegments(dd, 0.01f, 100);
+			pm.GapInterpolation(dd, 0.01f, 7);
+			b200mvs_filter_params fp;
+			b200mvs_filter_default_params(&fp);
+			std::vector<DepthData*> nb = {&dd, &dd};
+			Mat<float> nd, nc;
+			if (!pm.FilterDepthMap(dd, nb, fp, nd, nc)) { printf("adapter error: filter refused\n"); return 2; }
+			dd.depthMap = nd; dd.confMap = nc;
+		}
 		pm.Release();
 	} catch (const std::exception& e) {
 		printf("adapter error: %s\n", e.what());

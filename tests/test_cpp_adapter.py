@@ -69,3 +69,38 @@ def test_adapter_matches_python_host_path(tmp_path, tiny_scene):
 	finally:
 		OPTDENSE.nSubResolutionLevels, OPTDENSE.nEstimationGeometricIters, OPTDENSE.nEstimationIters = saved
 	assert np.array_equal(depth, dd.depthMap) and np.array_equal(normal, dd.normalMap) and np.array_equal(conf, dd.confMap)
+
+
+@pytest.mark.gpu
+def test_adapter_post_processing_matches_python_host_path(tmp_path, tiny_scene):
+	"""RemoveSmallSegments, GapInterpolation and FilterDepthMap through the C++ adapter == the Python host path"""
+	import torch
+	if not torch.cuda.is_available():
+		pytest.skip("no CUDA device")
+	from openmvs_b200.depth_estimator import OPTDENSE, Camera, ViewData, DepthData, DepthMapsData
+	exe = _build(str(tmp_path))
+	sc, ref, views = tiny_scene
+	scene, out = str(tmp_path/"scene.bin"), str(tmp_path/"out.bin")
+	_dump_scene(scene, views, sc.dmin, sc.dmax)
+	r = subprocess.run([exe, scene, out, "2", "post"], capture_output=True, text=True)
+	assert r.returncode == 0, r.stdout+r.stderr
+	h, w = views[0].image.shape
+	raw = np.fromfile(out, np.uint8)
+	depth = raw[:h*w*4].view(np.float32).reshape(h, w)
+	normal = raw[h*w*4:h*w*16].view(np.float32).reshape(h, w, 3)
+	conf = raw[h*w*16:h*w*20].view(np.float32).reshape(h, w)
+	saved = (OPTDENSE.nSubResolutionLevels, OPTDENSE.nEstimationGeometricIters, OPTDENSE.nEstimationIters)
+	try:
+		OPTDENSE.nSubResolutionLevels = 0; OPTDENSE.nEstimationGeometricIters = 0; OPTDENSE.nEstimationIters = 2
+		dd = DepthData([ViewData(np.ascontiguousarray(v.image), Camera(v.K, v.R, v.C)) for v in views], sc.dmin, sc.dmax)
+		dm = DepthMapsData([dd], 0, nCalibratedImages=3)
+		dm.EstimateDepthMap(0)
+		raw_valid = (dd.depthMap > 0).sum()
+		dm.RemoveSmallSegments(dd)
+		dm.GapInterpolation(dd)
+		nd, nc = dm.FilterDepthMap(dd, [dd, dd], True)
+		dm.pmCUDA.Release()
+	finally:
+		OPTDENSE.nSubResolutionLevels, OPTDENSE.nEstimationGeometricIters, OPTDENSE.nEstimationIters = saved
+	assert np.array_equal(depth, nd) and np.array_equal(conf, nc) and np.array_equal(normal, dd.normalMap)
+	assert 0.5*raw_valid < (nd > 0).sum()
