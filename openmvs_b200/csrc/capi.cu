@@ -937,7 +937,7 @@ int b200mvs_remove_small_segments_device(b200mvs_ctx* ctx, float* depth, float* 
 	CK(ctx->ppA.reserve(n*4)); CK(ctx->ppB.reserve(n*4));
 	CK(seg_launch_remove(depth, normal, conf, width, height, fDepthDiffThreshold*0.7f, nSpeckleSize, ctx->ppA.as<int>(), ctx->ppB.as<int>(),
 		stream ? (cudaStream_t)stream : ctx->stream));
-	ctx->launches = 4;
+	{ int rounds = 1; while ((1<<rounds) < width+height) ++rounds; ctx->launches = 4+2*rounds; }
 	return B200MVS_OK;
 }
 

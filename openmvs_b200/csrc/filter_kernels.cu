@@ -185,11 +185,19 @@ __global__ void flt_resolve_kernel(const unsigned long long* z, const float* nbr
 	if (conf) conf[o] = (k == ~0ull || !nbrConf) ? 0.f : nbrConf[key_src(k)];
 }
 
-// ---- RemoveSmallSegments: connected components by union-find over the 4-neighbour grid ----
+// ---- RemoveSmallSegments: connected components over the 4-neighbour grid ----
 // The reference grows segments breadth-first with a DIRECTED test IsDepthSimilar(current, neighbour);
 // an edge is taken here when the test holds in either direction (|a-b|/min(a,b) < th).  The two
 // differ only for pairs whose relative difference lies within th^2 of the threshold, where the
 // reference's own result depends on its traversal order.
+// Labelling: every pixel first links to its left (else upper) connected neighbour — a region that is
+// reasonably convex becomes one tree: row runs hang on their first pixel, which hangs on the row above —
+// pointer jumping flattens these chains in ceil(log2(W+H)) rounds, the upper edges the links did not
+// take are merged by an atomicMin union on the flat trees (mostly "same root already"), and a second
+// series of jumps flattens whatever chains of roots the unions built.
+__device__ __forceinline__ bool seg_edge(float a, float b, float th) {
+	return b > 0 && (depth_similar(a, b, th) || depth_similar(b, a, th));
+}
 __device__ __forceinline__ int uf_find(int* L, int i) {
 	int p;
 	while ((p = ((volatile int*)L)[i]) != i) i = p;
@@ -204,27 +212,45 @@ __device__ void uf_union(int* L, int a, int b) {
 		else done = true;
 	} while (!done);
 }
-__global__ void seg_init_kernel(const float* depth, int* L, int* size, int n) {
-	const int i = blockIdx.x*blockDim.x+threadIdx.x;
-	if (i >= n) return;
-	L[i] = depth[i] > 0 ? i : -1;
-	size[i] = 0;
-}
-__global__ void seg_merge_kernel(const float* depth, int* L, int W, int H, float th) {
+__global__ void seg_init_kernel(const float* __restrict__ depth, int* L, int* size, int W, int H, float th) {
 	const int x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y*blockDim.y+threadIdx.y;
 	if (x >= W || y >= H) return;
 	const int i = y*W+x;
 	const float a = depth[i];
+	int l = -1;
+	if (a > 0) {
+		l = i;
+		if (x > 0 && seg_edge(a, depth[i-1], th)) l = i-1;
+		else if (y > 0 && seg_edge(a, depth[i-W], th)) l = i-W;
+	}
+	L[i] = l;
+	size[i] = 0;
+}
+__global__ void seg_jump_kernel(int* L, int n) {
+	const int i = blockIdx.x*blockDim.x+threadIdx.x;
+	if (i >= n) return;
+	const int p = L[i];
+	if (p >= 0 && p != i) L[i] = ((volatile int*)L)[p]; // labels only ever move towards the root: safe in place
+}
+__global__ void seg_merge_kernel(const float* __restrict__ depth, int* L, int W, int H, float th) {
+	const int x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y*blockDim.y+threadIdx.y;
+	if (x < 1 || x >= W || y < 1 || y >= H) return;
+	const int i = y*W+x;
+	const float a = depth[i];
 	if (!(a > 0)) return;
-	if (x+1 < W) { const float b = depth[i+1]; if (b > 0 && (depth_similar(a, b, th) || depth_similar(b, a, th))) uf_union(L, i, i+1); }
-	if (y+1 < H) { const float b = depth[i+W]; if (b > 0 && (depth_similar(a, b, th) || depth_similar(b, a, th))) uf_union(L, i, i+W); }
+	// the link went left; the upper edge is still open
+	if (seg_edge(a, depth[i-1], th) && seg_edge(a, depth[i-W], th)) uf_union(L, i, i-W);
 }
 __global__ void seg_count_kernel(int* L, int* size, int n) {
 	const int i = blockIdx.x*blockDim.x+threadIdx.x;
-	if (i >= n || L[i] < 0) return;
-	const int r = uf_find(L, i);
-	L[i] = r;                       // roots keep L[r] == r, so concurrent finds stay correct
-	atomicAdd(size+r, 1);
+	int r = -1;
+	if (i < n && L[i] >= 0) {
+		r = uf_find(L, i);
+		L[i] = r;                   // roots keep L[r] == r, so concurrent finds stay correct
+	}
+	// one atomic per distinct root in the warp (large segments would otherwise serialise on one address)
+	const unsigned peers = __match_any_sync(0xFFFFFFFFu, r);
+	if (r >= 0 && (threadIdx.x&31) == __ffs(peers)-1) atomicAdd(size+r, __popc(peers));
 }
 __global__ void seg_remove_kernel(const int* L, const int* size, int n, unsigned speckle, float* depth, float* normal, float* conf) {
 	const int i = blockIdx.x*blockDim.x+threadIdx.x;
@@ -306,8 +332,15 @@ cudaError_t flt_launch_resolve(const unsigned long long* z, const float* nbrConf
 
 cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, int H, float th, unsigned speckle, int* labels, int* sizes, cudaStream_t s) {
 	const int n = W*H;
-	seg_init_kernel<<<(n+255)/256, 256, 0, s>>>(depth, labels, sizes, n);
-	seg_merge_kernel<<<dim3((W+31)/32, (H+7)/8), dim3(32, 8), 0, s>>>(depth, labels, W, H, th);
+	const dim3 b2(32, 8), g2((W+31)/32, (H+7)/8);
+	seg_init_kernel<<<g2, b2, 0, s>>>(depth, labels, sizes, W, H, th);
+	int rounds = 1;
+	while ((1<<rounds) < W+H) ++rounds;
+	for (int r = 0; r < rounds; ++r)
+		seg_jump_kernel<<<(n+255)/256, 256, 0, s>>>(labels, n);
+	seg_merge_kernel<<<g2, b2, 0, s>>>(depth, labels, W, H, th);
+	for (int r = 0; r < rounds; ++r)
+		seg_jump_kernel<<<(n+255)/256, 256, 0, s>>>(labels, n);
 	seg_count_kernel<<<(n+255)/256, 256, 0, s>>>(labels, sizes, n);
 	seg_remove_kernel<<<(n+255)/256, 256, 0, s>>>(labels, sizes, n, speckle, depth, normal, conf);
 	return cudaGetLastError();

@@ -12,9 +12,18 @@ dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 args = (dev(lg), dev(lc), dev(rg), torch.from_numpy(px.view(np.uint8).reshape(-1, 16).copy()).cuda(), n)
 m = SemiGlobalMatcher()
 costs = torch.zeros(n, dtype=torch.uint8, device="cuda"); accums = torch.zeros(n, dtype=torch.int16, device="cuda")
-for rep in range(2):
-	t = {}
-	for name, st in (("cost", 1), ("aggregate", 2), ("wta", 4), ("all", 7)):
-		m.MatchDevice(*args, stages=st, costs=costs, accums=accums)
-		t[name] = m.stats.ms_device
-print("D=%d" % D, " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6))
+ref = None
+for ring in ("0", "1"):
+	# B200MVS_SGM_RING=0: register-pipelined uniform kernel; 1 (default): bulk-copy ring kernel
+	os.environ["B200MVS_SGM_RING"] = ring
+	for rep in range(2):
+		t = {}
+		for name, st in (("cost", 1), ("aggregate", 2), ("wta", 4), ("all", 7)):
+			disp, cost = m.MatchDevice(*args, stages=st, costs=costs, accums=accums)
+			t[name] = m.stats.ms_device
+	same = ""
+	if ref is None:
+		ref = (accums.clone(), disp.clone())
+	else:
+		same = "| identical to ring=0: %s" % (torch.equal(ref[0], accums) and torch.equal(ref[1], disp))
+	print("D=%d ring=%s" % (D, ring), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same)

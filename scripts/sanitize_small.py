@@ -10,9 +10,9 @@ views = [sc.views[1], sc.views[0], sc.views[2]]
 OPTDENSE.nEstimationIters = 1; OPTDENSE.nEstimationGeometricIters = 1
 ONLY = os.environ.get("SANITIZE_ONLY", "")
 pm = PatchMatchB200(0)
-if ONLY == "post":
+if ONLY:
 	pm.Release()
-if ONLY != "post":
+if ONLY == "":
 	for levels in (0, 1):
 		OPTDENSE.nSubResolutionLevels = levels
 		dd = DepthData([ViewData(np.ascontiguousarray(v.image), Camera(v.K, v.R, v.C)) for v in views], sc.dmin, sc.dmax)
@@ -29,6 +29,15 @@ if ONLY != "post":
 	px, n = synth.sgm_pixel_map(131, 77, lo, hi, rng.rand(71, 125) < 0.1)
 	m = SemiGlobalMatcher(); disp, cost = m.Match(lg, lc, rg, px, n); m.Release()
 	print("sgm ok", disp.shape, int((disp != 32767).sum()))
+if ONLY in ("", "sgm"):
+	# uniform 16-byte aligned ranges: the bulk-copy ring aggregation kernel (mbarrier + cp.async.bulk)
+	lg, lc, rg, d = synth.make_stereo_pair(150, 90)
+	for num in (32, 144):
+		px, n = synth.sgm_pixel_map(150, 90, -8, -8+num)
+		m = SemiGlobalMatcher(); disp, cost = m.Match(lg, lc, rg, px, n); m.Release()
+		print("sgm ring num", num, "ok", int((disp != 32767).sum()))
+if ONLY == "sgm":
+	sys.exit(0)
 # depth-map post-processing: filter (both branches), speckles, gaps
 from openmvs_b200.depth_estimator import DepthMapsData
 maps = synth.make_noisy_dmaps(sc)

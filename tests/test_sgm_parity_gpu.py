@@ -133,10 +133,11 @@ def test_cross_check_and_subpixel_refinement_parity(sgm):
 	assert np.abs(want[valid]/4.0-disp_in[valid]).max() <= 0.5+1e-6  # the offset stays within half a pixel
 
 
-@pytest.mark.parametrize("num", [4, 36, 128, 132, 256])
+@pytest.mark.parametrize("num", [4, 36, 48, 128, 132, 144, 256])
 def test_uniform_range_fast_path_bit_exact(sgm, num):
-	"""One global disparity range (the non-tSGM branch): the packed, shared-memory-free aggregation
-	kernel (lane-contiguous disparities) against the oracle, with some invalid pixels."""
+	"""One global disparity range (the non-tSGM branch) against the oracle, with some invalid pixels: the packed
+	register-pipelined aggregation kernel (4, 36, 132: slices not 16-byte aligned) and the bulk-copy ring kernel
+	(48, 128: 4 disparities per lane; 144, 256: 8 per lane)."""
 	m, O = sgm
 	w, h = 150, 90
 	rng = np.random.RandomState(num)
