@@ -19,6 +19,7 @@
 cudaError_t pm_launch_score(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s);
 cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, int layout, bool geom, bool ws, cudaStream_t s);
 void pm_tma_box(int* w, int* h);
+int pm_layout3_half(int w);
 cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s);
 cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
 	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s);
@@ -132,7 +133,8 @@ struct b200mvs_ctx {
 	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgDisp, sgCost, sgMax; // SGM staging / scratch
 	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
 	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
-	int layout = 1;                           // 1 plain float rows, 2 row pairs (B200MVS_LAYOUT overrides)
+	int layout = 1;                           // 1 plain float rows, 2 row pairs, 3 column-parity planes (B200MVS_LAYOUT overrides)
+	bool pack = false;                        // taps two at a time with FMUL2/FFMA2 (B200MVS_PACK=1, experimental)
 	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
 	bool tma = true;                          // reference tile staged by TMA (B200MVS_TMA=0: plain loads)
 	DevBuf refPad;                            // 16-byte aligned copy of a reference image whose pitch TMA cannot address
@@ -244,9 +246,10 @@ int prepare_tex(b200mvs_ctx* ctx, DView* v, int nViews, cudaStream_t s) {
 	v[0].tex = v[0].img; v[0].tpitch = v[0].pitch;
 	for (int i = 1; i < nViews; ++i) {
 		if (ctx->layout == 1) { v[i].tex = v[i].img; v[i].tpitch = v[i].pitch; continue; }
-		CK(ctx->tex[i].reserve((size_t)v[i].w*v[i].h*sizeof(float)*ctx->layout));
+		const int tpitch = ctx->layout == 3 ? 2*pm_layout3_half(v[i].w) : v[i].w;
+		CK(ctx->tex[i].reserve((size_t)tpitch*v[i].h*sizeof(float)*(ctx->layout == 2 ? 2 : 1)));
 		CK(pm_launch_relayout(v[i].img, v[i].w, v[i].h, v[i].pitch, ctx->tex[i].p, ctx->layout, s)); ++ctx->launches;
-		v[i].tex = ctx->tex[i].p; v[i].tpitch = v[i].w;
+		v[i].tex = ctx->tex[i].p; v[i].tpitch = tpitch;
 	}
 	return B200MVS_OK;
 }
@@ -297,7 +300,7 @@ int launch_sweep_timed(b200mvs_ctx* ctx, const PMParams& P, bool geom, cudaStrea
 		}
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv], s));
 	}
-	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout, geom, ctx->wsmem, s)); ++ctx->launches;
+	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s)); ++ctx->launches;
 	if (ctx->timeSweeps) {
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv+1], s));
 		++ctx->nSweepEv;
@@ -381,7 +384,7 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 		build_params(o, lv.data(), nViews, dMin, dMax, lowres, plane, cost, best, P, geom);
 		P.nRandomIters = nR;
 		P.tma = ctx->tmapValid ? 1 : 0;
-		CK(pm_launch_score(P, ctx->layout, geom, ctx->wsmem, s)); ++ctx->launches;
+		CK(pm_launch_score(P, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s)); ++ctx->launches;
 		for (int it = iterBegin; it < iterEnd; ++it) {
 			for (int k = 0; k < spi; ++k) {
 				P.sweep = it*spi+k;
@@ -434,7 +437,8 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 	b200mvs_ctx* c = new b200mvs_ctx();
 	c->device = device;
 	b200mvs_default_params(&c->prm);
-	if (const char* e = getenv("B200MVS_LAYOUT")) { const int l = atoi(e); if (l == 1 || l == 2) c->layout = l; }
+	if (const char* e = getenv("B200MVS_LAYOUT")) { const int l = atoi(e); if (l >= 1 && l <= 3) c->layout = l; }
+	if (const char* e = getenv("B200MVS_PACK")) c->pack = atoi(e) != 0 && c->layout != 2;
 	if (const char* e = getenv("B200MVS_WSMEM")) c->wsmem = atoi(e) != 0;
 	if (const char* e = getenv("B200MVS_TMA")) c->tma = atoi(e) != 0;
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -658,7 +662,7 @@ int b200mvs_pm_score(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
 	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, s, P, geom);
 	if (rc) return rc;
-	CK(pm_launch_score(P, ctx->layout, geom, ctx->wsmem, s));
+	CK(pm_launch_score(P, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s));
 	return B200MVS_OK;
 }
 int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
@@ -674,7 +678,7 @@ int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	for (int colour = 0; colour < 2; ++colour) {
 		if (half >= 0 && half != colour) continue;
 		P.colour = colour;
-		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout, geom, ctx->wsmem, s));
+		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s));
 	}
 	return B200MVS_OK;
 }

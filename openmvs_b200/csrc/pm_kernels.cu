@@ -184,8 +184,47 @@ __device__ __forceinline__ bool sample_depth_masked(const float* __restrict__ im
 // Bilinear fetch of one warped tap.  LAYOUT selects how the neighbour image is stored in HBM:
 //   1: plain float rows                       4 x LDG.32 per tap
 //   2: row pairs  float2{I(y,x), I(y+1,x)}    2 x LDG.64 per tap (second at +8 B)
+//   3: rows de-interleaved by column parity [even columns | odd columns]: lanes are two pixels apart
+//      (red-black), so a warp's taps hit 32 nearly consecutive floats of ONE parity plane per load
+//      instead of every other float of a 64-pixel span (experimental, B200MVS_LAYOUT=3)
+// LAYOUT + 10 (11, 13): the same storage, taps evaluated two at a time with the packed fp32 instructions of
+// sm_100 (FMUL2 / FFMA2 through __fmul2_rn / __ffma2_rn): identical roundings, fewer issue slots
+// (experimental, B200MVS_PACK=1).
 // (measured and dropped, DESIGN.md §6: float4 quads with one LDG.128 per tap, texture gather TLD4,
 //  and a TLD4/LDG split across views — all slower than these two on B200)
+// the four texels of a tap at integer position (lx, ly); LAYOUT 3 returns them as (even column, odd column)
+// pairs: *par = lx & 1 tells which is the left one
+template <int L>
+__device__ __forceinline__ void fetch_texels(const void* __restrict__ tex, int pitch, int lx, int ly,
+	float& v00, float& v10, float& v01, float& v11, int& par)
+{
+	par = 0;
+	if (L == 1) {
+		unsigned long long addr;
+		const unsigned idx = (unsigned)(ly*pitch + lx);
+		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(4u), "l"((unsigned long long)tex));
+		const float* r0 = (const float*)addr;
+		const float* r1 = r0+pitch;
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v00) : "l"(r0));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v10) : "l"(r0));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v01) : "l"(r1));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v11) : "l"(r1));
+	} else {
+		// row = [even plane: pitch/2 floats | odd plane: pitch/2 floats]; texel lx is element lx>>1 of plane lx&1.
+		// The even texel of {lx, lx+1} is element (lx>>1)+(lx&1) of the even plane, the odd one element lx>>1 of the odd plane.
+		par = lx & 1;
+		const unsigned io = (unsigned)(ly*pitch + (lx>>1));
+		unsigned long long ae, ao;
+		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ao) : "r"(io), "r"(4u), "l"((unsigned long long)tex + 2ull*(unsigned)pitch));
+		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ae) : "r"(io+(unsigned)par), "r"(4u), "l"((unsigned long long)tex));
+		const float* e0 = (const float*)ae; const float* o0 = (const float*)ao;
+		const float* e1 = e0+pitch; const float* o1 = o0+pitch;
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v00) : "l"(e0));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v10) : "l"(o0));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v01) : "l"(e1));
+		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v11) : "l"(o1));
+	}
+}
 template <int LAYOUT>
 __device__ __forceinline__ float fetch_bilinear(const void* __restrict__ tex, int pitch, unsigned idx, float ax, float ay) {
 	float v00, v10, v01, v11;
@@ -254,6 +293,66 @@ __device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, 
 	// keep the per-view constants in registers (otherwise re-read from the constant bank per tap)
 	asm volatile("" : "+r"(pitch), "+l"(tex));
 	float sum = 0.f, sumSq = 0.f, num = 0.f;
+	if constexpr (LAYOUT >= 3) {
+		// experimental variants (see fetch_texels): L = 3 de-interleaved storage, PACK = taps two at a time
+		constexpr int L = LAYOUT%10;
+		constexpr bool PACK = LAYOUT >= 10;
+		const float2 NEG1 = make_float2(-1.f, -1.f);
+		#pragma unroll
+		for (int i = 0; i < 5; ++i) {
+			float X = bx, Y = by, Z = bz;
+			#pragma unroll
+			for (int j = 0; j < 5; j += 2) {
+				const bool two = j+1 < 5;
+				// tap a = j, tap b = j+1 (the fifth tap of a row runs alone in the .x halves)
+				const float Xa = X, Ya = Y, Za = Z;
+				const float Xb = Xa+c0x, Yb = Ya+c0y, Zb = Za+c0z;
+				if (two) { X = Xb+c0x; Y = Yb+c0y; Z = Zb+c0z; }
+				const float iza = fast_rcp(Za), izb = two ? fast_rcp(Zb) : 0.f;
+				float2 PX, PY;
+				if (PACK && two) { PX = __fmul2_rn(make_float2(Xa, Xb), make_float2(iza, izb)); PY = __fmul2_rn(make_float2(Ya, Yb), make_float2(iza, izb)); }
+				else { PX = make_float2(Xa*iza, Xb*izb); PY = make_float2(Ya*iza, Yb*izb); }
+				const int lxa = __float2int_rz(PX.x), lya = __float2int_rz(PY.x);
+				const int lxb = two ? __float2int_rz(PX.y) : 1, lyb = two ? __float2int_rz(PY.y) : 1;
+				const float2 FLX = make_float2((float)lxa, (float)lxb), FLY = make_float2((float)lya, (float)lyb);
+				float2 AX, AY;
+				if (PACK && two) { AX = __ffma2_rn(FLX, NEG1, PX); AY = __ffma2_rn(FLY, NEG1, PY); }
+				else { AX = make_float2(PX.x-FLX.x, PX.y-FLX.y); AY = make_float2(PY.x-FLY.x, PY.y-FLY.y); }
+				float2 V00, V10, V01, V11; int para, parb = 0;
+				fetch_texels<L>(tex, pitch, lxa, lya, V00.x, V10.x, V01.x, V11.x, para);
+				if (two) fetch_texels<L>(tex, pitch, lxb, lyb, V00.y, V10.y, V01.y, V11.y, parb);
+				else { V00.y = V10.y = V01.y = V11.y = 0.f; }
+				if (L == 3) {
+					// (even, odd) -> (left, right): base = left texel, and the horizontal weight changes sign when
+					// the left texel is the odd one: o + ax (e - o) == o - ax (o - e), same rounding
+					AX.x = para ? -AX.x : AX.x; AX.y = parb ? -AX.y : AX.y;
+				}
+				float2 DT, TOP, DB, BOT, DV, V;
+				float2 B0 = V00, B1 = V01;
+				if (L == 3) { B0.x = para ? V10.x : V00.x; B0.y = parb ? V10.y : V00.y; B1.x = para ? V11.x : V01.x; B1.y = parb ? V11.y : V01.y; }
+				if (PACK && two) {
+					DT = __ffma2_rn(V00, NEG1, V10); TOP = __ffma2_rn(AX, DT, B0);
+					DB = __ffma2_rn(V01, NEG1, V11); BOT = __ffma2_rn(AX, DB, B1);
+					DV = __ffma2_rn(TOP, NEG1, BOT); V = __ffma2_rn(AY, DV, TOP);
+				} else {
+					TOP = make_float2(fmaf(AX.x, V10.x-V00.x, B0.x), fmaf(AX.y, V10.y-V00.y, B0.y));
+					BOT = make_float2(fmaf(AX.x, V11.x-V01.x, B1.x), fmaf(AX.y, V11.y-V01.y, B1.y));
+					V = make_float2(fmaf(AY.x, BOT.x-TOP.x, TOP.x), fmaf(AY.y, BOT.y-TOP.y, TOP.y));
+				}
+				{
+					const float2 wk = pt.get(i*5+j);
+					const float vw = V.x*wk.x;
+					sum += vw; sumSq = fmaf(V.x, vw, sumSq); num = fmaf(V.x, wk.y, num);
+				}
+				if (two) {
+					const float2 wk = pt.get(i*5+j+1);
+					const float vw = V.y*wk.x;
+					sum += vw; sumSq = fmaf(V.y, vw, sumSq); num = fmaf(V.y, wk.y, num);
+				}
+			}
+			bx += c1x; by += c1y; bz += c1z;
+		}
+	} else
 	#pragma unroll
 	for (int i = 0; i < 5; ++i) {
 		float X = bx, Y = by, Z = bz;
@@ -670,6 +769,13 @@ __global__ void pm_pairs_kernel(const float* __restrict__ src, int w, int h, int
 	const int y1 = min(y+1, h-1);
 	dst[(size_t)y*w+x] = make_float2(src[(size_t)y*spitch+x], src[(size_t)y1*spitch+x]);
 }
+// LAYOUT 3: row y of dst = [even columns | odd columns], `half` floats each (zero padded)
+__global__ void pm_deint_kernel(const float* __restrict__ src, int w, int h, int spitch, float* __restrict__ dst, int half) {
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= 2*half || y >= h) return;
+	const int plane = x >= half, k = x-plane*half, sx = 2*k+plane;
+	dst[(size_t)y*2*half+x] = sx < w ? src[(size_t)y*spitch+sx] : 0.f;
+}
 __global__ void pm_pack_kernel(int n, const float* __restrict__ depth, const float* __restrict__ normal, float4* __restrict__ plane) {
 	const int i = blockIdx.x*blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -715,9 +821,19 @@ cudaError_t launch_layout(bool sweep, dim3 grid, dim3 block, cudaStream_t s, con
 	if (geom) return ws ? launch_one<LAYOUT, true, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, true, false>(sweep, grid, block, s, P, tmap);
 	return ws ? launch_one<LAYOUT, false, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, false, false>(sweep, grid, block, s, P, tmap);
 }
+// the experimental tap-loop variants (LAYOUT 3, 11, 13) exist with the patch weights in shared memory only
+template <int LAYOUT>
+cudaError_t launch_variant(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap, bool geom) {
+	return geom ? launch_one<LAYOUT, true, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, false, true>(sweep, grid, block, s, P, tmap);
+}
 cudaError_t launch_any(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap, int layout, bool geom, bool ws) {
-	if (layout == 2) return launch_layout<2>(sweep, grid, block, s, P, tmap, geom, ws);
-	return launch_layout<1>(sweep, grid, block, s, P, tmap, geom, ws);
+	switch (layout) {
+	case 2: return launch_layout<2>(sweep, grid, block, s, P, tmap, geom, ws);
+	case 3: return launch_variant<3>(sweep, grid, block, s, P, tmap, geom);
+	case 11: return launch_variant<11>(sweep, grid, block, s, P, tmap, geom);
+	case 13: return launch_variant<13>(sweep, grid, block, s, P, tmap, geom);
+	default: return launch_layout<1>(sweep, grid, block, s, P, tmap, geom, ws);
+	}
 }
 
 } // namespace
@@ -735,10 +851,13 @@ cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, int layout, 
 	return launch_any(true, grid, block, s, P, map, layout, geom, ws);
 }
 void pm_tma_box(int* w, int* h) { *w = TILE_W; *h = TILE_H; }
+// floats per parity plane of a LAYOUT 3 row (multiple of 4, room for the element after the last column)
+int pm_layout3_half(int w) { return ((w+1)/2+4+3)&~3; }
 // re-layout of a neighbour image for the tap fetch (see fetch_bilinear)
 cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s) {
 	dim3 block(32, 8), grid((w+31)/32, (h+7)/8);
 	if (layout == 2) pm_pairs_kernel<<<grid, block, 0, s>>>(src, w, h, spitch, (float2*)dst);
+	if (layout == 3) { const int half = pm_layout3_half(w); pm_deint_kernel<<<dim3((2*half+31)/32, (h+7)/8), block, 0, s>>>(src, w, h, spitch, (float*)dst, half); }
 	return cudaGetLastError();
 }
 cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
