@@ -299,12 +299,13 @@ def main():
 	achieved = bytes_launch/(k_ms*1e-3)/1e9
 	nR = (OPTDENSE.nRandomIters+OPTDENSE.nSweepsPerIter-1)//OPTDENSE.nSweepsPerIter
 	samples_launch = (w*h/2)*(4+nR)*N_NEIGH*25
-	roof = {"kernel": "pm_sweep_kernel<1,false,true> (one red-black half-sweep)", "bound": "hbm", "achieved": achieved, "peak": peak,
+	roof = {"kernel": "pm_sweep_kernel<11,false,true> (one red-black half-sweep; taps evaluated in FMUL2/FFMA2 pairs)", "bound": "hbm", "achieved": achieved, "peak": peak,
 		"unit": "GB/s", "frac": achieved/peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
 		"launch_ms": k_ms, "launches_timed": int(pm.stats.sweep_launches), "share_of_step": sweep_share, "algorithmic_bytes_per_launch": bytes_launch,
 		"secondary": {"bound": "issue/L1 (gather stencil, AI ~ 280 flop/B)", "bilinear_samples_per_launch": samples_launch,
 			"gsamples_per_s": samples_launch/(k_ms*1e-3)/1e9}}
 	# the honest bound of this kernel is the L1 LSU data pipe: quote its utilisation from the committed ncu capture
+	# (taken on the scalar-tap variant <1,false,true>; the packed-tap default issues about 10 % fewer instructions per tap)
 	try:
 		for line in open(os.path.join(ROOT, "profiles", "ncu_pm_sweep_r01.txt")):
 			if line.startswith("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"):

@@ -134,7 +134,7 @@ struct b200mvs_ctx {
 	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
 	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
 	int layout = 1;                           // 1 plain float rows, 2 row pairs, 3 column-parity planes (B200MVS_LAYOUT overrides)
-	bool pack = false;                        // taps two at a time with FMUL2/FFMA2 (B200MVS_PACK=1, experimental)
+	bool pack = true;                         // taps two at a time with FMUL2/FFMA2 (B200MVS_PACK=0: scalar taps)
 	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
 	bool tma = true;                          // reference tile staged by TMA (B200MVS_TMA=0: plain loads)
 	DevBuf refPad;                            // 16-byte aligned copy of a reference image whose pitch TMA cannot address
@@ -438,9 +438,10 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 	c->device = device;
 	b200mvs_default_params(&c->prm);
 	if (const char* e = getenv("B200MVS_LAYOUT")) { const int l = atoi(e); if (l >= 1 && l <= 3) c->layout = l; }
-	if (const char* e = getenv("B200MVS_PACK")) c->pack = atoi(e) != 0 && c->layout != 2;
+	if (const char* e = getenv("B200MVS_PACK")) c->pack = atoi(e) != 0;
 	if (const char* e = getenv("B200MVS_WSMEM")) c->wsmem = atoi(e) != 0;
 	if (const char* e = getenv("B200MVS_TMA")) c->tma = atoi(e) != 0;
+	if (c->layout == 2 || !c->wsmem) c->pack = false; // the packed-tap kernels exist for layouts 1 / 3 with the weights in shared memory
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
 		delete c;
