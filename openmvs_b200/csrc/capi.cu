@@ -134,7 +134,7 @@ struct b200mvs_ctx {
 	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
 	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
 	int layout = 1;                           // 1 plain float rows, 2 row pairs, 3 column-parity planes (B200MVS_LAYOUT overrides)
-	bool pack = true;                         // taps two at a time with FMUL2/FFMA2 (B200MVS_PACK=0: scalar taps)
+	int pack = 1;                             // taps two at a time with FMUL2/FFMA2: 0 never, 1 photometric passes (default), 2 also geometric passes (B200MVS_PACK)
 	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
 	bool tma = true;                          // reference tile staged by TMA (B200MVS_TMA=0: plain loads)
 	DevBuf refPad;                            // 16-byte aligned copy of a reference image whose pitch TMA cannot address
@@ -241,6 +241,13 @@ void to_dview(const b200mvs_view& s, const float* img, int pitch, const float* d
 inline int cvRoundI(double v) { return (int)std::nearbyint(v); }
 
 // store the neighbour images of one level in the tap-fetch layout of the kernels
+// kernel variant id of pm_launch_score / pm_launch_sweep: storage layout (+10: packed taps).  The packed-tap kernels were
+// verified bit-identical to the scalar ones on photometric runs (profiles/pm_variants_r01.txt); the geometric instantiations
+// share the tap loop but stay opt-in (B200MVS_PACK=2) until they have been through the GPU test-suite.
+int tap_variant(const b200mvs_ctx* ctx, bool geom) {
+	return ctx->layout + ((ctx->pack == 2 || (ctx->pack == 1 && !geom)) ? 10 : 0);
+}
+
 int prepare_tex(b200mvs_ctx* ctx, DView* v, int nViews, cudaStream_t s) {
 	if ((int)ctx->tex.size() < nViews) ctx->tex.resize(nViews);
 	v[0].tex = v[0].img; v[0].tpitch = v[0].pitch;
@@ -300,7 +307,7 @@ int launch_sweep_timed(b200mvs_ctx* ctx, const PMParams& P, bool geom, cudaStrea
 		}
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv], s));
 	}
-	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s)); ++ctx->launches;
+	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, tap_variant(ctx, geom), geom, ctx->wsmem, s)); ++ctx->launches;
 	if (ctx->timeSweeps) {
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv+1], s));
 		++ctx->nSweepEv;
@@ -384,7 +391,7 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 		build_params(o, lv.data(), nViews, dMin, dMax, lowres, plane, cost, best, P, geom);
 		P.nRandomIters = nR;
 		P.tma = ctx->tmapValid ? 1 : 0;
-		CK(pm_launch_score(P, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s)); ++ctx->launches;
+		CK(pm_launch_score(P, tap_variant(ctx, geom), geom, ctx->wsmem, s)); ++ctx->launches;
 		for (int it = iterBegin; it < iterEnd; ++it) {
 			for (int k = 0; k < spi; ++k) {
 				P.sweep = it*spi+k;
@@ -438,10 +445,10 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 	c->device = device;
 	b200mvs_default_params(&c->prm);
 	if (const char* e = getenv("B200MVS_LAYOUT")) { const int l = atoi(e); if (l >= 1 && l <= 3) c->layout = l; }
-	if (const char* e = getenv("B200MVS_PACK")) c->pack = atoi(e) != 0;
+	if (const char* e = getenv("B200MVS_PACK")) c->pack = std::min(std::max(atoi(e), 0), 2);
 	if (const char* e = getenv("B200MVS_WSMEM")) c->wsmem = atoi(e) != 0;
 	if (const char* e = getenv("B200MVS_TMA")) c->tma = atoi(e) != 0;
-	if (c->layout == 2 || !c->wsmem) c->pack = false; // the packed-tap kernels exist for layouts 1 / 3 with the weights in shared memory
+	if (c->layout == 2 || !c->wsmem) c->pack = 0; // the packed-tap kernels exist for layouts 1 / 3 with the weights in shared memory
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
 		delete c;
@@ -663,7 +670,7 @@ int b200mvs_pm_score(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
 	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, s, P, geom);
 	if (rc) return rc;
-	CK(pm_launch_score(P, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s));
+	CK(pm_launch_score(P, tap_variant(ctx, geom), geom, ctx->wsmem, s));
 	return B200MVS_OK;
 }
 int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
@@ -679,7 +686,7 @@ int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	for (int colour = 0; colour < 2; ++colour) {
 		if (half >= 0 && half != colour) continue;
 		P.colour = colour;
-		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, ctx->layout+(ctx->pack ? 10 : 0), geom, ctx->wsmem, s));
+		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, tap_variant(ctx, geom), geom, ctx->wsmem, s));
 	}
 	return B200MVS_OK;
 }
