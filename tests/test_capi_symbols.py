@@ -36,6 +36,30 @@ def test_struct_layouts_match_header_sizes():
 	assert C.sizeof(lib.Stats) == 8+8+8+8+4+4+8+4+4
 
 
+def test_struct_layouts_match_a_c_compiler(tmp_path):
+	"""sizeof / offsetof of every struct of include/b200mvs.h as gcc sees them == the ctypes mirrors in openmvs_b200/lib.py"""
+	import subprocess
+	from openmvs_b200 import lib
+	structs = {"b200mvs_view": lib.View, "b200mvs_params": lib.Params, "b200mvs_stats": lib.Stats, "b200mvs_job": lib.Job,
+		"b200mvs_sgm_params": lib.SgmParams, "b200mvs_dmap": lib.DMap, "b200mvs_filter_params": lib.FilterParams}
+	lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200mvs.h"', 'int main(void) {']
+	for cname, ct in structs.items():
+		lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+		for fname, _ in ct._fields_:
+			lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+	lines += ['printf("b200mvs_sgm_pixel %zu\\n", sizeof(b200mvs_sgm_pixel));', 'return 0; }']
+	src = tmp_path/"layout.c"
+	src.write_text("\n".join(lines))
+	exe = str(tmp_path/"layout")
+	subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)])
+	got = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+	for cname, ct in structs.items():
+		assert int(got[cname]) == C.sizeof(ct), cname
+		for fname, _ in ct._fields_:
+			assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
+	assert int(got["b200mvs_sgm_pixel"]) == 16  # SemiGlobalMatcher::PixelData
+
+
 def test_create_without_gpu_fails_loudly():
 	import torch
 	if torch.cuda.is_available():
@@ -72,3 +96,7 @@ def test_null_context_and_bad_arguments_return_status_codes():
 	assert dll.b200mvs_estimate_batch(None, 0, None, 0) == 1
 	assert dll.b200mvs_sgm_match(None, None, None, None, 0, 0, None, C.c_uint64(0), None, None, None, None) == 1
 	assert dll.b200mvs_last_error(None) == b"null context"
+	assert dll.b200mvs_filter_depth_map(None, None, None, 0, None, C.c_float(0), C.c_float(1), None, None, None, None) == 1
+	assert dll.b200mvs_filter_depth_map_device(None, None, None, 0, None, C.c_float(0), C.c_float(1), None, None, None, None, None, None) == 1
+	assert dll.b200mvs_remove_small_segments(None, None, None, None, 0, 0, C.c_float(0.01), 100, None) == 1
+	assert dll.b200mvs_gap_interpolation_device(None, None, None, None, 0, 0, C.c_float(0.01), 7, None) == 1
