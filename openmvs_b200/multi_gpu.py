@@ -8,7 +8,9 @@ estimation.  Two exchanges exist:
   * gather_maps      final gather of depth/normal/confidence to one rank (NCCL gather)
   * all_gather_depth depth-only all-gather before a geometric-consistency pass, which needs
                      the neighbours' pass-1 depth-maps (the reference reloads them from
-                     .dmap files, libs/MVS/SceneDensify.cpp:380-394)
+                     .dmap files, libs/MVS/SceneDensify.cpp:380-394); the same exchange with
+                     depth+confidence precedes the filter pass (filter_depth_maps), where the
+                     reference reloads the neighbours' .dmap files again (SceneDensify.cpp:2149-2167)
 """
 from __future__ import annotations
 
@@ -118,6 +120,59 @@ def compute_depth_maps(n_views: int, estimate: Callable, n_geometric_iters: int 
 	if not gather:
 		return packed
 	return gather_maps(packed, n_views, dst)
+
+
+def filter_depth_maps(n_views: int, local: Dict[int, dict], neighbors: Sequence[Sequence[int]], filter_view: Callable,
+		max_neighbors: int = 8) -> Dict[int, dict]:
+	"""The filter pass of Scene::DenseReconstructionFilter (libs/MVS/SceneDensify.cpp:2141-2181) over the ranks: one
+	exchange step (all-gather of depth+confidence, 8 B per pixel and view), then every rank filters its own views against
+	at most `max_neighbors` (numMaxNeighbors = 8) valid neighbour maps.  All views are filtered against the UNFILTERED
+	maps of the pass before — the reference swaps the filtered maps in only after every view is done (EVT_ADJUSTDEPTHMAP).
+
+	local: {view: dict(depth=(H,W), conf=(H,W))} of this rank; neighbors[v]: neighbour views of v, best first;
+	filter_view(v, ref, nbrs) -> (depth, conf) or None, with ref = dict(depth, conf) and nbrs = [(view, depth, conf), ...].
+	Returns {view: dict(depth, conf)} for the views of this rank (unfilterable views keep their maps)."""
+	rank = dist.get_rank() if dist.is_initialized() else 0
+	world = dist.get_world_size() if dist.is_initialized() else 1
+	mine = shard_views(n_views, rank, world)
+	assert sorted(local.keys()) == mine
+	packed = {v: torch.stack([local[v]["depth"], local[v]["conf"]], -1) for v in mine}
+	allm = all_gather_depth(packed, n_views) if mine or world > 1 else {}
+	out = {}
+	for v in mine:
+		nbrs = []
+		for i in neighbors[v]:
+			if i == v or i not in allm:
+				continue
+			d, c = allm[i][..., 0], allm[i][..., 1]
+			if not bool((d > 0).any()):   # !depthDataPair.IsValid()
+				continue
+			nbrs.append((i, d.contiguous(), c.contiguous()))
+			if len(nbrs) == max_neighbors:
+				break
+		res = filter_view(v, local[v], nbrs)
+		out[v] = dict(depth=res[0], conf=res[1]) if res is not None else dict(depth=local[v]["depth"], conf=local[v]["conf"])
+	return out
+
+
+class SceneFilter:
+	"""filter_view callable for filter_depth_maps on one GPU (DepthMapsData.FilterDepthMap on device tensors).
+	views: objects with .K .R .C; dmin/dmax: the depth range FilterDepthMap clips the adjusted depths to."""
+
+	def __init__(self, views, dmin: float, dmax: float, device=None, bAdjust: bool = True):
+		from .depth_estimator import Camera, DepthMapsData
+		self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+		self.dm = DepthMapsData([], self.dev.index or 0, nCalibratedImages=len(views))
+		self.cams = [Camera(v.K, v.R, v.C) for v in views]
+		self.dmin, self.dmax, self.bAdjust = dmin, dmax, bAdjust
+
+	def _dd(self, v, depth, conf):
+		from .depth_estimator import DepthData, ViewData
+		return DepthData([ViewData(None, self.cams[v])], self.dmin, self.dmax, depthMap=depth.to(self.dev).contiguous(),
+			confMap=conf.to(self.dev).contiguous())
+
+	def __call__(self, v, ref, nbrs):
+		return self.dm.FilterDepthMap(self._dd(v, ref["depth"], ref["conf"]), [self._dd(i, d, c) for i, d, c in nbrs], self.bAdjust)
 
 
 class SceneEstimator:

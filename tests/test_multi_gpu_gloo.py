@@ -1,5 +1,6 @@
-"""world_size-2 gloo test of the N>1 path: sharding of reference views, the final gather and
-the depth all-gather that precedes a geometric pass (no GPU: the per-view estimator is a stub)."""
+"""world_size-2 gloo test of the N>1 path: sharding of reference views, the final gather, the depth all-gather
+that precedes a geometric pass and the depth+confidence exchange of the filter pass (no GPU: the per-view
+estimator / filter are stubs)."""
 import os
 import socket
 import sys
@@ -52,6 +53,21 @@ def _check(rank, world, n_views, multi_gpu):
 		ok = ok and len(seen) == 2*len(mine) and all(s[2] and s[3] and s[4] for s in seen)
 		if rank == 0:
 			ok = ok and all(float(res[v][0, 0, 0]) == 200.0+v for v in range(n_views))
+		# filter pass: one depth+confidence exchange, every view sees at most 3 valid neighbours, unfiltered inputs
+		nb = [[(v+k) % n_views for k in (1, 2, 3, 4)] for v in range(n_views)]
+		loc = {v: dict(depth=torch.full((6, 8), 1.0+v) if v != 1 else torch.zeros(6, 8), conf=torch.full((6, 8), 0.5+v)) for v in mine}
+		calls = []
+		def flt(v, ref, nbrs):
+			calls.append((v, [i for i, _, _ in nbrs], all(float(d[0, 0]) == 1.0+i and float(c[0, 0]) == 0.5+i for i, d, c in nbrs)))
+			return None if v % 3 == 0 else (ref["depth"]*2, ref["conf"]*3)
+		fl = multi_gpu.filter_depth_maps(n_views, loc, nb, flt, max_neighbors=3)
+		ok = ok and sorted(fl.keys()) == mine and [c[0] for c in calls] == mine
+		for v, ids, vals in calls:
+			expect = [i for i in nb[v] if i != 1][:3]   # view 1 has an empty depth-map: skipped like !IsValid()
+			ok = ok and ids == expect and vals
+		for v in mine:
+			f = 1.0 if v % 3 == 0 else 2.0
+			ok = ok and float(fl[v]["depth"][0, 0]) == f*float(loc[v]["depth"][0, 0])
 		return bool(ok)
 
 
