@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
+#include "sgm_step.cuh"
 
 struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
 
@@ -431,7 +433,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, unsigne
 		:: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int NPL, int E>
+// DPX = true (experimental, B200MVS_SGM_DPX=1; needs NPL = 4 and num = 128, i.e. every lane full): the step runs on packed
+// u16x2 values (sgm_step.cuh: SIMD-in-a-word adds / mins and the DPX three-input minimum), about a third of the
+// arithmetic instructions of the scalar form; the results are the same integers.
+template <int NPL, int E, bool DPX>
 __global__ void __launch_bounds__(AGG_WARPS*32)
 sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, int dmin, int num)
 {
@@ -515,6 +520,7 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 	unsigned minLp = 0xFFFFu;
 	bool havePrev = false;
 	float Ip = 0.5f;
+	SgmLane4 lane4; lane4.PA = lane4.PB = 0xFFFFFFFFu;
 	uint4 rec; CW c; AW a;
 	fetch(0, rec, c, a);
 	#pragma unroll 1
@@ -528,6 +534,24 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 		uint4 recN = make_uint4(0u, 0u, 0u, 0u); CW cN; AW aN;
 		memset(&cN, 0, sizeof(cN)); memset(&aN, 0, sizeof(aN));
 		if (t+1 < n) fetch(t+1, recN, cN, aN);
+		if constexpr (DPX) {
+			if (rec.w & 1u) {
+				const float I = __uint_as_float(rec.z);
+				const unsigned P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
+				Ip = I;
+				unsigned cw; uint2 acc;
+				memcpy(&cw, &c, 4); memcpy(&acc, &a, 8);
+				unsigned below = __shfl_up_sync(0xFFFFFFFFu, lane4.PB>>16, 1), above = __shfl_down_sync(0xFFFFFFFFu, lane4.PA&0xFFFFu, 1);
+				if (lane == 0) below = 0xFFFFu;
+				if (lane == 31) above = 0xFFFFu;
+				const unsigned P1 = (unsigned)P.P1;
+				const unsigned mn = sgm_step_packed4(cw, below, above, P1|(P1<<16), P2|(P2<<16), minLp|(minLp<<16), havePrev, lane4, acc);
+				const unsigned long long idx = (unsigned long long)rec.x | ((unsigned long long)rec.y<<32);
+				((uint2*)(P.accums + idx))[lane] = acc;
+				minLp = __reduce_min_sync(0xFFFFFFFFu, mn);
+				havePrev = true;
+			}
+		} else
 		if (rec.w & 1u) {
 			const float I = __uint_as_float(rec.z);
 			const int P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
@@ -672,23 +696,27 @@ cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out6, cudaStream_
 }
 // uniform-range fast path: every valid pixel has the range [dmin, dmin+num), num % 4 == 0, 4-aligned slices;
 // ring: slices are 16-byte aligned (num % 16 == 0, idx % 16 == 0, aligned base pointers) -> bulk-copy ring kernel
-template <int NPL, int E>
+template <int NPL, int E, bool DPX = false>
 static cudaError_t launch_ring(const SGMParams& P, int dir, int dmin, int num, int grid, cudaStream_t s) {
 	const size_t smem = (size_t)AGG_WARPS*2*E*(3*(size_t)num+24);
 	static bool done[64] = {}; // per device
 	int dev = 0; cudaGetDevice(&dev); dev &= 63;
 	if (!done[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(sgm_aggregate_uniform_ring_kernel<NPL, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2*E*AGG_WARPS*(3*(NPL*32)+24));
+		cudaError_t e = cudaFuncSetAttribute(sgm_aggregate_uniform_ring_kernel<NPL, E, DPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2*E*AGG_WARPS*(3*(NPL*32)+24));
 		if (e != cudaSuccess) return e;
 		done[dev] = true;
 	}
-	sgm_aggregate_uniform_ring_kernel<NPL, E><<<grid, AGG_WARPS*32, smem, s>>>(P, dir, dmin, num);
+	sgm_aggregate_uniform_ring_kernel<NPL, E, DPX><<<grid, AGG_WARPS*32, smem, s>>>(P, dir, dmin, num);
 	return cudaGetLastError();
 }
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s) {
 	const int W = P.vw, H = P.vh;
 	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
 	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
+	if (ring && num == 128 && P.P1 >= 0 && P.P1 < 0x8000) {
+		static const bool dpx = [] { const char* e = getenv("B200MVS_SGM_DPX"); return e && atoi(e) != 0; }();
+		if (dpx) return launch_ring<4, 16, true>(P, dir, dmin, num, grid, s);
+	}
 	if (ring && (num & 15) == 0)
 		return num <= 128 ? launch_ring<4, 16>(P, dir, dmin, num, grid, s) : launch_ring<8, 8>(P, dir, dmin, num, grid, s);
 	if (num <= 128) sgm_aggregate_uniform_kernel<4, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
