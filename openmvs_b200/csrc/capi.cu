@@ -39,6 +39,8 @@ cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out, cudaStream_t
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s);
+cudaError_t sgm_launch_aggregate_dir(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s);
+cudaError_t sgm_launch_sum_dirs(const uint16_t* dirL, int nDirs, size_t n, uint16_t* accums, cudaStream_t s);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
@@ -131,6 +133,8 @@ struct b200mvs_ctx {
 	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
 	std::vector<DevBuf> tex;                  // neighbour images in the tap-fetch layout
 	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgDisp, sgCost, sgMax; // SGM staging / scratch
+	DevBuf sgDirL;                            // experimental: per-direction path costs (B200MVS_SGM_CONCURRENT=1)
+	cudaStream_t sgStreams[8] = {}; cudaEvent_t sgFork = nullptr, sgJoin[8] = {};
 	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
 	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
 	int layout = 1;                           // 1 plain float rows, 2 row pairs, 3 column-parity planes (B200MVS_LAYOUT overrides)
@@ -470,6 +474,9 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
 	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release();
 	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
+	c->sgDirL.release();
+	for (int i = 0; i < 8; ++i) { if (c->sgStreams[i]) cudaStreamDestroy(c->sgStreams[i]); if (c->sgJoin[i]) cudaEventDestroy(c->sgJoin[i]); }
+	if (c->sgFork) cudaEventDestroy(c->sgFork);
 	c->fltZ.release(); c->fltIn.release(); c->fltOutD.release(); c->fltOutC.release();
 	c->ppA.release(); c->ppB.release(); c->ppD.release(); c->ppN.release(); c->ppC.release();
 	c->plane.release(); c->cost.release(); c->best.release(); c->prior.release(); c->lowPlane.release();
@@ -754,6 +761,29 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 		ring = uniform && (st6[0] & 15) == 0 && st6[5] == 0 && !((uintptr_t)P.costs & 15) && !((uintptr_t)P.accums & 15) && !(re && atoi(re) == 0);
 	}
 	if (stages & 1) { CK(sgm_launch_cost(P, s)); ++ctx->launches; }
+	const char* conc = getenv("B200MVS_SGM_CONCURRENT");
+	if ((stages & 2) && ring && conc && atoi(conc) != 0 && (numCosts & 7) == 0) {
+		// experimental: the eight directions at the same time, each into its own buffer of path costs, summed afterwards
+		CK(ctx->sgDirL.reserve(8*numCosts*sizeof(uint16_t)));
+		if (!ctx->sgFork) {
+			CK(cudaEventCreateWithFlags(&ctx->sgFork, cudaEventDisableTiming));
+			for (int i = 0; i < 8; ++i) {
+				CK(cudaStreamCreateWithFlags(&ctx->sgStreams[i], cudaStreamNonBlocking));
+				CK(cudaEventCreateWithFlags(&ctx->sgJoin[i], cudaEventDisableTiming));
+			}
+		}
+		CK(cudaEventRecord(ctx->sgFork, s));
+		for (int dir = 0; dir < 8; ++dir) {
+			SGMParams Pd = P;
+			Pd.accums = ctx->sgDirL.as<uint16_t>() + (size_t)dir*numCosts;
+			CK(cudaStreamWaitEvent(ctx->sgStreams[dir], ctx->sgFork, 0));
+			CK(sgm_launch_aggregate_dir(Pd, dir, st6[1], st6[0], ctx->sgStreams[dir]));
+			CK(cudaEventRecord(ctx->sgJoin[dir], ctx->sgStreams[dir]));
+			CK(cudaStreamWaitEvent(s, ctx->sgJoin[dir], 0));
+			++ctx->launches;
+		}
+		CK(sgm_launch_sum_dirs(ctx->sgDirL.as<uint16_t>(), 8, (size_t)numCosts, accums, s)); ++ctx->launches;
+	} else
 	if (stages & 2) {
 		CK(cudaMemsetAsync(accums, 0, numCosts*sizeof(uint16_t), s));
 		for (int dir = 0; dir < 8; ++dir) {

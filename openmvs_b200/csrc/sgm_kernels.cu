@@ -436,7 +436,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, unsigne
 // DPX = true (experimental, B200MVS_SGM_DPX=1; needs NPL = 4 and num = 128, i.e. every lane full): the step runs on packed
 // u16x2 values (sgm_step.cuh: SIMD-in-a-word adds / mins and the DPX three-input minimum), about a third of the
 // arithmetic instructions of the scalar form; the results are the same integers.
-template <int NPL, int E, bool DPX>
+// ACC = false (experimental, B200MVS_SGM_CONCURRENT=1): the kernel writes the path costs L of ITS direction to P.accums
+// (a per-direction buffer) instead of adding them to the running sum, so it reads no accumulators and the eight directions
+// can run at the same time on eight streams; sgm_sum_dirs_kernel adds the eight buffers afterwards.
+template <int NPL, int E, bool DPX, bool ACC = true>
 __global__ void __launch_bounds__(AGG_WARPS*32)
 sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, int dmin, int num)
 {
@@ -454,7 +457,7 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 	int n = 0x7FFFFFFF;
 	if (dx > 0) n = min(n, P.vw-x0); else if (dx < 0) n = min(n, x0+1);
 	if (dy > 0) n = min(n, P.vh-y0); else if (dy < 0) n = min(n, y0+1);
-	const unsigned stageBytes = 3u*(unsigned)num;                       // costs | accumulators
+	const unsigned stageBytes = (ACC ? 3u : 1u)*(unsigned)num;          // costs | accumulators
 	const unsigned warpBytes = RING*(stageBytes+16u+8u);
 	unsigned char* base = ring_smem + (size_t)warp*warpBytes;
 	unsigned char* stages = base;                                        // RING x stageBytes (16-byte aligned: num % 16 == 0)
@@ -483,7 +486,7 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 					const uint32_t bar = smem_addr(bars+slot), dst = smem_addr(stages+(size_t)slot*stageBytes);
 					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(stageBytes) : "memory");
 					bulk_load(dst, P.costs+p.idx, (unsigned)num, bar);
-					bulk_load(dst+(unsigned)num, P.accums+p.idx, 2u*(unsigned)num, bar);
+					if (ACC) bulk_load(dst+(unsigned)num, P.accums+p.idx, 2u*(unsigned)num, bar);
 				}
 			}
 			recs[slot] = r;
@@ -502,12 +505,14 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 				const unsigned char* st = stages+(size_t)slot*stageBytes;
 				const uint32_t* cs = (const uint32_t*)st + lane*(NPL/4);
 				const uint2* as = (const uint2*)(st+num) + lane*(NPL/4);
-				if (NPL == 4) { uint32_t v = cs[0]; memcpy(&c, &v, 4); uint2 w = as[0]; memcpy(&a, &w, 8); }
+				if (NPL == 4) { uint32_t v = cs[0]; memcpy(&c, &v, 4); if (ACC) { uint2 w = as[0]; memcpy(&a, &w, 8); } }
 				else {
 					uint2 v; v.x = cs[0]; v.y = nval > 4 ? cs[1] : 0u; memcpy(&c, &v, 8);
-					uint4 w; const uint2 lo = as[0]; w.x = lo.x; w.y = lo.y; w.z = w.w = 0u;
-					if (nval > 4) { const uint2 hi = as[1]; w.z = hi.x; w.w = hi.y; }
-					memcpy(&a, &w, 16);
+					if (ACC) {
+						uint4 w; const uint2 lo = as[0]; w.x = lo.x; w.y = lo.y; w.z = w.w = 0u;
+						if (nval > 4) { const uint2 hi = as[1]; w.z = hi.x; w.w = hi.y; }
+						memcpy(&a, &w, 16);
+					}
 				}
 			}
 		}
@@ -696,17 +701,17 @@ cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out6, cudaStream_
 }
 // uniform-range fast path: every valid pixel has the range [dmin, dmin+num), num % 4 == 0, 4-aligned slices;
 // ring: slices are 16-byte aligned (num % 16 == 0, idx % 16 == 0, aligned base pointers) -> bulk-copy ring kernel
-template <int NPL, int E, bool DPX = false>
+template <int NPL, int E, bool DPX = false, bool ACC = true>
 static cudaError_t launch_ring(const SGMParams& P, int dir, int dmin, int num, int grid, cudaStream_t s) {
-	const size_t smem = (size_t)AGG_WARPS*2*E*(3*(size_t)num+24);
+	const size_t smem = (size_t)AGG_WARPS*2*E*((ACC ? 3 : 1)*(size_t)num+24);
 	static bool done[64] = {}; // per device
 	int dev = 0; cudaGetDevice(&dev); dev &= 63;
 	if (!done[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(sgm_aggregate_uniform_ring_kernel<NPL, E, DPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2*E*AGG_WARPS*(3*(NPL*32)+24));
+		cudaError_t e = cudaFuncSetAttribute(sgm_aggregate_uniform_ring_kernel<NPL, E, DPX, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2*E*AGG_WARPS*(3*(NPL*32)+24));
 		if (e != cudaSuccess) return e;
 		done[dev] = true;
 	}
-	sgm_aggregate_uniform_ring_kernel<NPL, E, DPX><<<grid, AGG_WARPS*32, smem, s>>>(P, dir, dmin, num);
+	sgm_aggregate_uniform_ring_kernel<NPL, E, DPX, ACC><<<grid, AGG_WARPS*32, smem, s>>>(P, dir, dmin, num);
 	return cudaGetLastError();
 }
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s) {
@@ -721,6 +726,30 @@ cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, 
 		return num <= 128 ? launch_ring<4, 16>(P, dir, dmin, num, grid, s) : launch_ring<8, 8>(P, dir, dmin, num, grid, s);
 	if (num <= 128) sgm_aggregate_uniform_kernel<4, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
 	else sgm_aggregate_uniform_kernel<8, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
+	return cudaGetLastError();
+}
+// experimental: one direction of the ring kernel writing its path costs into P.accums (a per-direction buffer)
+cudaError_t sgm_launch_aggregate_dir(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s) {
+	const int W = P.vw, H = P.vh;
+	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
+	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
+	if ((num & 15) != 0 || num > 256) return cudaErrorInvalidValue;
+	return num <= 128 ? launch_ring<4, 16, false, false>(P, dir, dmin, num, grid, s) : launch_ring<8, 8, false, false>(P, dir, dmin, num, grid, s);
+}
+// accums[i] = sum over the nDirs per-direction buffers dirL + d*n of L_d[i]; n % 8 == 0 (16-byte vectors of 8 x u16)
+__global__ void sgm_sum_dirs_kernel(const uint16_t* __restrict__ dirL, int nDirs, size_t n, uint16_t* __restrict__ accums) {
+	const size_t nv = n/8;
+	for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x*blockDim.x) {
+		uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+		for (int d = 0; d < nDirs; ++d) {
+			const uint4 v = ((const uint4*)(dirL + (size_t)d*n))[i];
+			acc.x = __vadd2(acc.x, v.x); acc.y = __vadd2(acc.y, v.y); acc.z = __vadd2(acc.z, v.z); acc.w = __vadd2(acc.w, v.w);
+		}
+		((uint4*)accums)[i] = acc;
+	}
+}
+cudaError_t sgm_launch_sum_dirs(const uint16_t* dirL, int nDirs, size_t n, uint16_t* accums, cudaStream_t s) {
+	sgm_sum_dirs_kernel<<<148*8, 256, 0, s>>>(dirL, nDirs, n, accums);
 	return cudaGetLastError();
 }
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s) {
