@@ -719,8 +719,8 @@ cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, 
 	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
 	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
 	if (ring && num == 128 && P.P1 >= 0 && P.P1 < 0x8000) {
-		static const bool dpx = [] { const char* e = getenv("B200MVS_SGM_DPX"); return e && atoi(e) != 0; }();
-		if (dpx) return launch_ring<4, 16, true>(P, dir, dmin, num, grid, s);
+		const char* e = getenv("B200MVS_SGM_DPX"); // read per call so that one process can compare the variants
+		if (e && atoi(e) != 0) return launch_ring<4, 16, true>(P, dir, dmin, num, grid, s);
 	}
 	if (ring && (num & 15) == 0)
 		return num <= 128 ? launch_ring<4, 16>(P, dir, dmin, num, grid, s) : launch_ring<8, 8>(P, dir, dmin, num, grid, s);

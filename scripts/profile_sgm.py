@@ -13,17 +13,23 @@ args = (dev(lg), dev(lc), dev(rg), torch.from_numpy(px.view(np.uint8).reshape(-1
 m = SemiGlobalMatcher()
 costs = torch.zeros(n, dtype=torch.uint8, device="cuda"); accums = torch.zeros(n, dtype=torch.int16, device="cuda")
 ref = None
-for ring in ("0", "1"):
-	# B200MVS_SGM_RING=0: register-pipelined uniform kernel; 1 (default): bulk-copy ring kernel
-	os.environ["B200MVS_SGM_RING"] = ring
+MODES = [("register pipeline", dict(B200MVS_SGM_RING="0")), ("bulk-copy ring (default)", dict(B200MVS_SGM_RING="1")),
+	("ring + packed u16x2 step", dict(B200MVS_SGM_RING="1", B200MVS_SGM_DPX="1")),
+	("ring, 8 directions concurrent", dict(B200MVS_SGM_RING="1", B200MVS_SGM_CONCURRENT="1"))]
+if len(sys.argv) > 2 and sys.argv[2] == "default":
+	MODES = MODES[:2]  # the two measured variants only
+for name, env in MODES:
+	for k in ("B200MVS_SGM_RING", "B200MVS_SGM_DPX", "B200MVS_SGM_CONCURRENT"):
+		os.environ.pop(k, None)
+	os.environ.update(env)
 	for rep in range(2):
 		t = {}
-		for name, st in (("cost", 1), ("aggregate", 2), ("wta", 4), ("all", 7)):
+		for stage_name, st in (("cost", 1), ("aggregate", 2), ("wta", 4), ("all", 7)):
 			disp, cost = m.MatchDevice(*args, stages=st, costs=costs, accums=accums)
-			t[name] = m.stats.ms_device
+			t[stage_name] = m.stats.ms_device
 	same = ""
 	if ref is None:
 		ref = (accums.clone(), disp.clone())
 	else:
-		same = "| identical to ring=0: %s" % (torch.equal(ref[0], accums) and torch.equal(ref[1], disp))
-	print("D=%d ring=%s" % (D, ring), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same)
+		same = "| identical to the register pipeline: %s" % (torch.equal(ref[0], accums) and torch.equal(ref[1], disp))
+	print("D=%d %-30s" % (D, name), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same, flush=True)
