@@ -257,6 +257,14 @@ int b200mvs_gap_interpolation(b200mvs_ctx* ctx, float* depth, float* normal, flo
 int b200mvs_gap_interpolation_device(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
 	float fDepthDiffThreshold, unsigned nIpolGapSize, void* stream);
 
+/* ---- image preparation before the estimation -------------------------
+ * TImage<Pixel8U>::toGray(out, cv::COLOR_BGR2GRAY, bNormalize = true) (libs/Common/Types.inl:2377-2431), applied by
+ * DepthMapsData::InitViews to every image (SceneDensify.cpp:324,345): 8-bit colour image (3 or 4 interleaved channels,
+ * bgr != 0: B,G,R order as cv::imread delivers; 0: R,G,B) -> float gray in [0,1], coefficients .114 / .587 / .299.
+ * DEVICE pointers: upload the 8-bit image once (3 B per pixel instead of 4) and convert in HBM; strides in bytes, 0 = packed. */
+int b200mvs_to_gray_device(b200mvs_ctx* ctx, const uint8_t* image, int width, int height, int stride_bytes, int channels, int bgr,
+	float* gray, int gray_stride_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,7 @@ cudaError_t gap_launch(float* depth, float* normal, float* conf, float* tDepth, 
 cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s);
+cudaError_t rs_launch_to_gray(const uint8_t* src, int w, int h, int sstride, int channels, int bgr, float* dst, int dpitch, cudaStream_t s);
 cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, cudaStream_t s);
 
 namespace {
@@ -1041,6 +1042,23 @@ int b200mvs_gap_interpolation(b200mvs_ctx* ctx, float* depth, float* normal, flo
 	float fDepthDiffThreshold, unsigned nIpolGapSize, b200mvs_stats* stats)
 {
 	return pp_host(ctx, 1, depth, normal, conf, width, height, fDepthDiffThreshold, nIpolGapSize, stats);
+}
+
+// ---- image preparation: toGray on the device ----
+int b200mvs_to_gray_device(b200mvs_ctx* ctx, const uint8_t* image, int width, int height, int stride_bytes, int channels, int bgr,
+	float* gray, int gray_stride_bytes, void* stream)
+{
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!image || !gray || width <= 0 || height <= 0 || (channels != 3 && channels != 4))
+		return fail(ctx, B200MVS_ERR_ARG, "to_gray: null pointer, empty image or channel count other than 3 / 4");
+	if (stride_bytes == 0) stride_bytes = width*channels;
+	if (gray_stride_bytes == 0) gray_stride_bytes = width*4;
+	if (stride_bytes < width*channels || gray_stride_bytes < width*4 || (gray_stride_bytes & 3))
+		return fail(ctx, B200MVS_ERR_ARG, "to_gray: invalid stride");
+	CK(cudaSetDevice(ctx->device));
+	CK(rs_launch_to_gray(image, width, height, stride_bytes, channels, bgr != 0, gray, gray_stride_bytes/4, stream ? (cudaStream_t)stream : ctx->stream));
+	ctx->launches = 1;
+	return B200MVS_OK;
 }
 
 } // extern "C"

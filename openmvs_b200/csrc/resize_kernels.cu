@@ -138,3 +138,22 @@ cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, f
 	plane_up_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, dst, prior, dw, dh, (double)sw/dw, (double)sh/dh);
 	return cudaGetLastError();
 }
+
+// TImage<Pixel8U>::toGray(out, COLOR_BGR2GRAY / COLOR_RGB2GRAY, bNormalize = true) (libs/Common/Types.inl:2377-2431), the
+// conversion DepthMapsData::InitViews applies to every image (SceneDensify.cpp:324,345): each channel is scaled by
+// float(1)/float(255) first (NormRGB_t, Types.inl:1610-1615), then gray = (cb*B + cg*G) + cr*R with cb, cg, cr = .114, .587, .299
+// in float.  Explicit _rn intrinsics: no FMA contraction, same bits as the oracle.
+__global__ void to_gray_kernel(const uint8_t* __restrict__ src, int w, int h, int sstride, int channels, int bgr, float* __restrict__ dst, int dpitch) {
+	const int x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y*blockDim.y+threadIdx.y;
+	if (x >= w || y >= h) return;
+	const uint8_t* p = src + (size_t)y*sstride + (size_t)x*channels;
+	const float inv = 1.f/255.f;
+	const float c0 = __fmul_rn((float)p[0], inv), c1 = __fmul_rn((float)p[1], inv), c2 = __fmul_rn((float)p[2], inv);
+	const float k0 = bgr ? 0.114f : 0.299f, k2 = bgr ? 0.299f : 0.114f;
+	dst[(size_t)y*dpitch+x] = __fadd_rn(__fadd_rn(__fmul_rn(k0, c0), __fmul_rn(0.587f, c1)), __fmul_rn(k2, c2));
+}
+cudaError_t rs_launch_to_gray(const uint8_t* src, int w, int h, int sstride, int channels, int bgr, float* dst, int dpitch, cudaStream_t s) {
+	dim3 b(32, 8);
+	to_gray_kernel<<<grid2(w, h, b), b, 0, s>>>(src, w, h, sstride, channels, bgr, dst, dpitch);
+	return cudaGetLastError();
+}

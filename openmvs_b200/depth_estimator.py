@@ -199,6 +199,19 @@ class PatchMatchB200:
 		except Exception:
 			pass
 
+	def ToGray(self, image, bgr: bool = True):
+		"""TImage::toGray(out, COLOR_BGR2GRAY, bNormalize=true) (libs/Common/Types.inl:2377-2431) on the device: uint8 CUDA tensor
+		(H, W, 3|4), channel order B,G,R(,A) as cv::imread delivers (bgr=False: R,G,B) -> float32 gray (H, W) in [0, 1]."""
+		import torch
+		if not (_is_torch(image) and image.is_cuda and image.dtype == torch.uint8 and image.dim() == 3 and image.shape[2] in (3, 4) and image.is_contiguous()):
+			raise ValueError("ToGray needs a contiguous uint8 CUDA tensor of shape (H, W, 3|4)")
+		h, w, ch = (int(v) for v in image.shape)
+		out = torch.empty((h, w), dtype=torch.float32, device=image.device)
+		rc = self._lib.b200mvs_to_gray_device(self._ctx, image.data_ptr(), w, h, w*ch, ch, int(bool(bgr)), out.data_ptr(), w*4,
+			C.c_void_p(_stream_handle(image.device)))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_to_gray_device")
+		return out
+
 	def _set_params(self):
 		p = OPTDENSE.snapshot()
 		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_params(self._ctx, C.byref(p)), "b200mvs_set_params")

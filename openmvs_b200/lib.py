@@ -70,6 +70,7 @@ SYMBOLS = [
 	"b200mvs_filter_default_params", "b200mvs_filter_depth_map", "b200mvs_filter_depth_map_device",
 	"b200mvs_remove_small_segments", "b200mvs_remove_small_segments_device",
 	"b200mvs_gap_interpolation", "b200mvs_gap_interpolation_device",
+	"b200mvs_to_gray_device",
 ]
 
 _LIB = None
@@ -122,6 +123,7 @@ def load(build_if_missing: bool = True):
 	lib.b200mvs_remove_small_segments_device.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, P]
 	lib.b200mvs_gap_interpolation.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, C.POINTER(Stats)]
 	lib.b200mvs_gap_interpolation_device.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, P]
+	lib.b200mvs_to_gray_device.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, P]
 	_LIB = lib
 	return lib
 

@@ -284,4 +284,16 @@ void oracle_gap_interpolation(float* depth, float* normal, float* conf, int W, i
 	}
 }
 
+// TImage<Pixel8U>::toGray(out, COLOR_BGR2GRAY / COLOR_RGB2GRAY, bNormalize = true) (libs/Common/Types.inl:2377-2431):
+// channels scaled by float(1)/float(255) (NormRGB_t, Types.inl:1610-1615), gray = (cb*c0 + cg*c1) + cr*c2 in float
+void oracle_to_gray(const uint8_t* src, int width, int height, int stride, int channels, int bgr, float* dst) {
+	const float inv = 1.f/255.f;
+	const float k0 = bgr ? 0.114f : 0.299f, k1 = 0.587f, k2 = bgr ? 0.299f : 0.114f;
+	for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) {
+		const uint8_t* p = src + (size_t)y*stride + (size_t)x*channels;
+		const float c0 = (float)p[0]*inv, c1 = (float)p[1]*inv, c2 = (float)p[2]*inv;
+		dst[(size_t)y*width+x] = (k0*c0 + k1*c1) + k2*c2;
+	}
+}
+
 } // extern "C"

@@ -139,6 +139,8 @@ void oracle_remove_small_segments(float* depth, float* normal, float* conf, int 
 int oracle_count_asymmetric_edges(const float* depth, int width, int height, float th);
 /* DepthMapsData::GapInterpolation; th = fDepthDiffThreshold*2.5; normal/conf nullable; in place */
 void oracle_gap_interpolation(float* depth, float* normal, float* conf, int width, int height, float th, unsigned gap);
+/* TImage<Pixel8U>::toGray(..., bNormalize = true) (libs/Common/Types.inl:2377-2431); stride in bytes */
+void oracle_to_gray(const uint8_t* src, int width, int height, int stride, int channels, int bgr, float* dst);
 
 #ifdef __cplusplus
 }

@@ -244,3 +244,12 @@ def gap_interpolation(depth, normal=None, conf=None, th=0.025, gap=7):
 	lib().oracle_gap_interpolation(_fptr(d), None if n is None else _fptr(n), None if c is None else _fptr(c),
 		d.shape[1], d.shape[0], C.c_float(th), C.c_uint(gap))
 	return d, n, c
+
+
+def to_gray(image, bgr=True):
+	"""uint8 (H, W, 3|4) -> float32 gray in [0, 1] (toGray with bNormalize)"""
+	a = np.ascontiguousarray(image, np.uint8)
+	h, w, ch = a.shape
+	out = np.zeros((h, w), np.float32)
+	lib().oracle_to_gray(_fptr(a), w, h, w*ch, ch, int(bool(bgr)), _fptr(out))
+	return out

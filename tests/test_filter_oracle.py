@@ -367,3 +367,21 @@ def test_gap_interpolation_matches_python_transcription(scene):
 	assert filled.sum() > 50 and (d == 0).sum() > filled.sum()
 	assert np.abs(od[filled]-v.depth_gt[filled]).max()/v.depth_gt.mean() < 5e-3
 	assert np.abs(np.linalg.norm(on[filled], axis=1)-1).max() < 1e-5
+
+
+# ---- toGray (image preparation before the estimation) ----
+def test_to_gray_known_answers():
+	rng = np.random.RandomState(2)
+	img = rng.randint(0, 256, (37, 53, 3)).astype(np.uint8)
+	inv = f32(1.0)/f32(255.0)
+	c = img.astype(f32)*inv
+	exp = (f32(0.114)*c[..., 0]+f32(0.587)*c[..., 1])+f32(0.299)*c[..., 2]   # numpy float32: one rounding per operation
+	assert np.array_equal(O.to_gray(img, True), exp)
+	assert np.array_equal(O.to_gray(img[..., ::-1], False), (f32(0.299)*c[..., 2]+f32(0.587)*c[..., 1])+f32(0.114)*c[..., 0])
+	bgra = np.concatenate([img, rng.randint(0, 256, (37, 53, 1)).astype(np.uint8)], -1)
+	assert np.array_equal(O.to_gray(bgra, True), exp)                          # the fourth channel is ignored
+	g = O.to_gray(np.array([[[255, 255, 255], [0, 0, 0], [255, 0, 0]]], np.uint8))
+	assert abs(g[0, 0]-1.0) < 1e-6 and g[0, 1] == 0 and abs(g[0, 2]-0.114) < 1e-6
+	# within float rounding of the double-precision value the fixture generator used
+	ref64 = (0.114*img[..., 0].astype(np.float64)+0.587*img[..., 1]+0.299*img[..., 2])/255.0
+	assert np.abs(O.to_gray(img)-ref64).max() < 2e-7
