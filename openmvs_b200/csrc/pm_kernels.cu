@@ -188,8 +188,9 @@ __device__ __forceinline__ bool sample_depth_masked(const float* __restrict__ im
 //      (red-black), so a warp's taps hit 32 nearly consecutive floats of ONE parity plane per load
 //      instead of every other float of a 64-pixel span (experimental, B200MVS_LAYOUT=3)
 // LAYOUT + 10 (11, 13): the same storage, taps evaluated two at a time with the packed fp32 instructions of
-// sm_100 (FMUL2 / FFMA2 through __fmul2_rn / __ffma2_rn): identical roundings, fewer issue slots
-// (experimental, B200MVS_PACK=1).
+// sm_100 (FMUL2 / FFMA2 through __fmul2_rn / __ffma2_rn): identical roundings, about 10 % fewer issue slots per 25 taps;
+// 11 is the default of the photometric passes (measured 3-4 % faster, whole-run output bit-identical to LAYOUT 1;
+// B200MVS_PACK selects, see capi.cu tap_variant).
 // (measured and dropped, DESIGN.md §6: float4 quads with one LDG.128 per tap, texture gather TLD4,
 //  and a TLD4/LDG split across views — all slower than these two on B200)
 // the four texels of a tap at integer position (lx, ly); LAYOUT 3 returns them as (even column, odd column)
@@ -294,7 +295,7 @@ __device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, 
 	asm volatile("" : "+r"(pitch), "+l"(tex));
 	float sum = 0.f, sumSq = 0.f, num = 0.f;
 	if constexpr (LAYOUT >= 3) {
-		// experimental variants (see fetch_texels): L = 3 de-interleaved storage, PACK = taps two at a time
+		// variants (see fetch_texels): L = 3 de-interleaved storage (experimental), PACK = taps two at a time
 		constexpr int L = LAYOUT%10;
 		constexpr bool PACK = LAYOUT >= 10;
 		const float2 NEG1 = make_float2(-1.f, -1.f);
