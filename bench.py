@@ -177,7 +177,8 @@ def main():
 		dist.init_process_group("nccl", device_id=dev)
 
 	OPTDENSE.nSubResolutionLevels = 0; OPTDENSE.nEstimationGeometricIters = 0
-	OPTDENSE.nEstimationIters = ITERS; OPTDENSE.nRandomIters = 6; OPTDENSE.nSweepsPerIter = 2; OPTDENSE.nPropagation = 4
+	OPTDENSE.nEstimationIters = ITERS; OPTDENSE.nRandomIters = 6; OPTDENSE.nSweepsPerIter = 0; OPTDENSE.nPropagation = 4
+	N_SWEEPS, N_REFINE = OPTDENSE.schedule()
 	scene = build_scene(dev, w, h)
 	nbrs = [scene.neighbors(r, N_NEIGH) for r in range(N_VIEWS)]
 	pm = PatchMatchB200(local_rank)
@@ -215,7 +216,7 @@ def main():
 				dd = DepthData([ViewData(d_imgs[r], cams[r])]+[ViewData(d_imgs[i], cams[i]) for i in nbrs[r]], scene.dmin, scene.dmax,
 					depthMap=m["depth"], normalMap=m["normal"], confMap=m["conf"], viewsMap=m["views"])
 				pms[k].EstimateDepthMap(dd, sync=False)
-			launches[0] += 1+1+ITERS*OPTDENSE.nSweepsPerIter*2+1
+			launches[0] += 1+1+N_SWEEPS*2+1
 		for st in streams:
 			main.wait_stream(st)
 		if world > 1:
@@ -297,9 +298,9 @@ def main():
 		pass
 	peak = float(peaks.get("hbm_gbs", 6650.0))
 	achieved = bytes_launch/(k_ms*1e-3)/1e9
-	nR = (OPTDENSE.nRandomIters+OPTDENSE.nSweepsPerIter-1)//OPTDENSE.nSweepsPerIter
+	nR = N_REFINE
 	samples_launch = (w*h/2)*(4+nR)*N_NEIGH*25
-	roof = {"kernel": "pm_sweep_kernel<11,false,true> (one red-black half-sweep; taps evaluated in FMUL2/FFMA2 pairs)", "bound": "hbm", "achieved": achieved, "peak": peak,
+	roof = {"kernel": "pm_sweep_kernel<true,false> (one red-black half-sweep; taps evaluated in FMUL2/FFMA2 pairs)", "bound": "hbm", "achieved": achieved, "peak": peak,
 		"unit": "GB/s", "frac": achieved/peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
 		"launch_ms": k_ms, "launches_timed": int(pm.stats.sweep_launches), "share_of_step": sweep_share, "algorithmic_bytes_per_launch": bytes_launch,
 		"secondary": {"bound": "issue/L1 (gather stencil, AI ~ 280 flop/B)", "bilinear_samples_per_launch": samples_launch,
@@ -332,7 +333,7 @@ def main():
 			"data": "synthetic",
 			"config": {"workload": "C2: 12x1920x1080 synthetic scene, 9 neighbours, PatchMatch 6 iters, single scale" if not args.small else "dev 12x640x360",
 				"views_per_gpu_per_step": N_VIEWS, "neighbours": N_NEIGH, "iters": ITERS,
-				"schedule": "red-black, %d sweeps/iter, 4 propagations + %d refinements per sweep" % (OPTDENSE.nSweepsPerIter, nR),
+				"schedule": "red-black, %d sweeps for %d reference iterations, <= 4 propagation candidates (best of distances 1/3/5 per direction, unchanged ones skipped) + %d refinements per sweep" % (N_SWEEPS, ITERS, nR),
 				"parallelism": "per-reference-view shards, %d GPU(s), NCCL gather of maps" % world,
 				"l2": "no flush: a step streams %.2f GB of distinct images+maps (> 126 MB L2)" % ((N_VIEWS*w*h*(4+24+20))/1e9)},
 			"clocks": clocks,

@@ -23,6 +23,7 @@
 extern "C" {
 #endif
 
+#define B200MVS_ABI_VERSION 3 /* struct layouts of this header; b200mvs_abi_version() returns the library's */
 #define B200MVS_MAX_VIEWS 32 /* neighbours per reference view (MAX_VIEWS, PatchMatchCUDA.inl:35) */
 
 typedef struct b200mvs_ctx b200mvs_ctx;
@@ -67,12 +68,26 @@ typedef struct {
 	float fRandomSmoothNormal;              /* 13 (deg) */
 	float fRandomSmoothBonus;               /* 0.93 */
 	float fEstimationGeometricWeight;       /* 0.1 */
-	/* engine schedule (not OPTDENSE): a reference iteration is nSweepsPerIter red-black
-	 * sweeps, each trying ceil(nRandomIters/nSweepsPerIter) refinement hypotheses */
-	int nSweepsPerIter;                     /* 2  */
+	/* engine schedule (not OPTDENSE).  The nEstimationIters reference iterations run as red-black sweeps:
+	 * nSweepsPerIter = 0 (default): max(8, ceil(1.5 x nEstimationIters)) sweeps that share the reference's
+	 * nRandomIters x nEstimationIters refinement tries; > 0: nSweepsPerIter sweeps per iteration, each with
+	 * ceil(nRandomIters/nSweepsPerIter) tries.  b200mvs_get_schedule() returns the resulting numbers. */
+	int nSweepsPerIter;                     /* 0  */
 	int nPropagation;                       /* 4: all 4-neighbours; 2: causal pair only */
 	uint32_t seed;                          /* Philox key */
+	int nPropagationFar;                    /* 2: per direction the candidate is the lowest-cost pixel at distance 1, 3, .. 2n+1 (0: adjacent only) */
+	int bSkipUnchanged;                     /* 1: a direction whose candidates kept their plane in their last update is not re-tested */
 } b200mvs_params;
+
+/* Diagnostic switches (all zero = the shipped kernels); replaces the environment variables of round 1. */
+typedef struct {
+	int scalarTaps;      /* 1: bilinear taps one at a time instead of the packed FMUL2/FFMA2 form (bit-identical results) */
+	int noTMA;           /* 1: the sweep kernel reads the reference patch with plain loads instead of the TMA-staged tile */
+	int sgmAggregation;  /* 0 auto; 1 general ragged kernel; 2 register-pipelined uniform kernel; 3 bulk-copy ring kernel (one launch
+	                        per direction); 4 front kernel (fused directions, auto default for uniform ranges) */
+	int sgmCost;         /* 0 auto; 1 SIMT cost kernel; 2 tensor-core (tcgen05) cost kernel */
+	int reserved[4];
+} b200mvs_debug;
 
 typedef struct {
 	double ms_total;      /* wall time of the call (host clock) */
@@ -90,6 +105,18 @@ int  b200mvs_create(int device, b200mvs_ctx** ctx);
 int  b200mvs_destroy(b200mvs_ctx* ctx);
 void b200mvs_default_params(b200mvs_params* p);
 int  b200mvs_set_params(b200mvs_ctx* ctx, const b200mvs_params* p);
+int  b200mvs_set_debug(b200mvs_ctx* ctx, const b200mvs_debug* d /* NULL: defaults */);
+/* sweeps and refinement tries per sweep the engine runs for p (geometric != 0: for one geometric-consistency pass) */
+int  b200mvs_get_schedule(const b200mvs_params* p, int geometric, int* nSweeps, int* nRefinePerSweep);
+int  b200mvs_abi_version(void);
+size_t b200mvs_sizeof(int what); /* 0 view, 1 params, 2 stats, 3 job, 4 sgm_pixel, 5 sgm_params, 6 dmap, 7 filter_params, 8 debug */
+/* Ignore-mask of the reference view for the following estimate calls (OPTDENSE::nIgnoreMaskLabel >= 0:
+ * DepthEstimator::ImportIgnoreMask + DepthData::ApplyIgnoreMask, libs/MVS/DepthMap.cpp:215-230,300-323;
+ * SceneDensify.cpp:660-664,679-693): one byte per pixel of the full-resolution reference image, 0 = ignored.  Ignored pixels
+ * are neither scored nor swept (depth = normal = conf = 0), every pyramid level uses the NEAREST-resized mask and the depth is
+ * up-sampled NEAREST instead of LINEAR, like the CPU path.  mask = NULL clears it.  on_device != 0: `mask` is a device pointer
+ * that stays valid until cleared; otherwise the host buffer is copied during the call. */
+int  b200mvs_set_ignore_mask(b200mvs_ctx* ctx, const uint8_t* mask, int width, int height, int stride_bytes, int on_device);
 const char* b200mvs_last_error(const b200mvs_ctx* ctx);
 int  b200mvs_device_count(void);
 

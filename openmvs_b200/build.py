@@ -32,8 +32,20 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
 	nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 	if not os.path.exists(nvcc):
 		raise RuntimeError("nvcc not found and %s is missing or stale" % LIB_PATH)
-	cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
-	subprocess.check_call(cmd, cwd=ROOT)
+	# build to a temporary name under a file lock and rename: concurrent ranks (torchrun) never see a half-written library
+	import fcntl
+	with open(LIB_PATH+".lock", "w") as lock:
+		fcntl.flock(lock, fcntl.LOCK_EX)
+		if not force and not is_stale():
+			return LIB_PATH
+		tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+		cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
+		try:
+			subprocess.check_call(cmd, cwd=ROOT)
+			os.replace(tmp, LIB_PATH)
+		finally:
+			if os.path.exists(tmp):
+				os.unlink(tmp)
 	return LIB_PATH
 
 

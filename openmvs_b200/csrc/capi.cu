@@ -16,11 +16,10 @@
 #include <algorithm>
 #include <cstdlib>
 
-cudaError_t pm_launch_score(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s);
-cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, int layout, bool geom, bool ws, cudaStream_t s);
+cudaError_t pm_configure_device();
+cudaError_t pm_launch_score(const PMParams& P, bool pack, bool geom, cudaStream_t s);
+cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, bool pack, bool geom, cudaStream_t s);
 void pm_tma_box(int* w, int* h);
-int pm_layout3_half(int w);
-cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s);
 cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
 	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s);
 cudaError_t pm_launch_pack(int n, const float* depth, const float* normal, float4* plane, cudaStream_t s);
@@ -35,12 +34,24 @@ struct SGMParams {
 	uint16_t P2s[256];
 	int maxNumDisp;
 };
-cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out, cudaStream_t s);
+cudaError_t sgm_configure_device();
+cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, unsigned long long numCosts, int* out8, cudaStream_t s);
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s);
-cudaError_t sgm_launch_aggregate_dir(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s);
-cudaError_t sgm_launch_sum_dirs(const uint16_t* dirL, int nDirs, size_t n, uint16_t* accums, cudaStream_t s);
+// wave-front aggregation (sgm_front.cu)
+struct FrontItem { int k0; short dir; short ph; int fb; int seq; int chain; int depCell; int depNeed; int cell; };
+struct FrontArgs {
+	const FrontItem* items; int nItems;
+	int* ticket; int* progress; int* cellDone; int* error;
+	uint16_t* state; float2* meta; int maxPaths;
+	int fa, fb, fc, FB; int storePhase0; int num;
+};
+struct FrontPassDesc { int fa, fb; int nDirs; int dirs[4]; };
+void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc);
+cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, cudaStream_t s);
+int sgm_front_blocks(int num);
+bool sgm_front_supports(int num);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
@@ -59,9 +70,10 @@ cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, i
 cudaError_t gap_launch(float* depth, float* normal, float* conf, float* tDepth, float* tNormal, float* tConf, int W, int H, float th, int gap, cudaStream_t s);
 cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
-cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s);
+cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
+cudaError_t rs_launch_nearest_u8(const uint8_t* src, int sw, int sh, int spitch, uint8_t* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_to_gray(const uint8_t* src, int w, int h, int sstride, int channels, int bgr, float* dst, int dpitch, cudaStream_t s);
-cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, cudaStream_t s);
+cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, bool nearestDepth, cudaStream_t s);
 
 namespace {
 
@@ -112,7 +124,6 @@ inline float d2r(float d) { return d*(3.14159265358979323846f/180.f); }
 // a view whose image (and optional depth-map) pointers are device pointers, pitch in floats
 struct DView {
 	const float* img; int w, h, pitch;
-	const void* tex; int tpitch;             // tap-fetch layout of img (set by prepare_tex)
 	double K[9], R[9], C[3];
 	const float* dmap; int dw, dh, dpitch;
 	double Kd[9], Rd[9], Cd[3];
@@ -132,16 +143,17 @@ struct b200mvs_ctx {
 	DevBuf plane, cost, best, prior, lowPlane;
 	DevBuf dDepth, dNormal, dConf, dViews;    // level scratch / staging of the maps (host API)
 	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
-	std::vector<DevBuf> tex;                  // neighbour images in the tap-fetch layout
 	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgDisp, sgCost, sgMax; // SGM staging / scratch
-	DevBuf sgDirL;                            // experimental: per-direction path costs (B200MVS_SGM_CONCURRENT=1)
-	cudaStream_t sgStreams[8] = {}; cudaEvent_t sgFork = nullptr, sgJoin[8] = {};
+	// wave-front aggregation: cached schedule of the last (size, mode) and its scratch
+	struct FrontPass { FrontPassDesc desc; DevBuf items; int nItems = 0, nFB = 0, maxBands = 0, fc = 0; };
+	std::vector<FrontPass> sgFront; int sgFrontKey[6] = {0, 0, 0, 0, 0, 0};
+	DevBuf sgFrontCtl, sgFrontState, sgFrontMeta;
+	const void* sgLastPx = nullptr; uint64_t sgLastNum = 0; // pixel map / size of the volume in sgAccums (b200mvs_sgm_refine_device check)
 	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
 	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
-	int layout = 1;                           // 1 plain float rows, 2 row pairs, 3 column-parity planes (B200MVS_LAYOUT overrides)
-	int pack = 1;                             // taps two at a time with FMUL2/FFMA2: 0 never, 1 photometric passes (default), 2 also geometric passes (B200MVS_PACK)
-	bool wsmem = true;                        // patch weights in shared memory (B200MVS_WSMEM=0: registers)
-	bool tma = true;                          // reference tile staged by TMA (B200MVS_TMA=0: plain loads)
+	b200mvs_debug dbg;                        // diagnostic switches (b200mvs_set_debug); all zero = the shipped kernels
+	const uint8_t* mask = nullptr; int maskW = 0, maskH = 0, maskPitch = 0; // ignore-mask of the reference view (device) or null
+	DevBuf maskBuf, maskLevel;                // staged host mask, mask of the current pyramid level
 	DevBuf refPad;                            // 16-byte aligned copy of a reference image whose pitch TMA cannot address
 	CUtensorMap tmapRef;                      // descriptor of the current level's reference image
 	bool tmapValid = false;
@@ -175,6 +187,7 @@ void build_params(const b200mvs_params& o, const DView* v, int nViews, float dMi
 	const double* K = v[0].K;
 	P.ifx = (float)(1.0/K[0]); P.sk = (float)(-K[1]/(K[0]*K[4])); P.ox = (float)((K[1]*K[5]-K[2]*K[4])/(K[0]*K[4]));
 	P.ify = (float)(1.0/K[4]); P.oy = (float)(-K[5]/K[4]);
+	P.ox0 = (float)(-K[2]/K[0]);
 	P.dMin = dMin; P.dMax = dMax; P.dMinSqr = std::sqrt(dMin); P.dMaxSqr = std::sqrt(dMax);
 	P.keep = o.fNCCThresholdKeep;
 	P.thMagnitudeSq = o.fDescriptorMinMagnitudeThreshold > 0 ? o.fDescriptorMinMagnitudeThreshold*o.fDescriptorMinMagnitudeThreshold : -1.f;
@@ -186,6 +199,7 @@ void build_params(const b200mvs_params& o, const DView* v, int nViews, float dMi
 	P.depthRatio = o.fRandomDepthRatio; P.angle1Range = d2r(o.fRandomAngle1Range); P.angle2Range = d2r(o.fRandomAngle2Range);
 	P.geomWeight = o.fEstimationGeometricWeight;
 	P.nRandomIters = o.nRandomIters; P.propagation = o.nPropagation;
+	P.farRings = o.nPropagationFar; P.skipUnchanged = 0; // the estimate call turns the changed-flag rule on; building blocks keep costs unsigned
 	P.seed = o.seed;
 	P.lowres = lowres; P.plane = plane; P.cost = cost; P.bestViews = best;
 	double RrT[9], Hr[9], KrRr[9];
@@ -204,7 +218,6 @@ void build_params(const b200mvs_params& o, const DView* v, int nViews, float dMi
 		for (int k=0;k<9;++k) V.A[k] = (float)A[k];
 		for (int k=0;k<3;++k) V.Hm[k] = (float)Hm[k];
 		V.img = v[i].img; V.w = v[i].w; V.h = v[i].h; V.pitch = v[i].pitch;
-		V.tex = v[i].tex; V.tpitch = v[i].tpitch;
 		V.dmap = v[i].dmap; V.dw = v[i].dw; V.dh = v[i].dh; V.dpitch = v[i].dpitch;
 		if (v[i].dmap) {
 			geom = true;
@@ -245,25 +258,20 @@ void to_dview(const b200mvs_view& s, const float* img, int pitch, const float* d
 
 inline int cvRoundI(double v) { return (int)std::nearbyint(v); }
 
-// store the neighbour images of one level in the tap-fetch layout of the kernels
-// kernel variant id of pm_launch_score / pm_launch_sweep: storage layout (+10: packed taps).  The packed-tap kernels were
-// verified bit-identical to the scalar ones on photometric runs (profiles/pm_variants_r01.txt); the geometric instantiations
-// share the tap loop but stay opt-in (B200MVS_PACK=2) until they have been through the GPU test-suite.
-int tap_variant(const b200mvs_ctx* ctx, bool geom) {
-	return ctx->layout + ((ctx->pack == 2 || (ctx->pack == 1 && !geom)) ? 10 : 0);
-}
-
-int prepare_tex(b200mvs_ctx* ctx, DView* v, int nViews, cudaStream_t s) {
-	if ((int)ctx->tex.size() < nViews) ctx->tex.resize(nViews);
-	v[0].tex = v[0].img; v[0].tpitch = v[0].pitch;
-	for (int i = 1; i < nViews; ++i) {
-		if (ctx->layout == 1) { v[i].tex = v[i].img; v[i].tpitch = v[i].pitch; continue; }
-		const int tpitch = ctx->layout == 3 ? 2*pm_layout3_half(v[i].w) : v[i].w;
-		CK(ctx->tex[i].reserve((size_t)tpitch*v[i].h*sizeof(float)*(ctx->layout == 2 ? 2 : 1)));
-		CK(pm_launch_relayout(v[i].img, v[i].w, v[i].h, v[i].pitch, ctx->tex[i].p, ctx->layout, s)); ++ctx->launches;
-		v[i].tex = ctx->tex[i].p; v[i].tpitch = tpitch;
+// The engine's red-black schedule for nEstimationIters reference iterations: nSweeps red-black sweeps with nR
+// refinement tries each.  nSweepsPerIter > 0 pins it (nSweeps = nSweepsPerIter x iterations, nR = ceil(nRandomIters /
+// nSweepsPerIter)); 0 (default) = max(8, ceil(1.5 x iterations)) sweeps sharing the reference's nRandomIters x iterations
+// tries.  A geometric pass (one reference iteration on a converged estimate) is 2 sweeps (or nSweepsPerIter).
+void engine_schedule(const b200mvs_params& o, bool geometric, int& nSweeps, int& nR) {
+	const int I = std::max(0, o.nEstimationIters);
+	if (o.nSweepsPerIter > 0 || geometric) {
+		const int spi = o.nSweepsPerIter > 0 ? o.nSweepsPerIter : 2;
+		nSweeps = geometric ? spi : spi*I;
+		nR = (o.nRandomIters+spi-1)/spi;
+	} else {
+		nSweeps = I > 0 ? std::max(8, (3*I+1)/2) : 0;
+		nR = nSweeps > 0 ? (o.nRandomIters*I+nSweeps-1)/nSweeps : 0;
 	}
-	return B200MVS_OK;
 }
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda)
@@ -285,7 +293,7 @@ EncodeTiledFn encode_tiled_fn() {
 // does not satisfy this (odd width, cv::Mat ROI) is first copied to an aligned scratch image.
 int prepare_ref_tmap(b200mvs_ctx* ctx, const DView& ref, cudaStream_t s) {
 	ctx->tmapValid = false;
-	EncodeTiledFn enc = ctx->tma ? encode_tiled_fn() : nullptr;
+	EncodeTiledFn enc = ctx->dbg.noTMA ? nullptr : encode_tiled_fn();
 	if (!enc) return B200MVS_OK;
 	const float* base = ref.img; size_t pitchB = (size_t)ref.pitch*4;
 	if (((uintptr_t)base & 15) || (pitchB & 15)) {
@@ -312,7 +320,7 @@ int launch_sweep_timed(b200mvs_ctx* ctx, const PMParams& P, bool geom, cudaStrea
 		}
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv], s));
 	}
-	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, tap_variant(ctx, geom), geom, ctx->wsmem, s)); ++ctx->launches;
+	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, !ctx->dbg.scalarTaps, geom, s)); ++ctx->launches;
 	if (ctx->timeSweeps) {
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv+1], s));
 		++ctx->nSweepEv;
@@ -327,18 +335,23 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 {
 	const b200mvs_params& o = ctx->prm;
 	const int W = views[0].w, H = views[0].h;
-	const int spi = std::max(1, o.nSweepsPerIter);
-	const int nR = (o.nRandomIters+spi-1)/spi;
-	const int iterBegin = nGeometricIter < 0 ? 0 : o.nEstimationIters+nGeometricIter;
-	const int iterEnd = nGeometricIter < 0 ? o.nEstimationIters : iterBegin+1;
-	const int totalScale = nGeometricIter < 0 ? std::max(0, o.nSubResolutionLevels) : 0;
+	const bool geometric = nGeometricIter >= 0;
+	int nSweepsPhoto, nRPhoto, nSweeps, nR;
+	engine_schedule(o, false, nSweepsPhoto, nRPhoto);
+	engine_schedule(o, geometric, nSweeps, nR);
+	// Philox phase of the first sweep of this call: photometric sweeps 0 .. nSweepsPhoto-1, then the geometric passes
+	const int sweepBase = geometric ? nSweepsPhoto + nGeometricIter*nSweeps : 0;
+	const int totalScale = !geometric ? std::max(0, o.nSubResolutionLevels) : 0;
 	const size_t P0 = (size_t)W*H;
+	if (ctx->mask && (ctx->maskW != W || ctx->maskH != H))
+		return fail(ctx, B200MVS_ERR_ARG, "ignore-mask size differs from the reference image");
 	CK(ctx->plane.reserve(P0*sizeof(float4)));
 	CK(ctx->cost.reserve(P0*sizeof(float)));
 	CK(ctx->best.reserve(P0*sizeof(uint32_t)));
 	if (totalScale > 0) {
 		CK(ctx->prior.reserve(P0*sizeof(float)));
 		CK(ctx->lowPlane.reserve((size_t)(W/2+2)*(H/2+2)*sizeof(float4)));
+		if (ctx->mask) CK(ctx->maskLevel.reserve((size_t)(W/2+2)*(H/2+2)));
 		if ((int)ctx->pyr.size() < nViews) ctx->pyr.resize(nViews);
 		// level 1 is the largest pyramid level: size the buffers once, so that no level re-allocates mid-stream
 		for (int i = 0; i < nViews; ++i) {
@@ -374,13 +387,12 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 			}
 		}
 		const int w = lv[0].w, h = lv[0].h;
-		{ const int rc = prepare_tex(ctx, lv.data(), nViews, s); if (rc) return rc; }
 		{ const int rc = prepare_ref_tmap(ctx, lv[0], s); if (rc) return rc; }
 		const float* lowres = nullptr;
 		if (sc != totalScale) {
 			// depth LINEAR / normal NEAREST up-sampling of the coarser level; the up-sampled
 			// depth is also the prior of this level (SceneDensify.cpp:660-664)
-			CK(rs_launch_plane_up(ctx->lowPlane.as<float4>(), lowW, lowH, plane, ctx->prior.as<float>(), w, h, s)); ++ctx->launches;
+			CK(rs_launch_plane_up(ctx->lowPlane.as<float4>(), lowW, lowH, plane, ctx->prior.as<float>(), w, h, ctx->mask != nullptr, s)); ++ctx->launches;
 			lowres = ctx->prior.as<float>();
 		} else if (sc == 0) {
 			CK(pm_launch_pack((int)P0, d_depth, d_normal, plane, s)); ++ctx->launches;
@@ -388,22 +400,28 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 			// coarsest level: the caller's initial estimate, NEAREST down-sampled
 			CK(ctx->dDepth.reserve((size_t)w*h*sizeof(float)));
 			CK(ctx->dNormal.reserve((size_t)w*h*3*sizeof(float)));
-			CK(rs_launch_nearest(d_depth, W, H, 1, ctx->dDepth.as<float>(), w, h, s));
-			CK(rs_launch_nearest(d_normal, W, H, 3, ctx->dNormal.as<float>(), w, h, s));
+			CK(rs_launch_nearest(d_depth, W, H, 1, ctx->dDepth.as<float>(), w, h, (double)(1<<sc), (double)(1<<sc), s));
+			CK(rs_launch_nearest(d_normal, W, H, 3, ctx->dNormal.as<float>(), w, h, (double)(1<<sc), (double)(1<<sc), s));
 			CK(pm_launch_pack(w*h, ctx->dDepth.as<float>(), ctx->dNormal.as<float>(), plane, s)); ctx->launches += 3;
 		}
 		PMParams P; bool geom;
 		build_params(o, lv.data(), nViews, dMin, dMax, lowres, plane, cost, best, P, geom);
 		P.nRandomIters = nR;
+		P.skipUnchanged = o.bSkipUnchanged ? 1 : 0;
 		P.tma = ctx->tmapValid ? 1 : 0;
-		CK(pm_launch_score(P, tap_variant(ctx, geom), geom, ctx->wsmem, s)); ++ctx->launches;
-		for (int it = iterBegin; it < iterEnd; ++it) {
-			for (int k = 0; k < spi; ++k) {
-				P.sweep = it*spi+k;
-				for (int colour = 0; colour < 2; ++colour) {
-					P.colour = colour;
-					{ const int rc = launch_sweep_timed(ctx, P, geom, s); if (rc) return rc; }
-				}
+		if (ctx->mask) {
+			// the mask of this level: cv::resize(..., INTER_NEAREST) of the full-resolution mask (DepthMap.cpp:309)
+			if (sc > 0) {
+				CK(rs_launch_nearest_u8(ctx->mask, W, H, ctx->maskPitch, ctx->maskLevel.as<uint8_t>(), w, h, s)); ++ctx->launches;
+				P.mask = ctx->maskLevel.as<uint8_t>(); P.maskPitch = w;
+			} else { P.mask = ctx->mask; P.maskPitch = ctx->maskPitch; }
+		}
+		CK(pm_launch_score(P, !ctx->dbg.scalarTaps, geom, s)); ++ctx->launches;
+		for (int k = 0; k < nSweeps; ++k) {
+			P.sweep = sweepBase+k;
+			for (int colour = 0; colour < 2; ++colour) {
+				P.colour = colour;
+				{ const int rc = launch_sweep_timed(ctx, P, geom, s); if (rc) return rc; }
 			}
 		}
 		if (sc > 0) {
@@ -415,6 +433,72 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 	if (nGeometricIter < 0 && o.nEstimationGeometricIters)
 		keep *= 1.333f;
 	CK(pm_launch_finalize((int)P0, keep, plane, cost, best, d_depth, d_normal, d_conf, d_views, s)); ++ctx->launches;
+	return B200MVS_OK;
+}
+
+// SGM path aggregation with the wave-front kernel (sgm_front.cu).  Pass layouts (b200mvs_debug.reserved[0]):
+//   0 (default) two tilted fronts f = +-(x + 2y): {right, right-down, down, left-down} then {left, left-up, up, right-up};
+//   1 four straight fronts: top-down {down, right-down, left-down}, bottom-up {up, right-up, left-up}, left-right, right-left;
+//   2 eight passes of one direction each (the traffic of the per-direction kernels with the new step).
+// reserved[1] = fronts per block (default 32), reserved[2] = queue lag between the phases of a block (default 2).
+int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStream_t s) {
+	const int layout = std::min(std::max(ctx->dbg.reserved[0], 0), 2);
+	const int FB = ctx->dbg.reserved[1] > 0 ? ctx->dbg.reserved[1] : (layout == 0 ? 32 : 16);
+	const int lag = ctx->dbg.reserved[2] > 0 ? ctx->dbg.reserved[2] : 2;
+	const int vw = P.vw, vh = P.vh;
+	const int key[6] = {vw, vh, layout, FB, lag, 1};
+	if (memcmp(key, ctx->sgFrontKey, sizeof(key)) != 0) {
+		std::vector<FrontPassDesc> descs;
+		if (layout == 0) {
+			descs.push_back(FrontPassDesc{1, 2, 4, {1, 4, 0, 5}});
+			descs.push_back(FrontPassDesc{-1, -2, 4, {3, 7, 2, 6}});
+		} else if (layout == 1) {
+			descs.push_back(FrontPassDesc{0, 1, 3, {0, 4, 5, 0}});
+			descs.push_back(FrontPassDesc{0, -1, 3, {2, 6, 7, 0}});
+			descs.push_back(FrontPassDesc{1, 0, 1, {1, 0, 0, 0}});
+			descs.push_back(FrontPassDesc{-1, 0, 1, {3, 0, 0, 0}});
+		} else {
+			const int f[8][2] = {{0, 1}, {1, 0}, {0, -1}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
+			for (int d = 0; d < 8; ++d) descs.push_back(FrontPassDesc{f[d][0], f[d][1], 1, {d, 0, 0, 0}});
+		}
+		for (auto& fp: ctx->sgFront) fp.items.release();
+		ctx->sgFront.clear(); ctx->sgFront.resize(descs.size());
+		std::vector<FrontItem> items;
+		for (size_t i = 0; i < descs.size(); ++i) {
+			b200mvs_ctx::FrontPass& fp = ctx->sgFront[i];
+			fp.desc = descs[i];
+			// one-direction passes of layout 2 need no blocks: one item per band walks the whole path
+			const int fbSize = layout == 2 ? (1<<28) : FB;
+			sgm_front_build(vw, vh, fp.desc, fbSize, lag, items, fp.nFB, fp.maxBands, fp.fc);
+			fp.nItems = (int)items.size();
+			CK(fp.items.reserve(items.size()*sizeof(FrontItem)));
+			CK(cudaMemcpyAsync(fp.items.p, items.data(), items.size()*sizeof(FrontItem), cudaMemcpyHostToDevice, s));
+			CK(cudaStreamSynchronize(s)); // `items` is reused for the next pass
+		}
+		memcpy(ctx->sgFrontKey, key, sizeof(key));
+	}
+	const int maxPaths = vw+vh+8;
+	int maxCtl = 0;
+	for (auto& fp: ctx->sgFront) maxCtl = std::max(maxCtl, 4*fp.maxBands + 4*fp.nFB);
+	CK(ctx->sgFrontCtl.reserve((size_t)(4+maxCtl)*sizeof(int)));
+	CK(ctx->sgFrontState.reserve((size_t)4*maxPaths*num*sizeof(uint16_t)));
+	CK(ctx->sgFrontMeta.reserve((size_t)4*maxPaths*sizeof(float2)));
+	int* ctl = ctx->sgFrontCtl.as<int>();
+	const int blocks = sgm_front_blocks(num);
+	const int FBeff = layout == 2 ? (1<<28) : FB;
+	for (size_t i = 0; i < ctx->sgFront.size(); ++i) {
+		b200mvs_ctx::FrontPass& fp = ctx->sgFront[i];
+		// [ticket, error, -, - | progress (4 x maxBands) | cellDone (4 x nFB)]; the error word survives the passes of one call
+		if (i == 0) CK(cudaMemsetAsync(ctl, 0, (size_t)(4+maxCtl)*sizeof(int), s));
+		else { CK(cudaMemsetAsync(ctl, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctl+4, 0, (size_t)maxCtl*sizeof(int), s)); }
+		FrontArgs A;
+		A.items = fp.items.as<FrontItem>(); A.nItems = fp.nItems;
+		A.ticket = ctl; A.error = ctl+1; A.progress = ctl+4; A.cellDone = ctl+4+4*fp.maxBands;
+		A.state = ctx->sgFrontState.as<uint16_t>(); A.meta = ctx->sgFrontMeta.as<float2>(); A.maxPaths = maxPaths;
+		A.fa = fp.desc.fa; A.fb = fp.desc.fb; A.fc = fp.fc; A.FB = FBeff;
+		A.storePhase0 = i == 0 ? 1 : 0; A.num = num;
+		CK(sgm_front_launch(P, A, blocks, s)); ++ctx->launches;
+	}
 	return B200MVS_OK;
 }
 
@@ -434,7 +518,25 @@ void b200mvs_default_params(b200mvs_params* p) {
 	p->fRandomDepthRatio = 0.003f; p->fRandomAngle1Range = 16.f; p->fRandomAngle2Range = 10.f;
 	p->fRandomSmoothDepth = 0.02f; p->fRandomSmoothNormal = 13.f; p->fRandomSmoothBonus = 0.93f;
 	p->fEstimationGeometricWeight = 0.1f;
-	p->nSweepsPerIter = 2; p->nPropagation = 4; p->seed = 1234u;
+	p->nSweepsPerIter = 0; p->nPropagation = 4; p->seed = 1234u;
+	p->nPropagationFar = 2; p->bSkipUnchanged = 1;
+}
+
+/* bumped whenever a struct of b200mvs.h changes layout; bindings compare it (and the struct sizes) at load time */
+int b200mvs_abi_version(void) { return B200MVS_ABI_VERSION; }
+size_t b200mvs_sizeof(int what) {
+	switch (what) {
+	case 0: return sizeof(b200mvs_view);
+	case 1: return sizeof(b200mvs_params);
+	case 2: return sizeof(b200mvs_stats);
+	case 3: return sizeof(b200mvs_job);
+	case 4: return sizeof(b200mvs_sgm_pixel);
+	case 5: return sizeof(b200mvs_sgm_params);
+	case 6: return sizeof(b200mvs_dmap);
+	case 7: return sizeof(b200mvs_filter_params);
+	case 8: return sizeof(b200mvs_debug);
+	default: return 0;
+	}
 }
 
 int b200mvs_create(int device, b200mvs_ctx** out) {
@@ -449,11 +551,9 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 	b200mvs_ctx* c = new b200mvs_ctx();
 	c->device = device;
 	b200mvs_default_params(&c->prm);
-	if (const char* e = getenv("B200MVS_LAYOUT")) { const int l = atoi(e); if (l >= 1 && l <= 3) c->layout = l; }
-	if (const char* e = getenv("B200MVS_PACK")) c->pack = std::min(std::max(atoi(e), 0), 2);
-	if (const char* e = getenv("B200MVS_WSMEM")) c->wsmem = atoi(e) != 0;
-	if (const char* e = getenv("B200MVS_TMA")) c->tma = atoi(e) != 0;
-	if (c->layout == 2 || !c->wsmem) c->pack = 0; // the packed-tap kernels exist for layouts 1 / 3 with the weights in shared memory
+	memset(&c->dbg, 0, sizeof(c->dbg));
+	// dynamic shared memory opt-in of the kernels on this device (per-device attributes; idempotent, thread-safe)
+	if (pm_configure_device() != cudaSuccess || sgm_configure_device() != cudaSuccess) { delete c; return B200MVS_ERR_CUDA; }
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
 		delete c;
@@ -470,14 +570,12 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto& b: c->imgs) b.release();
 	for (auto& b: c->dmaps) b.release();
 	for (auto& b: c->pyr) b.release();
-	for (auto& b: c->tex) b.release();
-	c->refPad.release();
+	c->refPad.release(); c->maskBuf.release(); c->maskLevel.release();
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
 	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release();
 	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
-	c->sgDirL.release();
-	for (int i = 0; i < 8; ++i) { if (c->sgStreams[i]) cudaStreamDestroy(c->sgStreams[i]); if (c->sgJoin[i]) cudaEventDestroy(c->sgJoin[i]); }
-	if (c->sgFork) cudaEventDestroy(c->sgFork);
+	for (auto& fp: c->sgFront) fp.items.release();
+	c->sgFrontCtl.release(); c->sgFrontState.release(); c->sgFrontMeta.release();
 	c->fltZ.release(); c->fltIn.release(); c->fltOutD.release(); c->fltOutC.release();
 	c->ppA.release(); c->ppB.release(); c->ppD.release(); c->ppN.release(); c->ppC.release();
 	c->plane.release(); c->cost.release(); c->best.release(); c->prior.release(); c->lowPlane.release();
@@ -491,10 +589,40 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 
 int b200mvs_set_params(b200mvs_ctx* ctx, const b200mvs_params* p) {
 	if (!ctx || !p) return B200MVS_ERR_ARG;
-	if (p->nEstimationIters < 0 || p->nRandomIters < 0 || p->nSweepsPerIter < 1 || (p->nPropagation != 2 && p->nPropagation != 4) ||
-		p->nSubResolutionLevels < 0 || !(p->fNCCThresholdKeep > 0))
+	if (p->nEstimationIters < 0 || p->nRandomIters < 0 || p->nSweepsPerIter < 0 || (p->nPropagation != 2 && p->nPropagation != 4) ||
+		p->nPropagationFar < 0 || p->nPropagationFar > 3 || p->nSubResolutionLevels < 0 || !(p->fNCCThresholdKeep > 0))
 		return fail(ctx, B200MVS_ERR_ARG, "invalid parameter block");
 	ctx->prm = *p;
+	return B200MVS_OK;
+}
+
+int b200mvs_set_debug(b200mvs_ctx* ctx, const b200mvs_debug* d) {
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (d) ctx->dbg = *d; else memset(&ctx->dbg, 0, sizeof(ctx->dbg));
+	return B200MVS_OK;
+}
+
+int b200mvs_get_schedule(const b200mvs_params* p, int geometric, int* nSweeps, int* nRefinePerSweep) {
+	if (!p || !nSweeps || !nRefinePerSweep) return B200MVS_ERR_ARG;
+	engine_schedule(*p, geometric != 0, *nSweeps, *nRefinePerSweep);
+	return B200MVS_OK;
+}
+
+int b200mvs_set_ignore_mask(b200mvs_ctx* ctx, const uint8_t* mask, int width, int height, int stride_bytes, int on_device) {
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!mask) { ctx->mask = nullptr; ctx->maskW = ctx->maskH = ctx->maskPitch = 0; return B200MVS_OK; }
+	if (width <= 0 || height <= 0 || (stride_bytes != 0 && stride_bytes < width))
+		return fail(ctx, B200MVS_ERR_ARG, "ignore-mask: invalid size or stride");
+	if (stride_bytes == 0) stride_bytes = width;
+	CK(cudaSetDevice(ctx->device));
+	if (on_device) { ctx->mask = mask; ctx->maskPitch = stride_bytes; }
+	else {
+		CK(ctx->maskBuf.reserve((size_t)width*height));
+		CK(cudaMemcpy2DAsync(ctx->maskBuf.p, width, mask, stride_bytes, width, height, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream)); // the caller's buffer may be released after the call
+		ctx->mask = ctx->maskBuf.as<uint8_t>(); ctx->maskPitch = width;
+	}
+	ctx->maskW = width; ctx->maskH = height;
 	return B200MVS_OK;
 }
 
@@ -663,7 +791,6 @@ static int block_params(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
 	for (int i = 0; i < nViews; ++i)
 		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
 			views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
-	{ const int rc2 = prepare_tex(ctx, dv.data(), nViews, s); if (rc2) return rc2; }
 	{ const int rc2 = prepare_ref_tmap(ctx, dv[0], s); if (rc2) return rc2; }
 	build_params(ctx->prm, dv.data(), nViews, dMin, dMax, lowres, (float4*)plane4, cost, nullptr, P, geom);
 	P.tma = ctx->tmapValid ? 1 : 0;
@@ -678,7 +805,7 @@ int b200mvs_pm_score(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
 	int rc = block_params(ctx, views, nViews, dMin, dMax, lowres, plane4, cost, s, P, geom);
 	if (rc) return rc;
-	CK(pm_launch_score(P, tap_variant(ctx, geom), geom, ctx->wsmem, s));
+	CK(pm_launch_score(P, !ctx->dbg.scalarTaps, geom, s));
 	return B200MVS_OK;
 }
 int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, float dMin, float dMax,
@@ -694,7 +821,7 @@ int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	for (int colour = 0; colour < 2; ++colour) {
 		if (half >= 0 && half != colour) continue;
 		P.colour = colour;
-		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, tap_variant(ctx, geom), geom, ctx->wsmem, s));
+		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, !ctx->dbg.scalarTaps, geom, s));
 	}
 	return B200MVS_OK;
 }
@@ -743,56 +870,43 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	P.costs = costs; P.accums = accums;
 	const auto t0 = std::chrono::steady_clock::now();
 	ctx->launches = 0;
-	int st6[6] = {0, 0, 0, 0, 0, 0}; bool uniform = false, ring = false;
+	int st8[8] = {0, 0, 0, 0, 0, 0, 0, 0}; bool uniform = false, ring = false, front = false;
+	const int mode = ctx->dbg.sgmAggregation;
 	if (stats) CK(cudaEventRecord(ctx->ev0, s));
 	if (stages & 2) {
 		// the warp-per-scanline kernel keeps one line of at most sgm_max_disparities() values
-		CK(ctx->sgMax.reserve(6*sizeof(int)));
-		CK(sgm_launch_maxdisp(P.px, P.vw*P.vh, ctx->sgMax.as<int>(), s)); ctx->launches += 2;
-		CK(cudaMemcpyAsync(st6, ctx->sgMax.p, 6*sizeof(int), cudaMemcpyDeviceToHost, s));
+		CK(ctx->sgMax.reserve(8*sizeof(int)));
+		CK(sgm_launch_maxdisp(P.px, P.vw*P.vh, numCosts, ctx->sgMax.as<int>(), s)); ctx->launches += 2;
+		CK(cudaMemcpyAsync(st8, ctx->sgMax.p, 8*sizeof(int), cudaMemcpyDeviceToHost, s));
 		CK(cudaStreamSynchronize(s));
-		if (st6[0] > sgm_max_disparities())
+		if (st8[7])
+			return fail(ctx, B200MVS_ERR_ARG, "sgm: a pixel's slice [idx, idx+dmax-dmin) ends beyond numCosts");
+		if (st8[0] > sgm_max_disparities())
 			return fail(ctx, B200MVS_ERR_ARG, "sgm: more than 256 disparities per pixel");
-		P.maxNumDisp = st6[0];
-		// one global range (the non-tSGM branch): packed, shared-memory-free aggregation kernel
-		uniform = st6[0] >= 4 && st6[1] == st6[2] && st6[3] == st6[4] && (st6[0] & 3) == 0 && (st6[5] & 3) == 0
-			&& !getenv("B200MVS_SGM_GENERAL");
-		// every slice 16-byte aligned: bulk-copy ring kernel (B200MVS_SGM_RING=0 keeps the register-pipelined one)
-		const char* re = getenv("B200MVS_SGM_RING");
-		ring = uniform && (st6[0] & 15) == 0 && st6[5] == 0 && !((uintptr_t)P.costs & 15) && !((uintptr_t)P.accums & 15) && !(re && atoi(re) == 0);
+		P.maxNumDisp = st8[0];
+		// one global range (the non-tSGM branch): packed, shared-memory-free aggregation kernels
+		uniform = st8[0] >= 4 && st8[1] == st8[2] && st8[3] == st8[4] && (st8[0] & 3) == 0 && (st8[5] & 3) == 0 && mode != 1;
+		// every slice 16-byte aligned: bulk-copy ring kernel (one launch per direction)
+		ring = uniform && (st8[0] & 15) == 0 && st8[5] == 0 && !((uintptr_t)P.costs & 15) && !((uintptr_t)P.accums & 15) && mode != 2;
+		// dense volume of a supported width: wave-front kernel (fused directions) — the default
+		front = ring && !st8[6] && sgm_front_supports(st8[0]) && (mode == 0 || mode == 4);
+		if (mode == 4 && !front)
+			return fail(ctx, B200MVS_ERR_ARG, "sgm: the wave-front kernel needs a dense volume with one range of 64, 128 or 256 disparities");
 	}
 	if (stages & 1) { CK(sgm_launch_cost(P, s)); ++ctx->launches; }
-	const char* conc = getenv("B200MVS_SGM_CONCURRENT");
-	if ((stages & 2) && ring && conc && atoi(conc) != 0 && (numCosts & 7) == 0) {
-		// experimental: the eight directions at the same time, each into its own buffer of path costs, summed afterwards
-		CK(ctx->sgDirL.reserve(8*numCosts*sizeof(uint16_t)));
-		if (!ctx->sgFork) {
-			CK(cudaEventCreateWithFlags(&ctx->sgFork, cudaEventDisableTiming));
-			for (int i = 0; i < 8; ++i) {
-				CK(cudaStreamCreateWithFlags(&ctx->sgStreams[i], cudaStreamNonBlocking));
-				CK(cudaEventCreateWithFlags(&ctx->sgJoin[i], cudaEventDisableTiming));
-			}
-		}
-		CK(cudaEventRecord(ctx->sgFork, s));
-		for (int dir = 0; dir < 8; ++dir) {
-			SGMParams Pd = P;
-			Pd.accums = ctx->sgDirL.as<uint16_t>() + (size_t)dir*numCosts;
-			CK(cudaStreamWaitEvent(ctx->sgStreams[dir], ctx->sgFork, 0));
-			CK(sgm_launch_aggregate_dir(Pd, dir, st6[1], st6[0], ctx->sgStreams[dir]));
-			CK(cudaEventRecord(ctx->sgJoin[dir], ctx->sgStreams[dir]));
-			CK(cudaStreamWaitEvent(s, ctx->sgJoin[dir], 0));
-			++ctx->launches;
-		}
-		CK(sgm_launch_sum_dirs(ctx->sgDirL.as<uint16_t>(), 8, (size_t)numCosts, accums, s)); ++ctx->launches;
+	if ((stages & 2) && front) {
+		const int rc = sgm_aggregate_fronts(ctx, P, st8[0], s);
+		if (rc) return rc;
 	} else
 	if (stages & 2) {
 		CK(cudaMemsetAsync(accums, 0, numCosts*sizeof(uint16_t), s));
 		for (int dir = 0; dir < 8; ++dir) {
-			if (uniform) CK(sgm_launch_aggregate_uniform(P, dir, st6[1], st6[0], ring, s));
+			if (uniform) CK(sgm_launch_aggregate_uniform(P, dir, st8[1], st8[0], ring, s));
 			else CK(sgm_launch_aggregate(P, dir, s));
 			++ctx->launches;
 		}
 	}
+	if (stages & 2) { ctx->sgLastPx = (accums == ctx->sgAccums.as<uint16_t>()) ? (const void*)pixels : nullptr; ctx->sgLastNum = numCosts; }
 	if (stages & 4) { CK(sgm_launch_wta(P, disparity, cost, s)); ++ctx->launches; }
 	if (stats) {
 		CK(cudaEventRecord(ctx->ev1, s));
@@ -849,8 +963,12 @@ int b200mvs_sgm_refine_device(b200mvs_ctx* ctx, const b200mvs_sgm_pixel* pixels,
 	int nPixels, int subpixelSteps, void* stream)
 {
 	if (!ctx || !pixels || !disparity || nPixels <= 0) return B200MVS_ERR_ARG;
-	if (!accums) accums = ctx->sgAccums.as<uint16_t>(); // the accumulated costs of the last match on this context
-	if (!accums) return fail(ctx, B200MVS_ERR_ARG, "sgm refine: no accumulated costs");
+	if (!accums) {
+		// the accumulated costs of the last match on this context: only valid for the pixel map they were computed for
+		accums = ctx->sgAccums.as<uint16_t>();
+		if (!accums || ctx->sgLastPx != (const void*)pixels)
+			return fail(ctx, B200MVS_ERR_ARG, "sgm refine: no accumulated costs of a match with this pixel map on the context");
+	}
 	if (subpixelSteps <= 1) return B200MVS_OK;
 	CK(cudaSetDevice(ctx->device));
 	CK(sgm_launch_refine((const SGMPixel*)pixels, accums, disparity, nPixels, subpixelSteps, stream ? (cudaStream_t)stream : ctx->stream));

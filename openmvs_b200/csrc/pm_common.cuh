@@ -13,7 +13,6 @@ struct PMView {
 	float A[9];
 	float Hm[3];
 	const float* img; int w, h, pitch;       // plain float image, pitch in floats
-	const void* tex; int tpitch;             // the image in the tap-fetch layout (pm_kernels.cu fetch_bilinear), pitch in texels
 	const float* dmap; int dw, dh, dpitch;   // known depth-map (geometric pass) or null
 	float Tl[9], Tm[3], Tr[9], Tn[3];
 };
@@ -22,16 +21,20 @@ struct PMParams {
 	const float* img0; int W, H, pitch0;
 	int nViews;
 	float ifx, sk, ox, ify, oy;              // Kref^-1 = [[ifx, sk, ox],[0, ify, oy],[0,0,1]]
+	float ox0;                               // -cx/fx: the skew-free x offset InterpolatePixel uses (DepthMap.cpp:915-959)
 	float dMin, dMax, dMinSqr, dMaxSqr;
 	float keep;                              // fNCCThresholdKeep
 	float thMagnitudeSq, thConfSmall, thConfBig, thConfRand, thRobust;
 	float smoothBonusDepth, smoothBonusNormal, smoothSigmaDepth, smoothSigmaNormal;
 	float depthRatio, angle1Range, angle2Range, geomWeight;
-	int nRandomIters, propagation;
+	int nRandomIters, propagation;           // refinement tries per sweep; directions that propagate (2 causal / 4)
+	int farRings;                            // propagation candidates per direction: distances 1, 3, .. 2*farRings+1
+	int skipUnchanged;                       // 1: a direction whose candidates kept their plane is not re-tested (sign bit of cost)
 	int sweep, colour;
 	int tma;                                 // reference tile staged by TMA (tensor map passed beside the params)
 	uint32_t seed;
 	const float* lowres;                     // low-resolution depth prior or null
+	const uint8_t* mask; int maskPitch;      // ignore-mask of this level (0 = skip the pixel) or null; pitch in bytes
 	float4* plane; float* cost; uint32_t* bestViews;
 	PMView views[PM_MAX_VIEWS];
 };

@@ -26,18 +26,9 @@ constexpr int BLOCK_Y = 8;
 
 constexpr int NTHREADS = BLOCK_X*BLOCK_Y;
 
-// bilateral weights of the 5x5 reference patch (WeightedPatchFix<25>, DepthMap.h:145-155).
-// WS=false: all 50 values in registers; WS=true: in shared memory as float2{w,tw}[tap][thread]
-// (conflict-free LDS.64), which frees ~50 registers per thread for occupancy.
-template <bool WS> struct PatchT;
-template <> struct PatchT<false> {
-	float w[PM_TEXELS];
-	float tw[PM_TEXELS];
-	float sumW, normSq0;
-	__device__ __forceinline__ void set(int k, float a, float b) { w[k] = a; tw[k] = b; }
-	__device__ __forceinline__ float2 get(int k) const { return make_float2(w[k], tw[k]); }
-};
-template <> struct PatchT<true> {
+// bilateral weights of the 5x5 reference patch (WeightedPatchFix<25>, DepthMap.h:145-155), kept in shared
+// memory as float2{w,tw}[tap][thread] (conflict-free LDS.64): 50 registers per thread less than a register copy
+struct PatchW {
 	float2* s; // &smem[threadIndex]; tap k at s[k*NTHREADS]
 	float sumW, normSq0;
 	__device__ __forceinline__ void set(int k, float a, float b) { s[k*NTHREADS] = make_float2(a, b); }
@@ -77,8 +68,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 }
 
 // FillPixelPatch + GetWeight from the staged tile; (lx, ly) = pixel position inside the tile
-template <bool WS>
-__device__ __forceinline__ void fill_patch_tile(const float* __restrict__ tile, int lx, int ly, PatchT<WS>& p) {
+__device__ __forceinline__ void fill_patch_tile(const float* __restrict__ tile, int lx, int ly, PatchW& p) {
 	const float sigmaColor = -1.f/(2.f*0.1f*0.1f);
 	const float sigmaSpatial = -1.f/(2.f*9.f);
 	const float center = tile[ly*TILE_W + lx];
@@ -113,8 +103,7 @@ __device__ __forceinline__ void fill_patch_tile(const float* __restrict__ tile, 
 
 // FillPixelPatch + GetWeight (DepthMap.cpp:422-462, DepthMap.h:403-412) from global memory (pass A, and
 // the sweep when no TMA descriptor is available)
-template <bool WS>
-__device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pitch, int x, int y, PatchT<WS>& p) {
+__device__ __forceinline__ void fill_patch(const float* __restrict__ img, int pitch, int x, int y, PatchW& p) {
 	const float sigmaColor = -1.f/(2.f*0.1f*0.1f);
 	const float sigmaSpatial = -1.f/(2.f*9.f);
 	const float center = __ldg(img + (size_t)y*pitch + x);
@@ -181,74 +170,23 @@ __device__ __forceinline__ bool sample_depth_masked(const float* __restrict__ im
 	return true;
 }
 
-// Bilinear fetch of one warped tap.  LAYOUT selects how the neighbour image is stored in HBM:
-//   1: plain float rows                       4 x LDG.32 per tap
-//   2: row pairs  float2{I(y,x), I(y+1,x)}    2 x LDG.64 per tap (second at +8 B)
-//   3: rows de-interleaved by column parity [even columns | odd columns]: lanes are two pixels apart
-//      (red-black), so a warp's taps hit 32 nearly consecutive floats of ONE parity plane per load
-//      instead of every other float of a 64-pixel span (experimental, B200MVS_LAYOUT=3)
-// LAYOUT + 10 (11, 13): the same storage, taps evaluated two at a time with the packed fp32 instructions of
-// sm_100 (FMUL2 / FFMA2 through __fmul2_rn / __ffma2_rn): identical roundings, about 10 % fewer issue slots per 25 taps;
-// 11 is the default of the photometric passes (measured 3-4 % faster, whole-run output bit-identical to LAYOUT 1;
-// B200MVS_PACK selects, see capi.cu tap_variant).
-// (measured and dropped, DESIGN.md §6: float4 quads with one LDG.128 per tap, texture gather TLD4,
-//  and a TLD4/LDG split across views — all slower than these two on B200)
-// the four texels of a tap at integer position (lx, ly); LAYOUT 3 returns them as (even column, odd column)
-// pairs: *par = lx & 1 tells which is the left one
-template <int L>
+// The four texels of one warped tap at integer position (lx, ly) of a plain float image (pitch in floats).
+// L1 evict-last: the warped footprints of successive hypotheses and of the CTA's other rows overlap, keeping
+// them in L1 against the streaming plane/cost traffic is worth 2.5 % (2.73 -> 2.66 ms).
+// (measured and dropped, DESIGN.md §5.1: row-pair and float4 quad layouts, column-parity planes, texture gather
+//  TLD4, a TLD4/LDG split across views — all slower than plain rows on B200)
 __device__ __forceinline__ void fetch_texels(const void* __restrict__ tex, int pitch, int lx, int ly,
-	float& v00, float& v10, float& v01, float& v11, int& par)
+	float& v00, float& v10, float& v01, float& v11)
 {
-	par = 0;
-	if (L == 1) {
-		unsigned long long addr;
-		const unsigned idx = (unsigned)(ly*pitch + lx);
-		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(4u), "l"((unsigned long long)tex));
-		const float* r0 = (const float*)addr;
-		const float* r1 = r0+pitch;
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v00) : "l"(r0));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v10) : "l"(r0));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v01) : "l"(r1));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v11) : "l"(r1));
-	} else {
-		// row = [even plane: pitch/2 floats | odd plane: pitch/2 floats]; texel lx is element lx>>1 of plane lx&1.
-		// The even texel of {lx, lx+1} is element (lx>>1)+(lx&1) of the even plane, the odd one element lx>>1 of the odd plane.
-		par = lx & 1;
-		const unsigned io = (unsigned)(ly*pitch + (lx>>1));
-		unsigned long long ae, ao;
-		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ao) : "r"(io), "r"(4u), "l"((unsigned long long)tex + 2ull*(unsigned)pitch));
-		asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ae) : "r"(io+(unsigned)par), "r"(4u), "l"((unsigned long long)tex));
-		const float* e0 = (const float*)ae; const float* o0 = (const float*)ao;
-		const float* e1 = e0+pitch; const float* o1 = o0+pitch;
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v00) : "l"(e0));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v10) : "l"(o0));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v01) : "l"(e1));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v11) : "l"(o1));
-	}
-}
-template <int LAYOUT>
-__device__ __forceinline__ float fetch_bilinear(const void* __restrict__ tex, int pitch, unsigned idx, float ax, float ay) {
-	float v00, v10, v01, v11;
-	// address = tex + idx*sizeof(texel) as one IMAD.WIDE.U32
 	unsigned long long addr;
-	asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"((unsigned)(4*LAYOUT)), "l"((unsigned long long)tex));
-	if (LAYOUT == 1) {
-		const float* r0 = (const float*)addr;
-		// L1 evict-last: the warped footprints of successive hypotheses and of the CTA's other rows overlap,
-		// keeping them in L1 against the streaming plane/cost traffic is worth 2.5 % (2.73 -> 2.66 ms)
-		const float* r1 = r0+pitch;
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v00) : "l"(r0));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v10) : "l"(r0));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v01) : "l"(r1));
-		asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v11) : "l"(r1));
-	} else {
-		const float2* r0 = (const float2*)addr;
-		const float2 a = __ldg(r0), b = __ldg(r0+1);
-		v00 = a.x; v01 = a.y; v10 = b.x; v11 = b.y;
-	}
-	const float top = fmaf(ax, v10-v00, v00);
-	const float bot = fmaf(ax, v11-v01, v01);
-	return fmaf(ay, bot-top, top);
+	const unsigned idx = (unsigned)(ly*pitch + lx);
+	asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(4u), "l"((unsigned long long)tex));
+	const float* r0 = (const float*)addr;
+	const float* r1 = r0+pitch;
+	asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v00) : "l"(r0));
+	asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v10) : "l"(r0));
+	asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v01) : "l"(r1));
+	asm("ld.global.nc.L1::evict_last.f32 %0, [%1+4];" : "=f"(v11) : "l"(r1));
 }
 
 // ScorePixelImage (DepthMap.cpp:465-564) for one neighbour view.
@@ -257,8 +195,11 @@ __device__ __forceinline__ float fetch_bilinear(const void* __restrict__ tex, in
 // projected corners as long as the depth Z keeps its sign, so "all 25 taps inside" is decided
 // once from the 4 corner taps; the tap loop itself is then branch-free and test-free, and the
 // loads of a whole tap row are in flight together.  Rejected lanes run the loop on texel (1,1).
-template <int LAYOUT, bool GEOM, bool WS>
-__device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, const PatchT<WS>& pt,
+// PACK: taps evaluated two at a time with the packed fp32 instructions of sm_100 (FMUL2 / FFMA2 through
+// __fmul2_rn / __ffma2_rn): identical roundings (whole-run output bit-identical to the scalar form, photometric
+// and geometric passes), about 10 % fewer issue slots per 25 taps.  PACK = false is the debug form.
+template <bool PACK, bool GEOM>
+__device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, const PatchW& pt,
 	float fx, float fy, float X0x, float X0y, const Hyp& h, float priorF, float priorD)
 {
 	// H = A + Hm (n^T Kref^-1)/(n.X0 d); columns 0/1 and the centre point H*(x,y,1)
@@ -289,89 +230,56 @@ __device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, 
 	if (!__any_sync(__activemask(), ok))
 		return P.thRobust;
 	if (!ok) { bx = by = bz = 1.f; c0x = c0y = c0z = c1x = c1y = c1z = 0.f; }
-	const void* tex = V.tex;
-	int pitch = V.tpitch;
+	const void* tex = V.img;
+	int pitch = V.pitch;
 	// keep the per-view constants in registers (otherwise re-read from the constant bank per tap)
 	asm volatile("" : "+r"(pitch), "+l"(tex));
 	float sum = 0.f, sumSq = 0.f, num = 0.f;
-	if constexpr (LAYOUT >= 3) {
-		// variants (see fetch_texels): L = 3 de-interleaved storage (experimental), PACK = taps two at a time
-		constexpr int L = LAYOUT%10;
-		constexpr bool PACK = LAYOUT >= 10;
-		const float2 NEG1 = make_float2(-1.f, -1.f);
-		#pragma unroll
-		for (int i = 0; i < 5; ++i) {
-			float X = bx, Y = by, Z = bz;
-			#pragma unroll
-			for (int j = 0; j < 5; j += 2) {
-				const bool two = j+1 < 5;
-				// tap a = j, tap b = j+1 (the fifth tap of a row runs alone in the .x halves)
-				const float Xa = X, Ya = Y, Za = Z;
-				const float Xb = Xa+c0x, Yb = Ya+c0y, Zb = Za+c0z;
-				if (two) { X = Xb+c0x; Y = Yb+c0y; Z = Zb+c0z; }
-				const float iza = fast_rcp(Za), izb = two ? fast_rcp(Zb) : 0.f;
-				float2 PX, PY;
-				if (PACK && two) { PX = __fmul2_rn(make_float2(Xa, Xb), make_float2(iza, izb)); PY = __fmul2_rn(make_float2(Ya, Yb), make_float2(iza, izb)); }
-				else { PX = make_float2(Xa*iza, Xb*izb); PY = make_float2(Ya*iza, Yb*izb); }
-				const int lxa = __float2int_rz(PX.x), lya = __float2int_rz(PY.x);
-				const int lxb = two ? __float2int_rz(PX.y) : 1, lyb = two ? __float2int_rz(PY.y) : 1;
-				const float2 FLX = make_float2((float)lxa, (float)lxb), FLY = make_float2((float)lya, (float)lyb);
-				float2 AX, AY;
-				if (PACK && two) { AX = __ffma2_rn(FLX, NEG1, PX); AY = __ffma2_rn(FLY, NEG1, PY); }
-				else { AX = make_float2(PX.x-FLX.x, PX.y-FLX.y); AY = make_float2(PY.x-FLY.x, PY.y-FLY.y); }
-				float2 V00, V10, V01, V11; int para, parb = 0;
-				fetch_texels<L>(tex, pitch, lxa, lya, V00.x, V10.x, V01.x, V11.x, para);
-				if (two) fetch_texels<L>(tex, pitch, lxb, lyb, V00.y, V10.y, V01.y, V11.y, parb);
-				else { V00.y = V10.y = V01.y = V11.y = 0.f; }
-				if (L == 3) {
-					// (even, odd) -> (left, right): base = left texel, and the horizontal weight changes sign when
-					// the left texel is the odd one: o + ax (e - o) == o - ax (o - e), same rounding
-					AX.x = para ? -AX.x : AX.x; AX.y = parb ? -AX.y : AX.y;
-				}
-				float2 DT, TOP, DB, BOT, DV, V;
-				float2 B0 = V00, B1 = V01;
-				if (L == 3) { B0.x = para ? V10.x : V00.x; B0.y = parb ? V10.y : V00.y; B1.x = para ? V11.x : V01.x; B1.y = parb ? V11.y : V01.y; }
-				if (PACK && two) {
-					DT = __ffma2_rn(V00, NEG1, V10); TOP = __ffma2_rn(AX, DT, B0);
-					DB = __ffma2_rn(V01, NEG1, V11); BOT = __ffma2_rn(AX, DB, B1);
-					DV = __ffma2_rn(TOP, NEG1, BOT); V = __ffma2_rn(AY, DV, TOP);
-				} else {
-					TOP = make_float2(fmaf(AX.x, V10.x-V00.x, B0.x), fmaf(AX.y, V10.y-V00.y, B0.y));
-					BOT = make_float2(fmaf(AX.x, V11.x-V01.x, B1.x), fmaf(AX.y, V11.y-V01.y, B1.y));
-					V = make_float2(fmaf(AY.x, BOT.x-TOP.x, TOP.x), fmaf(AY.y, BOT.y-TOP.y, TOP.y));
-				}
-				{
-					const float2 wk = pt.get(i*5+j);
-					const float vw = V.x*wk.x;
-					sum += vw; sumSq = fmaf(V.x, vw, sumSq); num = fmaf(V.x, wk.y, num);
-				}
-				if (two) {
-					const float2 wk = pt.get(i*5+j+1);
-					const float vw = V.y*wk.x;
-					sum += vw; sumSq = fmaf(V.y, vw, sumSq); num = fmaf(V.y, wk.y, num);
-				}
-			}
-			bx += c1x; by += c1y; bz += c1z;
-		}
-	} else
+	const float2 NEG1 = make_float2(-1.f, -1.f);
 	#pragma unroll
 	for (int i = 0; i < 5; ++i) {
 		float X = bx, Y = by, Z = bz;
 		#pragma unroll
-		for (int j = 0; j < 5; ++j) {
-			const float iz = fast_rcp(Z);
-			const float px = X*iz, py = Y*iz;
-			const int lx = __float2int_rz(px), ly = __float2int_rz(py);
-			const float flx = (float)lx, fly = (float)ly;
-			const float ax = px-flx, ay = py-fly;
-			const unsigned idx = (unsigned)(ly*pitch + lx);
-			const float v = fetch_bilinear<LAYOUT>(tex, pitch, idx, ax, ay);
-			const float2 wk = pt.get(i*5+j);
-			const float vw = v*wk.x;
-			sum += vw;
-			sumSq = fmaf(v, vw, sumSq);
-			num = fmaf(v, wk.y, num);
-			X += c0x; Y += c0y; Z += c0z;
+		for (int j = 0; j < 5; j += 2) {
+			const bool two = j+1 < 5;
+			// tap a = j, tap b = j+1 (the fifth tap of a row runs alone in the .x halves)
+			const float Xa = X, Ya = Y, Za = Z;
+			const float Xb = Xa+c0x, Yb = Ya+c0y, Zb = Za+c0z;
+			if (two) { X = Xb+c0x; Y = Yb+c0y; Z = Zb+c0z; }
+			const float iza = fast_rcp(Za), izb = two ? fast_rcp(Zb) : 0.f;
+			float2 PX, PY;
+			if (PACK && two) { PX = __fmul2_rn(make_float2(Xa, Xb), make_float2(iza, izb)); PY = __fmul2_rn(make_float2(Ya, Yb), make_float2(iza, izb)); }
+			else { PX = make_float2(Xa*iza, Xb*izb); PY = make_float2(Ya*iza, Yb*izb); }
+			const int lxa = __float2int_rz(PX.x), lya = __float2int_rz(PY.x);
+			const int lxb = two ? __float2int_rz(PX.y) : 1, lyb = two ? __float2int_rz(PY.y) : 1;
+			const float2 FLX = make_float2((float)lxa, (float)lxb), FLY = make_float2((float)lya, (float)lyb);
+			float2 AX, AY;
+			if (PACK && two) { AX = __ffma2_rn(FLX, NEG1, PX); AY = __ffma2_rn(FLY, NEG1, PY); }
+			else { AX = make_float2(PX.x-FLX.x, PX.y-FLX.y); AY = make_float2(PY.x-FLY.x, PY.y-FLY.y); }
+			float2 V00, V10, V01, V11;
+			fetch_texels(tex, pitch, lxa, lya, V00.x, V10.x, V01.x, V11.x);
+			if (two) fetch_texels(tex, pitch, lxb, lyb, V00.y, V10.y, V01.y, V11.y);
+			else { V00.y = V10.y = V01.y = V11.y = 0.f; }
+			float2 DT, TOP, DB, BOT, DV, VV;
+			if (PACK && two) {
+				DT = __ffma2_rn(V00, NEG1, V10); TOP = __ffma2_rn(AX, DT, V00);
+				DB = __ffma2_rn(V01, NEG1, V11); BOT = __ffma2_rn(AX, DB, V01);
+				DV = __ffma2_rn(TOP, NEG1, BOT); VV = __ffma2_rn(AY, DV, TOP);
+			} else {
+				TOP = make_float2(fmaf(AX.x, V10.x-V00.x, V00.x), fmaf(AX.y, V10.y-V00.y, V00.y));
+				BOT = make_float2(fmaf(AX.x, V11.x-V01.x, V01.x), fmaf(AX.y, V11.y-V01.y, V01.y));
+				VV = make_float2(fmaf(AY.x, BOT.x-TOP.x, TOP.x), fmaf(AY.y, BOT.y-TOP.y, TOP.y));
+			}
+			{
+				const float2 wk = pt.get(i*5+j);
+				const float vw = VV.x*wk.x;
+				sum += vw; sumSq = fmaf(VV.x, vw, sumSq); num = fmaf(VV.x, wk.y, num);
+			}
+			if (two) {
+				const float2 wk = pt.get(i*5+j+1);
+				const float vw = VV.y*wk.x;
+				sum += vw; sumSq = fmaf(VV.y, vw, sumSq); num = fmaf(VV.y, wk.y, num);
+			}
 		}
 		bx += c1x; by += c1y; bz += c1z;
 	}
@@ -419,15 +327,15 @@ __device__ __forceinline__ float score_view(const PMParams& P, const PMView& V, 
 }
 
 // ScorePixel (DepthMap.cpp:567-626): MINMEAN over the views; also reports the two best views
-template <int LAYOUT, bool GEOM, bool WS>
-__device__ __forceinline__ float score_pixel(const PMParams& P, const PatchT<WS>& pt,
+template <bool PACK, bool GEOM>
+__device__ __forceinline__ float score_pixel(const PMParams& P, const PatchW& pt,
 	float fx, float fy, float X0x, float X0y, const Hyp& h, float priorF, float priorD, uint32_t& best)
 {
 	float s0 = CUDART_INF_F, s1 = CUDART_INF_F;
 	int i0 = 255, i1 = 255;
 	#pragma unroll 1
 	for (int v = 0; v < P.nViews; ++v) {
-		const float s = score_view<LAYOUT, GEOM, WS>(P, P.views[v], pt, fx, fy, X0x, X0y, h, priorF, priorD);
+		const float s = score_view<PACK, GEOM>(P, P.views[v], pt, fx, fy, X0x, X0y, h, priorF, priorD);
 		if (s < s0) { s1 = s0; i1 = i0; s0 = s; i0 = v; }
 		else if (s < s1) { s1 = s; i1 = v; }
 	}
@@ -506,10 +414,14 @@ __device__ __forceinline__ void correct_normal(float3& n, float X0x, float X0y) 
 	}
 }
 
+// The cost field doubles as the "changed" memory of the red-black schedule: the sign bit of a pixel's stored
+// cost is set when its last update left its plane unchanged (costs are >= 0, so the bit is free; -0.f counts).
+__device__ __forceinline__ bool cost_unchanged(float c) { return (__float_as_uint(c)>>31) != 0u; }
+
 // ------------------------------------------------------------------------------------
 // pass A: score the initial estimate of every pixel (random where invalid)
-template <int LAYOUT, bool GEOM, bool WS>
-__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, WS ? 3 : 2)
+template <bool PACK, bool GEOM>
+__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, 3)
 pm_score_kernel(const __grid_constant__ PMParams P)
 {
 	extern __shared__ float2 smemW[];
@@ -519,11 +431,13 @@ pm_score_kernel(const __grid_constant__ PMParams P)
 		return;
 	const size_t idx = (size_t)y*P.W + x;
 	const bool inside = x >= PM_HALF && y >= PM_HALF && x < P.W-PM_HALF && y < P.H-PM_HALF;
-	PatchT<WS> pt;
-	if constexpr (WS) pt.s = smemW + threadIdx.y*BLOCK_X + threadIdx.x;
+	PatchW pt;
+	pt.s = smemW + threadIdx.y*BLOCK_X + threadIdx.x;
 	float priorD = 0.f, priorF = 0.f;
-	bool ok = inside;
-	if (inside) {
+	// ignore-mask (DepthData::ApplyIgnoreMask, DepthMap.cpp:215-230; masked pixels are not in the pixel list,
+	// DepthMap.cpp:343): depth / normal zero, never scored.  Internally their cost is 2 like every rejected pixel.
+	bool ok = inside && !(P.mask && P.mask[(size_t)y*P.maskPitch + x] == 0);
+	if (ok) {
 		fill_patch(P.img0, P.pitch0, x, y, pt);
 		if (P.lowres)
 			priorD = fmaxf(__ldg(P.lowres + idx), 0.f);
@@ -555,22 +469,30 @@ pm_score_kernel(const __grid_constant__ PMParams P)
 	Hyp h;
 	make_hyp(P, X0x, X0y, d, n, cl, false, h);
 	uint32_t best;
-	const float c = score_pixel<LAYOUT, GEOM, WS>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, best);
+	const float c = score_pixel<PACK, GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, best);
 	P.plane[idx] = make_float4(n.x, n.y, n.z, d);
 	P.cost[idx] = c;
 	if (P.bestViews) P.bestViews[idx] = best;
 }
 
 // ------------------------------------------------------------------------------------
-// pass B: one red-black half-sweep
-template <int LAYOUT, bool GEOM, bool WS>
-__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, WS ? 3 : 2)
+// pass B: one red-black half-sweep (ProcessPixel, DepthMap.cpp:630-852, on the engine schedule):
+//   1. gather the four 4-neighbours (smoothing set "close", DepthMap.cpp:641-766) and, per direction, the
+//      propagation candidate: the pixel of the other colour at distance 1, 3, .. 2*farRings+1 with the lowest
+//      stored cost (the nearest on ties) — the red-black stand-in for the transport along the scanline that
+//      the reference's sequential sweep performs within one iteration;
+//   2. test the candidates' planes (InterpolatePixel + CorrectNormal), skipping a direction whose candidates
+//      all kept their plane in their last update (they lost against this pixel one sweep ago) — P.skipUnchanged;
+//   3. the refinement state machine (DepthMap.cpp:800-852).
+// Every lane keeps its own to-do list of directions, so a warp runs max-over-lanes(list length) test steps.
+template <bool PACK, bool GEOM>
+__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, 3)
 pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUtensorMap tmapRef)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
-	// [ patch weights (WS) | reference tile | mbarrier ]
+	// [ patch weights | reference tile | mbarrier ]
 	float2* smemW = (float2*)smemRaw;
-	float* tile = (float*)(smemRaw + (WS ? PM_TEXELS*NTHREADS*sizeof(float2) : 0));
+	float* tile = (float*)(smemRaw + PM_TEXELS*NTHREADS*sizeof(float2));
 	uint64_t* bar = (uint64_t*)(tile + TILE_W*TILE_H);
 	const int tid = threadIdx.y*BLOCK_X + threadIdx.x;
 	if (P.tma) {
@@ -589,10 +511,12 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 	const int x = blockIdx.x*(2*BLOCK_X) + 2*threadIdx.x + ((y+P.colour)&1);
 	if (x < PM_HALF || y < PM_HALF || x >= P.W-PM_HALF || y >= P.H-PM_HALF)
 		return;
+	if (P.mask && P.mask[(size_t)y*P.maskPitch + x] == 0)
+		return;
 	const int W = P.W, H = P.H;
 	const size_t idx = (size_t)y*W + x;
-	PatchT<WS> pt;
-	if constexpr (WS) pt.s = smemW + tid;
+	PatchW pt;
+	pt.s = smemW + tid;
 	if (P.tma)
 		fill_patch_tile(tile, 2*(int)threadIdx.x + ((y+P.colour)&1) + PM_HALF, (int)threadIdx.y + PM_HALF, pt);
 	else
@@ -609,8 +533,10 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 
 	// neighbours: causal pair of the sweep direction first (DepthMap.cpp:641-766)
 	const int dir = P.sweep & 1;
+	const int nProp = P.propagation, farRings = P.farRings;
 	Close cl; cl.mask = 0;
-	float ncost[4];
+	unsigned todo = 0;    // bit k: direction k has a candidate to test
+	unsigned farSel = 0;  // 2 bits per direction: ring of the candidate (distance 2*ring+1)
 	#pragma unroll
 	for (int k = 0; k < 4; ++k) {
 		// dir 0: left, up, right, down;  dir 1: right, down, left, up
@@ -618,42 +544,95 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 		const int ox = (kk == 0) ? -1 : (kk == 2) ? 1 : 0;
 		const int oy = (kk == 1) ? -1 : (kk == 3) ? 1 : 0;
 		const bool ok = (kk == 0) ? (x > PM_HALF) : (kk == 1) ? (y > PM_HALF) : (kk == 2) ? (x < W-PM_HALF) : (y < H-PM_HALF);
-		cl.d[k] = 0.f; cl.n[k] = make_float3(0.f, 0.f, 0.f); cl.rx[k] = 0.f; cl.ry[k] = 0.f; ncost[k] = 2.f;
+		cl.d[k] = 0.f; cl.n[k] = make_float3(0.f, 0.f, 0.f); cl.rx[k] = 0.f; cl.ry[k] = 0.f;
 		if (ok) {
 			const size_t nidx = (size_t)(y+oy)*W + (x+ox);
 			const float4 np = P.plane[nidx];
+			const float nc = P.cost[nidx];
+			bool changed = !cost_unchanged(nc);
+			float bestC = 3.f;
 			if (np.w > 0.f) {
 				cl.mask |= 1u<<k;
 				cl.d[k] = np.w; cl.n[k] = make_float3(np.x, np.y, np.z);
 				const float nfx = float(x+ox), nfy = float(y+oy);
 				cl.rx[k] = nfx*P.ifx + nfy*P.sk + P.ox; cl.ry[k] = nfy*P.ify + P.oy;
-				ncost[k] = P.cost[nidx];
+				bestC = fabsf(nc);
+			}
+			if (k < nProp) {
+				unsigned ring = 0;
+				for (int f = 1; f <= farRings; ++f) {
+					const int qx = x+ox*(2*f+1), qy = y+oy*(2*f+1);
+					if (qx < PM_HALF || qy < PM_HALF || qx >= W-PM_HALF || qy >= H-PM_HALF)
+						break;
+					const float fc = P.cost[(size_t)qy*W + qx];
+					changed = changed || !cost_unchanged(fc);
+					if (fabsf(fc) < bestC) { bestC = fabsf(fc); ring = (unsigned)f; }
+				}
+				if (bestC < P.keep && (changed || !P.skipUnchanged)) {
+					todo |= 1u<<k;
+					farSel |= ring<<(2*k);
+				}
 			}
 		}
 	}
-	float4 pl = P.plane[idx];
-	float conf = P.cost[idx];
+	const float4 pl = P.plane[idx];
+	float conf = fabsf(P.cost[idx]);
 	float depth = pl.w;
 	float3 normal = make_float3(pl.x, pl.y, pl.z);
 	uint32_t bestViews = P.bestViews ? P.bestViews[idx] : 0xFFFFFFFFu;
 
+	// ---- propagation (DepthMap.cpp:775-799) ----
+	#pragma unroll 1
+	for (;;) {
+		const bool have = todo != 0u;
+		if (!__any_sync(__activemask(), have))
+			break;
+		if (have) {
+			const int k = __ffs((int)todo)-1;
+			todo &= todo-1u;
+			const int kk = dir ? (k^2) : k;
+			const int dist = 2*(int)((farSel>>(2*k))&3u)+1;
+			const int qx = x + ((kk == 0) ? -dist : (kk == 2) ? dist : 0);
+			const int qy = y + ((kk == 1) ? -dist : (kk == 3) ? dist : 0);
+			const float4 qp = P.plane[(size_t)qy*W + qx];
+			// InterpolatePixel (DepthMap.cpp:915-959): the candidate's plane intersected with this pixel's ray,
+			// restricted to the row / column; the reference's ray coordinates carry no skew term
+			const bool vertical = (kk & 1) != 0;
+			const float ncomp = vertical ? qp.y : qp.x;
+			const float nx1 = vertical ? X0y : fmaf(fx, P.ifx, P.ox0);
+			const float x1 = vertical ? fmaf(float(qy), P.ify, P.oy) : fmaf(float(qx), P.ifx, P.ox0);
+			const float denom = qp.z + nx1*ncomp;
+			float hd = qp.w;
+			if (!(fabsf(denom) < 0.0001f)) {
+				const float dn = qp.w*(qp.z + x1*ncomp)/denom;
+				if (P.dMin <= dn && dn < P.dMax)
+					hd = dn;
+			}
+			float3 hn = make_float3(qp.x, qp.y, qp.z);
+			correct_normal(hn, X0x, X0y);
+			Hyp h;
+			make_hyp(P, X0x, X0y, hd, hn, cl, true, h);
+			uint32_t bv;
+			const float nconf = score_pixel<PACK, GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
+			if (conf > nconf) { conf = nconf; depth = hd; normal = hn; bestViews = bv; }
+		}
+	}
+
+	// ---- refinement state machine (DepthMap.cpp:800-852) ----
+	// Lanes in restart mode spend their random tries in the same steps in which refine-mode lanes spend their
+	// perturbation tries; every try has its own Philox slot (restart try k: slot k, refinement try k: slot
+	// nR+k), so the result does not depend on the step at which a lane executes it.
 	const int nR = P.nRandomIters;
-	const int nProp = P.propagation;
 	const uint2 key = make_uint2(P.seed, 0xB200C0DEu);
 	const uint32_t phase = 1u + (uint32_t)P.sweep;
-	// refinement state machine (DepthMap.cpp:800-852).  Lanes in restart mode spend their random
-	// tries in the same steps in which refine-mode lanes spend their perturbation tries; every try
-	// has its own Philox slot (restart try k: slot k, refinement try k: slot nR+k), so the result
-	// does not depend on the step at which a lane executes it.
 	int mode = 0;               // 0 undecided, 1 restart (fully random), 2 refine, 3 done
 	bool useClose = true;
 	unsigned idxScale = 0;
 	float scaleRange = 1.f, depthRange = 0.f, pa = 0.f, pb = 0.f;
 	int nRestart = 0, nRefine = 0; // tries spent
-	const int nSteps = 4 + 2*nR;
 	#pragma unroll 1
-	for (int step = 0; step < nSteps; ++step) {
-		if (step == 4 || (mode == 1 && step > 4 && conf < P.thConfRand)) {
+	for (int step = 0; step < 2*nR; ++step) {
+		if (step == 0 || (mode == 1 && conf < P.thConfRand)) {
 			// RefineIters: choose the perturbation scale from the current score
 			bool toRefine = true;
 			if (conf <= P.thConfSmall) idxScale = 2;
@@ -667,40 +646,13 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 				pb = acosf(normal.z);
 			}
 		}
-		if (step >= 4) {
-			if (mode == 1 && nRestart >= nR) mode = 3; // all random tries failed: no refinement this sweep
-			const bool work = (mode == 1) || (mode == 2 && nRefine < nR);
-			if (!__any_sync(__activemask(), work))
-				break;
-		}
+		if (mode == 1 && nRestart >= nR) mode = 3; // all random tries failed: no refinement this sweep
+		const bool work = (mode == 1) || (mode == 2 && nRefine < nR);
+		if (!__any_sync(__activemask(), work))
+			break;
 		bool have = false, isRefine = false;
 		float hd = 0.f, na = 0.f, nb = 0.f; float3 hn = make_float3(0.f, 0.f, 1.f);
-		if (step < 4) {
-			// propagate the plane of neighbour `step` (InterpolatePixel, DepthMap.cpp:915-959)
-			if (step < nProp && (cl.mask & (1u<<step))) {
-				const float kd = step == 0 ? cl.d[0] : step == 1 ? cl.d[1] : step == 2 ? cl.d[2] : cl.d[3];
-				const float3 kn = step == 0 ? cl.n[0] : step == 1 ? cl.n[1] : step == 2 ? cl.n[2] : cl.n[3];
-				const float kc = step == 0 ? ncost[0] : step == 1 ? ncost[1] : step == 2 ? ncost[2] : ncost[3];
-				const float krx = step == 0 ? cl.rx[0] : step == 1 ? cl.rx[1] : step == 2 ? cl.rx[2] : cl.rx[3];
-				const float kry = step == 0 ? cl.ry[0] : step == 1 ? cl.ry[1] : step == 2 ? cl.ry[2] : cl.ry[3];
-				if (kc < P.keep) {
-					const bool vertical = ((dir ? (step^2) : step) & 1) != 0;
-					const float ncomp = vertical ? kn.y : kn.x;
-					const float nx1 = vertical ? X0y : X0x;
-					const float x1 = vertical ? kry : krx;
-					const float denom = kn.z + nx1*ncomp;
-					hd = kd;
-					if (!(fabsf(denom) < 0.0001f)) {
-						const float dn = kd*(kn.z + x1*ncomp)/denom;
-						if (P.dMin <= dn && dn < P.dMax)
-							hd = dn;
-					}
-					hn = kn;
-					correct_normal(hn, X0x, X0y);
-					have = true;
-				}
-			}
-		} else if (mode == 1) {
+		if (mode == 1) {
 			// completely random plane (DepthMap.cpp:810-825)
 			const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)nRestart, 0u), key);
 			++nRestart;
@@ -727,7 +679,7 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 			Hyp h;
 			make_hyp(P, X0x, X0y, hd, hn, cl, useClose, h);
 			uint32_t bv;
-			const float nconf = score_pixel<LAYOUT, GEOM, WS>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
+			const float nconf = score_pixel<PACK, GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
 			if (conf > nconf) {
 				conf = nconf; depth = hd; normal = hn; bestViews = bv;
 				if (isRefine) {
@@ -738,12 +690,14 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 			}
 		}
 	}
+	const bool same = depth == pl.w && normal.x == pl.x && normal.y == pl.y && normal.z == pl.z;
 	P.plane[idx] = make_float4(normal.x, normal.y, normal.z, depth);
-	P.cost[idx] = conf;
+	P.cost[idx] = (same && P.skipUnchanged) ? -conf : conf;
 	if (P.bestViews) P.bestViews[idx] = bestViews;
 }
 
-// pass C: threshold and convert cost to confidence (EndDepthMapTmp)
+// pass C: threshold and convert cost to confidence (EndDepthMapTmp).  viewsMap: the (at most two) views of the
+// MINMEAN score in ascending order, 255 padding — the order PatchMatchCUDA.cpp:374-391 emits its view ids in
 __global__ void pm_finalize_kernel(int n, float keep, const float4* __restrict__ plane, const float* __restrict__ cost,
 	const uint32_t* __restrict__ bestViews, float* __restrict__ depth, float* __restrict__ normal, float* __restrict__ conf,
 	uint32_t* __restrict__ viewsMap)
@@ -751,32 +705,21 @@ __global__ void pm_finalize_kernel(int n, float keep, const float4* __restrict__
 	const int i = blockIdx.x*blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const float4 p = plane[i];
-	const float c = cost[i];
+	const float c = fabsf(cost[i]);
 	float d = p.w, cf; float3 nn = make_float3(p.x, p.y, p.z);
 	uint32_t bv = bestViews ? bestViews[i] : 0xFFFFFFFFu;
 	if (d <= 0.f || c >= keep) {
 		d = 0.f; cf = 0.f; nn = make_float3(0.f, 0.f, 0.f); bv = 0xFFFFFFFFu;
 	} else {
 		cf = c >= 1.f ? 0.f : 1.f-c;
+		const uint32_t a = bv & 0xFFu, b = (bv>>8) & 0xFFu;
+		bv = 0xFFFF0000u | (max(a, b)<<8) | min(a, b);
 	}
 	depth[i] = d; conf[i] = cf;
 	normal[3*(size_t)i] = nn.x; normal[3*(size_t)i+1] = nn.y; normal[3*(size_t)i+2] = nn.z;
 	if (viewsMap) viewsMap[i] = bv;
 }
 
-__global__ void pm_pairs_kernel(const float* __restrict__ src, int w, int h, int spitch, float2* __restrict__ dst) {
-	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
-	if (x >= w || y >= h) return;
-	const int y1 = min(y+1, h-1);
-	dst[(size_t)y*w+x] = make_float2(src[(size_t)y*spitch+x], src[(size_t)y1*spitch+x]);
-}
-// LAYOUT 3: row y of dst = [even columns | odd columns], `half` floats each (zero padded)
-__global__ void pm_deint_kernel(const float* __restrict__ src, int w, int h, int spitch, float* __restrict__ dst, int half) {
-	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
-	if (x >= 2*half || y >= h) return;
-	const int plane = x >= half, k = x-plane*half, sx = 2*k+plane;
-	dst[(size_t)y*2*half+x] = sx < w ? src[(size_t)y*spitch+sx] : 0.f;
-}
 __global__ void pm_pack_kernel(int n, const float* __restrict__ depth, const float* __restrict__ normal, float4* __restrict__ plane) {
 	const int i = blockIdx.x*blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -791,76 +734,43 @@ __global__ void pm_unpack_kernel(int n, const float4* __restrict__ plane, float*
 }
 
 // ---- host launchers ---------------------------------------------------------------------
-template <int LAYOUT, bool GEOM, bool WS>
-cudaError_t launch_one(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap) {
-	const size_t wbytes = WS ? (size_t)PM_TEXELS*NTHREADS*sizeof(float2) : 0;
-	if (sweep) {
-		const size_t smem = wbytes + TILE_BYTES + 16;
-		// the attribute is per device: one flag per device of the process (several contexts / GPUs)
-		static bool done[64] = {};
-		int dev = 0; cudaGetDevice(&dev); dev &= 63;
-		if (!done[dev]) {
-			cudaError_t e = cudaFuncSetAttribute(pm_sweep_kernel<LAYOUT, GEOM, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e != cudaSuccess) return e;
-			done[dev] = true;
-		}
-		pm_sweep_kernel<LAYOUT, GEOM, WS><<<grid, block, smem, s>>>(P, tmap);
-	} else {
-		static bool done[64] = {};
-		int dev = 0; cudaGetDevice(&dev); dev &= 63;
-		if (WS && !done[dev]) {
-			cudaError_t e = cudaFuncSetAttribute(pm_score_kernel<LAYOUT, GEOM, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
-			if (e != cudaSuccess) return e;
-			done[dev] = true;
-		}
-		pm_score_kernel<LAYOUT, GEOM, WS><<<grid, block, wbytes, s>>>(P);
-	}
-	return cudaGetLastError();
-}
-template <int LAYOUT>
-cudaError_t launch_layout(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap, bool geom, bool ws) {
-	if (geom) return ws ? launch_one<LAYOUT, true, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, true, false>(sweep, grid, block, s, P, tmap);
-	return ws ? launch_one<LAYOUT, false, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, false, false>(sweep, grid, block, s, P, tmap);
-}
-// the experimental tap-loop variants (LAYOUT 3, 11, 13) exist with the patch weights in shared memory only
-template <int LAYOUT>
-cudaError_t launch_variant(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap, bool geom) {
-	return geom ? launch_one<LAYOUT, true, true>(sweep, grid, block, s, P, tmap) : launch_one<LAYOUT, false, true>(sweep, grid, block, s, P, tmap);
-}
-cudaError_t launch_any(bool sweep, dim3 grid, dim3 block, cudaStream_t s, const PMParams& P, const CUtensorMap& tmap, int layout, bool geom, bool ws) {
-	switch (layout) {
-	case 2: return launch_layout<2>(sweep, grid, block, s, P, tmap, geom, ws);
-	case 3: return launch_variant<3>(sweep, grid, block, s, P, tmap, geom);
-	case 11: return launch_variant<11>(sweep, grid, block, s, P, tmap, geom);
-	case 13: return launch_variant<13>(sweep, grid, block, s, P, tmap, geom);
-	default: return launch_layout<1>(sweep, grid, block, s, P, tmap, geom, ws);
-	}
+constexpr size_t W_BYTES = (size_t)PM_TEXELS*NTHREADS*sizeof(float2);
+constexpr size_t SWEEP_SMEM = W_BYTES + TILE_BYTES + 16;
+
+template <bool PACK, bool GEOM>
+cudaError_t configure_one() {
+	cudaError_t e = cudaFuncSetAttribute(pm_sweep_kernel<PACK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+	if (e != cudaSuccess) return e;
+	return cudaFuncSetAttribute(pm_score_kernel<PACK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
 }
 
 } // namespace
 
-cudaError_t pm_launch_score(const PMParams& P, int layout, bool geom, bool ws, cudaStream_t s) {
+// Opt the kernels of the current device into their dynamic shared memory sizes.  Called by b200mvs_create for its
+// device (function attributes are per device; the call is idempotent and safe from several host threads).
+cudaError_t pm_configure_device() {
+	cudaError_t e;
+	if ((e = configure_one<true, false>()) != cudaSuccess) return e;
+	if ((e = configure_one<true, true>()) != cudaSuccess) return e;
+	if ((e = configure_one<false, false>()) != cudaSuccess) return e;
+	return configure_one<false, true>();
+}
+cudaError_t pm_launch_score(const PMParams& P, bool pack, bool geom, cudaStream_t s) {
 	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+BLOCK_X-1)/BLOCK_X, (P.H+BLOCK_Y-1)/BLOCK_Y);
-	CUtensorMap none; memset(&none, 0, sizeof(none));
-	return launch_any(false, grid, block, s, P, none, layout, geom, ws);
+	if (pack) { if (geom) pm_score_kernel<true, true><<<grid, block, W_BYTES, s>>>(P); else pm_score_kernel<true, false><<<grid, block, W_BYTES, s>>>(P); }
+	else { if (geom) pm_score_kernel<false, true><<<grid, block, W_BYTES, s>>>(P); else pm_score_kernel<false, false><<<grid, block, W_BYTES, s>>>(P); }
+	return cudaGetLastError();
 }
 // tmapRef: TMA descriptor of the reference image with box {72, 16} (pm_tma_box), or null (P.tma must be 0)
-cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, int layout, bool geom, bool ws, cudaStream_t s) {
+cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, bool pack, bool geom, cudaStream_t s) {
 	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+2*BLOCK_X-1)/(2*BLOCK_X), (P.H+BLOCK_Y-1)/BLOCK_Y);
 	CUtensorMap map; memset(&map, 0, sizeof(map));
 	if (tmapRef) memcpy(&map, tmapRef, sizeof(map));
-	return launch_any(true, grid, block, s, P, map, layout, geom, ws);
-}
-void pm_tma_box(int* w, int* h) { *w = TILE_W; *h = TILE_H; }
-// floats per parity plane of a LAYOUT 3 row (multiple of 4, room for the element after the last column)
-int pm_layout3_half(int w) { return ((w+1)/2+4+3)&~3; }
-// re-layout of a neighbour image for the tap fetch (see fetch_bilinear)
-cudaError_t pm_launch_relayout(const float* src, int w, int h, int spitch, void* dst, int layout, cudaStream_t s) {
-	dim3 block(32, 8), grid((w+31)/32, (h+7)/8);
-	if (layout == 2) pm_pairs_kernel<<<grid, block, 0, s>>>(src, w, h, spitch, (float2*)dst);
-	if (layout == 3) { const int half = pm_layout3_half(w); pm_deint_kernel<<<dim3((2*half+31)/32, (h+7)/8), block, 0, s>>>(src, w, h, spitch, (float*)dst, half); }
+	if (pack) { if (geom) pm_sweep_kernel<true, true><<<grid, block, SWEEP_SMEM, s>>>(P, map); else pm_sweep_kernel<true, false><<<grid, block, SWEEP_SMEM, s>>>(P, map); }
+	else { if (geom) pm_sweep_kernel<false, true><<<grid, block, SWEEP_SMEM, s>>>(P, map); else pm_sweep_kernel<false, false><<<grid, block, SWEEP_SMEM, s>>>(P, map); }
 	return cudaGetLastError();
 }
+void pm_tma_box(int* w, int* h) { *w = TILE_W; *h = TILE_H; }
 cudaError_t pm_launch_finalize(int n, float keep, const float4* plane, const float* cost, const uint32_t* bestViews,
 	float* depth, float* normal, float* conf, uint32_t* viewsMap, cudaStream_t s) {
 	pm_finalize_kernel<<<(n+255)/256, 256, 0, s>>>(n, keep, plane, cost, bestViews, depth, normal, conf, viewsMap);

@@ -90,8 +90,17 @@ __global__ void resize_nearest_kernel(const float* __restrict__ src, int sw, int
 
 // next-level initialisation: depth bilinear (INTER_LINEAR), normal nearest, from the packed
 // low-resolution plane field; also writes the depth prior of the level
+// cv::resize(mask, mask, size, 0, 0, INTER_NEAREST) of the ignore-mask (DepthEstimator::ImportIgnoreMask, DepthMap.cpp:309)
+__global__ void resize_nearest_u8_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw, int dh, double ifx, double ify) {
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= dw || y >= dh) return;
+	const int sx = min((int)floor(x*ifx), sw-1), sy = min((int)floor(y*ify), sh-1);
+	dst[(size_t)y*dw+x] = src[(size_t)sy*spitch+sx];
+}
+
+// nearestDepth: the depth is up-sampled NEAREST instead of LINEAR (an ignore-mask is set, SceneDensify.cpp:661)
 __global__ void plane_up_kernel(const float4* __restrict__ src, int sw, int sh, float4* __restrict__ dst, float* __restrict__ prior,
-	int dw, int dh, double scx, double scy)
+	int dw, int dh, double scx, double scy, int nearestDepth)
 {
 	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
 	if (x >= dw || y >= dh) return;
@@ -101,9 +110,9 @@ __global__ void plane_up_kernel(const float4* __restrict__ src, int sw, int sh, 
 	const int x1 = min(x0+1, sw-1), y1 = min(y0+1, sh-1);
 	const float r0 = src[(size_t)y0*sw+x0].w*(1.f-fx) + src[(size_t)y0*sw+x1].w*fx;
 	const float r1 = src[(size_t)y1*sw+x0].w*(1.f-fx) + src[(size_t)y1*sw+x1].w*fx;
-	const float d = r0*(1.f-fy) + r1*fy;
 	const int sx = min((int)floor(x*scx), sw-1), sy = min((int)floor(y*scy), sh-1);
 	const float4 n = src[(size_t)sy*sw+sx];
+	const float d = nearestDepth ? n.w : r0*(1.f-fy) + r1*fy;
 	dst[(size_t)y*dw+x] = make_float4(n.x, n.y, n.z, d);
 	prior[(size_t)y*dw+x] = d;
 }
@@ -128,14 +137,21 @@ cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int d
 	resize_linear_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, dst, dw, dh, (double)sw/dw, (double)sh/dh);
 	return cudaGetLastError();
 }
-cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, cudaStream_t s) {
+// scx/scy: source/destination scale; 1/factor for the factor form cv::resize(..., Size(), fx, fy, INTER_NEAREST)
+// (ScaleDepthData, SceneDensify.cpp:596-599), <= 0 for the destination-size form (sw/dw)
+cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s) {
 	dim3 b(32, 8);
-	resize_nearest_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, ch, dst, dw, dh, (double)sw/dw, (double)sh/dh);
+	resize_nearest_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, ch, dst, dw, dh, scx > 0 ? scx : (double)sw/dw, scy > 0 ? scy : (double)sh/dh);
 	return cudaGetLastError();
 }
-cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, cudaStream_t s) {
+cudaError_t rs_launch_nearest_u8(const uint8_t* src, int sw, int sh, int spitch, uint8_t* dst, int dw, int dh, cudaStream_t s) {
 	dim3 b(32, 8);
-	plane_up_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, dst, prior, dw, dh, (double)sw/dw, (double)sh/dh);
+	resize_nearest_u8_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, spitch, dst, dw, dh, (double)sw/dw, (double)sh/dh);
+	return cudaGetLastError();
+}
+cudaError_t rs_launch_plane_up(const float4* src, int sw, int sh, float4* dst, float* prior, int dw, int dh, bool nearestDepth, cudaStream_t s) {
+	dim3 b(32, 8);
+	plane_up_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, dst, prior, dw, dh, (double)sw/dw, (double)sh/dh, nearestDepth ? 1 : 0);
 	return cudaGetLastError();
 }
 

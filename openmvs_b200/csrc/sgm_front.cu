@@ -1,0 +1,375 @@
+// sgm_front.cu — SGM path aggregation as wave fronts (sm_100a), the default for uniform disparity ranges.
+//
+// What it computes: the eight path recursions of SemiGlobalMatcher::Match and their sum
+//   L_r(p,d) = C(p,d) + min(L_r(q,d), L_r(q,d+-1)+P1, min_d' L_r(q,d')+P2) - min_d' L_r(q,d'),  S = sum_r L_r
+// (pixelAccum + path drivers, libs/MVS/SemiGlobalMatcher.cpp:1003-1269; exact O(D) form under P1 <= P2 as in sgm_kernels.cu).
+//
+// Why a new organisation (round-1 evidence, profiles/launches_r01_sgm.txt): one launch per direction read-modify-writes the
+// u16 sum volume eight times (11.2 GB of DRAM traffic against 2.9 GB algorithmic) and spends about 170 warp instructions per
+// pixel and direction on a 128-wide scanline step.  Here
+//   * 8 lanes own one pixel (16 disparities per lane as 8 packed u16x2 words): the step is SIMD-in-a-word arithmetic
+//     (VIADD.16x2 / VIMNMX.U16x2 / the DPX three-input minimum VIMNMX3.U16x2), a warp advances 4 adjacent paths, the per-step
+//     fixed cost (penalty lookup, neighbour shuffles, minimum reduction, loop) is shared by 4 pixels: about 25 warp
+//     instructions per pixel and direction;
+//   * directions whose step moves a tilted wave front f = x + 2y forward (right, right-down, down, left-down — and their
+//     mirror images in a second pass) are processed TOGETHER, front block by front block: a work item is (direction,
+//     band of 4 adjacent paths, block of FB consecutive fronts); items are handed out from one queue in front order, so all
+//     four directions touch a block's slice of the sum volume while it is resident in the 126 MB L2 — the volume
+//     crosses HBM once per pass instead of once per direction (2 passes: 2 x 263 MB of costs + 526 MB written + 526 MB
+//     read-modify-written for 1914 x 1074 x 128, instead of 8 x 1.3 GB);
+//   * ordering instead of atomics: within a block the directions are phases; an item waits (rarely — its predecessors are
+//     thousands of queue positions ahead) until the previous phase of its block is complete and until its own paths'
+//     previous segment has been stored (path state: the normalised previous line, 256 B per path, kept in a small L2-resident
+//     buffer between the segments).  Phase 0 of the first pass stores the sum, so the volume needs no memset.
+// Bit-exact against the oracle (tests/test_sgm_parity_gpu.py); the per-direction kernels of sgm_kernels.cu remain for
+// ragged (tSGM) ranges and as debug variants (b200mvs_debug.sgmAggregation).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
+struct SGMParams {
+	const float* lgray; const uchar3* lbgr; const float* rgray;
+	int w, h, vw, vh;
+	const SGMPixel* px;
+	uint8_t* costs; uint16_t* accums;
+	int P1;
+	uint16_t P2s[256];
+	int maxNumDisp;
+};
+
+// one work item: direction `dir` (phase `ph` of its pass), paths k0 .. k0+3, fronts [fb*FB, fb*FB+FB)
+struct FrontItem {
+	int k0; short dir; short ph;
+	int fb;
+	int seq;       // number of earlier items of the same band: wait until progress[chain] >= seq
+	int chain;     // index into progress[]
+	int depCell;   // cell (phase - 1, fb) whose completion this item waits for, or -1
+	int depNeed;   // number of items in that cell
+	int cell;      // this item's cell (completion counter to bump)
+};
+struct FrontArgs {
+	const FrontItem* items; int nItems;
+	int* ticket;         // queue head
+	int* progress;       // per (phase, band): segments completed
+	int* cellDone;       // per (phase, front block): items completed
+	int* error;          // set to 1 when a wait timed out (never in a correct schedule)
+	uint16_t* state;     // per (phase, path): the normalised previous line, num u16
+	float2* meta;        // per (phase, path): {previous intensity, have-previous flag}
+	int maxPaths;        // paths per phase slot in state / meta
+	int fa, fb, fc, FB;  // front f(x,y) = fa*x + fb*y + fc >= 0, block size
+	int storePhase0;     // 1: phase 0 stores the sum instead of adding to it (first pass)
+	int num;             // disparities per pixel (16 * NW)
+};
+
+// start pixel and step of scanline `k` of direction `dir` (order of SemiGlobalMatcher.cpp:1084-1199); host and device
+__host__ __device__ inline bool front_path_start(int dir, int k, int W, int H, int& x, int& y, int& dx, int& dy) {
+	switch (dir) {
+	case 0: if (k >= W) return false; x = k; y = 0; dx = 0; dy = 1; return true;        // width-down
+	case 1: if (k >= H) return false; x = 0; y = k; dx = 1; dy = 0; return true;        // height-right
+	case 2: if (k >= W) return false; x = k; y = H-1; dx = 0; dy = -1; return true;     // width-up
+	case 3: if (k >= H) return false; x = W-1; y = k; dx = -1; dy = 0; return true;     // height-left
+	case 4: dx = 1; dy = 1;                                                             // right-down
+		if (k < W) { x = k; y = 0; return true; } k -= W; if (k >= H-1) return false; x = 0; y = k+1; return true;
+	case 5: dx = -1; dy = 1;                                                            // left-down
+		if (k < W-1) { x = k; y = 0; return true; } k -= W-1; if (k >= H) return false; x = W-1; y = k; return true;
+	case 6: dx = 1; dy = -1;                                                            // right-up
+		if (k < W-1) { x = k+1; y = H-1; return true; } k -= W-1; if (k >= H) return false; x = 0; y = k; return true;
+	default: dx = -1; dy = -1;                                                          // left-up
+		if (k < W) { x = k; y = H-1; return true; } k -= W; if (k >= H-1) return false; x = W-1; y = k; return true;
+	}
+}
+__host__ __device__ inline int front_path_len(int x0, int y0, int dx, int dy, int W, int H) {
+	int n = 0x7FFFFFFF;
+	if (dx > 0) n = min(n, W-x0); else if (dx < 0) n = min(n, x0+1);
+	if (dy > 0) n = min(n, H-y0); else if (dy < 0) n = min(n, y0+1);
+	return n;
+}
+// first step s >= 0 of a path with f(s) = f0 + s*df (df > 0) at or beyond front `lo`
+__host__ __device__ inline int front_first_step(int lo, int f0, int df) {
+	const int a = lo-f0;
+	return a <= 0 ? 0 : (a+df-1)/df;
+}
+
+namespace {
+
+constexpr int FRONT_WARPS = 4;
+constexpr int PD = 4;          // software pipeline depth (steps whose loads are in flight)
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+	int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+	asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg((const uint4*)p); }
+__device__ __forceinline__ void stcg4(void* p, uint4 v) { __stcg((uint4*)p, v); }
+
+template <int NW> struct FrontVec;   // NW packed u16x2 words per lane = 2*NW disparities; cost bytes 2*NW, sum bytes 4*NW
+template <> struct FrontVec<8> {
+	struct C { uint4 v; }; struct S { uint4 a, b; };
+	static __device__ __forceinline__ C ldc(const uint8_t* p) { C c; c.v = __ldg((const uint4*)p); return c; }
+	static __device__ __forceinline__ S lds(const uint16_t* p) { S s; s.a = ldcg4(p); s.b = ldcg4(p+8); return s; }
+	static __device__ __forceinline__ void sts(uint16_t* p, const unsigned* w) { stcg4(p, make_uint4(w[0], w[1], w[2], w[3])); stcg4(p+8, make_uint4(w[4], w[5], w[6], w[7])); }
+	static __device__ __forceinline__ void unpackC(const C& c, unsigned* o) {
+		o[0] = __byte_perm(c.v.x, 0u, 0x4140); o[1] = __byte_perm(c.v.x, 0u, 0x4342);
+		o[2] = __byte_perm(c.v.y, 0u, 0x4140); o[3] = __byte_perm(c.v.y, 0u, 0x4342);
+		o[4] = __byte_perm(c.v.z, 0u, 0x4140); o[5] = __byte_perm(c.v.z, 0u, 0x4342);
+		o[6] = __byte_perm(c.v.w, 0u, 0x4140); o[7] = __byte_perm(c.v.w, 0u, 0x4342);
+	}
+	static __device__ __forceinline__ void unpackS(const S& s, unsigned* o) { o[0] = s.a.x; o[1] = s.a.y; o[2] = s.a.z; o[3] = s.a.w; o[4] = s.b.x; o[5] = s.b.y; o[6] = s.b.z; o[7] = s.b.w; }
+};
+template <> struct FrontVec<4> {
+	struct C { uint2 v; }; struct S { uint4 a; };
+	static __device__ __forceinline__ C ldc(const uint8_t* p) { C c; c.v = __ldg((const uint2*)p); return c; }
+	static __device__ __forceinline__ S lds(const uint16_t* p) { S s; s.a = ldcg4(p); return s; }
+	static __device__ __forceinline__ void sts(uint16_t* p, const unsigned* w) { stcg4(p, make_uint4(w[0], w[1], w[2], w[3])); }
+	static __device__ __forceinline__ void unpackC(const C& c, unsigned* o) {
+		o[0] = __byte_perm(c.v.x, 0u, 0x4140); o[1] = __byte_perm(c.v.x, 0u, 0x4342);
+		o[2] = __byte_perm(c.v.y, 0u, 0x4140); o[3] = __byte_perm(c.v.y, 0u, 0x4342);
+	}
+	static __device__ __forceinline__ void unpackS(const S& s, unsigned* o) { o[0] = s.a.x; o[1] = s.a.y; o[2] = s.a.z; o[3] = s.a.w; }
+};
+template <> struct FrontVec<16> {
+	struct C { uint4 v, u; }; struct S { uint4 a, b, c, d; };
+	static __device__ __forceinline__ C ldc(const uint8_t* p) { C c; c.v = __ldg((const uint4*)p); c.u = __ldg((const uint4*)(p+16)); return c; }
+	static __device__ __forceinline__ S lds(const uint16_t* p) { S s; s.a = ldcg4(p); s.b = ldcg4(p+8); s.c = ldcg4(p+16); s.d = ldcg4(p+24); return s; }
+	static __device__ __forceinline__ void sts(uint16_t* p, const unsigned* w) {
+		stcg4(p, make_uint4(w[0], w[1], w[2], w[3])); stcg4(p+8, make_uint4(w[4], w[5], w[6], w[7]));
+		stcg4(p+16, make_uint4(w[8], w[9], w[10], w[11])); stcg4(p+24, make_uint4(w[12], w[13], w[14], w[15]));
+	}
+	static __device__ __forceinline__ void unpackC(const C& c, unsigned* o) {
+		const unsigned s[8] = {c.v.x, c.v.y, c.v.z, c.v.w, c.u.x, c.u.y, c.u.z, c.u.w};
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) { o[2*i] = __byte_perm(s[i], 0u, 0x4140); o[2*i+1] = __byte_perm(s[i], 0u, 0x4342); }
+	}
+	static __device__ __forceinline__ void unpackS(const S& s, unsigned* o) {
+		const uint4 q[4] = {s.a, s.b, s.c, s.d};
+		#pragma unroll
+		for (int i = 0; i < 4; ++i) { o[4*i] = q[i].x; o[4*i+1] = q[i].y; o[4*i+2] = q[i].z; o[4*i+3] = q[i].w; }
+	}
+};
+
+// NW words per lane, 8 lanes per pixel, 4 pixels (adjacent paths) per warp.  Dense volumes only: every pixel of the valid
+// region is valid, owns `num` = 16*NW entries at idx = (y*vw + x)*num (checked by the caller).
+template <int NW>
+__global__ void __launch_bounds__(FRONT_WARPS*32)
+sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ FrontArgs A)
+{
+	typedef FrontVec<NW> V;
+	__shared__ unsigned sP2[256];   // adaptive P2 replicated in both halfwords (GenerateP2s, SemiGlobalMatcher.cpp:518-524)
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) sP2[i] = (unsigned)P.P2s[i]*0x10001u;
+	__syncthreads();
+	const int lane = threadIdx.x&31;
+	const int g = lane>>3, sub = lane&7;
+	const unsigned gmask = 0xFFu<<(g*8);
+	const unsigned P1x2 = (unsigned)P.P1*0x10001u;
+	const int vw = P.vw, vh = P.vh, num = A.num;
+	int ticket = 0;
+	if (lane == 0) ticket = atomicAdd(A.ticket, 1);
+	ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+	#pragma unroll 1
+	while (ticket < A.nItems) {
+		// the next ticket is requested now and consumed when this item is done (the atomic's latency is hidden)
+		int next = 0;
+		if (lane == 0) next = atomicAdd(A.ticket, 1);
+		const uint4 r0 = __ldg((const uint4*)(A.items+ticket)), r1 = __ldg((const uint4*)(A.items+ticket)+1);
+		const int k0 = (int)r0.x, dir = (int)(short)(r0.y&0xFFFFu), ph = (int)(short)(r0.y>>16), fblk = (int)r0.z, seq = (int)r0.w;
+		const int chain = (int)r1.x, depCell = (int)r1.y, depNeed = (int)r1.z, cell = (int)r1.w;
+		// geometry of this lane's path
+		int xs = 0, ys = 0, dx = 0, dy = 0;
+		const bool pv = front_path_start(dir, k0+g, vw, vh, xs, ys, dx, dy);
+		const int n = pv ? front_path_len(xs, ys, dx, dy, vw, vh) : 0;
+		const int f0 = A.fa*xs + A.fb*ys + A.fc, df = max(1, A.fa*dx + A.fb*dy);
+		const int s0 = min(n, front_first_step(fblk*A.FB, f0, df)), s1 = min(n, front_first_step((fblk+1)*A.FB, f0, df));
+		const int cnt = s1-s0;
+		const int maxcnt = __reduce_max_sync(0xFFFFFFFFu, cnt);
+		const bool add = !(A.storePhase0 && ph == 0);
+		// wait for the predecessors: the previous segment of this band, the previous phase of this front block
+		if (lane == 0) {
+			unsigned spins = 0;
+			while (ld_acquire(A.progress+chain) < seq) { __nanosleep(64); if (++spins > (1u<<22)) { *A.error = 1; break; } }
+			if (depCell >= 0)
+				while (ld_acquire(A.cellDone+depCell) < depNeed) { __nanosleep(64); if (++spins > (1u<<22)) { *A.error = 1; break; } }
+		}
+		__syncwarp();
+		// path state
+		const size_t slot = (size_t)ph*A.maxPaths + (size_t)(k0+g);
+		unsigned w[NW];
+		float Ip = 0.5f; bool havePrev = false;
+		#pragma unroll
+		for (int i = 0; i < NW; ++i) w[i] = 0xFFFFFFFFu;
+		if (s0 > 0 && cnt > 0) {
+			const float2 m = __ldcg(A.meta+slot);
+			Ip = m.x; havePrev = m.y != 0.f;
+			const uint16_t* st = A.state + slot*(size_t)num + (size_t)sub*(2*NW);
+			#pragma unroll
+			for (int i = 0; i < NW; i += 4) { const uint4 v = ldcg4(st+2*i); w[i] = v.x; w[i+1] = v.y; w[i+2] = v.z; w[i+3] = v.w; }
+		}
+		// pipeline stages
+		typename V::C cs[PD]; typename V::S ss[PD]; float is[PD];
+		auto load = [&](int j, int s) {
+			const int x = xs+s*dx, y = ys+s*dy;
+			const size_t idx = ((size_t)y*vw + x)*(size_t)num + (size_t)sub*(2*NW);
+			cs[j] = V::ldc(P.costs+idx);
+			if (add) ss[j] = V::lds(P.accums+idx);
+			is[j] = __ldg(P.lgray + (size_t)y*P.w + x);
+		};
+		#pragma unroll
+		for (int j = 0; j < PD; ++j) {
+			memset(&cs[j], 0, sizeof(cs[j])); memset(&ss[j], 0, sizeof(ss[j])); is[j] = 0.f;
+			if (j < cnt) load(j, s0+j);
+		}
+		#pragma unroll 1
+		for (int t = 0; t < maxcnt; t += PD) {
+			#pragma unroll
+			for (int j = 0; j < PD; ++j) {
+				const int tt = t+j;
+				if (tt >= maxcnt) break;
+				const bool act = tt < cnt;
+				unsigned C[NW], S[NW];
+				V::unpackC(cs[j], C);
+				V::unpackS(ss[j], S);
+				const float I = is[j];
+				const int s = s0+tt;
+				if (tt+PD < cnt) load(j, s+PD);
+				// penalty of this step: P2s[|round(255 (I - Ip))|] (SemiGlobalMatcher.cpp:1009, 518-524)
+				const int di = min(255, abs((int)floorf(255.f*(I-Ip)+.5f)));
+				const unsigned P2x2 = sP2[di];
+				unsigned L[NW];
+				// neighbours d-1 / d+1 across the lanes of the pixel (0xFFFF beyond the two ends of the range)
+				unsigned below = __shfl_up_sync(0xFFFFFFFFu, w[NW-1]>>16, 1), above = __shfl_down_sync(0xFFFFFFFFu, w[0]&0xFFFFu, 1);
+				if (sub == 0) below = 0xFFFFu;
+				if (sub == 7) above = 0xFFFFu;
+				if (havePrev) {
+					unsigned q[NW+1];
+					q[0] = __byte_perm(below, w[0], 0x5410);               // (L[-1], L[0])
+					#pragma unroll
+					for (int i = 1; i < NW; ++i) q[i] = __byte_perm(w[i-1], w[i], 0x5432);   // (L[2i-1], L[2i])
+					q[NW] = __byte_perm(w[NW-1], above, 0x5432);
+					#pragma unroll
+					for (int i = 0; i < NW; ++i) {
+						const unsigned nb = __vaddus2(__vminu2(q[i], q[i+1]), P1x2);
+						L[i] = __vadd2(C[i], __vimin3_u16x2(w[i], nb, P2x2));
+					}
+				} else {
+					#pragma unroll
+					for (int i = 0; i < NW; ++i) L[i] = __vadd2(C[i], P2x2);
+				}
+				// minimum of the new line over the pixel's 8 lanes
+				unsigned m = L[0];
+				#pragma unroll
+				for (int i = 1; i+1 < NW; i += 2) m = __vimin3_u16x2(m, L[i], L[i+1]);
+				if ((NW&1) == 0) m = __vminu2(m, L[NW-1]);
+				m = min(m&0xFFFFu, m>>16);
+				m = __reduce_min_sync(gmask, m);
+				const unsigned mx2 = m*0x10001u;
+				if (act) {
+					unsigned out[NW];
+					#pragma unroll
+					for (int i = 0; i < NW; ++i) { out[i] = add ? __vadd2(S[i], L[i]) : L[i]; w[i] = __vsub2(L[i], mx2); }
+					const int x = xs+s*dx, y = ys+s*dy;
+					V::sts(P.accums + ((size_t)y*vw + x)*(size_t)num + (size_t)sub*(2*NW), out);
+					Ip = I; havePrev = true;
+				}
+			}
+		}
+		// store the state for the next segment of these paths, then publish
+		if (cnt > 0 && s1 < n) {
+			uint16_t* st = A.state + slot*(size_t)num + (size_t)sub*(2*NW);
+			#pragma unroll
+			for (int i = 0; i < NW; i += 4) stcg4(st+2*i, make_uint4(w[i], w[i+1], w[i+2], w[i+3]));
+			if (sub == 0) __stcg(A.meta+slot, make_float2(Ip, havePrev ? 1.f : 0.f));
+		}
+		__threadfence();
+		__syncwarp();
+		if (lane == 0) {
+			st_release(A.progress+chain, seq+1);
+			atomicAdd(A.cellDone+cell, 1);
+		}
+		ticket = __shfl_sync(0xFFFFFFFFu, next, 0);
+	}
+}
+
+} // namespace
+
+// ---- host side: schedule --------------------------------------------------------------------------------------------
+struct FrontPassDesc { int fa, fb; int nDirs; int dirs[4]; };
+
+// Work items of one pass in queue order; returns the number of front blocks and chains through nFB / nChains.
+// lag: queue distance (in front blocks) between consecutive phases of the same block.
+void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc) {
+	// offset that makes the front coordinate non-negative
+	const int cx[2] = {0, vw-1}, cy[2] = {0, vh-1};
+	int fmin = 0x7FFFFFFF, fmax = -0x7FFFFFFF;
+	for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { const int f = pd.fa*cx[a] + pd.fb*cy[b]; fmin = std::min(fmin, f); fmax = std::max(fmax, f); }
+	fc = -fmin;
+	nFB = (fmax-fmin)/FB + 1;
+	maxBands = (vw+vh+3)/4 + 1;
+	items.clear();
+	std::vector<int> cellCount((size_t)pd.nDirs*nFB, 0);
+	for (int ph = 0; ph < pd.nDirs; ++ph) {
+		const int dir = pd.dirs[ph];
+		const int nPaths = dir == 0 || dir == 2 ? vw : dir == 1 || dir == 3 ? vh : vw+vh-1;
+		for (int band = 0; band*4 < nPaths; ++band) {
+			int s0v[4], nv[4], f0v[4], dfv[4]; bool pv[4];
+			int blo = 0x7FFFFFFF, bhi = -1;
+			for (int g = 0; g < 4; ++g) {
+				int x, y, dx, dy;
+				pv[g] = front_path_start(dir, band*4+g, vw, vh, x, y, dx, dy);
+				nv[g] = 0; f0v[g] = 0; dfv[g] = 1; s0v[g] = 0;
+				if (!pv[g]) continue;
+				nv[g] = front_path_len(x, y, dx, dy, vw, vh);
+				f0v[g] = pd.fa*x + pd.fb*y + fc; dfv[g] = pd.fa*dx + pd.fb*dy;
+				blo = std::min(blo, f0v[g]/FB); bhi = std::max(bhi, (f0v[g]+(nv[g]-1)*dfv[g])/FB);
+			}
+			int seq = 0;
+			for (int fb = blo; fb <= bhi; ++fb) {
+				bool any = false;
+				for (int g = 0; g < 4 && !any; ++g) {
+					if (!pv[g]) continue;
+					const int a = std::min(nv[g], front_first_step(fb*FB, f0v[g], dfv[g])), b = std::min(nv[g], front_first_step((fb+1)*FB, f0v[g], dfv[g]));
+					any = b > a;
+				}
+				if (!any) continue;
+				FrontItem it;
+				it.k0 = band*4; it.dir = (short)dir; it.ph = (short)ph; it.fb = fb; it.seq = seq++;
+				it.chain = ph*maxBands + band;
+				it.cell = ph*nFB + fb;
+				it.depCell = ph > 0 ? (ph-1)*nFB + fb : -1; it.depNeed = 0;
+				items.push_back(it);
+				++cellCount[it.cell];
+			}
+		}
+	}
+	for (auto& it: items) if (it.depCell >= 0) it.depNeed = cellCount[it.depCell];
+	// queue order: front blocks advance, phase ph runs `lag` blocks behind phase ph-1; every dependency is earlier in the queue
+	std::stable_sort(items.begin(), items.end(), [lag](const FrontItem& a, const FrontItem& b) {
+		const int ta = a.fb + lag*a.ph, tb = b.fb + lag*b.ph;
+		if (ta != tb) return ta < tb;
+		return a.ph > b.ph;
+	});
+}
+
+cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, cudaStream_t s) {
+	const int NW = A.num/16;
+	if (NW == 8) sgm_front_kernel<8><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
+	else if (NW == 4) sgm_front_kernel<4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
+	else if (NW == 16) sgm_front_kernel<16><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
+	else return cudaErrorInvalidValue;
+	return cudaGetLastError();
+}
+// resident CTAs of the kernel on the current device (the queue needs no particular number; this fills the SMs once)
+int sgm_front_blocks(int num) {
+	int dev = 0, sms = 148, per = 4;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int NW = num/16;
+	if (NW == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<8>, FRONT_WARPS*32, 0);
+	else if (NW == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<4>, FRONT_WARPS*32, 0);
+	else if (NW == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<16>, FRONT_WARPS*32, 0);
+	return sms*std::max(1, per);
+}
+bool sgm_front_supports(int num) { return num == 64 || num == 128 || num == 256; }

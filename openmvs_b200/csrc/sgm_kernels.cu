@@ -13,7 +13,6 @@
 #include <stdint.h>
 #include <string.h>
 #include <stdlib.h>
-#include "sgm_step.cuh"
 
 struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
 
@@ -433,13 +432,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, unsigne
 		:: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// DPX = true (experimental, B200MVS_SGM_DPX=1; needs NPL = 4 and num = 128, i.e. every lane full): the step runs on packed
-// u16x2 values (sgm_step.cuh: SIMD-in-a-word adds / mins and the DPX three-input minimum), about a third of the
-// arithmetic instructions of the scalar form; the results are the same integers.
-// ACC = false (experimental, B200MVS_SGM_CONCURRENT=1): the kernel writes the path costs L of ITS direction to P.accums
-// (a per-direction buffer) instead of adding them to the running sum, so it reads no accumulators and the eight directions
-// can run at the same time on eight streams; sgm_sum_dirs_kernel adds the eight buffers afterwards.
-template <int NPL, int E, bool DPX, bool ACC = true>
+template <int NPL, int E>
 __global__ void __launch_bounds__(AGG_WARPS*32)
 sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, int dmin, int num)
 {
@@ -457,7 +450,8 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 	int n = 0x7FFFFFFF;
 	if (dx > 0) n = min(n, P.vw-x0); else if (dx < 0) n = min(n, x0+1);
 	if (dy > 0) n = min(n, P.vh-y0); else if (dy < 0) n = min(n, y0+1);
-	const unsigned stageBytes = (ACC ? 3u : 1u)*(unsigned)num;          // costs | accumulators
+	constexpr bool ACC = true;
+	const unsigned stageBytes = 3u*(unsigned)num;                        // costs | accumulators
 	const unsigned warpBytes = RING*(stageBytes+16u+8u);
 	unsigned char* base = ring_smem + (size_t)warp*warpBytes;
 	unsigned char* stages = base;                                        // RING x stageBytes (16-byte aligned: num % 16 == 0)
@@ -525,7 +519,6 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 	unsigned minLp = 0xFFFFu;
 	bool havePrev = false;
 	float Ip = 0.5f;
-	SgmLane4 lane4; lane4.PA = lane4.PB = 0xFFFFFFFFu;
 	uint4 rec; CW c; AW a;
 	fetch(0, rec, c, a);
 	#pragma unroll 1
@@ -539,24 +532,6 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 		uint4 recN = make_uint4(0u, 0u, 0u, 0u); CW cN; AW aN;
 		memset(&cN, 0, sizeof(cN)); memset(&aN, 0, sizeof(aN));
 		if (t+1 < n) fetch(t+1, recN, cN, aN);
-		if constexpr (DPX) {
-			if (rec.w & 1u) {
-				const float I = __uint_as_float(rec.z);
-				const unsigned P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
-				Ip = I;
-				unsigned cw; uint2 acc;
-				memcpy(&cw, &c, 4); memcpy(&acc, &a, 8);
-				unsigned below = __shfl_up_sync(0xFFFFFFFFu, lane4.PB>>16, 1), above = __shfl_down_sync(0xFFFFFFFFu, lane4.PA&0xFFFFu, 1);
-				if (lane == 0) below = 0xFFFFu;
-				if (lane == 31) above = 0xFFFFu;
-				const unsigned P1 = (unsigned)P.P1;
-				const unsigned mn = sgm_step_packed4(cw, below, above, P1|(P1<<16), P2|(P2<<16), minLp|(minLp<<16), havePrev, lane4, acc);
-				const unsigned long long idx = (unsigned long long)rec.x | ((unsigned long long)rec.y<<32);
-				((uint2*)(P.accums + idx))[lane] = acc;
-				minLp = __reduce_min_sync(0xFFFFFFFFu, mn);
-				havePrev = true;
-			}
-		} else
 		if (rec.w & 1u) {
 			const float I = __uint_as_float(rec.z);
 			const int P2 = P.P2s[abs((int)floorf(255.f*(I-Ip)+.5f))];
@@ -665,9 +640,10 @@ __global__ void sgm_refine_kernel(const SGMPixel* __restrict__ px, const uint16_
 }
 
 // statistics of the pixel map: out[0] = largest disparity count, out[1]/out[2] = min/max of dmin,
-// out[3]/out[4] = min/max of dmax over the valid pixels, out[5] = OR of (idx & 15)
-__global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* __restrict__ out) {
-	int m = 0, lo0 = 0x7FFFFFFF, hi0 = -0x7FFFFFFF, lo1 = 0x7FFFFFFF, hi1 = -0x7FFFFFFF, al = 0;
+// out[3]/out[4] = min/max of dmax over the valid pixels, out[5] = OR of (idx & 15), out[6] = 1 when the volume is not
+// dense (an invalid pixel, or idx != pixel index x disparity count), out[7] = 1 when a slice ends beyond numCosts
+__global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, unsigned long long numCosts, int* __restrict__ out) {
+	int m = 0, lo0 = 0x7FFFFFFF, hi0 = -0x7FFFFFFF, lo1 = 0x7FFFFFFF, hi1 = -0x7FFFFFFF, al = 0, sparse = 0, oob = 0;
 	for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
 		const SGMPixel p = px[i];
 		if (p.dmin < p.dmax) {
@@ -675,7 +651,9 @@ __global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* 
 			lo0 = min(lo0, (int)p.dmin); hi0 = max(hi0, (int)p.dmin);
 			lo1 = min(lo1, (int)p.dmax); hi1 = max(hi1, (int)p.dmax);
 			al |= (int)(p.idx & 15ull);
-		}
+			if (p.idx != (unsigned long long)i*(unsigned long long)(p.dmax-p.dmin)) sparse = 1;
+			if (p.idx+(unsigned long long)(p.dmax-p.dmin) > numCosts) oob = 1;
+		} else sparse = 1;
 	}
 	#pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
@@ -683,84 +661,56 @@ __global__ void sgm_maxdisp_kernel(const SGMPixel* __restrict__ px, int n, int* 
 		lo0 = min(lo0, __shfl_xor_sync(0xFFFFFFFFu, lo0, o)); hi0 = max(hi0, __shfl_xor_sync(0xFFFFFFFFu, hi0, o));
 		lo1 = min(lo1, __shfl_xor_sync(0xFFFFFFFFu, lo1, o)); hi1 = max(hi1, __shfl_xor_sync(0xFFFFFFFFu, hi1, o));
 		al |= __shfl_xor_sync(0xFFFFFFFFu, al, o);
+		sparse |= __shfl_xor_sync(0xFFFFFFFFu, sparse, o); oob |= __shfl_xor_sync(0xFFFFFFFFu, oob, o);
 	}
 	if ((threadIdx.x&31) == 0) {
 		atomicMax(out, m); atomicMin(out+1, lo0); atomicMax(out+2, hi0); atomicMin(out+3, lo1); atomicMax(out+4, hi1); atomicOr(out+5, al);
+		if (sparse) atomicOr(out+6, 1);
+		if (oob) atomicOr(out+7, 1);
 	}
 }
 __global__ void sgm_stats_init_kernel(int* out) {
-	out[0] = 0; out[1] = 0x7FFFFFFF; out[2] = -0x7FFFFFFF; out[3] = 0x7FFFFFFF; out[4] = -0x7FFFFFFF; out[5] = 0;
+	out[0] = 0; out[1] = 0x7FFFFFFF; out[2] = -0x7FFFFFFF; out[3] = 0x7FFFFFFF; out[4] = -0x7FFFFFFF; out[5] = 0; out[6] = 0; out[7] = 0;
 }
 
 } // namespace
 
-cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, int* out6, cudaStream_t s) {
-	sgm_stats_init_kernel<<<1, 1, 0, s>>>(out6);
-	sgm_maxdisp_kernel<<<148*4, 256, 0, s>>>(px, n, out6);
+template <int NPL, int E>
+static cudaError_t configure_ring() {
+	return cudaFuncSetAttribute(sgm_aggregate_uniform_ring_kernel<NPL, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2*E*AGG_WARPS*(3*(NPL*32)+24));
+}
+// dynamic shared memory opt-in of the SGM kernels on the current device (called by b200mvs_create; idempotent)
+cudaError_t sgm_configure_device() {
+	cudaError_t e;
+	if ((e = configure_ring<4, 16>()) != cudaSuccess) return e;
+	if ((e = configure_ring<8, 8>()) != cudaSuccess) return e;
+	return cudaFuncSetAttribute(sgm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NT*COST_THREADS*sizeof(float2)));
+}
+cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, unsigned long long numCosts, int* out8, cudaStream_t s) {
+	sgm_stats_init_kernel<<<1, 1, 0, s>>>(out8);
+	sgm_maxdisp_kernel<<<148*4, 256, 0, s>>>(px, n, numCosts, out8);
 	return cudaGetLastError();
 }
 // uniform-range fast path: every valid pixel has the range [dmin, dmin+num), num % 4 == 0, 4-aligned slices;
 // ring: slices are 16-byte aligned (num % 16 == 0, idx % 16 == 0, aligned base pointers) -> bulk-copy ring kernel
-template <int NPL, int E, bool DPX = false, bool ACC = true>
+template <int NPL, int E>
 static cudaError_t launch_ring(const SGMParams& P, int dir, int dmin, int num, int grid, cudaStream_t s) {
-	const size_t smem = (size_t)AGG_WARPS*2*E*((ACC ? 3 : 1)*(size_t)num+24);
-	static bool done[64] = {}; // per device
-	int dev = 0; cudaGetDevice(&dev); dev &= 63;
-	if (!done[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(sgm_aggregate_uniform_ring_kernel<NPL, E, DPX, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2*E*AGG_WARPS*(3*(NPL*32)+24));
-		if (e != cudaSuccess) return e;
-		done[dev] = true;
-	}
-	sgm_aggregate_uniform_ring_kernel<NPL, E, DPX, ACC><<<grid, AGG_WARPS*32, smem, s>>>(P, dir, dmin, num);
+	const size_t smem = (size_t)AGG_WARPS*2*E*(3*(size_t)num+24);
+	sgm_aggregate_uniform_ring_kernel<NPL, E><<<grid, AGG_WARPS*32, smem, s>>>(P, dir, dmin, num);
 	return cudaGetLastError();
 }
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s) {
 	const int W = P.vw, H = P.vh;
 	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
 	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
-	if (ring && num == 128 && P.P1 >= 0 && P.P1 < 0x8000) {
-		const char* e = getenv("B200MVS_SGM_DPX"); // read per call so that one process can compare the variants
-		if (e && atoi(e) != 0) return launch_ring<4, 16, true>(P, dir, dmin, num, grid, s);
-	}
 	if (ring && (num & 15) == 0)
 		return num <= 128 ? launch_ring<4, 16>(P, dir, dmin, num, grid, s) : launch_ring<8, 8>(P, dir, dmin, num, grid, s);
 	if (num <= 128) sgm_aggregate_uniform_kernel<4, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
 	else sgm_aggregate_uniform_kernel<8, AGG_PD_UNIFORM><<<grid, AGG_WARPS*32, 0, s>>>(P, dir, dmin, num);
 	return cudaGetLastError();
 }
-// experimental: one direction of the ring kernel writing its path costs into P.accums (a per-direction buffer)
-cudaError_t sgm_launch_aggregate_dir(const SGMParams& P, int dir, int dmin, int num, cudaStream_t s) {
-	const int W = P.vw, H = P.vh;
-	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
-	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
-	if ((num & 15) != 0 || num > 256) return cudaErrorInvalidValue;
-	return num <= 128 ? launch_ring<4, 16, false, false>(P, dir, dmin, num, grid, s) : launch_ring<8, 8, false, false>(P, dir, dmin, num, grid, s);
-}
-// accums[i] = sum over the nDirs per-direction buffers dirL + d*n of L_d[i]; n % 8 == 0 (16-byte vectors of 8 x u16)
-__global__ void sgm_sum_dirs_kernel(const uint16_t* __restrict__ dirL, int nDirs, size_t n, uint16_t* __restrict__ accums) {
-	const size_t nv = n/8;
-	for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x*blockDim.x) {
-		uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-		for (int d = 0; d < nDirs; ++d) {
-			const uint4 v = ((const uint4*)(dirL + (size_t)d*n))[i];
-			acc.x = __vadd2(acc.x, v.x); acc.y = __vadd2(acc.y, v.y); acc.z = __vadd2(acc.z, v.z); acc.w = __vadd2(acc.w, v.w);
-		}
-		((uint4*)accums)[i] = acc;
-	}
-}
-cudaError_t sgm_launch_sum_dirs(const uint16_t* dirL, int nDirs, size_t n, uint16_t* accums, cudaStream_t s) {
-	sgm_sum_dirs_kernel<<<148*8, 256, 0, s>>>(dirL, nDirs, n, accums);
-	return cudaGetLastError();
-}
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s) {
 	const size_t smem = (size_t)NT*COST_THREADS*sizeof(float2);
-	static bool done[64] = {}; // per device
-	int dev = 0; cudaGetDevice(&dev); dev &= 63;
-	if (!done[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(sgm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return e;
-		done[dev] = true;
-	}
 	dim3 grid((P.vw+COST_THREADS-1)/COST_THREADS, P.vh);
 	sgm_cost_kernel<<<grid, COST_THREADS, smem, s>>>(P);
 	return cudaGetLastError();

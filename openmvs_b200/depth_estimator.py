@@ -50,10 +50,20 @@ class OPTDENSE:
 	fDepthDiffThreshold = 0.01
 	nSpeckleSize = 100
 	nIpolGapSize = 7
-	# engine schedule (not in the reference): red-black sweeps per reference iteration
-	nSweepsPerIter = 2
+	# engine schedule (not in the reference; include/b200mvs.h b200mvs_params): 0 = automatic number of red-black sweeps
+	nSweepsPerIter = 0
 	nPropagation = 4
+	nPropagationFar = 2
+	bSkipUnchanged = 1
 	nSeed = 1234
+
+	@classmethod
+	def schedule(cls, geometric: bool = False):
+		"""(red-black sweeps, refinement tries per sweep) the engine runs for the current options (b200mvs_get_schedule)."""
+		n, r = C.c_int(), C.c_int()
+		p = cls.snapshot()
+		_lib.load().b200mvs_get_schedule(C.byref(p), int(bool(geometric)), C.byref(n), C.byref(r))
+		return n.value, r.value
 
 	@classmethod
 	def snapshot(cls) -> _lib.Params:
@@ -143,6 +153,8 @@ def _make_views(images: List[ViewData]):
 			img = v.image
 			if img.dtype.__str__() != "torch.float32" or not img.is_cuda or img.dim() != 2 or img.stride(1) != 1:
 				raise ValueError("device image must be a 2-D float32 CUDA tensor with unit column stride")
+			if img.device != images[0].image.device:
+				raise ValueError("all views of a DepthData must live on the same device")
 			keep.append(img)
 			o.image = img.data_ptr(); o.height, o.width = img.shape; o.stride_bytes = img.stride(0)*4
 		else:
@@ -159,6 +171,8 @@ def _make_views(images: List[ViewData]):
 			cam = v.cameraDepthMap or v.camera
 			if dev:
 				dm = v.depthMap
+				if not _is_torch(dm) or dm.dtype.__str__() != "torch.float32" or not dm.is_cuda or dm.dim() != 2 or dm.stride(1) != 1 or dm.device != images[0].image.device:
+					raise ValueError("device depth-map must be a 2-D float32 CUDA tensor with unit column stride on the images' device")
 				keep.append(dm)
 				o.depth = dm.data_ptr(); o.dheight, o.dwidth = dm.shape; o.dstride_bytes = dm.stride(0)*4
 			else:
@@ -216,6 +230,35 @@ class PatchMatchB200:
 		p = OPTDENSE.snapshot()
 		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_params(self._ctx, C.byref(p)), "b200mvs_set_params")
 
+	def SetDebug(self, **kw):
+		"""b200mvs_set_debug: diagnostic kernel switches (scalarTaps, noTMA, sgmAggregation, sgmCost); no arguments = defaults."""
+		d = _lib.Debug()
+		for k, v in kw.items():
+			if not hasattr(d, k):
+				raise AttributeError(k)
+			setattr(d, k, int(v))
+		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_debug(self._ctx, C.byref(d)), "b200mvs_set_debug")
+
+	def SetIgnoreMask(self, mask=None):
+		"""Ignore-mask of the reference view for the following EstimateDepthMap calls (OPTDENSE::nIgnoreMaskLabel >= 0,
+		libs/MVS/DepthMap.cpp:215-230,300-323): (H, W) uint8, 0 = ignored; numpy array (copied) or torch CUDA tensor
+		(kept by reference until cleared); None clears it."""
+		self._mask_keep = None
+		if mask is None:
+			rc = self._lib.b200mvs_set_ignore_mask(self._ctx, None, 0, 0, 0, 0)
+		elif _is_torch(mask):
+			import torch
+			if mask.dtype != torch.uint8 or not mask.is_cuda or mask.dim() != 2 or mask.stride(1) != 1:
+				raise ValueError("device mask must be a 2-D uint8 CUDA tensor with unit column stride")
+			self._mask_keep = mask
+			rc = self._lib.b200mvs_set_ignore_mask(self._ctx, mask.data_ptr(), int(mask.shape[1]), int(mask.shape[0]), int(mask.stride(0)), 1)
+		else:
+			m = np.ascontiguousarray(mask, np.uint8)
+			if m.ndim != 2:
+				raise ValueError("mask must be 2-D")
+			rc = self._lib.b200mvs_set_ignore_mask(self._ctx, m.ctypes.data, m.shape[1], m.shape[0], m.strides[0], 0)
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_set_ignore_mask")
+
 	def EstimateDepthMap(self, depthData: DepthData, nGeometricIter: Optional[int] = None, stream=None, sync: bool = True):
 		"""PatchMatchCUDA::EstimateDepthMap(DepthData&): estimate depthMap/normalMap/confMap/viewsMap
 		of depthData in place.  nGeometricIter defaults to -1 (photometric) or 0 (after Init(true))."""
@@ -232,8 +275,8 @@ class PatchMatchB200:
 			def dmap(a, shape, dtype):
 				if a is None:
 					return torch.zeros(shape, dtype=dtype, device=t0.device)
-				if tuple(a.shape) != tuple(shape) or not a.is_contiguous():
-					raise ValueError("map has the wrong shape or is not contiguous")
+				if not _is_torch(a) or tuple(a.shape) != tuple(shape) or not a.is_contiguous() or a.dtype != dtype or a.device != t0.device:
+					raise ValueError("map must be a contiguous %s CUDA tensor of shape %s on the images' device" % (dtype, tuple(shape)))
 				return a
 			depthData.depthMap = dmap(depthData.depthMap, (h, w), torch.float32)
 			depthData.normalMap = dmap(depthData.normalMap, (h, w, 3), torch.float32)
@@ -301,8 +344,7 @@ class PatchMatchB200:
 		self._set_params()
 		arr, keep = self._dev_views(images)
 		if nRandomIters is None:
-			spi = max(1, OPTDENSE.nSweepsPerIter)
-			nRandomIters = (OPTDENSE.nRandomIters+spi-1)//spi
+			nRandomIters = OPTDENSE.schedule()[1]
 		s = _stream_handle(plane4.device)
 		rc = self._lib.b200mvs_pm_sweep(self._ctx, arr, len(arr), C.c_float(dMin), C.c_float(dMax),
 			lowres.data_ptr() if lowres is not None else None, int(sweep), int(half), int(nRandomIters),
@@ -465,6 +507,19 @@ class SemiGlobalMatcher:
 			self.Release()
 		except Exception:
 			pass
+
+	def SetDebug(self, **kw):
+		"""b200mvs_set_debug: sgmAggregation (0 auto, 1 general, 2 register-pipelined uniform, 3 bulk-copy ring, 4 wave fronts),
+		sgmCost, frontLayout / frontBlock / frontLag (reserved[0..2]); no arguments = defaults."""
+		d = _lib.Debug()
+		for k, v in kw.items():
+			if k in ("frontLayout", "frontBlock", "frontLag"):
+				d.reserved[("frontLayout", "frontBlock", "frontLag").index(k)] = int(v)
+			elif hasattr(d, k):
+				setattr(d, k, int(v))
+			else:
+				raise AttributeError(k)
+		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_debug(self._ctx, C.byref(d)), "b200mvs_set_debug")
 
 	def Match(self, leftGray, leftColor, rightGray, imagePixels, numCosts: int):
 		"""Host path: numpy images (gray float32 HxW, colour uint8 HxWx3 BGR) and the PixelMap

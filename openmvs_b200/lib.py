@@ -8,6 +8,7 @@ import os
 from . import build as _build
 
 MAX_VIEWS = 32
+ABI_VERSION = 3  # B200MVS_ABI_VERSION of include/b200mvs.h these structs mirror
 
 
 class View(C.Structure):
@@ -26,7 +27,13 @@ class Params(C.Structure):
 		("fRandomDepthRatio", C.c_float), ("fRandomAngle1Range", C.c_float), ("fRandomAngle2Range", C.c_float),
 		("fRandomSmoothDepth", C.c_float), ("fRandomSmoothNormal", C.c_float), ("fRandomSmoothBonus", C.c_float),
 		("fEstimationGeometricWeight", C.c_float),
-		("nSweepsPerIter", C.c_int), ("nPropagation", C.c_int), ("seed", C.c_uint32)]
+		("nSweepsPerIter", C.c_int), ("nPropagation", C.c_int), ("seed", C.c_uint32),
+		("nPropagationFar", C.c_int), ("bSkipUnchanged", C.c_int)]
+
+
+class Debug(C.Structure):
+	"""b200mvs_debug"""
+	_fields_ = [("scalarTaps", C.c_int), ("noTMA", C.c_int), ("sgmAggregation", C.c_int), ("sgmCost", C.c_int), ("reserved", C.c_int*4)]
 
 
 class Stats(C.Structure):
@@ -40,6 +47,11 @@ class Job(C.Structure):
 	"""b200mvs_job"""
 	_fields_ = [("views", C.POINTER(View)), ("nViews", C.c_int), ("dMin", C.c_float), ("dMax", C.c_float), ("nGeometricIter", C.c_int),
 		("depth", C.c_void_p), ("normal", C.c_void_p), ("conf", C.c_void_p), ("viewsMap", C.c_void_p), ("status", C.c_int)]
+
+
+class SgmPixel(C.Structure):
+	"""b200mvs_sgm_pixel"""
+	_fields_ = [("idx", C.c_uint64), ("dmin", C.c_int16), ("dmax", C.c_int16), ("reserved", C.c_int32)]
 
 
 class SgmParams(C.Structure):
@@ -63,6 +75,7 @@ MAX_FILTER_VIEWS = 16
 # every symbol include/b200mvs.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
 	"b200mvs_create", "b200mvs_destroy", "b200mvs_default_params", "b200mvs_set_params", "b200mvs_last_error",
+	"b200mvs_set_debug", "b200mvs_get_schedule", "b200mvs_abi_version", "b200mvs_sizeof", "b200mvs_set_ignore_mask",
 	"b200mvs_device_count", "b200mvs_estimate", "b200mvs_estimate_device", "b200mvs_estimate_async", "b200mvs_sync", "b200mvs_estimate_batch",
 	"b200mvs_pm_pack", "b200mvs_pm_unpack", "b200mvs_pm_score", "b200mvs_pm_sweep", "b200mvs_pm_finalize",
 	"b200mvs_sgm_default_params", "b200mvs_sgm_match", "b200mvs_sgm_match_device",
@@ -83,20 +96,28 @@ def load(build_if_missing: bool = True):
 		return _LIB
 	path = _build.LIB_PATH
 	if build_if_missing:
-		try:
-			path = _build.build_extension()
-		except Exception:
-			if not os.path.exists(path):
-				raise
+		# a stale library whose rebuild fails is NOT used: its struct layouts may differ from these bindings
+		path = _build.build_extension()
 	if not os.path.exists(path):
 		raise RuntimeError("CUDA extension %s is missing: run __graft_entry__.build() (no CPU fallback exists)" % path)
 	lib = C.CDLL(path)
+	if not hasattr(lib, "b200mvs_abi_version") or lib.b200mvs_abi_version() != ABI_VERSION:
+		raise RuntimeError("%s was built from another version of include/b200mvs.h (ABI %s, bindings %d): rebuild it" % (
+			path, lib.b200mvs_abi_version() if hasattr(lib, "b200mvs_abi_version") else "?", ABI_VERSION))
+	lib.b200mvs_sizeof.restype = C.c_size_t
+	lib.b200mvs_sizeof.argtypes = [C.c_int]
+	for what, T in enumerate((View, Params, Stats, Job, SgmPixel, SgmParams, DMap, FilterParams, Debug)):
+		if lib.b200mvs_sizeof(what) != C.sizeof(T):
+			raise RuntimeError("struct %s: library %d bytes, bindings %d bytes" % (T.__name__, lib.b200mvs_sizeof(what), C.sizeof(T)))
 	lib.b200mvs_last_error.restype = C.c_char_p
 	lib.b200mvs_last_error.argtypes = [C.c_void_p]
 	lib.b200mvs_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
 	lib.b200mvs_destroy.argtypes = [C.c_void_p]
 	lib.b200mvs_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
 	lib.b200mvs_default_params.argtypes = [C.POINTER(Params)]
+	lib.b200mvs_set_debug.argtypes = [C.c_void_p, C.POINTER(Debug)]
+	lib.b200mvs_get_schedule.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+	lib.b200mvs_set_ignore_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
 	F = C.c_float
 	P = C.c_void_p
 	lib.b200mvs_estimate.argtypes = [P, C.POINTER(View), C.c_int, F, F, C.c_int, P, P, P, P, C.POINTER(Stats)]

@@ -50,8 +50,10 @@ typedef struct {
 	int nSubResolutionLevels;      /* 2 */
 	int schedule;    /* 0 = ZZ: reference zig-zag order, sequential Gauss-Seidel, mt19937
 	                    1 = RB: red-black half-sweeps, Philox4x32-10 counter RNG */
-	int propagation; /* RB only: 2 = the two causal neighbours of the reference direction,
-	                             4 = all four 4-neighbours */
+	int propagation; /* RB only (the engine's schedule): bits 0-3: 2 = the two causal neighbours of the reference
+	                    direction, 4 = all four 4-neighbours; bits 4-7: F far rings, the candidate of a direction is the
+	                    lowest-cost pixel at distance 1, 3, .. 2F+1; bit 8 (0x100): a direction whose candidates kept
+	                    their plane in their last update is not re-tested */
 	uint32_t seed;
 	int threads;     /* ZZ: number of worker threads pulling from the shared counter */
 } oracle_params;
@@ -73,6 +75,12 @@ int oracle_pm_iterate(const oracle_view* views, int nViews, const oracle_params*
 	float dMin, float dMax, const float* lowres, int iter, int half,
 	float* depth, float* normal, float* conf);
 
+/* oracle_pm_iterate carrying the memory of the RB changed-flag rule (propagation & 0x100): changed = width x height bytes,
+ * 1 = the pixel's plane changed in its last update (or was never tested); read and updated.  NULL: rule off. */
+int oracle_pm_iterate_flags(const oracle_view* views, int nViews, const oracle_params* prm,
+	float dMin, float dMax, const float* lowres, int iter, int half,
+	float* depth, float* normal, float* conf, uint8_t* changed);
+
 /* pass C (EndDepthMapTmp): threshold + cost -> confidence */
 int oracle_pm_finalize(int width, int height, float keepThreshold,
 	float* depth, float* normal, float* conf);
@@ -81,6 +89,16 @@ int oracle_pm_finalize(int width, int height, float keepThreshold,
  * nGeometricIter < 0: photometric pass; >= 0: geometric pass (views need depth). */
 int oracle_pm_estimate(const oracle_view* views, int nViews, const oracle_params* prm,
 	float dMin, float dMax, int nGeometricIter,
+	float* depth, float* normal, float* conf);
+
+/* RB changed-flag rule (propagation & 0x100): {directions tested, directions skipped} since the last call */
+void oracle_pm_counters(long long out[2]);
+
+/* oracle_pm_estimate with an explicit range [iterBegin, iterEnd) of pass-B iterations (RB: sweeps) and an optional
+ * ignore-mask of the reference view (width x height bytes, 0 = ignored; DepthMap.cpp:215-230,300-323,343; the depth is then
+ * up-sampled NEAREST between the levels, SceneDensify.cpp:661).  geometric != 0: no scale loop, keep threshold x1. */
+int oracle_pm_estimate_range(const oracle_view* views, int nViews, const oracle_params* prm,
+	float dMin, float dMax, int geometric, int iterBegin, int iterEnd, const uint8_t* mask,
 	float* depth, float* normal, float* conf);
 
 /* single hypothesis score at pixel (x,y) with explicit smoothing neighbours

@@ -112,6 +112,36 @@ def pm_iterate(views, prm, dmin, dmax, depth, normal, conf, it, half=-1, lowres=
 	return d, n, c
 
 
+def pm_iterate_flags(views, prm, dmin, dmax, depth, normal, conf, changed, it, half=-1, lowres=None, depths=None):
+	"""pm_iterate carrying the changed-flag memory (uint8 H x W, updated copy returned as 4th value)"""
+	arr, keep = make_views(views, depths)
+	d = np.array(depth, np.float32, copy=True, order="C")
+	n = np.array(normal, np.float32, copy=True, order="C")
+	c = np.array(conf, np.float32, copy=True, order="C")
+	f = np.array(changed, np.uint8, copy=True, order="C")
+	lr = None if lowres is None else np.ascontiguousarray(lowres, np.float32)
+	rc = lib().oracle_pm_iterate_flags(arr, len(views), C.byref(prm), C.c_float(dmin), C.c_float(dmax),
+		None if lr is None else _fptr(lr), int(it), int(half), _fptr(d), _fptr(n), _fptr(c), _fptr(f))
+	assert rc == 0
+	return d, n, c, f
+
+
+def rb_propagation(nPropagation=4, nPropagationFar=2, bSkipUnchanged=1):
+	"""oracle_params.propagation for the engine's red-black schedule (include/b200mvs.h b200mvs_params)"""
+	return int(nPropagation) | (int(nPropagationFar) << 4) | (0x100 if bSkipUnchanged else 0)
+
+
+def pm_estimate_range(views, prm, dmin, dmax, it_begin, it_end, geometric=False, mask=None, depth=None, normal=None, depths=None):
+	"""passes A, B (iterations / RB sweeps [it_begin, it_end)), C with the scale loop (photometric) and an optional ignore-mask"""
+	arr, keep = make_views(views, depths)
+	d, n, c = _state(views, depth, normal)
+	m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+	rc = lib().oracle_pm_estimate_range(arr, len(views), C.byref(prm), C.c_float(dmin), C.c_float(dmax), int(bool(geometric)),
+		int(it_begin), int(it_end), None if m is None else _fptr(m), _fptr(d), _fptr(n), _fptr(c))
+	assert rc == 0
+	return d, n, c
+
+
 def pm_finalize(depth, normal, conf, keep):
 	d = np.array(depth, np.float32, copy=True, order="C")
 	n = np.array(normal, np.float32, copy=True, order="C")

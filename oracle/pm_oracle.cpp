@@ -193,7 +193,13 @@ struct Job {
 	oracle_params prm;
 	float* depth; float* normal; float* conf;
 	std::vector<WeightedPatch>* weights; // lazily filled cache (weightMap0)
+	// RB engine schedule with propagation bit 8 (0x100): a pixel remembers whether its plane changed during its last
+	// update; a direction whose candidates are all unchanged is not re-tested (it lost against this pixel last sweep)
+	uint8_t* changed;                    // nullable: per-pixel flag, 1 = changed (or never tested)
+	// ignore-mask of this level (0 = pixel not in the pixel list, DepthMap.cpp:343) or null
+	const uint8_t* mask;
 };
+std::atomic<long long> g_propTested(0), g_propSkipped(0);
 
 struct Estimator {
 	const Job& J;
@@ -453,6 +459,8 @@ struct Estimator {
 	// --- pass A pixel (ScoreDepthMapTmp, SceneDensify.cpp:490-517) ---------------------------
 	void ScorePixelInit(int x, int y) {
 		const size_t i = (size_t)y*J.w+x;
+		if (J.mask && !J.mask[i])
+			return; // not in the pixel list; DepthData::ApplyIgnoreMask zeroed the maps (DepthMap.cpp:215-230)
 		if (!PreparePixelPatch(x, y) || !FillPixelPatch()) {
 			J.depth[i] = 0; J.normal[i*3]=J.normal[i*3+1]=J.normal[i*3+2]=0; J.conf[i] = 2.f;
 			return;
@@ -474,10 +482,15 @@ struct Estimator {
 
 	// --- pass B pixel (ProcessPixel, DepthMap.cpp:630-852) -----------------------------------
 	void ProcessPixel(int x, int y) {
+		if (J.mask && !J.mask[(size_t)y*J.w+x])
+			return;
 		if (!PreparePixelPatch(x, y) || !FillPixelPatch())
 			return;
 		const int w = J.w, h = J.h;
 		int prop[4][2]; int nProp = 0;
+		int farXY[4][2]; bool farUse[4] = {false, false, false, false};
+		bool dirChanged[4] = {true, true, true, true};
+		const bool useFlags = J.prm.schedule == 1 && (J.prm.propagation & 0x100) && J.changed;
 		nClose = 0;
 		// neighbour order: causal pair first, then the anti-causal pair
 		const int offs[2][4][2] = {{{-1,0},{0,-1},{1,0},{0,1}}, {{1,0},{0,1},{-1,0},{0,-1}}};
@@ -489,10 +502,25 @@ struct Estimator {
 			if (!ok) continue;
 			const int nx = x0+ox, ny = y0+oy;
 			const float nd = J.depth[(size_t)ny*w+nx];
+			if (useFlags) dirChanged[k] = J.changed[(size_t)ny*w+nx] != 0;
 			if (nd > 0) {
-				const bool propagate = (k < 2) || (J.prm.schedule == 1 && J.prm.propagation == 4);
+				const bool propagate = (k < 2) || (J.prm.schedule == 1 && (J.prm.propagation & 15) == 4);
 				if (propagate) { prop[nProp][0] = nClose; prop[nProp][1] = k; ++nProp; }
 				addClose(nx, ny, nd);
+			}
+			// RB far propagation (engine schedule, not in the reference): in direction k the candidate is the
+			// pixel of the other colour at distance 1, 3, ... 2F+1 with the lowest stored cost (ties: the nearest)
+			const int F = J.prm.schedule == 1 ? ((J.prm.propagation >> 4) & 15) : 0;
+			if (F > 0 && ((k < 2) || (J.prm.propagation & 15) == 4)) {
+				float bestC = nd > 0 ? J.conf[(size_t)ny*w+nx] : 3.f;
+				for (int f = 1; f <= F; ++f) {
+					const int fx = x0+ox*(2*f+1), fy = y0+oy*(2*f+1);
+					if (fx < kHalf || fy < kHalf || fx >= w-kHalf || fy >= h-kHalf) break;
+					const size_t fi = (size_t)fy*w+fx;
+					if (useFlags && J.changed[fi]) dirChanged[k] = true;
+					if (J.depth[fi] > 0 && J.conf[fi] < bestC) { bestC = J.conf[fi]; farUse[k] = true; farXY[k][0] = fx; farXY[k][1] = fy; }
+				}
+				if (farUse[k] && !(nd > 0)) { prop[nProp][0] = -1; prop[nProp][1] = k; ++nProp; } // near neighbour invalid: the far one still propagates
 			}
 		}
 		const size_t i0 = (size_t)y0*w+x0;
@@ -501,13 +529,26 @@ struct Estimator {
 		float* pn = J.normal + i0*3;
 		V3 normal{pn[0], pn[1], pn[2]};
 		const V3 vd = viewDir();
+		const float depthIn = depth; const V3 normalIn = normal;
+		struct FlagSetter { // on every exit path: record whether the plane changed
+			const Job& J; size_t i; const float& d; const float* pn; float d0; V3 n0;
+			~FlagSetter() { if (J.changed) J.changed[i] = (d != d0 || pn[0] != n0.x || pn[1] != n0.y || pn[2] != n0.z) ? 1 : 0; }
+		} flagSetter{J, i0, depth, pn, depthIn, normalIn};
 		// propagation
 		for (int p=0; p<nProp; ++p) {
 			const int c = prop[p][0], k = prop[p][1];
-			const int nx = x0+offs[dir][k][0], ny = y0+offs[dir][k][1];
+			if (!dirChanged[k]) { g_propSkipped.fetch_add(1, std::memory_order_relaxed); continue; }
+			g_propTested.fetch_add(1, std::memory_order_relaxed);
+			int nx = x0+offs[dir][k][0], ny = y0+offs[dir][k][1];
+			Close nb;
+			if (farUse[k]) {
+				nx = farXY[k][0]; ny = farXY[k][1];
+				const float* fn = J.normal + ((size_t)ny*w+nx)*3;
+				nb.depth = J.depth[(size_t)ny*w+nx]; nb.normal = V3{fn[0], fn[1], fn[2]};
+			} else
+				nb = close[c];
 			if (J.conf[(size_t)ny*w+nx] >= J.prm.fNCCThresholdKeep)
 				continue;
-			Close nb = close[c];
 			nb.depth = InterpolatePixel(nx, ny, nb.depth, nb.normal);
 			CorrectNormal(nb.normal);
 			InitPlane(nb.depth, nb.normal);
@@ -609,6 +650,8 @@ void buildJob(const oracle_view* views, int nViews, const oracle_params* prm, fl
 		for (auto& w: weights) w.normSq0 = 0;
 	}
 	J.weights = &weights;
+	J.changed = nullptr;
+	J.mask = nullptr;
 }
 
 template <typename F>
@@ -774,8 +817,8 @@ void resizeLinear(const float* src, int sw, int sh, float* dst, int dw, int dh) 
 		}
 	}
 }
-void resizeNearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh) {
-	const double ifx = (double)sw/dw, ify = (double)sh/dh;
+// ifx/ify: source/destination scale (1/fx for the factor form of cv::resize, sw/dw for the destination-size form)
+void resizeNearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, double ifx, double ify) {
 	for (int y=0; y<dh; ++y) {
 		const int sy = std::min((int)std::floor(y*ify), sh-1);
 		for (int x=0; x<dw; ++x) {
@@ -829,19 +872,32 @@ int oracle_pm_iterate(const oracle_view* views, int nViews, const oracle_params*
 	return 0;
 }
 
+/* oracle_pm_iterate with the memory of the RB changed-flag rule carried by the caller: changed = width x height bytes
+ * (1 = plane changed in the pixel's last update / never tested), read and updated; NULL = no rule */
+int oracle_pm_iterate_flags(const oracle_view* views, int nViews, const oracle_params* prm,
+	float dMin, float dMax, const float* lowres, int iter, int half, float* depth, float* normal, float* conf, uint8_t* changed)
+{
+	if (nViews < 2) return 1;
+	Job J; std::vector<WeightedPatch> weights;
+	buildJob(views, nViews, prm, dMin, dMax, lowres, depth, normal, conf, weights, J);
+	J.changed = changed;
+	passB(J, iter, half);
+	return 0;
+}
+
 int oracle_pm_finalize(int width, int height, float keep, float* depth, float* normal, float* conf) {
 	passC(width, height, keep, depth, normal, conf);
 	return 0;
 }
 
-int oracle_pm_estimate(const oracle_view* views, int nViews, const oracle_params* prm,
-	float dMin, float dMax, int nGeometricIter, float* depth, float* normal, float* conf)
+// the scale loop of DepthMapsData::EstimateDepthMap (SceneDensify.cpp:640-805) around passes A, B (iterations
+// [iterBegin, iterEnd)) and C; mask: ignore-mask of the reference view at full resolution or null
+static int estimateImpl(const oracle_view* views, int nViews, const oracle_params* prm,
+	float dMin, float dMax, bool geometric, int iterBegin, int iterEnd, const uint8_t* mask, float* depth, float* normal, float* conf)
 {
 	if (nViews < 2) return 1;
 	const int W = views[0].width, H = views[0].height;
-	const int iterBegin = nGeometricIter < 0 ? 0 : prm->nEstimationIters+nGeometricIter;
-	const int iterEnd = nGeometricIter < 0 ? prm->nEstimationIters : iterBegin+1;
-	const int totalScale = nGeometricIter < 0 ? prm->nSubResolutionLevels : 0;
+	const int totalScale = !geometric ? prm->nSubResolutionLevels : 0;
 	std::vector<float> lowD, lowN; int lowW = 0, lowH = 0;
 	std::vector<float> prior;
 	for (int s = totalScale; s >= 0; --s) {
@@ -868,21 +924,36 @@ int oracle_pm_estimate(const oracle_view* views, int nViews, const oracle_params
 		std::vector<float> d((size_t)w*h), n((size_t)w*h*3), c((size_t)w*h);
 		const float* lowres = nullptr;
 		if (s != totalScale) {
-			resizeLinear(lowD.data(), lowW, lowH, d.data(), w, h);
-			resizeNearest(lowN.data(), lowW, lowH, 3, n.data(), w, h);
+			// depth LINEAR (NEAREST when an ignore-mask is set), normal NEAREST (SceneDensify.cpp:660-664)
+			if (mask) resizeNearest(lowD.data(), lowW, lowH, 1, d.data(), w, h, (double)lowW/w, (double)lowH/h);
+			else resizeLinear(lowD.data(), lowW, lowH, d.data(), w, h);
+			resizeNearest(lowN.data(), lowW, lowH, 3, n.data(), w, h, (double)lowW/w, (double)lowH/h);
 			prior = d;
 			lowres = prior.data();
 		} else if (s == 0) {
 			memcpy(d.data(), depth, sizeof(float)*w*h);
 			memcpy(n.data(), normal, sizeof(float)*w*h*3);
 		} else {
-			// coarsest level of a multi-scale run: the initial estimate is the caller's,
-			// scaled by nearest neighbour (ScaleDepthData)
-			resizeNearest(depth, W, H, 1, d.data(), w, h);
-			resizeNearest(normal, W, H, 3, n.data(), w, h);
+			// coarsest level of a multi-scale run: the initial estimate is the caller's, scaled by nearest
+			// neighbour with the factor form cv::resize(..., Size(), scale, scale, INTER_NEAREST) (ScaleDepthData)
+			resizeNearest(depth, W, H, 1, d.data(), w, h, 1.0/scale, 1.0/scale);
+			resizeNearest(normal, W, H, 3, n.data(), w, h, 1.0/scale, 1.0/scale);
 		}
 		Job J; std::vector<WeightedPatch> weights;
 		buildJob(sv.data(), nViews, prm, dMin, dMax, lowres, d.data(), n.data(), c.data(), weights, J);
+		std::vector<uint8_t> changed, lmask;
+		if (prm->schedule == 1 && (prm->propagation & 0x100)) { changed.assign((size_t)w*h, 1); J.changed = changed.data(); }
+		if (mask) {
+			// ImportIgnoreMask: cv::resize(mask, size, INTER_NEAREST) (DepthMap.cpp:309), then ApplyIgnoreMask (DepthMap.cpp:215-230)
+			lmask.resize((size_t)w*h);
+			for (int y=0; y<h; ++y) for (int x=0; x<w; ++x) {
+				const int sx = std::min((int)std::floor(x*((double)W/w)), W-1), sy = std::min((int)std::floor(y*((double)H/h)), H-1);
+				lmask[(size_t)y*w+x] = mask[(size_t)sy*W+sx];
+			}
+			for (size_t i=0; i<(size_t)w*h; ++i)
+				if (!lmask[i]) { d[i] = 0; n[i*3] = n[i*3+1] = n[i*3+2] = 0; c[i] = 0; }
+			J.mask = lmask.data();
+		}
 		passA(J);
 		for (int it=iterBegin; it<iterEnd; ++it)
 			passB(J, it, -1);
@@ -894,11 +965,30 @@ int oracle_pm_estimate(const oracle_view* views, int nViews, const oracle_params
 		}
 	}
 	float keep = prm->fNCCThresholdKeep;
-	if (nGeometricIter < 0 && prm->nEstimationGeometricIters)
+	if (!geometric && prm->nEstimationGeometricIters)
 		keep *= 1.333f;
 	passC(W, H, keep, depth, normal, conf);
 	return 0;
 }
+
+int oracle_pm_estimate(const oracle_view* views, int nViews, const oracle_params* prm,
+	float dMin, float dMax, int nGeometricIter, float* depth, float* normal, float* conf)
+{
+	const int iterBegin = nGeometricIter < 0 ? 0 : prm->nEstimationIters+nGeometricIter;
+	const int iterEnd = nGeometricIter < 0 ? prm->nEstimationIters : iterBegin+1;
+	return estimateImpl(views, nViews, prm, dMin, dMax, nGeometricIter >= 0, iterBegin, iterEnd, nullptr, depth, normal, conf);
+}
+
+/* the same with an explicit range of pass-B iterations (RB: sweeps) and an optional ignore-mask: the form the engine's
+ * schedule maps to (photometric: sweeps [0, T); geometric pass g: sweeps [T + g*S, T + (g+1)*S), no scale loop) */
+int oracle_pm_estimate_range(const oracle_view* views, int nViews, const oracle_params* prm,
+	float dMin, float dMax, int geometric, int iterBegin, int iterEnd, const uint8_t* mask, float* depth, float* normal, float* conf)
+{
+	return estimateImpl(views, nViews, prm, dMin, dMax, geometric != 0, iterBegin, iterEnd, mask, depth, normal, conf);
+}
+
+/* experiment counters of the RB changed-flag rule: {directions tested, directions skipped} since the last call */
+void oracle_pm_counters(long long out[2]) { out[0] = g_propTested.exchange(0); out[1] = g_propSkipped.exchange(0); }
 
 float oracle_pm_score_pixel(const oracle_view* views, int nViews, const oracle_params* prm,
 	float dMin, float dMax, const float* lowres, int x, int y,
@@ -950,7 +1040,7 @@ void oracle_zigzag(int width, int height, int rawStride, uint16_t* coordsXY) {
 }
 void oracle_resize_area(const float* src, int sw, int sh, float* dst, int dw, int dh, double scx, double scy) { resizeArea(src, sw, sh, dst, dw, dh, scx > 0 ? scx : (double)sw/dw, scy > 0 ? scy : (double)sh/dh); }
 void oracle_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh) { resizeLinear(src, sw, sh, dst, dw, dh); }
-void oracle_resize_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh) { resizeNearest(src, sw, sh, ch, dst, dw, dh); }
+void oracle_resize_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh) { resizeNearest(src, sw, sh, ch, dst, dw, dh, (double)sw/dw, (double)sh/dh); }
 void oracle_scale_K(const double K[9], int sw, int sh, int dw, int dh, double Kout[9]) { scaleK(K, sw, sh, dw, dh, Kout); }
 
 } // extern "C"

@@ -1,4 +1,6 @@
-"""1080p SGM pair for profiling: prints per-stage device times."""
+"""1080p SGM pair for profiling: per-stage device times of the aggregation variants (b200mvs_debug.sgmAggregation) and of the
+wave-front layouts / block sizes, with an identity check against the register-pipelined kernel.
+usage: profile_sgm.py [D] [default]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,15 +15,16 @@ args = (dev(lg), dev(lc), dev(rg), torch.from_numpy(px.view(np.uint8).reshape(-1
 m = SemiGlobalMatcher()
 costs = torch.zeros(n, dtype=torch.uint8, device="cuda"); accums = torch.zeros(n, dtype=torch.int16, device="cuda")
 ref = None
-MODES = [("register pipeline", dict(B200MVS_SGM_RING="0")), ("bulk-copy ring (default)", dict(B200MVS_SGM_RING="1")),
-	("ring + packed u16x2 step", dict(B200MVS_SGM_RING="1", B200MVS_SGM_DPX="1")),
-	("ring, 8 directions concurrent", dict(B200MVS_SGM_RING="1", B200MVS_SGM_CONCURRENT="1"))]
+MODES = [("register pipeline", dict(sgmAggregation=2)), ("bulk-copy ring, 8 launches", dict(sgmAggregation=3)),
+	("wave fronts (default: tilted, FB 32, lag 2)", dict()),
+	("wave fronts tilted FB 16 lag 2", dict(sgmAggregation=4, frontBlock=16)), ("wave fronts tilted FB 64 lag 2", dict(sgmAggregation=4, frontBlock=64)),
+	("wave fronts tilted FB 32 lag 1", dict(sgmAggregation=4, frontLag=1)), ("wave fronts tilted FB 32 lag 3", dict(sgmAggregation=4, frontLag=3)),
+	("wave fronts straight FB 16", dict(sgmAggregation=4, frontLayout=1)), ("wave fronts straight FB 32", dict(sgmAggregation=4, frontLayout=1, frontBlock=32)),
+	("wave fronts, 8 single passes", dict(sgmAggregation=4, frontLayout=2))]
 if len(sys.argv) > 2 and sys.argv[2] == "default":
-	MODES = MODES[:2]  # the two measured variants only
-for name, env in MODES:
-	for k in ("B200MVS_SGM_RING", "B200MVS_SGM_DPX", "B200MVS_SGM_CONCURRENT"):
-		os.environ.pop(k, None)
-	os.environ.update(env)
+	MODES = MODES[2:3]
+for name, dbg in MODES:
+	m.SetDebug(**dbg)
 	for rep in range(2):
 		t = {}
 		for stage_name, st in (("cost", 1), ("aggregate", 2), ("wta", 4), ("all", 7)):
@@ -32,4 +35,4 @@ for name, env in MODES:
 		ref = (accums.clone(), disp.clone())
 	else:
 		same = "| identical to the register pipeline: %s" % (torch.equal(ref[0], accums) and torch.equal(ref[1], disp))
-	print("D=%d %-30s" % (D, name), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same, flush=True)
+	print("D=%d %-46s" % (D, name), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same, flush=True)

@@ -42,3 +42,18 @@ def agreement(da, db, rel_tol=1e-3):
 	iou = both.sum()/max(1, union)
 	rel = np.abs(da-db)[both]/da[both]
 	return float(iou), float((rel < rel_tol).mean()) if both.any() else 0.0
+
+
+def rb_oracle(views, dmin, dmax, geometric_iter=-1, threads=8, mask=None, depth=None, normal=None, depths=None):
+	"""The CPU oracle on the engine's red-black schedule for the current OPTDENSE options: the same sweeps, refinement tries,
+	propagation candidates and changed-flag rule as b200mvs_estimate* runs (b200mvs_get_schedule), same Philox stream."""
+	from oracle import oracle as O
+	from openmvs_b200.depth_estimator import OPTDENSE as OPT
+	T, nR = OPT.schedule(False)
+	S, nRg = OPT.schedule(True)
+	geo = geometric_iter >= 0
+	prm = O.default_params(schedule=1, propagation=O.rb_propagation(OPT.nPropagation, OPT.nPropagationFar, OPT.bSkipUnchanged),
+		nRandomIters=nRg if geo else nR, nSubResolutionLevels=OPT.nSubResolutionLevels, nEstimationGeometricIters=OPT.nEstimationGeometricIters,
+		fEstimationGeometricWeight=OPT.fEstimationGeometricWeight, fNCCThresholdKeep=OPT.fNCCThresholdKeep, seed=OPT.nSeed, threads=threads)
+	b, e = (T+geometric_iter*S, T+(geometric_iter+1)*S) if geo else (0, T)
+	return O.pm_estimate_range(views, prm, dmin, dmax, b, e, geometric=geo, mask=mask, depth=depth, normal=normal, depths=depths)

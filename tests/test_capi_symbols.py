@@ -32,7 +32,7 @@ def test_struct_layouts_match_header_sizes():
 	from openmvs_b200 import lib
 	# b200mvs_view: pointer, 3 ints (+pad), 21 doubles, pointer, 3 ints (+pad), 21 doubles
 	assert C.sizeof(lib.View) == 8+16+21*8+8+16+21*8-8+8 or C.sizeof(lib.View) % 8 == 0
-	assert C.sizeof(lib.Params) == 16*4
+	assert C.sizeof(lib.Params) == 18*4
 	assert C.sizeof(lib.Stats) == 8+8+8+8+4+4+8+4+4
 
 
@@ -41,7 +41,8 @@ def test_struct_layouts_match_a_c_compiler(tmp_path):
 	import subprocess
 	from openmvs_b200 import lib
 	structs = {"b200mvs_view": lib.View, "b200mvs_params": lib.Params, "b200mvs_stats": lib.Stats, "b200mvs_job": lib.Job,
-		"b200mvs_sgm_params": lib.SgmParams, "b200mvs_dmap": lib.DMap, "b200mvs_filter_params": lib.FilterParams}
+		"b200mvs_sgm_params": lib.SgmParams, "b200mvs_dmap": lib.DMap, "b200mvs_filter_params": lib.FilterParams,
+		"b200mvs_debug": lib.Debug, "b200mvs_sgm_pixel": lib.SgmPixel}
 	lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200mvs.h"', 'int main(void) {']
 	for cname, ct in structs.items():
 		lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
@@ -90,6 +91,11 @@ def test_null_context_and_bad_arguments_return_status_codes():
 	from openmvs_b200 import lib
 	dll = lib.load()
 	assert dll.b200mvs_set_params(None, None) == 1
+	assert dll.b200mvs_set_debug(None, None) == 1 and dll.b200mvs_set_ignore_mask(None, None, 0, 0, 0, 0) == 1
+	assert dll.b200mvs_get_schedule(None, 0, None, None) == 1
+	assert dll.b200mvs_abi_version() == lib.ABI_VERSION
+	# the library reports the struct sizes it was compiled with (checked against the bindings by lib.load())
+	assert dll.b200mvs_sizeof(1) == C.sizeof(lib.Params) and dll.b200mvs_sizeof(99) == 0
 	assert dll.b200mvs_destroy(None) == 1
 	assert dll.b200mvs_estimate(None, None, 0, C.c_float(1), C.c_float(2), -1, None, None, None, None, None) == 1
 	assert dll.b200mvs_sync(None, None) == 1

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import agreement
+from conftest import agreement, rb_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -112,7 +112,7 @@ def test_single_sweep_parity_from_identical_state(env, small_scene, propagation)
 	sc, ref, views = small_scene
 	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nPropagation=propagation)
 	nR = 3
-	prm = e.O.default_params(schedule=1, propagation=propagation, nRandomIters=nR, nSubResolutionLevels=0, threads=4)
+	prm = e.O.default_params(schedule=1, propagation=e.O.rb_propagation(propagation, e.OPT.nPropagationFar, 0), nRandomIters=nR, nSubResolutionLevels=0, threads=4)
 	d, n, c = e.O.pm_score(views, prm, sc.dmin, sc.dmax)
 	dv = _dev_views(e, views)
 	for sweep in range(3):
@@ -135,7 +135,7 @@ def test_half_sweeps_touch_only_their_colour(env, small_scene):
 	e = env
 	sc, ref, views = small_scene
 	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nPropagation=4)
-	prm = e.O.default_params(schedule=1, nRandomIters=3, nSubResolutionLevels=0, threads=4)
+	prm = e.O.default_params(schedule=1, propagation=e.O.rb_propagation(4, e.OPT.nPropagationFar, 0), nRandomIters=3, nSubResolutionLevels=0, threads=4)
 	d, n, c = e.O.pm_score(views, prm, sc.dmin, sc.dmax)
 	plane = _plane(e, d, n); cost = torch.from_numpy(c).to(e.dev)
 	before = plane.cpu().numpy().copy()
@@ -155,12 +155,13 @@ def test_full_estimate_parity_rb_and_zz(env, small_scene):
 	schedule), with the reference's own run-to-run agreement as the yardstick."""
 	e = env
 	sc, ref, views = small_scene
-	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=2, nRandomIters=6, nPropagation=4)
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=0, nRandomIters=6, nPropagation=4)
+	assert e.OPT.schedule() == (9, 4)  # the shipped schedule for 6 reference iterations
 	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
 	e.pm.EstimateDepthMap(dd)
 	gd, gn, gc = dd.depthMap.cpu().numpy(), dd.normalMap.cpu().numpy(), dd.confMap.cpu().numpy()
 	base = dict(nSubResolutionLevels=0, nEstimationGeometricIters=0)
-	od, on, oc = e.O.pm_estimate(views, e.O.default_params(schedule=1, propagation=4, nEstimationIters=12, nRandomIters=3, threads=4, **base), sc.dmin, sc.dmax)
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, threads=4)
 	iou, agree = agreement(od, gd)
 	assert iou > 0.999 and agree > 0.98
 	both = (od > 0) & (gd > 0)
@@ -192,6 +193,8 @@ def test_full_estimate_parity_rb_and_zz(env, small_scene):
 	assert gd[m].min() >= sc.dmin and gd[m].max() < sc.dmax
 	vm = dd.viewsMap.cpu().numpy()
 	assert np.all(vm[~m] == 255) and vm[m][:, 0].max() < 4 and np.all(vm[m][:, 2:] == 255)
+	two = vm[m][:, 1] != 255
+	assert np.all(vm[m][two, 0] < vm[m][two, 1])  # view ids ascending, like PatchMatchCUDA.cpp:374-391
 
 
 def test_host_api_equals_device_api_and_is_deterministic(env, small_scene):
@@ -231,8 +234,7 @@ def test_initial_estimate_is_used_and_single_neighbour_min_branch(env, small_sce
 	dd = e.DepthData(_dev_views(e, two), sc.dmin, sc.dmax, depthMap=torch.from_numpy(gt_d).to(e.dev), normalMap=torch.from_numpy(init_n).to(e.dev))
 	e.pm.EstimateDepthMap(dd)
 	gd = dd.depthMap.cpu().numpy()
-	prm = e.O.default_params(schedule=1, propagation=4, nEstimationIters=2, nRandomIters=3, nSubResolutionLevels=0, nEstimationGeometricIters=0, threads=4)
-	od, on, oc = e.O.pm_estimate(two, prm, sc.dmin, sc.dmax, depth=gt_d, normal=init_n)
+	od, on, oc = rb_oracle(two, sc.dmin, sc.dmax, threads=4, depth=gt_d, normal=init_n)
 	iou, agree = agreement(od, gd)
 	assert iou > 0.999 and agree > 0.99
 	# with one neighbour 5 degrees away the refinement wanders inside the flat NCC optimum: the
@@ -263,8 +265,7 @@ def test_textureless_and_odd_size_and_mixed_resolution(env):
 	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
 	e.pm.EstimateDepthMap(dd)
 	gd = dd.depthMap.cpu().numpy()
-	prm = e.O.default_params(schedule=1, propagation=4, nEstimationIters=6, nRandomIters=3, nSubResolutionLevels=0, nEstimationGeometricIters=0, threads=4)
-	od, on, oc = e.O.pm_estimate(views, prm, sc.dmin, sc.dmax)
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, threads=4)
 	assert np.all(od[66:84, 8:-8] == 0) and np.all(gd[66:84, 8:-8] == 0)  # textureless rows rejected by both
 	iou, agree = agreement(od, gd)
 	assert e.pm.stats.tma_active == 1  # odd width: the reference image is re-pitched for the TMA descriptor
@@ -292,12 +293,8 @@ def test_geometric_consistency_pass_parity(env, small_scene):
 	e.pm.EstimateDepthMap(dd, nGeometricIter=0)
 	e.pm.Init(False)
 	gd, gc = dd.depthMap.cpu().numpy(), dd.confMap.cpu().numpy()
-	# oracle: pass A + sweeps 6,7 (iteration 3 = nEstimationIters+0) + pass C with keep 0.9
-	prm = e.O.default_params(schedule=1, propagation=4, nRandomIters=3, nSubResolutionLevels=0, nEstimationGeometricIters=2, threads=4)
-	d, n, c = e.O.pm_score(views, prm, sc.dmin, sc.dmax, depth=init_d, normal=init_n, depths=depths)
-	for sweep in (6, 7):
-		d, n, c = e.O.pm_iterate(views, prm, sc.dmin, sc.dmax, d, n, c, sweep, depths=depths)
-	od, on, oc = e.O.pm_finalize(d, n, c, 0.9)
+	# oracle: pass A + the two sweeps of geometric pass 0 (Philox phases after the photometric sweeps) + pass C with keep 0.9
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, geometric_iter=0, threads=4, depth=init_d, normal=init_n, depths=depths)
 	iou, agree = agreement(od, gd)
 	assert iou > 0.995 and agree > 0.985
 	both = (od > 0) & (gd > 0)
@@ -311,13 +308,12 @@ def test_multi_scale_parity(env, small_scene):
 	low-resolution depth prior (SceneDensify.cpp:651-769, DepthMap.cpp:552-561)."""
 	e = env
 	sc, ref, views = small_scene
-	_set(e, nSubResolutionLevels=2, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=2, nRandomIters=6)
+	_set(e, nSubResolutionLevels=2, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=0, nRandomIters=6)
 	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
 	e.pm.EstimateDepthMap(dd)
 	gd = dd.depthMap.cpu().numpy()
 	assert e.pm.stats.levels == 3
-	prm = e.O.default_params(schedule=1, propagation=4, nEstimationIters=6, nRandomIters=3, nSubResolutionLevels=2, nEstimationGeometricIters=0, threads=4)
-	od, on, oc = e.O.pm_estimate(views, prm, sc.dmin, sc.dmax)
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, threads=4)
 	iou, agree = agreement(od, gd)
 	assert iou > 0.995 and agree > 0.97
 	gt = sc.views[ref].depth_gt
@@ -333,7 +329,7 @@ def test_full_size_properties_1080p(env):
 	sc = synth.make_scene(1920, 1080, 10, step_deg=4.0, device=e.dev)
 	ref = 4
 	views = [sc.views[ref]]+[sc.views[i] for i in sc.neighbors(ref, 9)]
-	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=2, nRandomIters=6)
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=0, nRandomIters=6)
 	dv = _dev_views(e, views)
 	a = e.DepthData(dv, sc.dmin, sc.dmax); e.pm.EstimateDepthMap(a)
 	b = e.DepthData(dv, sc.dmin, sc.dmax); e.pm.EstimateDepthMap(b)
@@ -352,6 +348,124 @@ def test_full_size_properties_1080p(env):
 	X0 = np.stack([(xx-K[0, 2])/K[0, 0], (yy-K[1, 2])/K[1, 1], np.ones_like(xx, float)], -1)
 	assert ((gn*X0).sum(-1)[m] < 1e-6).all()  # normals face the camera
 	assert gc[m].min() > 0 and gc.max() <= 1 and gd[m].min() >= sc.dmin and gd[m].max() < sc.dmax
+
+
+def _ang(na, nb, m):
+	return np.degrees(np.arccos(np.clip((na*nb).sum(-1), -1, 1)))[m]
+
+
+def test_bench_configuration_parity_c2_1080p(env):
+	"""The bench configuration itself (BASELINE configs[1]): ONE reference view of the 12-view 1920x1080 scene, 9 neighbours,
+	6 iterations, single scale, shipped schedule (nSweepsPerIter = 0) — engine vs oracle-RB (same schedule, same Philox stream)
+	and vs oracle-ZZ (the reference's schedule, all host threads), with ZZ's own thread-count variation beside it.
+	Numbers are recorded in gpurun_out/parity_metrics.json (committed as profiles/parity_metrics_r02.json)."""
+	e = env
+	import os
+	from openmvs_b200 import synth
+	sc = synth.make_scene(1920, 1080, 12, step_deg=4.0, device=e.dev)
+	ref = 5
+	views = [sc.views[ref]]+[sc.views[i] for i in sc.neighbors(ref, 9)]
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=0, nRandomIters=6, nPropagation=4)
+	assert e.OPT.schedule() == (9, 4)
+	dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd)
+	gd, gn, gc = dd.depthMap.cpu().numpy(), dd.normalMap.cpu().numpy(), dd.confMap.cpu().numpy()
+	threads = max(2, len(os.sched_getaffinity(0)))
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, threads=threads)
+	iou_rb, agree_rb = agreement(od, gd)
+	both = (od > 0) & (gd > 0)
+	base = dict(nSubResolutionLevels=0, nEstimationGeometricIters=0)
+	zzA = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=6, threads=threads, **base), sc.dmin, sc.dmax)
+	zzB = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=6, threads=max(1, threads//2), **base), sc.dmin, sc.dmax)
+	iou_zz, agree_zz = agreement(zzA[0], gd)
+	iou_self, agree_self = agreement(zzA[0], zzB[0])
+	bz = (zzA[0] > 0) & (gd > 0); bs = (zzA[0] > 0) & (zzB[0] > 0)
+	gt, gtn = sc.views[ref].depth_gt, sc.views[ref].normal_gt
+	acc = lambda d: float((np.abs(d-gt)[d > 0]/gt[d > 0] < 1e-3).mean())
+	_record("c2_1080p_N9_I6_bench_config", threads=threads, iou_rb=iou_rb, agree_rb=agree_rb, med_ang_rb=np.median(_ang(on, gn, both)),
+		conf_close_rb=(np.abs(oc-gc)[both] < 1e-2).mean(),
+		iou_gpu_zz=iou_zz, agree_gpu_zz=agree_zz, med_ang_gpu_zz=np.median(_ang(zzA[1], gn, bz)),
+		iou_zz_self=iou_self, agree_zz_self=agree_self, med_ang_zz_self=np.median(_ang(zzA[1], zzB[1], bs)),
+		acc_gpu=acc(gd), acc_rb=acc(od), acc_zz=acc(zzA[0]),
+		med_ang_gt_gpu=np.median(_ang(gn, gtn, gd > 0)), med_ang_gt_rb=np.median(_ang(on, gtn, od > 0)), med_ang_gt_zz=np.median(_ang(zzA[1], gtn, zzA[0] > 0)),
+		valid_gpu=(gd > 0).mean(), valid_zz=(zzA[0] > 0).mean())
+	# same schedule, same hypotheses: only accept tests that flip on float rounding separate the two chains
+	assert iou_rb > 0.999 and agree_rb > 0.98 and np.median(_ang(on, gn, both)) < 1.5
+	# reference schedule: same confidence mask, agreement within 2 % of the reference's own thread-count variation,
+	# normals as close to the reference's as two reference runs are to each other (+ 1 deg), equally accurate
+	assert iou_zz > 0.995 and agree_zz > agree_self-0.02
+	assert np.median(_ang(zzA[1], gn, bz)) < np.median(_ang(zzA[1], zzB[1], bs))+1.0
+	assert acc(gd) > acc(zzA[0])-0.01
+	assert np.median(_ang(gn, gtn, gd > 0)) < np.median(_ang(zzA[1], gtn, zzA[0] > 0))+1.0
+
+
+def test_c5_size_view_geometric_pass_parity(env):
+	"""BASELINE configs[4] size: one 4032x3024 reference view, 4 neighbours carrying depth-maps, ONE geometric-consistency pass
+	from a perturbed estimate — engine vs oracle-RB (same schedule) and vs oracle-ZZ (one reference iteration)."""
+	e = env
+	import os
+	from openmvs_b200 import synth
+	w, h = 4032, 3024
+	sc = synth.make_scene(w, h, 5, step_deg=4.0, device=e.dev)
+	ref = 2
+	views = [sc.views[ref]]+[sc.views[i] for i in sc.neighbors(ref, 4)]
+	rng = np.random.RandomState(11)
+	depths = [None]+[(v.depth_gt, v.K, v.R, v.C) for v in views[1:]]
+	gt = sc.views[ref].depth_gt
+	init_d = (gt*(1+0.002*rng.randn(h, w).astype(np.float32))).astype(np.float32)
+	init_d[rng.rand(h, w) < 0.05] = 0
+	init_n = sc.views[ref].normal_gt.copy()
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=2, nEstimationIters=3, nSweepsPerIter=0, nRandomIters=6, fEstimationGeometricWeight=0.1)
+	dd = e.DepthData(_dev_views(e, views, depths), sc.dmin, sc.dmax, depthMap=torch.from_numpy(init_d).to(e.dev), normalMap=torch.from_numpy(init_n).to(e.dev))
+	e.pm.Init(True); e.pm.EstimateDepthMap(dd, nGeometricIter=0); e.pm.Init(False)
+	gd, gn = dd.depthMap.cpu().numpy(), dd.normalMap.cpu().numpy()
+	threads = max(2, len(os.sched_getaffinity(0)))
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, geometric_iter=0, threads=threads, depth=init_d, normal=init_n, depths=depths)
+	iou_rb, agree_rb = agreement(od, gd)
+	zz = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=3, nEstimationGeometricIters=2, nSubResolutionLevels=0, threads=threads),
+		sc.dmin, sc.dmax, geometric_iter=0, depth=init_d, normal=init_n, depths=depths)
+	iou_zz, agree_zz = agreement(zz[0], gd)
+	acc = lambda d: float((np.abs(d-gt)[d > 0]/gt[d > 0] < 1e-3).mean())
+	_record("c5_4032x3024_N4_geometric_pass", iou_rb=iou_rb, agree_rb=agree_rb, iou_gpu_zz=iou_zz, agree_gpu_zz=agree_zz,
+		acc_gpu=acc(gd), acc_rb=acc(od), acc_zz=acc(zz[0]), valid_gpu=(gd > 0).mean(), valid_zz=(zz[0] > 0).mean())
+	assert iou_rb > 0.995 and agree_rb > 0.98
+	assert iou_zz > 0.98 and agree_zz > 0.9 and acc(gd) > acc(zz[0])-0.02
+	_set(e, nEstimationGeometricIters=0)
+
+
+def test_ignore_mask_parity(env, small_scene):
+	"""OPTDENSE::nIgnoreMaskLabel >= 0: masked pixels are neither scored nor swept (DepthMap.cpp:215-230,343), every level uses
+	the NEAREST-resized mask and the depth is up-sampled NEAREST (SceneDensify.cpp:660-664,679-693) — engine vs oracle, 3 levels."""
+	e = env
+	sc, ref, views = small_scene
+	h, w = views[0].image.shape
+	yy, xx = np.mgrid[0:h, 0:w]
+	mask = np.full((h, w), 255, np.uint8)
+	mask[(xx-200)**2+(yy-90)**2 < 40**2] = 0
+	mask[150:190, 30:120] = 0
+	_set(e, nSubResolutionLevels=2, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=0, nRandomIters=6)
+	try:
+		e.pm.SetIgnoreMask(torch.from_numpy(mask).to(e.dev))
+		dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+		e.pm.EstimateDepthMap(dd)
+		e.pm.SetIgnoreMask(mask)              # host mask (copied), host images
+		hd = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
+		e.pm.EstimateDepthMap(hd)
+	finally:
+		e.pm.SetIgnoreMask(None)
+	gd, gn, gc = dd.depthMap.cpu().numpy(), dd.normalMap.cpu().numpy(), dd.confMap.cpu().numpy()
+	assert np.array_equal(gd, hd.depthMap) and np.array_equal(gc, hd.confMap)
+	assert np.all(gd[mask == 0] == 0) and np.all(gn[mask == 0] == 0) and np.all(gc[mask == 0] == 0)
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, threads=4, mask=mask)
+	assert np.all(od[mask == 0] == 0)
+	iou, agree = agreement(od, gd)
+	_record("ignore_mask_320x240_3levels", iou=iou, agree=agree, masked=(mask == 0).mean())
+	assert iou > 0.995 and agree > 0.97
+	# without the mask the same pixels are estimated
+	dd2 = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd2)
+	assert (dd2.depthMap.cpu().numpy()[mask == 0] > 0).mean() > 0.8
+	_set(e, nSubResolutionLevels=0)
 
 
 def test_high_resolution_geometric_pass_properties(env):
@@ -484,13 +598,13 @@ def test_baseline_config0_two_view_640x480(env):
 	from openmvs_b200 import synth
 	sc = synth.make_scene(640, 480, 2, step_deg=5.0, cols=2)
 	views = [sc.views[0], sc.views[1]]
-	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=4, nRandomIters=6)
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=3, nSweepsPerIter=0, nRandomIters=6)
+	assert e.OPT.schedule() == (8, 3)  # the same rule as at C2 (6 iterations -> 9 sweeps x 4 tries): no per-test knob
 	dd = e.DepthData(_host_views(e, views), sc.dmin, sc.dmax)
 	e.pm.EstimateDepthMap(dd)
 	gd = dd.depthMap
 	base = dict(nSubResolutionLevels=0, nEstimationGeometricIters=0)
-	# same schedule: 3 iterations x 4 sweeps, ceil(6/4) = 2 refinements per sweep
-	od, on, oc = e.O.pm_estimate(views, e.O.default_params(schedule=1, propagation=4, nEstimationIters=12, nRandomIters=2, threads=8, **base), sc.dmin, sc.dmax)
+	od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, threads=8)
 	iou, agree = agreement(od, gd)
 	assert iou > 0.999 and agree > 0.97
 	zz1 = e.O.pm_estimate(views, e.O.default_params(schedule=0, nEstimationIters=3, threads=1, **base), sc.dmin, sc.dmax)
@@ -501,5 +615,11 @@ def test_baseline_config0_two_view_640x480(env):
 	acc_g = (np.abs(gd-gt)[gd > 0]/gt[gd > 0] < 1e-3).mean()
 	acc_z = (np.abs(zz1[0]-gt)[zz1[0] > 0]/gt[zz1[0] > 0] < 1e-3).mean()
 	_record("config0_640x480_N1_I3", iou_rb=iou, agree_rb=agree, iou_zz_self=iou_ref, agree_zz_self=agree_ref, iou_gpu_zz=iou_g, agree_gpu_zz=agree_g, acc_gpu=acc_g, acc_zz=acc_z)
-	assert iou_g > 0.99 and agree_g > agree_ref-0.08 and acc_g > acc_z-0.05
-	_set(e, nSweepsPerIter=2)
+	assert iou_g > 0.99 and agree_g > agree_ref-0.02 and acc_g > acc_z-0.02
+	# the committed oracle-generated fixture of this configuration (tests/golden/c1_golden.npz, made by make_c1_golden.py):
+	# the engine against the reference schedule's result without depending on thread timing at test time
+	import os
+	g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_golden.npz"))
+	iou_f, agree_f = agreement(g["zz1_depth"].astype(np.float32), gd)
+	_record("config0_vs_golden_fixture", iou=iou_f, agree=agree_f, agree_zz_self_fixture=float(g["agree_zz1_zz8"]))
+	assert iou_f > 0.99 and agree_f > float(g["agree_zz1_zz8"])-0.02

@@ -101,6 +101,13 @@ def test_full_size_sgm_properties_1080p(sgm):
 	ms = m.stats.ms_device
 	gd2, gc2 = m.MatchDevice(*args)
 	assert torch.equal(gd, gd2) and torch.equal(gc, gc2)
+	# the per-direction ring kernel gives the same integers
+	try:
+		m.SetDebug(sgmAggregation=3)
+		gd3, gc3 = m.MatchDevice(*args)
+	finally:
+		m.SetDebug()
+	assert torch.equal(gd, gd3) and torch.equal(gc, gc3)
 	gt = d[3:-3, 3:-3]
 	err = np.abs(gd.cpu().numpy()-gt)[8:-8, 8:-140]
 	assert (err <= 1).mean() > 0.97
@@ -149,6 +156,50 @@ def test_uniform_range_fast_path_bit_exact(sgm, num):
 	gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
 	assert np.array_equal(accums.cpu().numpy().view(np.uint16), a)
 	assert np.array_equal(gd.cpu().numpy(), disp) and np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
+
+
+@pytest.mark.parametrize("layout,block,lag", [(0, 0, 0), (0, 8, 1), (0, 16, 3), (1, 0, 0), (1, 4, 1), (2, 0, 0)])
+@pytest.mark.parametrize("num", [64, 128, 256])
+def test_wave_front_aggregation_bit_exact(sgm, num, layout, block, lag):
+	"""The wave-front kernel (dense volume, one range of 64 / 128 / 256 disparities; the default of the non-tSGM branch) against the
+	oracle: two tilted fronts (default), four straight fronts, eight single-direction passes; small blocks and lags exercise the
+	ordering of the phases and the hand-over of the path state between the segments of a path."""
+	m, O = sgm
+	w, h = 151, 92   # valid region 145 x 86: neither a multiple of the 4-path bands
+	rng = np.random.RandomState(num+layout)
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	px, n = synth.sgm_pixel_map(w, h, -9, -9+num)
+	costs = rng.randint(0, 256, n).astype(np.uint8)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n, costs=costs)
+	accums = torch.full((n,), -1, dtype=torch.int16, device="cuda")   # phase 0 of the first pass stores: no memset needed
+	try:
+		m.SetDebug(sgmAggregation=4, frontLayout=layout, frontBlock=block, frontLag=lag)
+		gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
+	finally:
+		m.SetDebug()
+	assert np.array_equal(accums.cpu().numpy().view(np.uint16), a)
+	assert np.array_equal(gd.cpu().numpy(), disp) and np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
+
+
+def test_wave_front_aggregation_larger_image_and_variants_agree(sgm):
+	"""403 x 251, D = 128: default (wave fronts) == bulk-copy ring kernel == register-pipelined kernel == general kernel == oracle"""
+	m, O = sgm
+	w, h = 403, 251
+	rng = np.random.RandomState(5)
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	px, n = synth.sgm_pixel_map(w, h, 0, 128)
+	costs = rng.randint(0, 256, n).astype(np.uint8)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n, costs=costs)
+	try:
+		for mode in (0, 3, 2, 1):
+			m.SetDebug(sgmAggregation=mode)
+			accums = torch.zeros(n, dtype=torch.int16, device="cuda")
+			gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
+			assert np.array_equal(accums.cpu().numpy().view(np.uint16), a), mode
+			assert np.array_equal(gd.cpu().numpy(), disp), mode
+			assert m.stats.kernel_launches == (2+2+1 if mode == 0 else 2+8+1)
+	finally:
+		m.SetDebug()
 
 
 def test_pair_pipeline_matches_oracle_and_ground_truth(sgm):
