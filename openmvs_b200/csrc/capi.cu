@@ -37,6 +37,9 @@ struct SGMParams {
 cudaError_t sgm_configure_device();
 cudaError_t sgm_launch_maxdisp(const SGMPixel* px, int n, unsigned long long numCosts, int* out8, cudaStream_t s);
 cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
+cudaError_t sgm_cost_tc_configure();
+bool sgm_cost_tc_supports(int num);
+cudaError_t sgm_cost_tc_launch(const SGMParams& P, int dmin, int num, cudaStream_t s);
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s);
 // wave-front aggregation (sgm_front.cu)
@@ -553,7 +556,7 @@ int b200mvs_create(int device, b200mvs_ctx** out) {
 	b200mvs_default_params(&c->prm);
 	memset(&c->dbg, 0, sizeof(c->dbg));
 	// dynamic shared memory opt-in of the kernels on this device (per-device attributes; idempotent, thread-safe)
-	if (pm_configure_device() != cudaSuccess || sgm_configure_device() != cudaSuccess) { delete c; return B200MVS_ERR_CUDA; }
+	if (pm_configure_device() != cudaSuccess || sgm_configure_device() != cudaSuccess || sgm_cost_tc_configure() != cudaSuccess) { delete c; return B200MVS_ERR_CUDA; }
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 		cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
 		delete c;
@@ -873,7 +876,7 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	int st8[8] = {0, 0, 0, 0, 0, 0, 0, 0}; bool uniform = false, ring = false, front = false;
 	const int mode = ctx->dbg.sgmAggregation;
 	if (stats) CK(cudaEventRecord(ctx->ev0, s));
-	if (stages & 2) {
+	if (stages & 3) {
 		// the warp-per-scanline kernel keeps one line of at most sgm_max_disparities() values
 		CK(ctx->sgMax.reserve(8*sizeof(int)));
 		CK(sgm_launch_maxdisp(P.px, P.vw*P.vh, numCosts, ctx->sgMax.as<int>(), s)); ctx->launches += 2;
@@ -893,7 +896,16 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 		if (mode == 4 && !front)
 			return fail(ctx, B200MVS_ERR_ARG, "sgm: the wave-front kernel needs a dense volume with one range of 64, 128 or 256 disparities");
 	}
-	if (stages & 1) { CK(sgm_launch_cost(P, s)); ++ctx->launches; }
+	if (stages & 1) {
+		// dense volume with one range of 64 / 128 disparities: the banded-GEMM cost kernel on the tensor cores (sgm_cost_tc.cu)
+		const bool dense = uniform && (st8[0] & 15) == 0 && !st8[6] && !((uintptr_t)P.costs & 15);
+		const bool tc = dense && sgm_cost_tc_supports(st8[0]) && ctx->dbg.sgmCost == 2;
+		if (ctx->dbg.sgmCost == 2 && !tc)
+			return fail(ctx, B200MVS_ERR_ARG, "sgm: the tensor-core cost kernel needs a dense volume with one range of 64 or 128 disparities");
+		if (tc) CK(sgm_cost_tc_launch(P, st8[1], st8[0], s));
+		else CK(sgm_launch_cost(P, s));
+		++ctx->launches;
+	}
 	if ((stages & 2) && front) {
 		const int rc = sgm_aggregate_fronts(ctx, P, st8[0], s);
 		if (rc) return rc;

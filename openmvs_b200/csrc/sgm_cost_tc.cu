@@ -1,0 +1,321 @@
+// sgm_cost_tc.cu — the WZNCC 7x7 cost volume of the SGM pair matcher on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// What it computes: per valid pixel x of a row and disparity d, the three weighted sums of the 49-tap window
+//   sum = S_n w_x(n) f_n,  sumSq = S_n w_x(n) f_n^2,  nom = S_n tw_x(n) f_n,   f_n = right(y+i, x+d+j), n = (i,j)
+// and from them the uint8 cost (SemiGlobalMatcher.cpp:875-985; the SIMT form is sgm_cost_kernel in sgm_kernels.cu).
+//
+// Why tensor cores fit: for a block of 128 pixels of one row the sums are a banded GEMM.  With A[x, n] = w_x(n) (M = 128 pixels,
+// K = 49 taps padded to 64) and the Toeplitz matrix B[n, u] = right(y+i, u+j) (u = x + d, the right-image column), the wanted
+// entries are D[x, u] for u - x in [dmin, dmin+D).  The band is cut into 64-column tiles of u; a tile serves two pixel blocks, a
+// block needs (128+D)/64 tiles (band utilisation 50 % at D = 128).  Precision: the operands are split into fp16 high and low
+// parts (w = wh + wl, error 2^-22) and every sum is three kind::f16 MMAs with fp32 accumulation in TMEM (wh fh + wh fl + wl fh) —
+// the dropped wl fl term is 2^-22 relative — so the uint8 cost stays within the +-1 level of the SIMT kernel.
+//
+// Structure (one 256-thread CTA per SM, persistent over the rows of the valid region):
+//   warps 0-3  build A (bilateral weights of the block's 128 pixels: 49 expf per pixel, split, 16-byte stores in the UMMA
+//              K-major no-swizzle core-matrix layout) | warps 4-7 build the two new B tiles (im2col of 7 right-image rows);
+//   one thread issues the MMAs of a tile (9 products x 4 K-steps of 128 x 64 x 16) into one of two TMEM accumulator buffers
+//              and commits them to an mbarrier; the next tile's MMAs run while
+//   all 8 warps read the finished buffer (tcgen05.ld 32x32b), turn sums into costs and scatter them into a shared cost tile,
+//              which is finally written to the volume with coalesced 16-byte stores.
+// SASS: UTCHMMA (tcgen05.mma), UTCBAR (commit), LDTM (tcgen05.ld), UTCATOMSWS / UTCALLOC (alloc).
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string.h>
+
+struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
+struct SGMParams {
+	const float* lgray; const uchar3* lbgr; const float* rgray;
+	int w, h, vw, vh;
+	const SGMPixel* px;
+	uint8_t* costs; uint16_t* accums;
+	int P1;
+	uint16_t P2s[256];
+	int maxNumDisp;
+};
+
+namespace {
+
+constexpr int HW = 3, NT = 49;
+constexpr int BM = 128;          // pixels per block (MMA M)
+constexpr int BN = 64;           // right-image columns per tile (MMA N)
+constexpr int KP = 64;           // taps padded to the MMA K granularity (4 x 16)
+constexpr int TC_THREADS = 256;
+constexpr int A_ARRAY = BM*KP*2;         // one fp16 operand array of a block: 16 KB
+constexpr int B_ARRAY = BN*KP*2;         // one fp16 operand array of a tile: 8 KB
+constexpr int B_SLOT = 4*B_ARRAY;        // fh, fl, qh, ql
+constexpr int RING = 4;                  // B tiles kept (a block of D <= 128 needs (128+D)/64 <= 4)
+constexpr int TILE_PITCH = 132;          // bytes per pixel row of the shared cost tile (bank-conflict-free byte scatter)
+constexpr int SMEM_A = 4*A_ARRAY;        // wh, wl, th, tl
+constexpr int SMEM_B = RING*B_SLOT;
+constexpr int SMEM_TILE = BM*TILE_PITCH;
+constexpr int SMEM_CONST = BM*8;         // {normSq0, sumW} per pixel
+constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_TILE + SMEM_CONST + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle (INTERLEAVE): a K-chunk of 8 halves (16 B) of row r sits at chunk*rows*16 + r*16; 8 consecutive rows are one
+// 128-byte core matrix: stride between 8-row groups SBO = 128 B, between the two 16-byte K-chunks of one MMA LBO = rows*16 B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+	uint64_t d = 0;
+	d |= (uint64_t)((saddr>>4) & 0x3FFFu);
+	d |= (uint64_t)((lbo_bytes>>4) & 0x3FFFu) << 16;
+	d |= (uint64_t)((128u>>4) & 0x3FFFu) << 32;
+	d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
+	return d;                 // layout type 0 = no swizzle, base offset 0
+}
+// instruction descriptor of kind::f16: D = F32, A = B = F16, both K-major, M = 128, N = 64
+constexpr uint32_t IDESC = (1u<<4) | ((uint32_t)(BN>>3)<<17) | ((uint32_t)(BM>>4)<<24);
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+	asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+		:: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// bounded: a tensor-core batch takes microseconds; a wait of seconds means a malformed descriptor — trap instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+	unsigned ok = 0;
+	for (unsigned spins = 0; !ok; ++spins) {
+		asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+			: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (!ok && spins > (1u<<26)) asm volatile("trap;");
+	}
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+		  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+		: "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b)<<16); }
+// x = hi + lo with hi = fp16(x): two fp16 numbers carrying 22 bits of x
+__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) { hi = __float2half_rn(x); lo = __float2half_rn(x-__half2float(hi)); }
+
+// Dense volumes only (every pixel valid with the range [dmin, dmin+num), idx = pixel index x num); num in {64, 128}.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	unsigned char* sA = smem;
+	unsigned char* sB = smem + SMEM_A;
+	unsigned char* sTile = sB + SMEM_B;
+	float2* sConst = (float2*)(sTile + SMEM_TILE);
+	uint64_t* bars = (uint64_t*)((unsigned char*)sConst + SMEM_CONST);   // 2 mbarriers
+	uint32_t* sTmem = (uint32_t*)(bars+2);
+	const int tid = threadIdx.x, warp = tid>>5, lane = tid&31;
+	const int w = P.w, vw = P.vw, vh = P.vh;
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sTmem)), "r"(512u) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	if (tid == 32) {
+		mbar_init(bars, 1); mbar_init(bars+1, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	// the K padding (taps 49..63) of every operand array is zero and stays zero: only chunks 0..6 are rewritten (chunk 6 holds
+	// taps 48..55, its upper seven halves are written as zeros by the builders)
+	for (int i = tid; i < (SMEM_A+SMEM_B)/16; i += TC_THREADS) ((uint4*)smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem = *sTmem;
+	const int nTiles = (BM+num)/BN;             // u tiles a block needs: 3 (D = 64) or 4 (D = 128)
+	const int nBlocks = (vw+BM-1)/BM;
+	const float sigmaColor = -1.f/(2.f*(0.3f*255)*(0.3f*255));
+	const float sigmaSpatial = -1.f/(2.f*(0.4f*7)*(0.4f*7));
+	unsigned phase[2] = {0u, 0u};
+
+	// one B tile: thread `c` (0..63) of the building half-CTA owns column u' = 64 t + c of the band
+	auto build_b_tile = [&](int r, int t, int c) {
+		unsigned char* slot = sB + (size_t)(t&(RING-1))*B_SLOT;
+		const int lcol = BN*t + c + dmin;         // image column of the window's left edge
+		#pragma unroll 1
+		for (int kc = 0; kc < 7; ++kc) {
+			__half fh[8], fl[8], qh[8], ql[8];
+			#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				const int n = kc*8+e;
+				float f = 0.f;
+				if (n < NT) {
+					const int i = n/7, j = n-7*i;
+					const int col = min(max(lcol+j, 0), w-1);
+					f = __ldg(P.rgray + (size_t)(r+i)*w + col);
+				}
+				split_h(f, fh[e], fl[e]);
+				split_h(f*f, qh[e], ql[e]);
+			}
+			const size_t off = (size_t)kc*(BN*16) + (size_t)c*16;
+			*(uint4*)(slot+0*B_ARRAY+off) = make_uint4(pack_h2(fh[0], fh[1]), pack_h2(fh[2], fh[3]), pack_h2(fh[4], fh[5]), pack_h2(fh[6], fh[7]));
+			*(uint4*)(slot+1*B_ARRAY+off) = make_uint4(pack_h2(fl[0], fl[1]), pack_h2(fl[2], fl[3]), pack_h2(fl[4], fl[5]), pack_h2(fl[6], fl[7]));
+			*(uint4*)(slot+2*B_ARRAY+off) = make_uint4(pack_h2(qh[0], qh[1]), pack_h2(qh[2], qh[3]), pack_h2(qh[4], qh[5]), pack_h2(qh[6], qh[7]));
+			*(uint4*)(slot+3*B_ARRAY+off) = make_uint4(pack_h2(ql[0], ql[1]), pack_h2(ql[2], ql[3]), pack_h2(ql[4], ql[5]), pack_h2(ql[6], ql[7]));
+		}
+	};
+	// the block's A operands: thread `row` (0..127) owns pixel x0 + row
+	auto build_a = [&](int r, int x0, int row) {
+		const int col = x0+row;
+		float wv[NT], gv[NT];
+		float sumW = 0.f, normSq0 = 0.f;
+		if (col < vw) {
+			const int ux = col+HW, uy = r+HW;
+			const uchar3 cc = P.lbgr[(size_t)uy*w + ux];
+			float acc = 0.f;
+			#pragma unroll
+			for (int i = 0; i < 7; ++i) {
+				#pragma unroll
+				for (int j = 0; j < 7; ++j) {
+					const size_t o = (size_t)(uy+i-HW)*w + (ux+j-HW);
+					const uchar3 pc = P.lbgr[o];
+					const int d0 = abs((int)pc.x-(int)cc.x), d1 = abs((int)pc.y-(int)cc.y), d2 = abs((int)pc.z-(int)cc.z);
+					const float wgt = expf(float(d0*d0+d1*d1+d2*d2)*sigmaColor + float((j-HW)*(j-HW)+(i-HW)*(i-HW))*sigmaSpatial);
+					const float g = __ldg(P.lgray + o);
+					wv[i*7+j] = wgt; gv[i*7+j] = g;
+					acc += g*wgt;
+					sumW += wgt;
+				}
+			}
+			const float tm = acc/sumW;
+			#pragma unroll
+			for (int n = 0; n < NT; ++n) {
+				const float t = gv[n]-tm;
+				gv[n] = wv[n]*t;          // tempWeight
+				normSq0 += gv[n]*t;
+			}
+		} else {
+			#pragma unroll
+			for (int n = 0; n < NT; ++n) { wv[n] = 0.f; gv[n] = 0.f; }
+			sumW = 1.f;
+		}
+		sConst[row] = make_float2(normSq0, sumW);
+		#pragma unroll
+		for (int kc = 0; kc < 7; ++kc) {
+			__half wh[8], wl[8], th[8], tl[8];
+			#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				const int n = kc*8+e;
+				split_h(n < NT ? wv[n < NT ? n : 0] : 0.f, wh[e], wl[e]);
+				split_h(n < NT ? gv[n < NT ? n : 0] : 0.f, th[e], tl[e]);
+			}
+			const size_t off = (size_t)kc*(BM*16) + (size_t)row*16;
+			*(uint4*)(sA+0*A_ARRAY+off) = make_uint4(pack_h2(wh[0], wh[1]), pack_h2(wh[2], wh[3]), pack_h2(wh[4], wh[5]), pack_h2(wh[6], wh[7]));
+			*(uint4*)(sA+1*A_ARRAY+off) = make_uint4(pack_h2(wl[0], wl[1]), pack_h2(wl[2], wl[3]), pack_h2(wl[4], wl[5]), pack_h2(wl[6], wl[7]));
+			*(uint4*)(sA+2*A_ARRAY+off) = make_uint4(pack_h2(th[0], th[1]), pack_h2(th[2], th[3]), pack_h2(th[4], th[5]), pack_h2(th[6], th[7]));
+			*(uint4*)(sA+3*A_ARRAY+off) = make_uint4(pack_h2(tl[0], tl[1]), pack_h2(tl[2], tl[3]), pack_h2(tl[4], tl[5]), pack_h2(tl[6], tl[7]));
+		}
+	};
+	// the 36 MMAs of tile t into accumulator buffer `buf` (columns buf*256 + {0, 64, 128}: sum, sumSq, nom), then commit
+	auto issue_tile = [&](int t, int buf) {
+		const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB + (size_t)(t&(RING-1))*B_SLOT);
+		const uint32_t dBase = tmem + (uint32_t)buf*256u;
+		// {A array, B array, accumulator}: wh fh, wh fl, wl fh -> sum | wh qh, wh ql, wl qh -> sumSq | th fh, th fl, tl fh -> nom
+		const int prod[9][3] = {{0, 0, 0}, {0, 1, 0}, {1, 0, 0}, {0, 2, 1}, {0, 3, 1}, {1, 2, 1}, {2, 0, 2}, {2, 1, 2}, {3, 0, 2}};
+		#pragma unroll
+		for (int p = 0; p < 9; ++p) {
+			#pragma unroll
+			for (int kk = 0; kk < KP/16; ++kk) {
+				const uint64_t ad = umma_desc(aBase + prod[p][0]*A_ARRAY + kk*2*(BM*16), BM*16);
+				const uint64_t bd = umma_desc(bBase + prod[p][1]*B_ARRAY + kk*2*(BN*16), BN*16);
+				const bool first = (p == 0 || p == 3 || p == 6) && kk == 0;
+				umma_f16(dBase + (uint32_t)prod[p][2]*64u, ad, bd, first ? 0u : 1u);
+			}
+		}
+		umma_commit(bars+buf);
+	};
+	// sums -> costs of tile t (block b) from accumulator buffer `buf` into the shared cost tile
+	auto epilogue = [&](int r, int b, int t, int buf) {
+		mbar_wait(bars+buf, phase[buf]); phase[buf] ^= 1u;
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+		const int row = 32*(warp&3) + lane;         // TMEM lane = pixel of the block
+		const int cbase = 32*(warp>>2);             // this warp's half of the 64 columns
+		const float2 cst = sConst[row];
+		const int col = BM*b + row;                 // valid-region column of the pixel
+		const float eps = 1e-3f;
+		#pragma unroll
+		for (int ch = 0; ch < 2; ++ch) {
+			uint32_t s0[16], s1[16], s2[16];
+			const uint32_t ta = tmem + ((uint32_t)(32*(warp&3))<<16) + (uint32_t)buf*256u + (uint32_t)(cbase+16*ch);
+			tmem_ld16(ta, s0); tmem_ld16(ta+64u, s1); tmem_ld16(ta+128u, s2);
+			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+			#pragma unroll
+			for (int e = 0; e < 16; ++e) {
+				const int c = cbase+16*ch+e;
+				const int d = BN*(t-2*b) + c - row;      // disparity index of (pixel, column)
+				if (d >= 0 && d < num) {
+					const float sum = __uint_as_float(s0[e]), sumSq = __uint_as_float(s1[e]), nom = __uint_as_float(s2[e]);
+					const float normSq1 = sumSq - sum*sum/cst.y;
+					const float ncc = nom/sqrtf(cst.x*normSq1+eps);
+					uint8_t cv = ncc <= 0.f ? (uint8_t)255 : (uint8_t)(int)floorf((1.f-fminf(ncc, 1.f))*255.f+.5f);
+					const int left = col+d+dmin;           // image column of the right window's left edge
+					if (left < 0 || left+2*HW >= w) cv = 255;
+					sTile[row*TILE_PITCH + d] = cv;
+				}
+			}
+		}
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	};
+
+	#pragma unroll 1
+	for (int r = blockIdx.x; r < vh; r += gridDim.x) {
+		#pragma unroll 1
+		for (int b = 0; b < nBlocks; ++b) {
+			// operands of this block: A by warps 0-3; the tiles not yet in the ring by warps 4-7
+			if (tid < BM) build_a(r, BM*b, tid);
+			else {
+				const int q = tid-BM;                       // 0..127: tile q>>6 of the pair, column q&63
+				if (b == 0)
+					for (int t = 0; t < nTiles-2; t += 2) build_b_tile(r, t+(q>>6), q&63);
+				build_b_tile(r, 2*b+nTiles-2+(q>>6), q&63);
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+			__syncthreads();
+			if (tid == 0) {
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				issue_tile(2*b, 0); issue_tile(2*b+1, 1);
+			}
+			for (int k = 0; k < nTiles; ++k) {
+				epilogue(r, b, 2*b+k, k&1);
+				__syncthreads();                               // every warp has drained buffer k&1
+				if (tid == 0 && k+2 < nTiles) {
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					issue_tile(2*b+k+2, k&1);
+				}
+			}
+			// the block's costs: num bytes per pixel, coalesced 16-byte stores
+			const int chunks = num/16;
+			for (int i = tid; i < BM*chunks; i += TC_THREADS) {
+				const int row = i/chunks, c16 = i-row*chunks;
+				const int col = BM*b+row;
+				if (col < vw) {
+					const uint32_t* src = (const uint32_t*)(sTile + row*TILE_PITCH + 16*c16);
+					const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+					*(uint4*)(P.costs + ((size_t)r*vw + col)*(size_t)num + 16*c16) = v;
+				}
+			}
+			__syncthreads();                                   // tile and A are free for the next block
+		}
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if (warp == 0)
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+} // namespace
+
+cudaError_t sgm_cost_tc_configure() {
+	return cudaFuncSetAttribute(sgm_cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+}
+bool sgm_cost_tc_supports(int num) { return num == 64 || num == 128; }
+cudaError_t sgm_cost_tc_launch(const SGMParams& P, int dmin, int num, cudaStream_t s) {
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	sgm_cost_tc_kernel<<<sms, TC_THREADS, SMEM_TOTAL, s>>>(P, dmin, num);
+	return cudaGetLastError();
+}

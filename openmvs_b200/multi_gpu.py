@@ -80,6 +80,68 @@ def all_gather_depth(local: Dict[int, torch.Tensor], n_views: int) -> Dict[int, 
 	return res
 
 
+class ViewStack:
+	"""The maps of this rank's reference views as preallocated stacks — depth [K,H,W], normal [K,H,W,3], conf [K,H,W],
+	views [K,H,W,4] (K = views per rank, rounded up) — so that EstimateDepthMap writes straight into slices of them and the
+	two exchanges take the stacks as they are: no packing, no staging copies, no per-step allocation.
+	  gather(dst)          ncclGather of depth, normal and confidence to `dst` (the final hand-over, 20 B per pixel)
+	  all_gather_depth()   ncclAllGather of the depth stack (4 B per pixel) before a geometric-consistency pass"""
+
+	def __init__(self, n_views: int, height: int, width: int, device, rank: int = None, world: int = None):
+		self.rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
+		self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
+		self.n_views, self.h, self.w = n_views, height, width
+		self.mine = shard_views(n_views, self.rank, self.world)
+		self.kmax = (n_views+self.world-1)//self.world
+		z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=device)
+		self.depth, self.normal, self.conf = z(self.kmax, height, width), z(self.kmax, height, width, 3), z(self.kmax, height, width)
+		self.views = z(self.kmax, height, width, 4, dt=torch.uint8)
+		self.all_depth = None   # [world*K, H, W] after all_gather_depth()
+		self._recv = None       # receive stacks on the gather destination
+
+	def slot(self, view: int) -> int:
+		return self.mine.index(view)
+
+	def maps(self, view: int) -> dict:
+		k = self.slot(view)
+		return dict(depth=self.depth[k], normal=self.normal[k], conf=self.conf[k], views=self.views[k])
+
+	def gather(self, dst: int = 0):
+		"""-> {view: dict(depth, normal, conf)} on dst (views of the receive stacks), None elsewhere"""
+		if self.world == 1:
+			return {v: self.maps(v) for v in self.mine}
+		if self.rank == dst and self._recv is None:
+			self._recv = [[torch.empty_like(t) for _ in range(self.world)] for t in (self.depth, self.normal, self.conf)]
+		for i, t in enumerate((self.depth, self.normal, self.conf)):
+			dist.gather(t, self._recv[i] if self.rank == dst else None, dst=dst)
+		if self.rank != dst:
+			return None
+		res = {}
+		for r in range(self.world):
+			for k, v in enumerate(shard_views(self.n_views, r, self.world)):
+				res[v] = dict(depth=self._recv[0][r][k], normal=self._recv[1][r][k], conf=self._recv[2][r][k])
+		return res
+
+	def all_gather_depth(self):
+		"""every rank receives every view's depth-map; depth_of(view) indexes the result"""
+		if self.world == 1:
+			self.all_depth = self.depth
+			return self.all_depth
+		if self.all_depth is None or self.all_depth is self.depth:
+			self.all_depth = torch.empty((self.world*self.kmax, self.h, self.w), dtype=torch.float32, device=self.depth.device)
+		dist.all_gather_into_tensor(self.all_depth, self.depth)
+		return self.all_depth
+
+	def depth_of(self, view: int):
+		return self.all_depth[owner_of(view, self.world)*self.kmax + view//self.world]
+
+	def bytes_gather(self) -> int:
+		return self.kmax*self.h*self.w*20
+
+	def bytes_all_gather(self) -> int:
+		return self.world*self.kmax*self.h*self.w*4
+
+
 def _default_device():
 	if dist.is_initialized() and dist.get_backend() == "nccl":
 		return torch.device("cuda", torch.cuda.current_device())

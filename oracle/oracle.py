@@ -38,12 +38,58 @@ def build(force: bool = False) -> str:
 	return so
 
 
+def _cpu_model() -> str:
+	try:
+		for line in open("/proc/cpuinfo"):
+			if line.startswith("model name"):
+				return line.split(":", 1)[1].strip()
+	except Exception:
+		pass
+	return "unknown"
+
+
+def build_fast() -> str:
+	"""Throughput build of the same sources (-O3 -march=native, FP contraction allowed) for the CPU baseline of bench.py.  It is
+	compiled on the machine that runs it (the marker file names the CPU it was built for): -march=native code must not travel."""
+	so = os.path.join(_HERE, "liboracle_fast.so")
+	tag = os.path.join(_HERE, "liboracle_fast.cpu")
+	srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.cpp", "sgm_oracle.cpp", "filter_oracle.cpp", "oracle.h")]
+	fresh = os.path.exists(so) and os.path.exists(tag) and open(tag).read() == _cpu_model() and all(
+		os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs)
+	if not fresh:
+		subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle_fast.so"])
+		open(tag, "w").write(_cpu_model())
+	return so
+
+
+_LIBS = {}
+_FAST = False
+
+
+def use_fast_build(on: bool) -> bool:
+	"""Route the calls of this module to the throughput build (True) or back to the parity build (False).  Returns True when
+	the fast build is in use.  Parity tests never call this: they run the -O2 -ffp-contract=off build."""
+	global _FAST, _LIB
+	if on:
+		try:
+			build_fast()
+		except Exception:
+			return False
+	_FAST = bool(on)
+	_LIB = None
+	return _FAST
+
+
 def lib():
 	global _LIB
 	if _LIB is None:
-		_LIB = C.CDLL(build())
-		_LIB.oracle_pm_score_pixel.restype = C.c_float
-		_LIB.oracle_interpolate_pixel.restype = C.c_float
+		key = "fast" if _FAST else "parity"
+		if key not in _LIBS:
+			L = C.CDLL(build_fast() if _FAST else build())
+			L.oracle_pm_score_pixel.restype = C.c_float
+			L.oracle_interpolate_pixel.restype = C.c_float
+			_LIBS[key] = L
+		_LIB = _LIBS[key]
 	return _LIB
 
 

@@ -21,6 +21,7 @@ MODES = [("register pipeline", dict(sgmAggregation=2)), ("bulk-copy ring, 8 laun
 	("wave fronts tilted FB 32 lag 1", dict(sgmAggregation=4, frontLag=1)), ("wave fronts tilted FB 32 lag 3", dict(sgmAggregation=4, frontLag=3)),
 	("wave fronts straight FB 16", dict(sgmAggregation=4, frontLayout=1)), ("wave fronts straight FB 32", dict(sgmAggregation=4, frontLayout=1, frontBlock=32)),
 	("wave fronts, 8 single passes", dict(sgmAggregation=4, frontLayout=2))]
+MODES.append(("tensor-core cost kernel + wave fronts", dict(sgmCost=2)))
 if len(sys.argv) > 2 and sys.argv[2] == "default":
 	MODES = MODES[2:3]
 for name, dbg in MODES:
@@ -35,4 +36,6 @@ for name, dbg in MODES:
 		ref = (accums.clone(), disp.clone())
 	else:
 		same = "| identical to the register pipeline: %s" % (torch.equal(ref[0], accums) and torch.equal(ref[1], disp))
+		if "sgmCost" in dbg:
+			same = "| disparities equal to the SIMT-cost run on %.4f of the pixels" % float((ref[1] == disp).float().mean())
 	print("D=%d %-46s" % (D, name), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same, flush=True)

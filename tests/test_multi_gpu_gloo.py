@@ -68,6 +68,22 @@ def _check(rank, world, n_views, multi_gpu):
 		for v in mine:
 			f = 1.0 if v % 3 == 0 else 2.0
 			ok = ok and float(fl[v]["depth"][0, 0]) == f*float(loc[v]["depth"][0, 0])
+		# ViewStack: preallocated stacks, estimates written into slices, collectives on the stacks (bench / scene path)
+		st = multi_gpu.ViewStack(n_views, 6, 8, torch.device("cpu"))
+		ok = ok and st.mine == mine and st.kmax == (n_views+world-1)//world
+		for v in mine:
+			m = st.maps(v)
+			m["depth"].fill_(10.0+v); m["normal"].fill_(0.25*v); m["conf"].fill_(0.5+v)
+		st.all_gather_depth()
+		ok = ok and all(float(st.depth_of(v)[0, 0]) == 10.0+v and st.depth_of(v).shape == (6, 8) for v in range(n_views))
+		for rep in range(2):   # the receive buffers are reused
+			g = st.gather(dst=0)
+			if rank == 0:
+				ok = ok and sorted(g.keys()) == list(range(n_views)) and all(
+					float(g[v]["depth"][0, 0]) == 10.0+v and float(g[v]["normal"][0, 0, 2]) == 0.25*v and float(g[v]["conf"][5, 7]) == 0.5+v for v in range(n_views))
+			else:
+				ok = ok and g is None
+		ok = ok and st.bytes_all_gather() == world*st.kmax*6*8*4
 		return bool(ok)
 
 

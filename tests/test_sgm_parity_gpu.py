@@ -43,6 +43,30 @@ def test_cost_volume_parity(sgm):
 	assert np.array_equal(g == 255, c == 255) or ((g == 255) != (c == 255)).mean() < 1e-4
 
 
+@pytest.mark.parametrize("num,dmin,w", [(128, 0, 403), (128, -40, 300), (64, 5, 261), (64, -70, 200)])
+def test_cost_volume_on_tensor_cores(sgm, num, dmin, w):
+	"""The banded-GEMM cost kernel (tcgen05, fp16 hi/lo split operands, fp32 accumulation in TMEM; sgm_cost_tc.cu) against the
+	oracle and against the SIMT kernel: within one uint8 level on a small fraction of the entries, out-of-image windows exact."""
+	m, O = sgm
+	h = 61
+	lg, lc, rg, d = synth.make_stereo_pair(w, h)
+	px, n = synth.sgm_pixel_map(w, h, dmin, dmin+num)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n, stage=1)
+	simt = torch.zeros(n, dtype=torch.uint8, device="cuda"); tc = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+	args = (_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n)
+	try:
+		m.SetDebug(sgmCost=1); m.MatchDevice(*args, stages=1, costs=simt)
+		m.SetDebug(sgmCost=2); m.MatchDevice(*args, stages=1, costs=tc)
+	finally:
+		m.SetDebug()
+	g = tc.cpu().numpy().astype(np.int32); s = simt.cpu().numpy().astype(np.int32)
+	for name, ref in (("oracle", c.astype(np.int32)), ("simt", s)):
+		diff = np.abs(g-ref)
+		assert diff.max() <= 1, (name, int(diff.max()), float((diff > 1).mean()))
+		assert (diff > 0).mean() < 5e-3, (name, float((diff > 0).mean()))
+	assert ((g == 255) != (c == 255)).mean() < 1e-4
+
+
 @pytest.mark.parametrize("ragged", [False, True])
 def test_aggregation_and_wta_bit_exact(sgm, ragged):
 	m, O = sgm
