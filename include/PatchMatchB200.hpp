@@ -54,6 +54,7 @@ public:
 		for (int i = 0; i < n; ++i) {
 			auto& v = depthData.images[i];
 			b200mvs_view& o = views[i];
+			o.image8 = nullptr; o.channels8 = o.bgr8 = o.stride8_bytes = 0;
 			o.image = v.image.template ptr<float>();
 			o.width = v.image.cols; o.height = v.image.rows; o.stride_bytes = (int)v.image.step[0];
 			copy9(v.camera.K.val, o.K); copy9(v.camera.R.val, o.R); copy3(v.camera.C.ptr(), o.C);
@@ -75,6 +76,41 @@ public:
 		check(b200mvs_estimate(ctx_, views.data(), n, depthData.dMin, depthData.dMax, geom_ ? nGeometricIter : -1,
 			depthData.depthMap.template ptr<float>(), depthData.normalMap.template ptr<float>(),
 			depthData.confMap.template ptr<float>(), depthData.viewsMap.template ptr<uint8_t>(), stats), "b200mvs_estimate");
+	}
+
+#ifdef _MVS_DEPTHMAP_H_
+	// The reference's own signature, PatchMatchCUDA::EstimateDepthMap(DepthData&) (PatchMatchCUDA.inl:108, called at
+	// SceneDensify.cpp:618-623): compiled when this header is included after libs/MVS/DepthMap.h.  It snapshots the
+	// MVS::OPTDENSE globals itself, so the reference's call sites compile unchanged with `PatchMatchB200* pmCUDA`.
+	// Like the reference's CUDA branch it does not receive the geometric iteration index; Init(true) selects the
+	// geometric-consistency pass (iteration 0 of the engine's numbering: only the random stream depends on it).
+	static OptDense SnapshotOPTDENSE() {
+		OptDense o;
+		o.nEstimationIters = (int)MVS::OPTDENSE::nEstimationIters;
+		o.nEstimationGeometricIters = (int)MVS::OPTDENSE::nEstimationGeometricIters;
+		o.nRandomIters = (int)MVS::OPTDENSE::nRandomIters;
+		o.nSubResolutionLevels = (int)MVS::OPTDENSE::nSubResolutionLevels;
+		o.fNCCThresholdKeep = MVS::OPTDENSE::fNCCThresholdKeep;
+		o.fDescriptorMinMagnitudeThreshold = MVS::OPTDENSE::fDescriptorMinMagnitudeThreshold;
+		o.fRandomDepthRatio = MVS::OPTDENSE::fRandomDepthRatio;
+		o.fRandomAngle1Range = MVS::OPTDENSE::fRandomAngle1Range;
+		o.fRandomAngle2Range = MVS::OPTDENSE::fRandomAngle2Range;
+		o.fRandomSmoothDepth = MVS::OPTDENSE::fRandomSmoothDepth;
+		o.fRandomSmoothNormal = MVS::OPTDENSE::fRandomSmoothNormal;
+		o.fRandomSmoothBonus = MVS::OPTDENSE::fRandomSmoothBonus;
+		o.fEstimationGeometricWeight = MVS::OPTDENSE::fEstimationGeometricWeight;
+		return o;
+	}
+	void EstimateDepthMap(MVS::DepthData& depthData) { EstimateDepthMap(depthData, SnapshotOPTDENSE(), 0, nullptr); }
+#endif
+
+	// Ignore-mask of the reference view for the following calls (OPTDENSE::nIgnoreMaskLabel >= 0; DepthEstimator::ImportIgnoreMask
+	// with pMask, libs/MVS/DepthMap.cpp:300-323, delivers it as an Image8U: 0 = ignored).  An empty mask clears it.
+	template <typename MASK>
+	void SetIgnoreMask(MASK& mask) {
+		if (!ctx_) throw std::runtime_error("PatchMatchB200 used after Release()");
+		if (mask.empty()) check(b200mvs_set_ignore_mask(ctx_, nullptr, 0, 0, 0, 0), "b200mvs_set_ignore_mask");
+		else check(b200mvs_set_ignore_mask(ctx_, mask.template ptr<uint8_t>(), mask.cols, mask.rows, (int)mask.step[0], 0), "b200mvs_set_ignore_mask");
 	}
 
 	// DepthMapsData::RemoveSmallSegments(DepthData&) (SceneDensify.cpp:810-900); the OPTDENSE values are

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200MVS_ABI_VERSION 3 /* struct layouts of this header; b200mvs_abi_version() returns the library's */
+#define B200MVS_ABI_VERSION 4 /* struct layouts of this header; b200mvs_abi_version() returns the library's */
 #define B200MVS_MAX_VIEWS 32 /* neighbours per reference view (MAX_VIEWS, PatchMatchCUDA.inl:35) */
 
 typedef struct b200mvs_ctx b200mvs_ctx;
@@ -49,6 +49,13 @@ typedef struct {
 	const float* depth;   /* nullable: enables the geometric term for this view */
 	int dwidth, dheight, dstride_bytes;
 	double Kd[9], Rd[9], Cd[3];
+	/* Alternative to `image` (used when image == NULL): the 8-bit colour image as cv::imread delivers it, converted on the
+	 * device with the reference's toGray(..., bNormalize = true) arithmetic (libs/Common/Types.inl:2377-2431, applied by
+	 * InitViews, SceneDensify.cpp:324,345).  The host path then uploads 3 bytes per pixel instead of 4. */
+	const uint8_t* image8; /* width x height x channels8, row-major */
+	int channels8;         /* 3 or 4 interleaved channels */
+	int bgr8;              /* != 0: B,G,R order (cv::imread); 0: R,G,B */
+	int stride8_bytes;     /* bytes between rows; 0 = width*channels8 */
 } b200mvs_view;
 
 /* Snapshot of the OPTDENSE knobs the estimator consumes (libs/MVS/DepthMap.cpp:69-114),
@@ -270,7 +277,10 @@ int b200mvs_filter_depth_map_device(b200mvs_ctx* ctx, const b200mvs_dmap* ref, c
 	float* projDepth, float* projConf, int* filtered, void* stream);
 
 /* RemoveSmallSegments(depthData): zero every 4-connected segment of similar depths
- * (threshold fDepthDiffThreshold*0.7) smaller than nSpeckleSize pixels; in place; normal / conf nullable. */
+ * (threshold fDepthDiffThreshold*0.7) smaller than nSpeckleSize pixels; in place; normal / conf nullable.
+ * Segments are the reference's: grown breadth-first from seeds in column-major order with the directed test
+ * IsDepthSimilar(current, neighbour) (SceneDensify.cpp:828-895).  The device form reads the (few) one-way edges back to
+ * resolve them on the host, so it synchronises `stream` once. */
 int b200mvs_remove_small_segments(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
 	float fDepthDiffThreshold, unsigned nSpeckleSize, b200mvs_stats* stats);
 int b200mvs_remove_small_segments_device(b200mvs_ctx* ctx, float* depth, float* normal, float* conf, int width, int height,
@@ -291,6 +301,15 @@ int b200mvs_gap_interpolation_device(b200mvs_ctx* ctx, float* depth, float* norm
  * DEVICE pointers: upload the 8-bit image once (3 B per pixel instead of 4) and convert in HBM; strides in bytes, 0 = packed. */
 int b200mvs_to_gray_device(b200mvs_ctx* ctx, const uint8_t* image, int width, int height, int stride_bytes, int channels, int bgr,
 	float* gray, int gray_stride_bytes, void* stream);
+
+/* DepthData::ViewData::ScaleImage (libs/MVS/DepthMap.h:193-203), applied by DepthMapsData::InitViews to a neighbour whose footprint
+ * scale differs from 1 by 15 % or more (SceneDensify.cpp:324-326,345-347): cv::resize(image, Size(), scale, scale,
+ * scale > 1 ? INTER_CUBIC : INTER_AREA) of the float gray image; the caller recomputes the camera for the new size
+ * (Image::GetCamera).  b200mvs_scaled_size gives the size cv::resize produces.  DEVICE pointers; `scaled` holds
+ * scaledWidth x scaledHeight contiguous floats.  *applied (nullable) = 0 when |scale - 1| < 0.15 (nothing written), else 1. */
+int b200mvs_scaled_size(int width, int height, float scale, int* scaledWidth, int* scaledHeight);
+int b200mvs_scale_image_device(b200mvs_ctx* ctx, const float* image, int width, int height, int stride_bytes, float scale,
+	float* scaled, int* applied, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,9 +69,13 @@ struct FltParams {
 };
 cudaError_t flt_launch_filter(const FltParams& P, int maxNbrPixels, bool adjust, cudaStream_t s);
 cudaError_t flt_launch_resolve(const unsigned long long* z, const float* nbrConf, size_t np, float* depth, float* conf, cudaStream_t s);
-cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, int H, float th, unsigned speckle, int* labels, int* sizes, cudaStream_t s);
+struct SegArc { int src, dst, srcSize, dstSize, srcKey, dstKey; };
+cudaError_t seg_launch_label(const float* depth, int W, int H, float th, int* labels, int* sizes, int* minKey, void* arcs, int* count, int cap, cudaStream_t s);
+cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, int H, unsigned speckle, const int* labels, int* sizes,
+	const int* patch, int nPatch, cudaStream_t s);
 cudaError_t gap_launch(float* depth, float* normal, float* conf, float* tDepth, float* tNormal, float* tConf, int W, int H, float th, int gap, cudaStream_t s);
 cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
+cudaError_t rs_launch_cubic(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, int dpitch, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s);
 cudaError_t rs_launch_nearest(const float* src, int sw, int sh, int ch, float* dst, int dw, int dh, double scx, double scy, cudaStream_t s);
 cudaError_t rs_launch_nearest_u8(const uint8_t* src, int sw, int sh, int spitch, uint8_t* dst, int dw, int dh, cudaStream_t s);
@@ -141,7 +145,7 @@ struct b200mvs_ctx {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	// grow-only device scratch
-	std::vector<DevBuf> imgs, dmaps;          // staged images / depth-maps (host API)
+	std::vector<DevBuf> imgs, dmaps, img8;    // staged images / depth-maps / 8-bit colour images (host API; gray images converted on the device)
 	std::vector<DevBuf> pyr;                  // per-view pyramid levels (all levels packed)
 	DevBuf plane, cost, best, prior, lowPlane;
 	DevBuf dDepth, dNormal, dConf, dViews;    // level scratch / staging of the maps (host API)
@@ -154,6 +158,7 @@ struct b200mvs_ctx {
 	const void* sgLastPx = nullptr; uint64_t sgLastNum = 0; // pixel map / size of the volume in sgAccums (b200mvs_sgm_refine_device check)
 	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
 	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
+	DevBuf ppK, ppArcs, ppPatch;              // RemoveSmallSegments: seed keys, one-way edges (+ counter), patched segment sizes
 	b200mvs_debug dbg;                        // diagnostic switches (b200mvs_set_debug); all zero = the shipped kernels
 	const uint8_t* mask = nullptr; int maskW = 0, maskH = 0, maskPitch = 0; // ignore-mask of the reference view (device) or null
 	DevBuf maskBuf, maskLevel;                // staged host mask, mask of the current pyramid level
@@ -246,9 +251,12 @@ int check_views(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews) {
 	if (!ctx) return B200MVS_ERR_ARG;
 	if (!views || nViews < 2 || nViews > B200MVS_MAX_VIEWS+1)
 		return fail(ctx, B200MVS_ERR_ARG, "need 2..33 views (reference first)");
-	for (int i = 0; i < nViews; ++i)
-		if (!views[i].image || views[i].width < 2*PM_HALF+2 || views[i].height < 2*PM_HALF+2)
+	for (int i = 0; i < nViews; ++i) {
+		if ((!views[i].image && !views[i].image8) || views[i].width < 2*PM_HALF+2 || views[i].height < 2*PM_HALF+2)
 			return fail(ctx, B200MVS_ERR_ARG, "view without image or image too small");
+		if (!views[i].image && views[i].channels8 != 3 && views[i].channels8 != 4)
+			return fail(ctx, B200MVS_ERR_ARG, "8-bit image needs 3 or 4 channels");
+	}
 	return B200MVS_OK;
 }
 
@@ -572,6 +580,7 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	if (c->stream) cudaStreamSynchronize(c->stream); // an enqueued asynchronous call may still use the buffers
 	for (auto& b: c->imgs) b.release();
 	for (auto& b: c->dmaps) b.release();
+	for (auto& b: c->img8) b.release();
 	for (auto& b: c->pyr) b.release();
 	c->refPad.release(); c->maskBuf.release(); c->maskLevel.release();
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
@@ -581,6 +590,7 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	c->sgFrontCtl.release(); c->sgFrontState.release(); c->sgFrontMeta.release();
 	c->fltZ.release(); c->fltIn.release(); c->fltOutD.release(); c->fltOutC.release();
 	c->ppA.release(); c->ppB.release(); c->ppD.release(); c->ppN.release(); c->ppC.release();
+	c->ppK.release(); c->ppArcs.release(); c->ppPatch.release();
 	c->plane.release(); c->cost.release(); c->best.release(); c->prior.release(); c->lowPlane.release();
 	c->dDepth.release(); c->dNormal.release(); c->dConf.release(); c->dViews.release(); c->mapD.release(); c->mapN.release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -641,11 +651,21 @@ int b200mvs_estimate_device(b200mvs_ctx* ctx, const b200mvs_view* views, int nVi
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
 	std::vector<DView> dv(nViews);
-	for (int i = 0; i < nViews; ++i)
-		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
-			views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
+	ctx->launches = 0;
+	for (int i = 0; i < nViews; ++i) {
+		const float* img = views[i].image; int pitch = views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width;
+		if (!img) {
+			// 8-bit colour image resident in HBM: toGray into the context's scratch
+			if ((int)ctx->imgs.size() < nViews) { ctx->imgs.resize(nViews); ctx->dmaps.resize(nViews); ctx->img8.resize(nViews); }
+			CK(ctx->imgs[i].reserve((size_t)views[i].width*views[i].height*sizeof(float)));
+			CK(rs_launch_to_gray(views[i].image8, views[i].width, views[i].height, views[i].stride8_bytes ? views[i].stride8_bytes : views[i].width*views[i].channels8,
+				views[i].channels8, views[i].bgr8 != 0, ctx->imgs[i].as<float>(), views[i].width, s)); ++ctx->launches;
+			img = ctx->imgs[i].as<float>(); pitch = views[i].width;
+		}
+		to_dview(views[i], img, pitch, views[i].depth, views[i].dstride_bytes ? views[i].dstride_bytes/4 : views[i].dwidth, dv[i]);
+	}
 	const auto t0 = std::chrono::steady_clock::now();
-	ctx->launches = 0; ctx->nSweepEv = 0; ctx->timeSweeps = stats != nullptr;
+	ctx->nSweepEv = 0; ctx->timeSweeps = stats != nullptr;
 	if (stats) CK(cudaEventRecord(ctx->ev0, s));
 	rc = estimate_on_device(ctx, dv.data(), nViews, dMin, dMax, nGeometricIter, depth, normal, conf, (uint32_t*)viewsMap, s);
 	if (rc) return rc;
@@ -675,15 +695,25 @@ int b200mvs_estimate_async(b200mvs_ctx* ctx, const b200mvs_view* views, int nVie
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t s = ctx->stream;
 	ctx->t0 = std::chrono::steady_clock::now();
-	if ((int)ctx->imgs.size() < nViews) { ctx->imgs.resize(nViews); ctx->dmaps.resize(nViews); }
+	if ((int)ctx->imgs.size() < nViews) { ctx->imgs.resize(nViews); ctx->dmaps.resize(nViews); ctx->img8.resize(nViews); }
 	std::vector<DView> dv(nViews);
 	uint64_t h2d = 0, d2h = 0;
+	ctx->launches = 0;
 	for (int i = 0; i < nViews; ++i) {
 		const b200mvs_view& v = views[i];
 		const size_t row = (size_t)v.width*sizeof(float);
 		CK(ctx->imgs[i].reserve(row*v.height));
-		CK(cudaMemcpy2DAsync(ctx->imgs[i].p, row, v.image, v.stride_bytes ? v.stride_bytes : row, row, v.height, cudaMemcpyHostToDevice, s));
-		h2d += row*v.height;
+		if (v.image) {
+			CK(cudaMemcpy2DAsync(ctx->imgs[i].p, row, v.image, v.stride_bytes ? v.stride_bytes : row, row, v.height, cudaMemcpyHostToDevice, s));
+			h2d += row*v.height;
+		} else {
+			// 8-bit colour image: upload channels8 bytes per pixel, convert on the device (toGray)
+			const size_t row8 = (size_t)v.width*v.channels8;
+			CK(ctx->img8[i].reserve(row8*v.height));
+			CK(cudaMemcpy2DAsync(ctx->img8[i].p, row8, v.image8, v.stride8_bytes ? v.stride8_bytes : row8, row8, v.height, cudaMemcpyHostToDevice, s));
+			h2d += row8*v.height;
+			CK(rs_launch_to_gray(ctx->img8[i].as<uint8_t>(), v.width, v.height, (int)row8, v.channels8, v.bgr8 != 0, ctx->imgs[i].as<float>(), v.width, s)); ++ctx->launches;
+		}
 		const float* dm = nullptr;
 		if (v.depth) {
 			const size_t drow = (size_t)v.dwidth*sizeof(float);
@@ -701,7 +731,7 @@ int b200mvs_estimate_async(b200mvs_ctx* ctx, const b200mvs_view* views, int nVie
 	CK(cudaMemcpyAsync(dD.p, depth, P0*sizeof(float), cudaMemcpyHostToDevice, s));
 	CK(cudaMemcpyAsync(dN.p, normal, P0*3*sizeof(float), cudaMemcpyHostToDevice, s));
 	h2d += P0*16;
-	ctx->launches = 0; ctx->nSweepEv = 0; ctx->timeSweeps = true;
+	ctx->nSweepEv = 0; ctx->timeSweeps = true;
 	CK(cudaEventRecord(ctx->ev0, s));
 	rc = estimate_on_device(ctx, dv.data(), nViews, dMin, dMax, nGeometricIter, dD.as<float>(), dN.as<float>(),
 		ctx->dConf.as<float>(), ctx->dViews.as<uint32_t>(), s);
@@ -747,9 +777,36 @@ int b200mvs_estimate(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	return b200mvs_sync(ctx, stats);
 }
 
+// Page-locks the caller's buffers for the duration of a batch: cudaMemcpyAsync from / to pageable memory blocks the host
+// (and serialises the contexts); already pinned or unregistrable ranges are left alone.
+namespace {
+struct PinGuard {
+	std::vector<void*> regs;
+	void add(const void* p, size_t bytes) {
+		if (!p || !bytes) return;
+		if (cudaHostRegister((void*)p, bytes, cudaHostRegisterPortable) == cudaSuccess) regs.push_back((void*)p);
+		else (void)cudaGetLastError(); // already registered (pinned by the caller, or shared between jobs): fine
+	}
+	~PinGuard() { for (void* p: regs) cudaHostUnregister(p); }
+};
+}
+
 int b200mvs_estimate_batch(b200mvs_ctx** ctxs, int nCtx, b200mvs_job* jobs, int nJobs) {
 	if (!ctxs || nCtx <= 0 || (!jobs && nJobs > 0) || nJobs < 0) return B200MVS_ERR_ARG;
 	for (int k = 0; k < nCtx; ++k) if (!ctxs[k]) return B200MVS_ERR_ARG;
+	PinGuard pin;
+	for (int j = 0; j < nJobs; ++j) {
+		const b200mvs_job& J = jobs[j];
+		if (!J.views || J.nViews <= 0) continue;
+		for (int i = 0; i < J.nViews; ++i) {
+			const b200mvs_view& v = J.views[i];
+			if (v.image) pin.add(v.image, (size_t)(v.stride_bytes ? v.stride_bytes : v.width*4)*v.height);
+			else if (v.image8) pin.add(v.image8, (size_t)(v.stride8_bytes ? v.stride8_bytes : v.width*v.channels8)*v.height);
+			if (v.depth) pin.add(v.depth, (size_t)(v.dstride_bytes ? v.dstride_bytes : v.dwidth*4)*v.dheight);
+		}
+		const size_t P0 = (size_t)J.views[0].width*J.views[0].height;
+		pin.add(J.depth, P0*4); pin.add(J.normal, P0*12); pin.add(J.conf, P0*4); pin.add(J.viewsMap, P0*4);
+	}
 	int first = B200MVS_OK;
 	std::vector<int> inflight(nCtx, -1); // job running on each context
 	auto drain = [&](int k) {
@@ -790,6 +847,8 @@ static int block_params(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews,
 	int rc = check_views(ctx, views, nViews);
 	if (rc) return rc;
 	if (!plane4 || !cost) return fail(ctx, B200MVS_ERR_ARG, "null state pointer");
+	for (int i = 0; i < nViews; ++i)
+		if (!views[i].image) return fail(ctx, B200MVS_ERR_ARG, "the building blocks take float gray images");
 	std::vector<DView> dv(nViews);
 	for (int i = 0; i < nViews; ++i)
 		to_dview(views[i], views[i].image, views[i].stride_bytes ? views[i].stride_bytes/4 : views[i].width,
@@ -1107,10 +1166,76 @@ int b200mvs_remove_small_segments_device(b200mvs_ctx* ctx, float* depth, float* 
 		return fail(ctx, B200MVS_ERR_ARG, "remove_small_segments: invalid argument");
 	CK(cudaSetDevice(ctx->device));
 	const size_t n = (size_t)width*height;
-	CK(ctx->ppA.reserve(n*4)); CK(ctx->ppB.reserve(n*4));
-	CK(seg_launch_remove(depth, normal, conf, width, height, fDepthDiffThreshold*0.7f, nSpeckleSize, ctx->ppA.as<int>(), ctx->ppB.as<int>(),
-		stream ? (cudaStream_t)stream : ctx->stream));
-	{ int rounds = 1; while ((1<<rounds) < width+height) ++rounds; ctx->launches = 4+2*rounds; }
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	const float th = fDepthDiffThreshold*0.7f;
+	const int cap = 1<<18;   // one-way edges kept (a 1080p map has tens); beyond it the call fails loudly
+	CK(ctx->ppA.reserve(n*4)); CK(ctx->ppB.reserve(n*4)); CK(ctx->ppK.reserve(n*4));
+	CK(ctx->ppArcs.reserve(sizeof(int)*4 + (size_t)cap*sizeof(SegArc)));
+	int* count = ctx->ppArcs.as<int>();
+	SegArc* arcs = (SegArc*)(ctx->ppArcs.as<int>()+4);
+	CK(seg_launch_label(depth, width, height, th, ctx->ppA.as<int>(), ctx->ppB.as<int>(), ctx->ppK.as<int>(), arcs, count, cap, s));
+	// the condensed graph is resolved on the host: one small read-back (the call synchronises the stream)
+	int nArcs = 0;
+	CK(cudaMemcpyAsync(&nArcs, count, sizeof(int), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	if (nArcs > cap) return fail(ctx, B200MVS_ERR_ARG, "remove_small_segments: too many direction-dependent edges in the depth-map");
+	int nPatch = 0;
+	if (nArcs > 0) {
+		std::vector<SegArc> h(nArcs);
+		CK(cudaMemcpyAsync(h.data(), arcs, (size_t)nArcs*sizeof(SegArc), cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		// nodes: the components an arc touches; replay of the reference's loop (SceneDensify.cpp:828-895) on them
+		struct Node { int label, size, key; std::vector<int> out; int seg = -1; };
+		std::vector<Node> nodes;
+		std::vector<std::pair<int, int>> index; // (label, node)
+		auto node_of = [&](int label, int size, int key) {
+			for (auto& p: index) if (p.first == label) return p.second;  // few nodes: linear search is fine ...
+			index.push_back({label, (int)nodes.size()});
+			Node nd; nd.label = label; nd.size = size; nd.key = key; nodes.push_back(nd);
+			return (int)nodes.size()-1;
+		};
+		if (nArcs > 4096) {  // ... but not for pathological maps: sort once and search
+			std::sort(h.begin(), h.end(), [](const SegArc& a, const SegArc& b) { return a.src != b.src ? a.src < b.src : a.dst < b.dst; });
+		}
+		std::vector<std::pair<int, int>> sortedIndex;
+		if (nArcs > 4096) {
+			std::vector<std::pair<int, std::pair<int, int>>> all; // label -> (size, key)
+			for (auto& a: h) { all.push_back({a.src, {a.srcSize, a.srcKey}}); all.push_back({a.dst, {a.dstSize, a.dstKey}}); }
+			std::sort(all.begin(), all.end());
+			all.erase(std::unique(all.begin(), all.end(), [](const auto& x, const auto& y) { return x.first == y.first; }), all.end());
+			for (auto& e: all) { Node nd; nd.label = e.first; nd.size = e.second.first; nd.key = e.second.second; sortedIndex.push_back({e.first, (int)nodes.size()}); nodes.push_back(nd); }
+		}
+		auto find_node = [&](int label, int size, int key) {
+			if (sortedIndex.empty()) return node_of(label, size, key);
+			return std::lower_bound(sortedIndex.begin(), sortedIndex.end(), std::make_pair(label, -1))->second;
+		};
+		for (auto& a: h) {
+			const int u = find_node(a.src, a.srcSize, a.srcKey), v = find_node(a.dst, a.dstSize, a.dstKey);
+			nodes[u].out.push_back(v);
+		}
+		std::vector<int> order(nodes.size());
+		for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+		std::sort(order.begin(), order.end(), [&](int a, int b) { return nodes[a].key < nodes[b].key; });
+		std::vector<int> patch; std::vector<int> stack, members;
+		for (int seed: order) {
+			if (nodes[seed].seg >= 0) continue;
+			// the segment grown from this seed: every unvisited component reachable along one-way edges
+			long long total = 0;
+			stack.assign(1, seed); members.clear(); nodes[seed].seg = seed;
+			while (!stack.empty()) {
+				const int u = stack.back(); stack.pop_back();
+				members.push_back(u); total += nodes[u].size;
+				for (int v: nodes[u].out) if (nodes[v].seg < 0) { nodes[v].seg = seed; stack.push_back(v); }
+			}
+			for (int u: members) { patch.push_back(nodes[u].label); patch.push_back((int)std::min<long long>(total, 0x7FFFFFFF)); }
+		}
+		nPatch = (int)patch.size()/2;
+		CK(ctx->ppPatch.reserve(patch.size()*sizeof(int)));
+		CK(cudaMemcpyAsync(ctx->ppPatch.p, patch.data(), patch.size()*sizeof(int), cudaMemcpyHostToDevice, s));
+		CK(cudaStreamSynchronize(s)); // `patch` is a local
+	}
+	CK(seg_launch_remove(depth, normal, conf, width, height, nSpeckleSize, ctx->ppA.as<int>(), ctx->ppB.as<int>(), ctx->ppPatch.as<int>(), nPatch, s));
+	{ int rounds = 1; while ((1<<rounds) < width+height) ++rounds; ctx->launches = 5+2*rounds+(nPatch > 0 ? 1 : 0); }
 	return B200MVS_OK;
 }
 
@@ -1188,6 +1313,35 @@ int b200mvs_to_gray_device(b200mvs_ctx* ctx, const uint8_t* image, int width, in
 	CK(cudaSetDevice(ctx->device));
 	CK(rs_launch_to_gray(image, width, height, stride_bytes, channels, bgr != 0, gray, gray_stride_bytes/4, stream ? (cudaStream_t)stream : ctx->stream));
 	ctx->launches = 1;
+	return B200MVS_OK;
+}
+
+// DepthData::ViewData::ScaleImage (libs/MVS/DepthMap.h:193-203): a neighbour whose footprint differs from the reference's by
+// 15 % or more is resampled by `scale` — cv::resize(image, Size(), scale, scale, scale > 1 ? INTER_CUBIC : INTER_AREA)
+int b200mvs_scaled_size(int width, int height, float scale, int* scaledWidth, int* scaledHeight) {
+	if (!scaledWidth || !scaledHeight || width <= 0 || height <= 0 || !(scale > 0)) return B200MVS_ERR_ARG;
+	// cv::resize with dsize = Size(): saturate_cast<int>(src.cols * fx) = cvRound
+	*scaledWidth = (int)std::nearbyint(width*(double)scale); *scaledHeight = (int)std::nearbyint(height*(double)scale);
+	return B200MVS_OK;
+}
+int b200mvs_scale_image_device(b200mvs_ctx* ctx, const float* image, int width, int height, int stride_bytes, float scale,
+	float* scaled, int* applied, void* stream)
+{
+	if (!ctx) return B200MVS_ERR_ARG;
+	if (!image || !scaled || width <= 0 || height <= 0 || !(scale > 0) || (stride_bytes & 3))
+		return fail(ctx, B200MVS_ERR_ARG, "scale_image: null pointer, empty image, scale <= 0 or stride not a multiple of 4");
+	if (applied) *applied = 0;
+	if (std::fabs(scale-1.f) < 0.15f) return B200MVS_OK;  // !NeedScaleImage: the caller keeps the image and its camera
+	int dw, dh; b200mvs_scaled_size(width, height, scale, &dw, &dh);
+	if (dw <= 0 || dh <= 0) return fail(ctx, B200MVS_ERR_ARG, "scale_image: scaled image is empty");
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	const int pitch = stride_bytes ? stride_bytes/4 : width;
+	const double inv = 1.0/(double)scale;
+	if (scale > 1.f) CK(rs_launch_cubic(image, width, height, pitch, scaled, dw, dh, dw, inv, inv, s));
+	else CK(rs_launch_area(image, width, height, pitch, scaled, dw, dh, inv, inv, s));
+	ctx->launches = 1;
+	if (applied) *applied = 1;
 	return B200MVS_OK;
 }
 

@@ -186,17 +186,23 @@ __global__ void flt_resolve_kernel(const unsigned long long* z, const float* nbr
 }
 
 // ---- RemoveSmallSegments: connected components over the 4-neighbour grid ----
-// The reference grows segments breadth-first with a DIRECTED test IsDepthSimilar(current, neighbour);
-// an edge is taken here when the test holds in either direction (|a-b|/min(a,b) < th).  The two
-// differ only for pairs whose relative difference lies within th^2 of the threshold, where the
-// reference's own result depends on its traversal order.
+// The reference grows segments breadth-first, seeds in column-major order, with a DIRECTED test
+// IsDepthSimilar(current, neighbour) = |d0-d1|/d0 < th (SceneDensify.cpp:810-900).  Where a pair passes in both directions the
+// segment does not depend on the order; where it passes in one direction only (relative difference within th^2 of the threshold)
+// it does.  Exact parallel form:
+//   1. label the components over TWO-WAY edges (every breadth-first segment is a union of such components);
+//   2. list the one-way edges between different components ("arcs": a handful per map) with the sizes and the first pixel (in the
+//      reference's seed order) of the components they join;
+//   3. replay the reference's loop on that condensed graph on the host — components in seed order, a segment = every
+//      not-yet-visited component reachable along arcs — and patch the sizes of the components involved;
+//   4. remove the pixels whose segment is smaller than nSpeckleSize.
 // Labelling: every pixel first links to its left (else upper) connected neighbour — a region that is
 // reasonably convex becomes one tree: row runs hang on their first pixel, which hangs on the row above —
 // pointer jumping flattens these chains in ceil(log2(W+H)) rounds, the upper edges the links did not
 // take are merged by an atomicMin union on the flat trees (mostly "same root already"), and a second
 // series of jumps flattens whatever chains of roots the unions built.
 __device__ __forceinline__ bool seg_edge(float a, float b, float th) {
-	return b > 0 && (depth_similar(a, b, th) || depth_similar(b, a, th));
+	return b > 0 && depth_similar(a, b, th) && depth_similar(b, a, th);
 }
 __device__ __forceinline__ int uf_find(int* L, int i) {
 	int p;
@@ -212,7 +218,7 @@ __device__ void uf_union(int* L, int a, int b) {
 		else done = true;
 	} while (!done);
 }
-__global__ void seg_init_kernel(const float* __restrict__ depth, int* L, int* size, int W, int H, float th) {
+__global__ void seg_init_kernel(const float* __restrict__ depth, int* L, int* size, int* minKey, int W, int H, float th) {
 	const int x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y*blockDim.y+threadIdx.y;
 	if (x >= W || y >= H) return;
 	const int i = y*W+x;
@@ -225,6 +231,7 @@ __global__ void seg_init_kernel(const float* __restrict__ depth, int* L, int* si
 	}
 	L[i] = l;
 	size[i] = 0;
+	minKey[i] = 0x7FFFFFFF;
 }
 __global__ void seg_jump_kernel(int* L, int n) {
 	const int i = blockIdx.x*blockDim.x+threadIdx.x;
@@ -241,16 +248,49 @@ __global__ void seg_merge_kernel(const float* __restrict__ depth, int* L, int W,
 	// the link went left; the upper edge is still open
 	if (seg_edge(a, depth[i-1], th) && seg_edge(a, depth[i-W], th)) uf_union(L, i, i-W);
 }
-__global__ void seg_count_kernel(int* L, int* size, int n) {
+// sizes of the components and their first pixel in the reference's seed order (x outer, y inner: key = x*H + y)
+__global__ void seg_count_kernel(int* L, int* size, int* minKey, int W, int H) {
+	const int n = W*H;
 	const int i = blockIdx.x*blockDim.x+threadIdx.x;
-	int r = -1;
+	int r = -1, key = 0x7FFFFFFF;
 	if (i < n && L[i] >= 0) {
 		r = uf_find(L, i);
 		L[i] = r;                   // roots keep L[r] == r, so concurrent finds stay correct
+		key = (i%W)*H + i/W;
 	}
 	// one atomic per distinct root in the warp (large segments would otherwise serialise on one address)
 	const unsigned peers = __match_any_sync(0xFFFFFFFFu, r);
-	if (r >= 0 && (threadIdx.x&31) == __ffs(peers)-1) atomicAdd(size+r, __popc(peers));
+	const int kmin = __reduce_min_sync(peers, key);
+	if (r >= 0 && (threadIdx.x&31) == __ffs(peers)-1) { atomicAdd(size+r, __popc(peers)); atomicMin(minKey+r, kmin); }
+}
+// one-way edges between different two-way components: arcs[k] = {source label, target label, sizes, seed keys}
+struct SegArc { int src, dst, srcSize, dstSize, srcKey, dstKey; };
+__global__ void seg_arcs_kernel(const float* __restrict__ depth, const int* __restrict__ L, const int* __restrict__ size, const int* __restrict__ minKey,
+	int W, int H, float th, SegArc* arcs, int* count, int cap)
+{
+	const int x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y*blockDim.y+threadIdx.y;
+	if (x >= W || y >= H) return;
+	const int i = y*W+x;
+	const float a = depth[i];
+	if (!(a > 0)) return;
+	#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		if (k == 0 ? x+1 >= W : y+1 >= H) continue;
+		const int j = k == 0 ? i+1 : i+W;
+		const float b = depth[j];
+		if (!(b > 0)) continue;
+		const bool ab = depth_similar(a, b, th), ba = depth_similar(b, a, th);
+		if (ab == ba) continue;
+		const int li = L[i], lj = L[j];
+		if (li == lj) continue;
+		const int src = ab ? li : lj, dst = ab ? lj : li;
+		const int slot = atomicAdd(count, 1);
+		if (slot < cap) arcs[slot] = SegArc{src, dst, size[src], size[dst], minKey[src], minKey[dst]};
+	}
+}
+__global__ void seg_patch_kernel(const int2* __restrict__ patch, int n, int* size) {
+	const int i = blockIdx.x*blockDim.x+threadIdx.x;
+	if (i < n) size[patch[i].x] = patch[i].y;
 }
 __global__ void seg_remove_kernel(const int* L, const int* size, int n, unsigned speckle, float* depth, float* normal, float* conf) {
 	const int i = blockIdx.x*blockDim.x+threadIdx.x;
@@ -330,10 +370,12 @@ cudaError_t flt_launch_resolve(const unsigned long long* z, const float* nbrConf
 	return cudaGetLastError();
 }
 
-cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, int H, float th, unsigned speckle, int* labels, int* sizes, cudaStream_t s) {
+// phase 1: two-way components, their sizes / seed keys, the arcs; *count (device) receives the number of arcs found
+cudaError_t seg_launch_label(const float* depth, int W, int H, float th, int* labels, int* sizes, int* minKey, void* arcs, int* count, int cap, cudaStream_t s) {
 	const int n = W*H;
 	const dim3 b2(32, 8), g2((W+31)/32, (H+7)/8);
-	seg_init_kernel<<<g2, b2, 0, s>>>(depth, labels, sizes, W, H, th);
+	cudaMemsetAsync(count, 0, sizeof(int), s);
+	seg_init_kernel<<<g2, b2, 0, s>>>(depth, labels, sizes, minKey, W, H, th);
 	int rounds = 1;
 	while ((1<<rounds) < W+H) ++rounds;
 	for (int r = 0; r < rounds; ++r)
@@ -341,7 +383,15 @@ cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, i
 	seg_merge_kernel<<<g2, b2, 0, s>>>(depth, labels, W, H, th);
 	for (int r = 0; r < rounds; ++r)
 		seg_jump_kernel<<<(n+255)/256, 256, 0, s>>>(labels, n);
-	seg_count_kernel<<<(n+255)/256, 256, 0, s>>>(labels, sizes, n);
+	seg_count_kernel<<<(n+255)/256, 256, 0, s>>>(labels, sizes, minKey, W, H);
+	seg_arcs_kernel<<<g2, b2, 0, s>>>(depth, labels, sizes, minKey, W, H, th, (SegArc*)arcs, count, cap);
+	return cudaGetLastError();
+}
+// phase 2: sizes of the components the arcs join replaced by the sizes of their breadth-first segments, then the removal
+cudaError_t seg_launch_remove(float* depth, float* normal, float* conf, int W, int H, unsigned speckle, const int* labels, int* sizes,
+	const int* patch, int nPatch, cudaStream_t s) {
+	const int n = W*H;
+	if (nPatch > 0) seg_patch_kernel<<<(nPatch+255)/256, 256, 0, s>>>((const int2*)patch, nPatch, sizes);
 	seg_remove_kernel<<<(n+255)/256, 256, 0, s>>>(labels, sizes, n, speckle, depth, normal, conf);
 	return cudaGetLastError();
 }

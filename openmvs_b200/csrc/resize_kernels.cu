@@ -117,6 +117,36 @@ __global__ void plane_up_kernel(const float4* __restrict__ src, int sw, int sh, 
 	prior[(size_t)y*dw+x] = d;
 }
 
+// cv::resize(..., INTER_CUBIC) of a float image (ViewData::ScaleImage with scale > 1, DepthMap.h:197-203): OpenCV's bicubic
+// kernel (A = -0.75), source coordinate (d + 0.5) * scale - 0.5, taps clamped to the image, horizontal pass then vertical pass,
+// all in float like cv::resize's generic float path
+__device__ __forceinline__ void cubic_taps(int d, int ssize, double scale, int* idx, float* cf) {
+	float f = (float)((d+0.5)*scale-0.5);
+	const int s = (int)floorf(f);
+	f -= s;
+	const float A = -0.75f;
+	cf[0] = ((A*(f+1.f) - 5.f*A)*(f+1.f) + 8.f*A)*(f+1.f) - 4.f*A;
+	cf[1] = ((A+2.f)*f - (A+3.f))*f*f + 1.f;
+	cf[2] = ((A+2.f)*(1.f-f) - (A+3.f))*(1.f-f)*(1.f-f) + 1.f;
+	cf[3] = 1.f - cf[0] - cf[1] - cf[2];
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) idx[k] = min(max(s-1+k, 0), ssize-1);
+}
+__global__ void resize_cubic_kernel(const float* __restrict__ src, int sw, int sh, int spitch, float* __restrict__ dst, int dw, int dh, int dpitch, double scx, double scy) {
+	const int x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y;
+	if (x >= dw || y >= dh) return;
+	int ix[4], iy[4]; float cx[4], cy[4];
+	cubic_taps(x, sw, scx, ix, cx);
+	cubic_taps(y, sh, scy, iy, cy);
+	float rows[4];
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const float* r = src + (size_t)iy[k]*spitch;
+		rows[k] = __ldg(r+ix[0])*cx[0] + __ldg(r+ix[1])*cx[1] + __ldg(r+ix[2])*cx[2] + __ldg(r+ix[3])*cx[3];
+	}
+	dst[(size_t)y*dpitch+x] = rows[0]*cy[0] + rows[1]*cy[1] + rows[2]*cy[2] + rows[3]*cy[3];
+}
+
 inline dim3 grid2(int w, int h, dim3 b) { return dim3((w+b.x-1)/b.x, (h+b.y-1)/b.y); }
 
 } // namespace
@@ -130,6 +160,11 @@ cudaError_t rs_launch_area(const float* src, int sw, int sh, int spitch, float* 
 	const bool integer = (double)ix == scx && (double)iy == scy;
 	dim3 b(32, 8);
 	resize_area_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, spitch, dst, dw, dh, scx, scy, integer ? ix : 0, integer ? iy : 0);
+	return cudaGetLastError();
+}
+cudaError_t rs_launch_cubic(const float* src, int sw, int sh, int spitch, float* dst, int dw, int dh, int dpitch, double scx, double scy, cudaStream_t s) {
+	dim3 b(32, 8);
+	resize_cubic_kernel<<<grid2(dw, dh, b), b, 0, s>>>(src, sw, sh, spitch, dst, dw, dh, dpitch, scx, scy);
 	return cudaGetLastError();
 }
 cudaError_t rs_launch_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t s) {

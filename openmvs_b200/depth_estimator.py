@@ -86,10 +86,11 @@ class Camera:
 @dataclasses.dataclass
 class ViewData:
 	"""DepthData::ViewData: gray float image in [0,1] + camera (+ known depth-map and its camera)."""
-	image: object            # (H, W) float32 numpy array or torch CUDA tensor
+	image: object            # (H, W) float32 gray image, or the (H, W, 3|4) uint8 colour image (converted on the device); numpy or torch CUDA
 	camera: Camera
 	depthMap: object = None  # optional (H, W) float32
 	cameraDepthMap: Optional[Camera] = None
+	bgr: bool = True         # channel order of a uint8 colour image: B,G,R as cv::imread delivers (False: R,G,B)
 
 
 @dataclasses.dataclass
@@ -151,18 +152,33 @@ def _make_views(images: List[ViewData]):
 			raise ValueError("mixing host and device images in one DepthData")
 		if dev:
 			img = v.image
-			if img.dtype.__str__() != "torch.float32" or not img.is_cuda or img.dim() != 2 or img.stride(1) != 1:
-				raise ValueError("device image must be a 2-D float32 CUDA tensor with unit column stride")
-			if img.device != images[0].image.device:
-				raise ValueError("all views of a DepthData must live on the same device")
-			keep.append(img)
-			o.image = img.data_ptr(); o.height, o.width = img.shape; o.stride_bytes = img.stride(0)*4
+			if not img.is_cuda or img.device != images[0].image.device:
+				raise ValueError("all views of a DepthData must live on the same CUDA device")
+			if img.dtype.__str__() == "torch.uint8":
+				# 8-bit colour image: toGray runs on the device inside the call
+				if img.dim() != 3 or img.shape[2] not in (3, 4) or img.stride(2) != 1 or img.stride(1) != img.shape[2]:
+					raise ValueError("device colour image must be a (H, W, 3|4) uint8 CUDA tensor with packed pixels")
+				keep.append(img)
+				o.image = None; o.image8 = img.data_ptr(); o.height, o.width, o.channels8 = (int(x) for x in img.shape)
+				o.stride8_bytes = img.stride(0); o.bgr8 = int(bool(v.bgr))
+			else:
+				if img.dtype.__str__() != "torch.float32" or img.dim() != 2 or img.stride(1) != 1:
+					raise ValueError("device image must be a 2-D float32 CUDA tensor with unit column stride")
+				keep.append(img)
+				o.image = img.data_ptr(); o.height, o.width = img.shape; o.stride_bytes = img.stride(0)*4
 		else:
 			img = np.asarray(v.image)
-			if img.dtype != np.float32 or img.ndim != 2 or img.strides[1] != 4:
-				raise ValueError("image must be a 2-D float32 array with contiguous rows (Image32F)")
-			keep.append(img)
-			o.image = img.ctypes.data; o.height, o.width = img.shape; o.stride_bytes = img.strides[0]
+			if img.dtype == np.uint8:
+				if img.ndim != 3 or img.shape[2] not in (3, 4) or img.strides[2] != 1 or img.strides[1] != img.shape[2]:
+					raise ValueError("colour image must be a (H, W, 3|4) uint8 array with packed pixels (Image8U3)")
+				keep.append(img)
+				o.image = None; o.image8 = img.ctypes.data; o.height, o.width, o.channels8 = img.shape
+				o.stride8_bytes = img.strides[0]; o.bgr8 = int(bool(v.bgr))
+			else:
+				if img.dtype != np.float32 or img.ndim != 2 or img.strides[1] != 4:
+					raise ValueError("image must be a 2-D float32 array with contiguous rows (Image32F)")
+				keep.append(img)
+				o.image = img.ctypes.data; o.height, o.width = img.shape; o.stride_bytes = img.strides[0]
 		o.K[:] = np.asarray(v.camera.K, np.float64).ravel()
 		o.R[:] = np.asarray(v.camera.R, np.float64).ravel()
 		o.C[:] = np.asarray(v.camera.C, np.float64).ravel()
@@ -226,6 +242,22 @@ class PatchMatchB200:
 		_lib.check(self._lib, self._ctx, rc, "b200mvs_to_gray_device")
 		return out
 
+	def ScaleImage(self, image, scale: float):
+		"""DepthData::ViewData::ScaleImage (libs/MVS/DepthMap.h:193-203) on the device: float32 CUDA tensor (H, W) ->
+		cv::resize(image, Size(), scale, scale, scale > 1 ? INTER_CUBIC : INTER_AREA), or None when |scale - 1| < 0.15
+		(the reference keeps the image then)."""
+		import torch
+		if not (_is_torch(image) and image.is_cuda and image.dtype == torch.float32 and image.dim() == 2 and image.stride(1) == 1):
+			raise ValueError("ScaleImage needs a 2-D float32 CUDA tensor with unit column stride")
+		h, w = (int(v) for v in image.shape)
+		dw, dh, ok = C.c_int(), C.c_int(), C.c_int()
+		self._lib.b200mvs_scaled_size(w, h, C.c_float(scale), C.byref(dw), C.byref(dh))
+		out = torch.empty((max(dh.value, 1), max(dw.value, 1)), dtype=torch.float32, device=image.device)
+		rc = self._lib.b200mvs_scale_image_device(self._ctx, image.data_ptr(), w, h, image.stride(0)*4, C.c_float(scale), out.data_ptr(),
+			C.byref(ok), C.c_void_p(_stream_handle(image.device)))
+		_lib.check(self._lib, self._ctx, rc, "b200mvs_scale_image_device")
+		return out if ok.value else None
+
 	def _set_params(self):
 		p = OPTDENSE.snapshot()
 		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_params(self._ctx, C.byref(p)), "b200mvs_set_params")
@@ -268,7 +300,7 @@ class PatchMatchB200:
 			nGeometricIter = 0 if self.bGeomConsistency else -1
 		self._set_params()
 		arr, keep, dev = _make_views(depthData.images)
-		h, w = depthData.images[0].image.shape
+		h, w = depthData.images[0].image.shape[:2]
 		if dev:
 			import torch
 			t0 = depthData.images[0].image
@@ -364,7 +396,7 @@ def EstimateDepthMapsBatch(arrDepthData: List[DepthData], engines: List["PatchMa
 		arr, k, dev = _make_views(dd.images)
 		if dev:
 			raise ValueError("the batch call takes host buffers")
-		h, w = dd.images[0].image.shape
+		h, w = dd.images[0].image.shape[:2]
 		dd.depthMap = np.zeros((h, w), np.float32) if dd.depthMap is None else np.ascontiguousarray(dd.depthMap, np.float32)
 		dd.normalMap = np.zeros((h, w, 3), np.float32) if dd.normalMap is None else np.ascontiguousarray(dd.normalMap, np.float32)
 		dd.confMap = np.zeros((h, w), np.float32); dd.viewsMap = np.zeros((h, w, 4), np.uint8)

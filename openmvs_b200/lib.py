@@ -8,7 +8,7 @@ import os
 from . import build as _build
 
 MAX_VIEWS = 32
-ABI_VERSION = 3  # B200MVS_ABI_VERSION of include/b200mvs.h these structs mirror
+ABI_VERSION = 4  # B200MVS_ABI_VERSION of include/b200mvs.h these structs mirror
 
 
 class View(C.Structure):
@@ -16,7 +16,8 @@ class View(C.Structure):
 	_fields_ = [("image", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("stride_bytes", C.c_int),
 		("K", C.c_double*9), ("R", C.c_double*9), ("C", C.c_double*3),
 		("depth", C.c_void_p), ("dwidth", C.c_int), ("dheight", C.c_int), ("dstride_bytes", C.c_int),
-		("Kd", C.c_double*9), ("Rd", C.c_double*9), ("Cd", C.c_double*3)]
+		("Kd", C.c_double*9), ("Rd", C.c_double*9), ("Cd", C.c_double*3),
+		("image8", C.c_void_p), ("channels8", C.c_int), ("bgr8", C.c_int), ("stride8_bytes", C.c_int)]
 
 
 class Params(C.Structure):
@@ -83,7 +84,7 @@ SYMBOLS = [
 	"b200mvs_filter_default_params", "b200mvs_filter_depth_map", "b200mvs_filter_depth_map_device",
 	"b200mvs_remove_small_segments", "b200mvs_remove_small_segments_device",
 	"b200mvs_gap_interpolation", "b200mvs_gap_interpolation_device",
-	"b200mvs_to_gray_device",
+	"b200mvs_to_gray_device", "b200mvs_scaled_size", "b200mvs_scale_image_device",
 ]
 
 _LIB = None
@@ -145,6 +146,8 @@ def load(build_if_missing: bool = True):
 	lib.b200mvs_gap_interpolation.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, C.POINTER(Stats)]
 	lib.b200mvs_gap_interpolation_device.argtypes = [P, P, P, P, C.c_int, C.c_int, F, C.c_uint, P]
 	lib.b200mvs_to_gray_device.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, P]
+	lib.b200mvs_scaled_size.argtypes = [C.c_int, C.c_int, F, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+	lib.b200mvs_scale_image_device.argtypes = [P, P, C.c_int, C.c_int, C.c_int, F, P, C.POINTER(C.c_int), P]
 	_LIB = lib
 	return lib
 

@@ -1,10 +1,12 @@
 // Drives include/PatchMatchB200.hpp with a minimal stand-in for MVS::DepthData (the reference's
 // type needs OpenCV/Eigen, absent here).  Reads a scene dumped by tests/test_cpp_adapter.py,
 // runs EstimateDepthMap through the adapter and writes the maps back.
-#include "../../include/PatchMatchB200.hpp"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
+#include <vector>
+#include <algorithm>
 
 // the slice of cv::Mat the adapter touches
 template <typename T, int CH = 1>
@@ -19,11 +21,23 @@ struct Mat3 { double val[9]; };
 struct Pt3 { double v[3]; const double* ptr() const { return v; } };
 struct Camera { Mat3 K, R; Pt3 C; };
 struct ViewData { Mat<float> image; Camera camera; Mat<float> depthMap; Camera cameraDepthMap; };
+// the reference's names, so that the adapter's PatchMatchCUDA-signature overload EstimateDepthMap(MVS::DepthData&) compiles as it
+// would after `#include "DepthMap.h"`: MVS::DepthData and the MVS::OPTDENSE globals it snapshots (libs/MVS/DepthMap.h:88-142)
+#define _MVS_DEPTHMAP_H_
+namespace MVS {
 struct DepthData {
 	std::vector<ViewData> images;
 	Mat<float> depthMap; Mat<float, 3> normalMap; Mat<float> confMap; Mat<uint8_t, 4> viewsMap;
 	float dMin, dMax;
 };
+namespace OPTDENSE {
+unsigned nEstimationIters = 3, nEstimationGeometricIters = 2, nRandomIters = 6, nSubResolutionLevels = 2;
+float fNCCThresholdKeep = 0.9f, fDescriptorMinMagnitudeThreshold = 0.02f, fRandomDepthRatio = 0.003f, fRandomAngle1Range = 16.f,
+	fRandomAngle2Range = 10.f, fRandomSmoothDepth = 0.02f, fRandomSmoothNormal = 13.f, fRandomSmoothBonus = 0.93f, fEstimationGeometricWeight = 0.1f;
+}
+}
+using MVS::DepthData;
+#include "../../include/PatchMatchB200.hpp"
 
 int main(int argc, char** argv) {
 	if (argc < 3) { fprintf(stderr, "usage: adapter_main scene.bin out.bin [iters]\n"); return 64; }
@@ -47,7 +61,14 @@ int main(int argc, char** argv) {
 		opt.nSubResolutionLevels = 0; opt.nEstimationGeometricIters = 0;
 		opt.nEstimationIters = argc > 3 ? atoi(argv[3]) : 2;
 		b200mvs_stats st;
-		pm.EstimateDepthMap(dd, opt, 0, &st);
+		if (argc > 4 && !strcmp(argv[4], "seam")) {
+			// the reference's call site, unchanged: pmCUDA->EstimateDepthMap(depthData) with the OPTDENSE globals
+			MVS::OPTDENSE::nSubResolutionLevels = 0; MVS::OPTDENSE::nEstimationGeometricIters = 0;
+			MVS::OPTDENSE::nEstimationIters = (unsigned)opt.nEstimationIters;
+			pm.EstimateDepthMap(dd);
+			memset(&st, 0, sizeof(st));
+		} else
+			pm.EstimateDepthMap(dd, opt, 0, &st);
 		printf("adapter: %dx%d, %d launches, %.2f ms device\n", hdr[1], hdr[2], st.kernel_launches, st.ms_device);
 		if (argc > 4 && !strcmp(argv[4], "post")) {
 			// the post-processing members: speckles, gaps, then the filter with the map as its own two neighbours

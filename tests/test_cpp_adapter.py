@@ -69,6 +69,11 @@ def test_adapter_matches_python_host_path(tmp_path, tiny_scene):
 	finally:
 		OPTDENSE.nSubResolutionLevels, OPTDENSE.nEstimationGeometricIters, OPTDENSE.nEstimationIters = saved
 	assert np.array_equal(depth, dd.depthMap) and np.array_equal(normal, dd.normalMap) and np.array_equal(conf, dd.confMap)
+	# the reference's own call-site signature, pmCUDA->EstimateDepthMap(depthData) with the OPTDENSE globals: same maps
+	out2 = str(tmp_path/"out2.bin")
+	r = subprocess.run([exe, scene, out2, "2", "seam"], capture_output=True, text=True)
+	assert r.returncode == 0, r.stdout+r.stderr
+	assert np.array_equal(np.fromfile(out2, np.uint8), raw)
 
 
 @pytest.mark.gpu

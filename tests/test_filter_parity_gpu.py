@@ -122,29 +122,36 @@ def test_small_segments_exact_without_direction_dependent_edges(eng, scene):
 
 
 def test_small_segments_with_direction_dependent_edges(eng, scene):
-	"""noisy map: the kernel keeps the components over edges similar in either direction; it may differ from the
-	breadth-first oracle only on pixels whose two-way component is < speckle while their one-way component is >= speckle"""
+	"""Noisy maps with edges that pass IsDepthSimilar in one direction only: the reference's segments depend on its seed order
+	(column-major) there.  The engine labels the two-way components on the GPU and replays the reference's loop on the condensed
+	graph of one-way edges: bit-identical to the breadth-first oracle, also on a map built to contain many such edges."""
 	dm, O = eng
 	sc, maps = scene
-	d = maps[2][0]
 	th = f32(f32(0.01)*f32(0.7))
 	from openmvs_b200.depth_estimator import DepthData, OPTDENSE
-	strong = component_sizes(d, th, True); weak = component_sizes(d, th, False)
-	for speckle in (20, 100):
-		OPTDENSE.nSpeckleSize = speckle
-		try:
-			dd = DepthData([], 0, 0, d.copy())
-			dm.RemoveSmallSegments(dd)
-		finally:
-			OPTDENSE.nSpeckleSize = 100
-		exp = np.where(weak < speckle, 0, d).astype(f32)
-		assert np.array_equal(dd.depthMap, exp)
-		od, _, _ = O.remove_small_segments(d, None, None, th, speckle)
-		differ = (dd.depthMap != od)
-		ambiguous = (d > 0) & (strong < speckle) & (weak >= speckle)
-		assert not (differ & ~ambiguous).any()
-		_record("segments_speckle%d_200x150" % speckle, differ=differ.mean(), ambiguous=ambiguous.mean(), asym_edges=O.count_asymmetric_edges(d, th))
-		assert differ.mean() < 0.02
+	rng = np.random.RandomState(4)
+	# (a) an estimator-like noisy map; (b) a staircase whose steps sit right at the threshold: hundreds of one-way edges
+	stairs = np.full((150, 200), 5.0, f32)
+	for k in range(1, 40):
+		stairs[:, 5*k:] *= f32(1.0+float(th)*(0.9965+0.007*rng.rand()))
+	stairs[rng.rand(150, 200) < 0.08] = 0
+	blobs = maps[2][0].copy()
+	for name, d in (("noisy", maps[2][0]), ("stairs", stairs), ("noisy_sparse", np.where(rng.rand(*blobs.shape) < 0.25, 0, blobs).astype(f32))):
+		asym = O.count_asymmetric_edges(d, th)
+		for speckle in (20, 100, 1000):
+			OPTDENSE.nSpeckleSize = speckle
+			try:
+				dd = DepthData([], 0, 0, d.copy())
+				dm.RemoveSmallSegments(dd)
+				t = torch.from_numpy(d.copy()).cuda()
+				dm.RemoveSmallSegments(DepthData([], 0, 0, t))
+			finally:
+				OPTDENSE.nSpeckleSize = 100
+			od, _, _ = O.remove_small_segments(d, None, None, th, speckle)
+			assert np.array_equal(dd.depthMap, od), (name, speckle, int((dd.depthMap != od).sum()))
+			assert np.array_equal(t.cpu().numpy(), od)
+			_record("segments_%s_speckle%d" % (name, speckle), asym_edges=asym, removed=((d > 0) & (od == 0)).mean(), differ=float((dd.depthMap != od).mean()))
+	assert O.count_asymmetric_edges(stairs, th) > 50
 
 
 def _gap_inputs(sc, seed=5):
