@@ -6,6 +6,7 @@
 // no host synchronisation between kernels.
 #include "../../include/b200mvs.h"
 #include "pm_common.cuh"
+#include "sgm_front_sched.h"
 #include <cuda.h>
 #include <cmath>
 #include <cstdio>
@@ -43,15 +44,6 @@ cudaError_t sgm_cost_tc_launch(const SGMParams& P, int dmin, int num, cudaStream
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s);
 // wave-front aggregation (sgm_front.cu)
-struct FrontItem { int k0; short dir; short ph; int fb; int seq; int chain; int depCell; int depNeed; int cell; };
-struct FrontArgs {
-	const FrontItem* items; int nItems;
-	int* ticket; int* progress; int* cellDone; int* error;
-	uint16_t* state; float2* meta; int maxPaths;
-	int fa, fb, fc, FB; int storePhase0; int num;
-};
-struct FrontPassDesc { int fa, fb; int nDirs; int dirs[4]; };
-void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc);
 cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, cudaStream_t s);
 int sgm_front_blocks(int num);
 bool sgm_front_supports(int num);
@@ -459,19 +451,7 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 	const int vw = P.vw, vh = P.vh;
 	const int key[6] = {vw, vh, layout, FB, lag, 1};
 	if (memcmp(key, ctx->sgFrontKey, sizeof(key)) != 0) {
-		std::vector<FrontPassDesc> descs;
-		if (layout == 0) {
-			descs.push_back(FrontPassDesc{1, 2, 4, {1, 4, 0, 5}});
-			descs.push_back(FrontPassDesc{-1, -2, 4, {3, 7, 2, 6}});
-		} else if (layout == 1) {
-			descs.push_back(FrontPassDesc{0, 1, 3, {0, 4, 5, 0}});
-			descs.push_back(FrontPassDesc{0, -1, 3, {2, 6, 7, 0}});
-			descs.push_back(FrontPassDesc{1, 0, 1, {1, 0, 0, 0}});
-			descs.push_back(FrontPassDesc{-1, 0, 1, {3, 0, 0, 0}});
-		} else {
-			const int f[8][2] = {{0, 1}, {1, 0}, {0, -1}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
-			for (int d = 0; d < 8; ++d) descs.push_back(FrontPassDesc{f[d][0], f[d][1], 1, {d, 0, 0, 0}});
-		}
+		const std::vector<FrontPassDesc> descs = sgm_front_layout(layout);
 		for (auto& fp: ctx->sgFront) fp.items.release();
 		ctx->sgFront.clear(); ctx->sgFront.resize(descs.size());
 		std::vector<FrontItem> items;

@@ -40,58 +40,7 @@ struct SGMParams {
 	int maxNumDisp;
 };
 
-// one work item: direction `dir` (phase `ph` of its pass), paths k0 .. k0+3, fronts [fb*FB, fb*FB+FB)
-struct FrontItem {
-	int k0; short dir; short ph;
-	int fb;
-	int seq;       // number of earlier items of the same band: wait until progress[chain] >= seq
-	int chain;     // index into progress[]
-	int depCell;   // cell (phase - 1, fb) whose completion this item waits for, or -1
-	int depNeed;   // number of items in that cell
-	int cell;      // this item's cell (completion counter to bump)
-};
-struct FrontArgs {
-	const FrontItem* items; int nItems;
-	int* ticket;         // queue head
-	int* progress;       // per (phase, band): segments completed
-	int* cellDone;       // per (phase, front block): items completed
-	int* error;          // set to 1 when a wait timed out (never in a correct schedule)
-	uint16_t* state;     // per (phase, path): the normalised previous line, num u16
-	float2* meta;        // per (phase, path): {previous intensity, have-previous flag}
-	int maxPaths;        // paths per phase slot in state / meta
-	int fa, fb, fc, FB;  // front f(x,y) = fa*x + fb*y + fc >= 0, block size
-	int storePhase0;     // 1: phase 0 stores the sum instead of adding to it (first pass)
-	int num;             // disparities per pixel (16 * NW)
-};
-
-// start pixel and step of scanline `k` of direction `dir` (order of SemiGlobalMatcher.cpp:1084-1199); host and device
-__host__ __device__ inline bool front_path_start(int dir, int k, int W, int H, int& x, int& y, int& dx, int& dy) {
-	switch (dir) {
-	case 0: if (k >= W) return false; x = k; y = 0; dx = 0; dy = 1; return true;        // width-down
-	case 1: if (k >= H) return false; x = 0; y = k; dx = 1; dy = 0; return true;        // height-right
-	case 2: if (k >= W) return false; x = k; y = H-1; dx = 0; dy = -1; return true;     // width-up
-	case 3: if (k >= H) return false; x = W-1; y = k; dx = -1; dy = 0; return true;     // height-left
-	case 4: dx = 1; dy = 1;                                                             // right-down
-		if (k < W) { x = k; y = 0; return true; } k -= W; if (k >= H-1) return false; x = 0; y = k+1; return true;
-	case 5: dx = -1; dy = 1;                                                            // left-down
-		if (k < W-1) { x = k; y = 0; return true; } k -= W-1; if (k >= H) return false; x = W-1; y = k; return true;
-	case 6: dx = 1; dy = -1;                                                            // right-up
-		if (k < W-1) { x = k+1; y = H-1; return true; } k -= W-1; if (k >= H) return false; x = 0; y = k; return true;
-	default: dx = -1; dy = -1;                                                          // left-up
-		if (k < W) { x = k; y = H-1; return true; } k -= W; if (k >= H-1) return false; x = W-1; y = k; return true;
-	}
-}
-__host__ __device__ inline int front_path_len(int x0, int y0, int dx, int dy, int W, int H) {
-	int n = 0x7FFFFFFF;
-	if (dx > 0) n = min(n, W-x0); else if (dx < 0) n = min(n, x0+1);
-	if (dy > 0) n = min(n, H-y0); else if (dy < 0) n = min(n, y0+1);
-	return n;
-}
-// first step s >= 0 of a path with f(s) = f0 + s*df (df > 0) at or beyond front `lo`
-__host__ __device__ inline int front_first_step(int lo, int f0, int df) {
-	const int a = lo-f0;
-	return a <= 0 ? 0 : (a+df-1)/df;
-}
+#include "sgm_front_sched.h"
 
 namespace {
 
@@ -294,64 +243,6 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 }
 
 } // namespace
-
-// ---- host side: schedule --------------------------------------------------------------------------------------------
-struct FrontPassDesc { int fa, fb; int nDirs; int dirs[4]; };
-
-// Work items of one pass in queue order; returns the number of front blocks and chains through nFB / nChains.
-// lag: queue distance (in front blocks) between consecutive phases of the same block.
-void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc) {
-	// offset that makes the front coordinate non-negative
-	const int cx[2] = {0, vw-1}, cy[2] = {0, vh-1};
-	int fmin = 0x7FFFFFFF, fmax = -0x7FFFFFFF;
-	for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { const int f = pd.fa*cx[a] + pd.fb*cy[b]; fmin = std::min(fmin, f); fmax = std::max(fmax, f); }
-	fc = -fmin;
-	nFB = (fmax-fmin)/FB + 1;
-	maxBands = (vw+vh+3)/4 + 1;
-	items.clear();
-	std::vector<int> cellCount((size_t)pd.nDirs*nFB, 0);
-	for (int ph = 0; ph < pd.nDirs; ++ph) {
-		const int dir = pd.dirs[ph];
-		const int nPaths = dir == 0 || dir == 2 ? vw : dir == 1 || dir == 3 ? vh : vw+vh-1;
-		for (int band = 0; band*4 < nPaths; ++band) {
-			int s0v[4], nv[4], f0v[4], dfv[4]; bool pv[4];
-			int blo = 0x7FFFFFFF, bhi = -1;
-			for (int g = 0; g < 4; ++g) {
-				int x, y, dx, dy;
-				pv[g] = front_path_start(dir, band*4+g, vw, vh, x, y, dx, dy);
-				nv[g] = 0; f0v[g] = 0; dfv[g] = 1; s0v[g] = 0;
-				if (!pv[g]) continue;
-				nv[g] = front_path_len(x, y, dx, dy, vw, vh);
-				f0v[g] = pd.fa*x + pd.fb*y + fc; dfv[g] = pd.fa*dx + pd.fb*dy;
-				blo = std::min(blo, f0v[g]/FB); bhi = std::max(bhi, (f0v[g]+(nv[g]-1)*dfv[g])/FB);
-			}
-			int seq = 0;
-			for (int fb = blo; fb <= bhi; ++fb) {
-				bool any = false;
-				for (int g = 0; g < 4 && !any; ++g) {
-					if (!pv[g]) continue;
-					const int a = std::min(nv[g], front_first_step(fb*FB, f0v[g], dfv[g])), b = std::min(nv[g], front_first_step((fb+1)*FB, f0v[g], dfv[g]));
-					any = b > a;
-				}
-				if (!any) continue;
-				FrontItem it;
-				it.k0 = band*4; it.dir = (short)dir; it.ph = (short)ph; it.fb = fb; it.seq = seq++;
-				it.chain = ph*maxBands + band;
-				it.cell = ph*nFB + fb;
-				it.depCell = ph > 0 ? (ph-1)*nFB + fb : -1; it.depNeed = 0;
-				items.push_back(it);
-				++cellCount[it.cell];
-			}
-		}
-	}
-	for (auto& it: items) if (it.depCell >= 0) it.depNeed = cellCount[it.depCell];
-	// queue order: front blocks advance, phase ph runs `lag` blocks behind phase ph-1; every dependency is earlier in the queue
-	std::stable_sort(items.begin(), items.end(), [lag](const FrontItem& a, const FrontItem& b) {
-		const int ta = a.fb + lag*a.ph, tb = b.fb + lag*b.ph;
-		if (ta != tb) return ta < tb;
-		return a.ph > b.ph;
-	});
-}
 
 cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, cudaStream_t s) {
 	const int NW = A.num/16;
