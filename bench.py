@@ -252,6 +252,14 @@ def main():
 		threads = len(os.sched_getaffinity(0)) or 1
 	except Exception:
 		threads = os.cpu_count() or 1
+	# a cgroup CPU quota below the affinity size (seen on the GPU boxes: 128 logical CPUs, quota 16) makes more threads than the
+	# quota only fight for the same CPU time: the CPU arm uses the quota, and reports it
+	try:
+		q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+		if q != "max":
+			threads = max(1, min(threads, int(round(int(q)/int(per)))))
+	except Exception:
+		pass
 
 	if args.impl == "reference":
 		# the reference's own CPU implementation of the path: the oracle port (the reference cannot be compiled in this image,

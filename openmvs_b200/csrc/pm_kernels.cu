@@ -485,8 +485,10 @@ pm_score_kernel(const __grid_constant__ PMParams P)
 //      all kept their plane in their last update (they lost against this pixel one sweep ago) — P.skipUnchanged;
 //   3. the refinement state machine (DepthMap.cpp:800-852).
 // Every lane keeps its own to-do list of directions, so a warp runs max-over-lanes(list length) test steps.
-template <bool PACK, bool GEOM>
-__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, 3)
+// MINB: resident CTAs per SM the register allocation aims at: 3 (80 registers, the default) or 4 (64 registers: one more CTA of
+// latency hiding against more spill traffic — b200mvs_debug.reserved[3], measured in profiles/)
+template <bool PACK, bool GEOM, int MINB>
+__global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, MINB)
 pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUtensorMap tmapRef)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -739,7 +741,9 @@ constexpr size_t SWEEP_SMEM = W_BYTES + TILE_BYTES + 16;
 
 template <bool PACK, bool GEOM>
 cudaError_t configure_one() {
-	cudaError_t e = cudaFuncSetAttribute(pm_sweep_kernel<PACK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+	cudaError_t e = cudaFuncSetAttribute(pm_sweep_kernel<PACK, GEOM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(pm_sweep_kernel<PACK, GEOM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
 	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(pm_score_kernel<PACK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
 }
@@ -762,12 +766,17 @@ cudaError_t pm_launch_score(const PMParams& P, bool pack, bool geom, cudaStream_
 	return cudaGetLastError();
 }
 // tmapRef: TMA descriptor of the reference image with box {72, 16} (pm_tma_box), or null (P.tma must be 0)
-cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, bool pack, bool geom, cudaStream_t s) {
+template <int MINB>
+static void launch_sweep(const PMParams& P, const CUtensorMap& map, bool pack, bool geom, dim3 grid, dim3 block, cudaStream_t s) {
+	if (pack) { if (geom) pm_sweep_kernel<true, true, MINB><<<grid, block, SWEEP_SMEM, s>>>(P, map); else pm_sweep_kernel<true, false, MINB><<<grid, block, SWEEP_SMEM, s>>>(P, map); }
+	else { if (geom) pm_sweep_kernel<false, true, MINB><<<grid, block, SWEEP_SMEM, s>>>(P, map); else pm_sweep_kernel<false, false, MINB><<<grid, block, SWEEP_SMEM, s>>>(P, map); }
+}
+cudaError_t pm_launch_sweep(const PMParams& P, const void* tmapRef, bool pack, bool geom, bool fourCtas, cudaStream_t s) {
 	dim3 block(BLOCK_X, BLOCK_Y), grid((P.W+2*BLOCK_X-1)/(2*BLOCK_X), (P.H+BLOCK_Y-1)/BLOCK_Y);
 	CUtensorMap map; memset(&map, 0, sizeof(map));
 	if (tmapRef) memcpy(&map, tmapRef, sizeof(map));
-	if (pack) { if (geom) pm_sweep_kernel<true, true><<<grid, block, SWEEP_SMEM, s>>>(P, map); else pm_sweep_kernel<true, false><<<grid, block, SWEEP_SMEM, s>>>(P, map); }
-	else { if (geom) pm_sweep_kernel<false, true><<<grid, block, SWEEP_SMEM, s>>>(P, map); else pm_sweep_kernel<false, false><<<grid, block, SWEEP_SMEM, s>>>(P, map); }
+	if (fourCtas) launch_sweep<4>(P, map, pack, geom, grid, block, s);
+	else launch_sweep<3>(P, map, pack, geom, grid, block, s);
 	return cudaGetLastError();
 }
 void pm_tma_box(int* w, int* h) { *w = TILE_W; *h = TILE_H; }

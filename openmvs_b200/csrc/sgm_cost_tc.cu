@@ -12,8 +12,8 @@
 // the dropped wl fl term is 2^-22 relative — so the uint8 cost stays within the +-1 level of the SIMT kernel.
 //
 // Structure (one 256-thread CTA per SM, persistent over the rows of the valid region):
-//   warps 0-3  build A (bilateral weights of the block's 128 pixels: 49 expf per pixel, split, 16-byte stores in the UMMA
-//              K-major no-swizzle core-matrix layout) | warps 4-7 build the two new B tiles (im2col of 7 right-image rows);
+//   all 8 warps build A (bilateral weights of the block's 128 pixels: 49 expf per pixel shared by two threads, fp16 split, 16-byte
+//              stores in the UMMA K-major no-swizzle core-matrix layout), then the two new B tiles (im2col of 7 right-image rows);
 //   one thread issues the MMAs of a tile (9 products x 4 K-steps of 128 x 64 x 16) into one of two TMEM accumulator buffers
 //              and commits them to an mbarrier; the next tile's MMAs run while
 //   all 8 warps read the finished buffer (tcgen05.ld 32x32b), turn sums into costs and scatter them into a shared cost tile,
@@ -50,7 +50,7 @@ constexpr int TILE_PITCH = 132;          // bytes per pixel row of the shared co
 constexpr int SMEM_A = 4*A_ARRAY;        // wh, wl, th, tl
 constexpr int SMEM_B = RING*B_SLOT;
 constexpr int SMEM_TILE = BM*TILE_PITCH;
-constexpr int SMEM_CONST = BM*8;         // {normSq0, sumW} per pixel
+constexpr int SMEM_CONST = BM*8;         // {normSq0, 1/sumW} per pixel
 constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_TILE + SMEM_CONST + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,12 +131,14 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 	const float sigmaSpatial = -1.f/(2.f*(0.4f*7)*(0.4f*7));
 	unsigned phase[2] = {0u, 0u};
 
-	// one B tile: thread `c` (0..63) of the building half-CTA owns column u' = 64 t + c of the band
-	auto build_b_tile = [&](int r, int t, int c) {
+	// Operand builders: every pixel / column is shared by two threads, `half` 0 owns taps 0..23 (K-chunks 0..2), `half` 1 taps
+	// 24..48 (K-chunks 3..6), so that all 256 threads build — A (128 pixels x 2) first, then the two new B tiles (2 x 64 columns x 2).
+	// one B tile column: u' = 64 t + c of the band
+	auto build_b_tile = [&](int r, int t, int c, int half) {
 		unsigned char* slot = sB + (size_t)(t&(RING-1))*B_SLOT;
 		const int lcol = BN*t + c + dmin;         // image column of the window's left edge
 		#pragma unroll 1
-		for (int kc = 0; kc < 7; ++kc) {
+		for (int kc = half ? 3 : 0; kc < (half ? 7 : 3); ++kc) {
 			__half fh[8], fl[8], qh[8], ql[8];
 			#pragma unroll
 			for (int e = 0; e < 8; ++e) {
@@ -157,50 +159,60 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 			*(uint4*)(slot+3*B_ARRAY+off) = make_uint4(pack_h2(ql[0], ql[1]), pack_h2(ql[2], ql[3]), pack_h2(ql[4], ql[5]), pack_h2(ql[6], ql[7]));
 		}
 	};
-	// the block's A operands: thread `row` (0..127) owns pixel x0 + row
-	auto build_a = [&](int r, int x0, int row) {
+	// the block's A operands: threads 2*row and 2*row+1 (adjacent lanes) own pixel x0 + row
+	auto build_a = [&](int r, int x0, int row, int half) {
+		constexpr int NH = 25;                        // taps per half: 24 | 25
+		const int n0 = half ? 24 : 0, nn = half ? 25 : 24;
 		const int col = x0+row;
-		float wv[NT], gv[NT];
-		float sumW = 0.f, normSq0 = 0.f;
-		if (col < vw) {
+		float wv[NH], gv[NH];
+		float sumW = 0.f, acc = 0.f, normSq0 = 0.f;
+		const bool valid = col < vw;
+		if (valid) {
 			const int ux = col+HW, uy = r+HW;
 			const uchar3 cc = P.lbgr[(size_t)uy*w + ux];
-			float acc = 0.f;
 			#pragma unroll
-			for (int i = 0; i < 7; ++i) {
-				#pragma unroll
-				for (int j = 0; j < 7; ++j) {
+			for (int k = 0; k < NH; ++k) {
+				wv[k] = 0.f; gv[k] = 0.f;
+				if (k < nn) {
+					const int n = n0+k, i = n/7, j = n-7*i;
 					const size_t o = (size_t)(uy+i-HW)*w + (ux+j-HW);
 					const uchar3 pc = P.lbgr[o];
 					const int d0 = abs((int)pc.x-(int)cc.x), d1 = abs((int)pc.y-(int)cc.y), d2 = abs((int)pc.z-(int)cc.z);
 					const float wgt = expf(float(d0*d0+d1*d1+d2*d2)*sigmaColor + float((j-HW)*(j-HW)+(i-HW)*(i-HW))*sigmaSpatial);
 					const float g = __ldg(P.lgray + o);
-					wv[i*7+j] = wgt; gv[i*7+j] = g;
+					wv[k] = wgt; gv[k] = g;
 					acc += g*wgt;
 					sumW += wgt;
 				}
 			}
-			const float tm = acc/sumW;
-			#pragma unroll
-			for (int n = 0; n < NT; ++n) {
-				const float t = gv[n]-tm;
-				gv[n] = wv[n]*t;          // tempWeight
-				normSq0 += gv[n]*t;
-			}
 		} else {
 			#pragma unroll
-			for (int n = 0; n < NT; ++n) { wv[n] = 0.f; gv[n] = 0.f; }
-			sumW = 1.f;
+			for (int k = 0; k < NH; ++k) { wv[k] = 0.f; gv[k] = 0.f; }
 		}
-		sConst[row] = make_float2(normSq0, sumW);
+		// the two halves of a pixel sit in adjacent lanes
+		acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+		sumW += __shfl_xor_sync(0xFFFFFFFFu, sumW, 1);
+		if (!valid) sumW = 1.f;
+		const float tm = acc/sumW;
 		#pragma unroll
-		for (int kc = 0; kc < 7; ++kc) {
+		for (int k = 0; k < NH; ++k) {
+			const float t = gv[k]-tm;
+			gv[k] = wv[k]*t;          // tempWeight (0 for the unused tap of the short half: w = 0)
+			normSq0 += gv[k]*t;
+		}
+		normSq0 += __shfl_xor_sync(0xFFFFFFFFu, normSq0, 1);
+		if (half == 0) sConst[row] = make_float2(normSq0, 1.f/sumW);
+		#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int kc = (half ? 3 : 0)+q;
+			if (!half && q == 3) break;
 			__half wh[8], wl[8], th[8], tl[8];
 			#pragma unroll
 			for (int e = 0; e < 8; ++e) {
-				const int n = kc*8+e;
-				split_h(n < NT ? wv[n < NT ? n : 0] : 0.f, wh[e], wl[e]);
-				split_h(n < NT ? gv[n < NT ? n : 0] : 0.f, th[e], tl[e]);
+				const int k = q*8+e;                    // index into this half's taps (half 1: tap 24+k)
+				const bool in = k < nn;
+				split_h(in ? wv[k < NH ? k : 0] : 0.f, wh[e], wl[e]);
+				split_h(in ? gv[k < NH ? k : 0] : 0.f, th[e], tl[e]);
 			}
 			const size_t off = (size_t)kc*(BM*16) + (size_t)row*16;
 			*(uint4*)(sA+0*A_ARRAY+off) = make_uint4(pack_h2(wh[0], wh[1]), pack_h2(wh[2], wh[3]), pack_h2(wh[4], wh[5]), pack_h2(wh[6], wh[7]));
@@ -236,24 +248,28 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 		const float2 cst = sConst[row];
 		const int col = BM*b + row;                 // valid-region column of the pixel
 		const float eps = 1e-3f;
+		const int kq = BN*(t-2*b);                  // disparity index of (row 0, column 0) of this tile
 		#pragma unroll
 		for (int ch = 0; ch < 2; ++ch) {
+			// the band 0 <= d < num covers about half of a tile: a 32-row x 16-column chunk wholly outside it is skipped (warp-uniform)
+			const int c0 = cbase+16*ch, row0 = 32*(warp&3);
+			if (kq+c0+15-row0 < 0 || kq+c0-(row0+31) >= num) continue;
 			uint32_t s0[16], s1[16], s2[16];
-			const uint32_t ta = tmem + ((uint32_t)(32*(warp&3))<<16) + (uint32_t)buf*256u + (uint32_t)(cbase+16*ch);
+			const uint32_t ta = tmem + ((uint32_t)row0<<16) + (uint32_t)buf*256u + (uint32_t)c0;
 			tmem_ld16(ta, s0); tmem_ld16(ta+64u, s1); tmem_ld16(ta+128u, s2);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			#pragma unroll
 			for (int e = 0; e < 16; ++e) {
-				const int c = cbase+16*ch+e;
-				const int d = BN*(t-2*b) + c - row;      // disparity index of (pixel, column)
+				const int d = kq + c0+e - row;            // disparity index of (pixel, column)
 				if (d >= 0 && d < num) {
 					const float sum = __uint_as_float(s0[e]), sumSq = __uint_as_float(s1[e]), nom = __uint_as_float(s2[e]);
-					const float normSq1 = sumSq - sum*sum/cst.y;
-					const float ncc = nom/sqrtf(cst.x*normSq1+eps);
-					uint8_t cv = ncc <= 0.f ? (uint8_t)255 : (uint8_t)(int)floorf((1.f-fminf(ncc, 1.f))*255.f+.5f);
+					const float normSq1 = fmaf(-sum*cst.y, sum, sumSq);
+					const float ncc = nom*rsqrtf(fmaf(cst.x, normSq1, eps));
+					// ncc <= 0 ? 255 : floor((1 - min(ncc, 1)) * 255 + .5)
+					int cv = ncc <= 0.f ? 255 : __float2int_rd(fmaf(-255.f, fminf(ncc, 1.f), 255.5f));
 					const int left = col+d+dmin;           // image column of the right window's left edge
 					if (left < 0 || left+2*HW >= w) cv = 255;
-					sTile[row*TILE_PITCH + d] = cv;
+					sTile[row*TILE_PITCH + d] = (uint8_t)cv;
 				}
 			}
 		}
@@ -265,12 +281,12 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 		#pragma unroll 1
 		for (int b = 0; b < nBlocks; ++b) {
 			// operands of this block: A by warps 0-3; the tiles not yet in the ring by warps 4-7
-			if (tid < BM) build_a(r, BM*b, tid);
-			else {
-				const int q = tid-BM;                       // 0..127: tile q>>6 of the pair, column q&63
+			build_a(r, BM*b, tid>>1, tid&1);
+			{
+				const int tsel = tid>>7, c = (tid>>1)&63, half = tid&1;   // tile of the pair, column, tap half
 				if (b == 0)
-					for (int t = 0; t < nTiles-2; t += 2) build_b_tile(r, t+(q>>6), q&63);
-				build_b_tile(r, 2*b+nTiles-2+(q>>6), q&63);
+					for (int t = 0; t < nTiles-2; t += 2) build_b_tile(r, t+tsel, c, half);
+				build_b_tile(r, 2*b+nTiles-2+tsel, c, half);
 			}
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
 			__syncthreads();

@@ -113,7 +113,6 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 	__syncthreads();
 	const int lane = threadIdx.x&31;
 	const int g = lane>>3, sub = lane&7;
-	const unsigned gmask = 0xFFu<<(g*8);
 	const unsigned P1x2 = (unsigned)P.P1*0x10001u;
 	const int vw = P.vw, vh = P.vh, num = A.num;
 	int ticket = 0;
@@ -157,19 +156,26 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 			#pragma unroll
 			for (int i = 0; i < NW; i += 4) { const uint4 v = ldcg4(st+2*i); w[i] = v.x; w[i+1] = v.y; w[i+2] = v.z; w[i+3] = v.w; }
 		}
-		// pipeline stages
+		// pipeline stages.  Addresses advance by constant strides along the path: the load pointers run PD steps ahead of the
+		// store pointer (no per-step 64-bit multiplies).
 		typename V::C cs[PD]; typename V::S ss[PD]; float is[PD];
-		auto load = [&](int j, int s) {
-			const int x = xs+s*dx, y = ys+s*dy;
-			const size_t idx = ((size_t)y*vw + x)*(size_t)num + (size_t)sub*(2*NW);
-			cs[j] = V::ldc(P.costs+idx);
-			if (add) ss[j] = V::lds(P.accums+idx);
-			is[j] = __ldg(P.lgray + (size_t)y*P.w + x);
+		const long long pstep = (long long)dy*vw + dx;                    // pixel index stride of one step
+		const long long pix0 = (long long)(ys+s0*dy)*vw + (xs+s0*dx);
+		const uint8_t* cptr = P.costs + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		const uint16_t* sptr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		uint16_t* optr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		const float* iptr = P.lgray + (size_t)(ys+s0*dy)*P.w + (xs+s0*dx);
+		const long long cstep = pstep*num, istep = (long long)dy*P.w + dx;
+		auto load = [&](int j) {   // loads of the next step not yet requested, then advance
+			cs[j] = V::ldc(cptr);
+			if (add) ss[j] = V::lds(sptr);
+			is[j] = __ldg(iptr);
+			cptr += cstep; sptr += cstep; iptr += istep;
 		};
 		#pragma unroll
 		for (int j = 0; j < PD; ++j) {
 			memset(&cs[j], 0, sizeof(cs[j])); memset(&ss[j], 0, sizeof(ss[j])); is[j] = 0.f;
-			if (j < cnt) load(j, s0+j);
+			if (j < cnt) load(j);
 		}
 		#pragma unroll 1
 		for (int t = 0; t < maxcnt; t += PD) {
@@ -182,8 +188,7 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 				V::unpackC(cs[j], C);
 				V::unpackS(ss[j], S);
 				const float I = is[j];
-				const int s = s0+tt;
-				if (tt+PD < cnt) load(j, s+PD);
+				if (tt+PD < cnt) load(j);
 				// penalty of this step: P2s[|round(255 (I - Ip))|] (SemiGlobalMatcher.cpp:1009, 518-524)
 				const int di = min(255, abs((int)floorf(255.f*(I-Ip)+.5f)));
 				const unsigned P2x2 = sP2[di];
@@ -212,15 +217,19 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 				#pragma unroll
 				for (int i = 1; i+1 < NW; i += 2) m = __vimin3_u16x2(m, L[i], L[i+1]);
 				if ((NW&1) == 0) m = __vminu2(m, L[NW-1]);
+				// over the pixel's 8 lanes: three butterfly steps on the packed pair (a sub-warp redux.sync with a per-group mask
+				// compiles to a WARPSYNC.COLLECTIVE loop over the groups: measured at about 2000 cycles per step)
+				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 4));
+				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
 				m = min(m&0xFFFFu, m>>16);
-				m = __reduce_min_sync(gmask, m);
 				const unsigned mx2 = m*0x10001u;
 				if (act) {
 					unsigned out[NW];
 					#pragma unroll
 					for (int i = 0; i < NW; ++i) { out[i] = add ? __vadd2(S[i], L[i]) : L[i]; w[i] = __vsub2(L[i], mx2); }
-					const int x = xs+s*dx, y = ys+s*dy;
-					V::sts(P.accums + ((size_t)y*vw + x)*(size_t)num + (size_t)sub*(2*NW), out);
+					V::sts(optr, out);
+					optr += cstep;
 					Ip = I; havePrev = true;
 				}
 			}

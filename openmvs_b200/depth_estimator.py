@@ -266,9 +266,12 @@ class PatchMatchB200:
 		"""b200mvs_set_debug: diagnostic kernel switches (scalarTaps, noTMA, sgmAggregation, sgmCost); no arguments = defaults."""
 		d = _lib.Debug()
 		for k, v in kw.items():
-			if not hasattr(d, k):
+			if k == "fourCtas":   # reserved[3]: the 64-register instantiation of the sweep kernel (4 CTAs per SM)
+				d.reserved[3] = int(v)
+			elif not hasattr(d, k):
 				raise AttributeError(k)
-			setattr(d, k, int(v))
+			else:
+				setattr(d, k, int(v))
 		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_debug(self._ctx, C.byref(d)), "b200mvs_set_debug")
 
 	def SetIgnoreMask(self, mask=None):

@@ -24,6 +24,8 @@ MODES = [("register pipeline", dict(sgmAggregation=2)), ("bulk-copy ring, 8 laun
 MODES.append(("tensor-core cost kernel + wave fronts", dict(sgmCost=2)))
 if len(sys.argv) > 2 and sys.argv[2] == "default":
 	MODES = MODES[2:3]
+if len(sys.argv) > 2 and sys.argv[2] == "tc":
+	MODES = MODES[-1:]
 for name, dbg in MODES:
 	m.SetDebug(**dbg)
 	for rep in range(2):
