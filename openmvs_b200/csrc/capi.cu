@@ -48,6 +48,7 @@ cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks,
 int sgm_front_blocks(int num);
 bool sgm_front_supports(int num);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
+cudaError_t sgm_launch_wta_uniform(const SGMParams& P, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
 cudaError_t sgm_launch_refine(const SGMPixel* px, const uint16_t* accums, int16_t* disparity, int n, int steps, cudaStream_t s);
@@ -915,7 +916,7 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	int st8[8] = {0, 0, 0, 0, 0, 0, 0, 0}; bool uniform = false, ring = false, front = false;
 	const int mode = ctx->dbg.sgmAggregation;
 	if (stats) CK(cudaEventRecord(ctx->ev0, s));
-	if (stages & 3) {
+	if (stages & 7) {
 		// the warp-per-scanline kernel keeps one line of at most sgm_max_disparities() values
 		CK(ctx->sgMax.reserve(8*sizeof(int)));
 		CK(sgm_launch_maxdisp(P.px, P.vw*P.vh, numCosts, ctx->sgMax.as<int>(), s)); ctx->launches += 2;
@@ -958,7 +959,12 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 		}
 	}
 	if (stages & 2) { ctx->sgLastPx = (accums == ctx->sgAccums.as<uint16_t>()) ? (const void*)pixels : nullptr; ctx->sgLastNum = numCosts; }
-	if (stages & 4) { CK(sgm_launch_wta(P, disparity, cost, s)); ++ctx->launches; }
+	if (stages & 4) {
+		const bool denseWta = uniform && (st8[0] & 15) == 0 && !st8[6] && !((uintptr_t)P.accums & 15);
+		if (denseWta) CK(sgm_launch_wta_uniform(P, st8[1], st8[0], disparity, cost, s));
+		else CK(sgm_launch_wta(P, disparity, cost, s));
+		++ctx->launches;
+	}
 	if (stats) {
 		CK(cudaEventRecord(ctx->ev1, s));
 		CK(cudaStreamSynchronize(s));

@@ -590,6 +590,29 @@ __global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int16_t* __r
 	if (lane == 0) { disparity[gw] = (int16_t)(p.dmin+(int)(best&0xFFFFu)); cost[gw] = (uint16_t)(best>>16); }
 }
 
+// Uniform dense volumes (num % 16 == 0, 16-byte aligned slices): 8 lanes per pixel, 16-byte loads, the arg-min carried as
+// (value << 16 | index) per lane.  HBM-bound: one read of the u16 sum volume.
+__global__ void sgm_wta_uniform_kernel(const uint16_t* __restrict__ accums, int nPixels, int dmin, int num, int16_t* __restrict__ disparity, uint16_t* __restrict__ cost)
+{
+	const int gp = (blockIdx.x*blockDim.x + threadIdx.x)>>3, sub = threadIdx.x&7;
+	const bool live = gp < nPixels;                         // every lane stays for the full-mask shuffles
+	const uint16_t* a = accums + (size_t)(live ? gp : 0)*num;
+	unsigned best = 0xFFFFFFFFu;
+	for (int k = sub*8; k < num; k += 64) {
+		const uint4 v = __ldcs((const uint4*)(a+k));
+		const unsigned w[4] = {v.x, v.y, v.z, v.w};
+		#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			best = min(best, ((w[i]&0xFFFFu)<<16) | (unsigned)(k+2*i));
+			best = min(best, (w[i]&0xFFFF0000u) | (unsigned)(k+2*i+1));
+		}
+	}
+	best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, 4));
+	best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, 2));
+	best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, 1));
+	if (live && sub == 0) { disparity[gp] = (int16_t)(dmin+(int)(best&0xFFFFu)); cost[gp] = (uint16_t)(best>>16); }
+}
+
 // ConsistencyCrossCheck (SemiGlobalMatcher.cpp:1449-1489): every pixel reads r2l and writes only
 // its own l2r entry, so the in-place update is race-free
 __global__ void sgm_cross_check_kernel(int16_t* __restrict__ l2r, const int16_t* __restrict__ r2l, int w, int h, int th) {
@@ -733,6 +756,12 @@ cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cos
 	return cudaGetLastError();
 }
 
+// dense uniform volume: every pixel valid, slice of pixel i at i*num
+cudaError_t sgm_launch_wta_uniform(const SGMParams& P, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
+	const long long threads = (long long)P.vw*P.vh*8;
+	sgm_wta_uniform_kernel<<<(unsigned)((threads+255)/256), 256, 0, s>>>(P.accums, P.vw*P.vh, dmin, num, disparity, cost);
+	return cudaGetLastError();
+}
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s) {
 	sgm_cross_check_kernel<<<dim3((w+255)/256, h), 256, 0, s>>>(l2r, r2l, w, h, th);
 	return cudaGetLastError();
