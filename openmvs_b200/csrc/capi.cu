@@ -44,8 +44,8 @@ cudaError_t sgm_cost_tc_launch(const SGMParams& P, int dmin, int num, cudaStream
 cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s);
 // wave-front aggregation (sgm_front.cu)
-cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, cudaStream_t s);
-int sgm_front_blocks(int num);
+cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, int pd, cudaStream_t s);
+int sgm_front_blocks_per_sm(int num, int pd);
 bool sgm_front_supports(int num);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 cudaError_t sgm_launch_wta_uniform(const SGMParams& P, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s);
@@ -476,7 +476,12 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 	CK(ctx->sgFrontState.reserve((size_t)4*maxPaths*num*sizeof(uint16_t)));
 	CK(ctx->sgFrontMeta.reserve((size_t)4*maxPaths*sizeof(float2)));
 	int* ctl = ctx->sgFrontCtl.as<int>();
-	const int blocks = sgm_front_blocks(num);
+	// resident CTAs: the queue needs no particular number; fewer warps in flight leave more queue distance between an item and
+	// its predecessors (reserved[4] = CTAs per SM, 0 = default), reserved[5] = pipeline depth (4 default, 6)
+	const int pd = ctx->dbg.reserved[5] == 6 ? 6 : 4;
+	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	const int perSm = std::min(sgm_front_blocks_per_sm(num, pd), ctx->dbg.reserved[4] > 0 ? ctx->dbg.reserved[4] : 2);
+	const int blocks = sms*perSm;
 	const int FBeff = layout == 2 ? (1<<28) : FB;
 	for (size_t i = 0; i < ctx->sgFront.size(); ++i) {
 		b200mvs_ctx::FrontPass& fp = ctx->sgFront[i];
@@ -489,7 +494,7 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 		A.state = ctx->sgFrontState.as<uint16_t>(); A.meta = ctx->sgFrontMeta.as<float2>(); A.maxPaths = maxPaths;
 		A.fa = fp.desc.fa; A.fb = fp.desc.fb; A.fc = fp.fc; A.FB = FBeff;
 		A.storePhase0 = i == 0 ? 1 : 0; A.num = num;
-		CK(sgm_front_launch(P, A, blocks, s)); ++ctx->launches;
+		CK(sgm_front_launch(P, A, blocks, pd, s)); ++ctx->launches;
 	}
 	return B200MVS_OK;
 }

@@ -45,7 +45,6 @@ struct SGMParams {
 namespace {
 
 constexpr int FRONT_WARPS = 4;
-constexpr int PD = 4;          // software pipeline depth (steps whose loads are in flight)
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
 	int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -101,9 +100,12 @@ template <> struct FrontVec<16> {
 	}
 };
 
-// NW words per lane, 8 lanes per pixel, 4 pixels (adjacent paths) per warp.  Dense volumes only: every pixel of the valid
-// region is valid, owns `num` = 16*NW entries at idx = (y*vw + x)*num (checked by the caller).
-template <int NW>
+// NW words per lane, 8 lanes per pixel, 4 pixels (adjacent paths) per warp; PD = steps whose loads are in flight.
+// Dense volumes only: every pixel of the valid region is valid, owns `num` = 16*NW entries at idx = (y*vw + x)*num (checked by
+// the caller).  Per-item overhead is kept off the critical path: the ticket of the item after next and the record of the next item
+// are requested while the current item runs; the read-only loads of the first steps (costs, intensities) are issued before the
+// dependency wait; the wait polls with relaxed loads (no L1 invalidation per poll) and fences once.
+template <int NW, int PD>
 __global__ void __launch_bounds__(FRONT_WARPS*32)
 sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ FrontArgs A)
 {
@@ -115,15 +117,18 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 	const int g = lane>>3, sub = lane&7;
 	const unsigned P1x2 = (unsigned)P.P1*0x10001u;
 	const int vw = P.vw, vh = P.vh, num = A.num;
-	int ticket = 0;
-	if (lane == 0) ticket = atomicAdd(A.ticket, 1);
-	ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+	// queue: `ticket` is being processed, `next` is already claimed, the one after is requested at the top of the loop
+	int ticket = 0, next = 0;
+	if (lane == 0) { ticket = atomicAdd(A.ticket, 1); next = atomicAdd(A.ticket, 1); }
+	ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0); next = __shfl_sync(0xFFFFFFFFu, next, 0);
+	uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+	if (ticket < A.nItems) { r0 = __ldg((const uint4*)(A.items+ticket)); r1 = __ldg((const uint4*)(A.items+ticket)+1); }
 	#pragma unroll 1
 	while (ticket < A.nItems) {
-		// the next ticket is requested now and consumed when this item is done (the atomic's latency is hidden)
-		int next = 0;
-		if (lane == 0) next = atomicAdd(A.ticket, 1);
-		const uint4 r0 = __ldg((const uint4*)(A.items+ticket)), r1 = __ldg((const uint4*)(A.items+ticket)+1);
+		int next2 = 0;
+		if (lane == 0) next2 = atomicAdd(A.ticket, 1);
+		uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+		if (next < A.nItems) { n0 = __ldg((const uint4*)(A.items+next)); n1 = __ldg((const uint4*)(A.items+next)+1); }
 		const int k0 = (int)r0.x, dir = (int)(short)(r0.y&0xFFFFu), ph = (int)(short)(r0.y>>16), fblk = (int)r0.z, seq = (int)r0.w;
 		const int chain = (int)r1.x, depCell = (int)r1.y, depNeed = (int)r1.z, cell = (int)r1.w;
 		// geometry of this lane's path
@@ -135,12 +140,36 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 		const int cnt = s1-s0;
 		const int maxcnt = __reduce_max_sync(0xFFFFFFFFu, cnt);
 		const bool add = !(A.storePhase0 && ph == 0);
+		// pipeline stages.  Addresses advance by constant strides along the path: the load pointers run PD steps ahead of the
+		// store pointer (no per-step 64-bit multiplies).
+		typename V::C cs[PD]; typename V::S ss[PD]; float is[PD];
+		const long long pstep = (long long)dy*vw + dx;                    // pixel index stride of one step
+		const long long pix0 = (long long)(ys+s0*dy)*vw + (xs+s0*dx);
+		const uint8_t* cptr = P.costs + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		const uint16_t* sptr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		uint16_t* optr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		const float* iptr = P.lgray + (size_t)(ys+s0*dy)*P.w + (xs+s0*dx);
+		const long long cstep = pstep*num, istep = (long long)dy*P.w + dx;
+		// read-only inputs of the first PD steps: no dependency, issued before the wait
+		#pragma unroll
+		for (int j = 0; j < PD; ++j) {
+			memset(&cs[j], 0, sizeof(cs[j])); memset(&ss[j], 0, sizeof(ss[j])); is[j] = 0.f;
+			if (j < cnt) { cs[j] = V::ldc(cptr + j*cstep); is[j] = __ldg(iptr + j*istep); }
+		}
 		// wait for the predecessors: the previous segment of this band, the previous phase of this front block
 		if (lane == 0) {
+			const int* pp = A.progress+chain; const int* pc = A.cellDone+(depCell >= 0 ? depCell : 0);
+			const int need = depCell >= 0 ? depNeed : 0;
 			unsigned spins = 0;
-			while (ld_acquire(A.progress+chain) < seq) { __nanosleep(64); if (++spins > (1u<<22)) { *A.error = 1; break; } }
-			if (depCell >= 0)
-				while (ld_acquire(A.cellDone+depCell) < depNeed) { __nanosleep(64); if (++spins > (1u<<22)) { *A.error = 1; break; } }
+			for (;;) {
+				int a, c;
+				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(pp) : "memory");
+				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(pc) : "memory");
+				if (a >= seq && c >= need) break;
+				__nanosleep(256);
+				if (++spins > (1u<<21)) { *A.error = 1; break; }
+			}
+			__threadfence();   // acquire: the predecessors' stores are visible to the loads below (which go to the L2)
 		}
 		__syncwarp();
 		// path state
@@ -156,27 +185,17 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 			#pragma unroll
 			for (int i = 0; i < NW; i += 4) { const uint4 v = ldcg4(st+2*i); w[i] = v.x; w[i+1] = v.y; w[i+2] = v.z; w[i+3] = v.w; }
 		}
-		// pipeline stages.  Addresses advance by constant strides along the path: the load pointers run PD steps ahead of the
-		// store pointer (no per-step 64-bit multiplies).
-		typename V::C cs[PD]; typename V::S ss[PD]; float is[PD];
-		const long long pstep = (long long)dy*vw + dx;                    // pixel index stride of one step
-		const long long pix0 = (long long)(ys+s0*dy)*vw + (xs+s0*dx);
-		const uint8_t* cptr = P.costs + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
-		const uint16_t* sptr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
-		uint16_t* optr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
-		const float* iptr = P.lgray + (size_t)(ys+s0*dy)*P.w + (xs+s0*dx);
-		const long long cstep = pstep*num, istep = (long long)dy*P.w + dx;
+		if (add) {
+			#pragma unroll
+			for (int j = 0; j < PD; ++j) if (j < cnt) ss[j] = V::lds(sptr + j*cstep);
+		}
+		cptr += (long long)min(cnt, PD)*cstep; sptr += (long long)min(cnt, PD)*cstep; iptr += (long long)min(cnt, PD)*istep;
 		auto load = [&](int j) {   // loads of the next step not yet requested, then advance
 			cs[j] = V::ldc(cptr);
 			if (add) ss[j] = V::lds(sptr);
 			is[j] = __ldg(iptr);
 			cptr += cstep; sptr += cstep; iptr += istep;
 		};
-		#pragma unroll
-		for (int j = 0; j < PD; ++j) {
-			memset(&cs[j], 0, sizeof(cs[j])); memset(&ss[j], 0, sizeof(ss[j])); is[j] = 0.f;
-			if (j < cnt) load(j);
-		}
 		#pragma unroll 1
 		for (int t = 0; t < maxcnt; t += PD) {
 			#pragma unroll
@@ -247,29 +266,29 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 			st_release(A.progress+chain, seq+1);
 			atomicAdd(A.cellDone+cell, 1);
 		}
-		ticket = __shfl_sync(0xFFFFFFFFu, next, 0);
+		ticket = next; next = __shfl_sync(0xFFFFFFFFu, next2, 0);
+		r0 = n0; r1 = n1;
 	}
 }
 
 } // namespace
 
-cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, cudaStream_t s) {
+// pd: software pipeline depth (4 or 6 steps in flight)
+cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, int pd, cudaStream_t s) {
 	const int NW = A.num/16;
-	if (NW == 8) sgm_front_kernel<8><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
-	else if (NW == 4) sgm_front_kernel<4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
-	else if (NW == 16) sgm_front_kernel<16><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
+	if (NW == 8) { if (pd == 6) sgm_front_kernel<8, 6><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); else sgm_front_kernel<8, 4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); }
+	else if (NW == 4) { if (pd == 6) sgm_front_kernel<4, 6><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); else sgm_front_kernel<4, 4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); }
+	else if (NW == 16) sgm_front_kernel<16, 4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
 	else return cudaErrorInvalidValue;
 	return cudaGetLastError();
 }
-// resident CTAs of the kernel on the current device (the queue needs no particular number; this fills the SMs once)
-int sgm_front_blocks(int num) {
-	int dev = 0, sms = 148, per = 4;
-	cudaGetDevice(&dev);
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+// resident CTAs of the kernel per SM on the current device
+int sgm_front_blocks_per_sm(int num, int pd) {
+	int per = 1;
 	const int NW = num/16;
-	if (NW == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<8>, FRONT_WARPS*32, 0);
-	else if (NW == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<4>, FRONT_WARPS*32, 0);
-	else if (NW == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<16>, FRONT_WARPS*32, 0);
-	return sms*std::max(1, per);
+	if (NW == 8) { if (pd == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<8, 6>, FRONT_WARPS*32, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<8, 4>, FRONT_WARPS*32, 0); }
+	else if (NW == 4) { if (pd == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<4, 6>, FRONT_WARPS*32, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<4, 4>, FRONT_WARPS*32, 0); }
+	else if (NW == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<16, 4>, FRONT_WARPS*32, 0);
+	return std::max(1, per);
 }
 bool sgm_front_supports(int num) { return num == 64 || num == 128 || num == 256; }

@@ -548,8 +548,8 @@ class SemiGlobalMatcher:
 		sgmCost, frontLayout / frontBlock / frontLag (reserved[0..2]); no arguments = defaults."""
 		d = _lib.Debug()
 		for k, v in kw.items():
-			if k in ("frontLayout", "frontBlock", "frontLag"):
-				d.reserved[("frontLayout", "frontBlock", "frontLag").index(k)] = int(v)
+			if k in ("frontLayout", "frontBlock", "frontLag", "fourCtas", "frontCtas", "frontDepth"):
+				d.reserved[("frontLayout", "frontBlock", "frontLag", "fourCtas", "frontCtas", "frontDepth").index(k)] = int(v)
 			elif hasattr(d, k):
 				setattr(d, k, int(v))
 			else:

@@ -4,9 +4,9 @@ mkdir -p gpurun_out
 echo "== sgm tests"
 timeout 600 python -m pytest tests/test_sgm_parity_gpu.py -m gpu -x -q 2>&1 | tail -6
 echo "== sgm variants"
-timeout 300 python scripts/profile_sgm.py 128 2>&1 | tail -12 | tee gpurun_out/sgm_variants.txt
+timeout 400 python scripts/profile_sgm.py 128 2>&1 | tail -40 | tee gpurun_out/sgm_variants.txt
 echo "== pm + other tests"
-timeout 1500 python -m pytest tests/test_pm_parity_gpu.py tests/test_image_prep_gpu.py tests/test_real_fixture.py tests/test_cpp_adapter.py tests/test_filter_parity_gpu.py -m gpu -q 2>&1 | tail -25
+timeout 1500 python -m pytest tests/test_pm_parity_gpu.py tests/test_image_prep_gpu.py tests/test_real_fixture.py tests/test_cpp_adapter.py tests/test_filter_parity_gpu.py -m gpu -q 2>&1 | tail -40
 echo "== ncu: wave-front kernel (default layout, both passes), tensor-core cost kernel"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sgm_front_kernel -s 2 -c 2 -o gpurun_out/sgm_front -f python scripts/profile_sgm.py 128 default > gpurun_out/ncu_front.log 2>&1
 for i in 0 1; do timeout 60 python scripts/ncu_summary.py gpurun_out/sgm_front.ncu-rep $i > gpurun_out/ncu_sgm_front_pass$i.txt 2>&1; done; head -30 gpurun_out/ncu_sgm_front_pass0.txt

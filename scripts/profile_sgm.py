@@ -16,11 +16,15 @@ m = SemiGlobalMatcher()
 costs = torch.zeros(n, dtype=torch.uint8, device="cuda"); accums = torch.zeros(n, dtype=torch.int16, device="cuda")
 ref = None
 MODES = [("register pipeline", dict(sgmAggregation=2)), ("bulk-copy ring, 8 launches", dict(sgmAggregation=3)),
-	("wave fronts (default: tilted, FB 32, lag 2)", dict()),
-	("wave fronts tilted FB 16 lag 2", dict(sgmAggregation=4, frontBlock=16)), ("wave fronts tilted FB 64 lag 2", dict(sgmAggregation=4, frontBlock=64)),
-	("wave fronts tilted FB 32 lag 1", dict(sgmAggregation=4, frontLag=1)), ("wave fronts tilted FB 32 lag 3", dict(sgmAggregation=4, frontLag=3)),
-	("wave fronts straight FB 16", dict(sgmAggregation=4, frontLayout=1)), ("wave fronts straight FB 32", dict(sgmAggregation=4, frontLayout=1, frontBlock=32)),
-	("wave fronts, 8 single passes", dict(sgmAggregation=4, frontLayout=2))]
+	("wave fronts (default)", dict())]
+for layout, name in ((0, "tilted"), (1, "straight")):
+	for fbk in (32, 64):
+		for ctas in (1, 2, 3):
+			for pd in (4, 6):
+				MODES.append(("fronts %s FB %d ctas %d depth %d" % (name, fbk, ctas, pd), dict(sgmAggregation=4, frontLayout=layout, frontBlock=fbk, frontCtas=ctas, frontDepth=pd)))
+MODES += [("fronts tilted FB 32 lag 1 ctas 2", dict(sgmAggregation=4, frontLag=1, frontCtas=2)), ("fronts tilted FB 32 lag 3 ctas 2", dict(sgmAggregation=4, frontLag=3, frontCtas=2)),
+	("fronts tilted FB 128 ctas 2", dict(sgmAggregation=4, frontBlock=128, frontCtas=2)), ("fronts straight FB 8 ctas 2", dict(sgmAggregation=4, frontLayout=1, frontBlock=8, frontCtas=2)),
+	("fronts, 8 single passes", dict(sgmAggregation=4, frontLayout=2))]
 MODES.append(("tensor-core cost kernel + wave fronts", dict(sgmCost=2)))
 if len(sys.argv) > 2 and sys.argv[2] == "default":
 	MODES = MODES[2:3]
@@ -40,4 +44,4 @@ for name, dbg in MODES:
 		same = "| identical to the register pipeline: %s" % (torch.equal(ref[0], accums) and torch.equal(ref[1], disp))
 		if "sgmCost" in dbg:
 			same = "| disparities equal to the SIMT-cost run on %.4f of the pixels" % float((ref[1] == disp).float().mean())
-	print("D=%d %-46s" % (D, name), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same, flush=True)
+	print("D=%d %-40s" % (D, name), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same, flush=True)

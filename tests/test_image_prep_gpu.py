@@ -37,13 +37,14 @@ def test_scale_image_device_matches_cv2():
 	rng = np.random.RandomState(5)
 	img = cv2.GaussianBlur(rng.rand(241, 323).astype(np.float32), (0, 0), 1.2)
 	pm = PatchMatchB200(0)
-	for scale in (0.5, 0.62, 0.8, 0.85, 1.15, 1.3, 1.7, 2.0):
+	for scale in (0.5, 0.62, 0.8, 0.84, 1.16, 1.3, 1.7, 2.0):
 		got = pm.ScaleImage(_dev(img), scale)
 		want = cv2.resize(img, None, fx=float(np.float32(scale)), fy=float(np.float32(scale)), interpolation=cv2.INTER_CUBIC if scale > 1 else cv2.INTER_AREA)
 		assert got is not None and tuple(got.shape) == want.shape, (scale, got.shape, want.shape)
 		err = np.abs(got.cpu().numpy()-want)
 		assert err.max() < 3e-5, (scale, float(err.max()))
-	for scale in (0.9, 1.0, 1.1):
+	# NeedScaleImage is |scale - 1.f| >= 0.15f in float: 0.85f and 1.15f fall just below it, like in the reference
+	for scale in (0.85, 0.9, 1.0, 1.1, 1.15):
 		assert pm.ScaleImage(_dev(img), scale) is None
 	# a row-strided source (cv::Mat ROI)
 	wide = torch.zeros((241, 330), dtype=torch.float32, device="cuda"); wide[:, :323] = _dev(img)
