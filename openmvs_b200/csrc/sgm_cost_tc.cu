@@ -11,12 +11,12 @@
 // parts (w = wh + wl, error 2^-22) and every sum is three kind::f16 MMAs with fp32 accumulation in TMEM (wh fh + wh fl + wl fh) —
 // the dropped wl fl term is 2^-22 relative — so the uint8 cost stays within the +-1 level of the SIMT kernel.
 //
-// Structure (one 256-thread CTA per SM, persistent over the rows of the valid region):
-//   all 8 warps build A (bilateral weights of the block's 128 pixels: 49 expf per pixel shared by two threads, fp16 split, 16-byte
+// Structure (one 512-thread CTA per SM, persistent over the rows of the valid region):
+//   all 16 warps build A (bilateral weights of the block's 128 pixels: 49 expf per pixel shared by four threads, fp16 split, 16-byte
 //              stores in the UMMA K-major no-swizzle core-matrix layout), then the two new B tiles (im2col of 7 right-image rows);
 //   one thread issues the MMAs of a tile (9 products x 4 K-steps of 128 x 64 x 16) into one of two TMEM accumulator buffers
 //              and commits them to an mbarrier; the next tile's MMAs run while
-//   all 8 warps read the finished buffer (tcgen05.ld 32x32b), turn sums into costs and scatter them into a shared cost tile,
+//   all 16 warps read the finished buffer (tcgen05.ld 32x32b), turn sums into costs and scatter them into a shared cost tile,
 //              which is finally written to the volume with coalesced 16-byte stores.
 // SASS: UTCHMMA (tcgen05.mma), UTCBAR (commit), LDTM (tcgen05.ld), UTCATOMSWS / UTCALLOC (alloc).
 #include <cuda_runtime.h>
@@ -41,7 +41,7 @@ constexpr int HW = 3, NT = 49;
 constexpr int BM = 128;          // pixels per block (MMA M)
 constexpr int BN = 64;           // right-image columns per tile (MMA N)
 constexpr int KP = 64;           // taps padded to the MMA K granularity (4 x 16)
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512;
 constexpr int A_ARRAY = BM*KP*2;         // one fp16 operand array of a block: 16 KB
 constexpr int B_ARRAY = BN*KP*2;         // one fp16 operand array of a tile: 8 KB
 constexpr int B_SLOT = 4*B_ARRAY;        // fh, fl, qh, ql
@@ -131,14 +131,15 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 	const float sigmaSpatial = -1.f/(2.f*(0.4f*7)*(0.4f*7));
 	unsigned phase[2] = {0u, 0u};
 
-	// Operand builders: every pixel / column is shared by two threads, `half` 0 owns taps 0..23 (K-chunks 0..2), `half` 1 taps
-	// 24..48 (K-chunks 3..6), so that all 256 threads build — A (128 pixels x 2) first, then the two new B tiles (2 x 64 columns x 2).
+	// Operand builders: every pixel / column is shared by four threads (adjacent lanes); quarter q owns K-chunks 2q and 2q+1
+	// (taps 16q .. 16q+15), quarter 3 the chunk of tap 48 — all 512 threads build: A (128 pixels x 4) first, then the two new B
+	// tiles (2 x 64 columns x 4).
 	// one B tile column: u' = 64 t + c of the band
-	auto build_b_tile = [&](int r, int t, int c, int half) {
+	auto build_b_tile = [&](int r, int t, int c, int q) {
 		unsigned char* slot = sB + (size_t)(t&(RING-1))*B_SLOT;
 		const int lcol = BN*t + c + dmin;         // image column of the window's left edge
 		#pragma unroll 1
-		for (int kc = half ? 3 : 0; kc < (half ? 7 : 3); ++kc) {
+		for (int kc = 2*q; kc < (q == 3 ? 7 : 2*q+2); ++kc) {
 			__half fh[8], fl[8], qh[8], ql[8];
 			#pragma unroll
 			for (int e = 0; e < 8; ++e) {
@@ -159,20 +160,21 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 			*(uint4*)(slot+3*B_ARRAY+off) = make_uint4(pack_h2(ql[0], ql[1]), pack_h2(ql[2], ql[3]), pack_h2(ql[4], ql[5]), pack_h2(ql[6], ql[7]));
 		}
 	};
-	// the block's A operands: threads 2*row and 2*row+1 (adjacent lanes) own pixel x0 + row
-	auto build_a = [&](int r, int x0, int row, int half) {
-		constexpr int NH = 25;                        // taps per half: 24 | 25
-		const int n0 = half ? 24 : 0, nn = half ? 25 : 24;
+	// the block's A operands: threads 4*row .. 4*row+3 (adjacent lanes) own pixel x0 + row
+	auto build_a = [&](int r, int x0, int row, int q) {
+		constexpr int NQ = 16;                        // taps per quarter: 16 | 16 | 16 | 1
+		const int n0 = 16*q, nn = q == 3 ? 1 : 16;
 		const int col = x0+row;
-		float wv[NH], gv[NH];
+		float wv[NQ], gv[NQ];
 		float sumW = 0.f, acc = 0.f, normSq0 = 0.f;
 		const bool valid = col < vw;
+		#pragma unroll
+		for (int k = 0; k < NQ; ++k) { wv[k] = 0.f; gv[k] = 0.f; }
 		if (valid) {
 			const int ux = col+HW, uy = r+HW;
 			const uchar3 cc = P.lbgr[(size_t)uy*w + ux];
 			#pragma unroll
-			for (int k = 0; k < NH; ++k) {
-				wv[k] = 0.f; gv[k] = 0.f;
+			for (int k = 0; k < NQ; ++k) {
 				if (k < nn) {
 					const int n = n0+k, i = n/7, j = n-7*i;
 					const size_t o = (size_t)(uy+i-HW)*w + (ux+j-HW);
@@ -185,34 +187,30 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 					sumW += wgt;
 				}
 			}
-		} else {
-			#pragma unroll
-			for (int k = 0; k < NH; ++k) { wv[k] = 0.f; gv[k] = 0.f; }
 		}
-		// the two halves of a pixel sit in adjacent lanes
-		acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
-		sumW += __shfl_xor_sync(0xFFFFFFFFu, sumW, 1);
+		// the four quarters of a pixel sit in adjacent lanes
+		acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1); acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+		sumW += __shfl_xor_sync(0xFFFFFFFFu, sumW, 1); sumW += __shfl_xor_sync(0xFFFFFFFFu, sumW, 2);
 		if (!valid) sumW = 1.f;
 		const float tm = acc/sumW;
 		#pragma unroll
-		for (int k = 0; k < NH; ++k) {
+		for (int k = 0; k < NQ; ++k) {
 			const float t = gv[k]-tm;
-			gv[k] = wv[k]*t;          // tempWeight (0 for the unused tap of the short half: w = 0)
+			gv[k] = wv[k]*t;          // tempWeight (0 for the unused taps: w = 0)
 			normSq0 += gv[k]*t;
 		}
-		normSq0 += __shfl_xor_sync(0xFFFFFFFFu, normSq0, 1);
-		if (half == 0) sConst[row] = make_float2(normSq0, 1.f/sumW);
+		normSq0 += __shfl_xor_sync(0xFFFFFFFFu, normSq0, 1); normSq0 += __shfl_xor_sync(0xFFFFFFFFu, normSq0, 2);
+		if (q == 0) sConst[row] = make_float2(normSq0, 1.f/sumW);
 		#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const int kc = (half ? 3 : 0)+q;
-			if (!half && q == 3) break;
+		for (int c2 = 0; c2 < 2; ++c2) {
+			if (q == 3 && c2 == 1) break;
+			const int kc = 2*q+c2;
 			__half wh[8], wl[8], th[8], tl[8];
 			#pragma unroll
 			for (int e = 0; e < 8; ++e) {
-				const int k = q*8+e;                    // index into this half's taps (half 1: tap 24+k)
-				const bool in = k < nn;
-				split_h(in ? wv[k < NH ? k : 0] : 0.f, wh[e], wl[e]);
-				split_h(in ? gv[k < NH ? k : 0] : 0.f, th[e], tl[e]);
+				const int k = c2*8+e;                   // index into this quarter's taps
+				split_h(wv[k], wh[e], wl[e]);
+				split_h(gv[k], th[e], tl[e]);
 			}
 			const size_t off = (size_t)kc*(BM*16) + (size_t)row*16;
 			*(uint4*)(sA+0*A_ARRAY+off) = make_uint4(pack_h2(wh[0], wh[1]), pack_h2(wh[2], wh[3]), pack_h2(wh[4], wh[5]), pack_h2(wh[6], wh[7]));
@@ -243,21 +241,20 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 	auto epilogue = [&](int r, int b, int t, int buf) {
 		mbar_wait(bars+buf, phase[buf]); phase[buf] ^= 1u;
 		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-		const int row = 32*(warp&3) + lane;         // TMEM lane = pixel of the block
-		const int cbase = 32*(warp>>2);             // this warp's half of the 64 columns
+		const int row0 = 32*(warp&3), row = row0 + lane;   // TMEM lane = pixel of the block
+		const int c0 = 16*(warp>>2);                        // this warp's 16 of the 64 columns
 		const float2 cst = sConst[row];
-		const int col = BM*b + row;                 // valid-region column of the pixel
+		const int col = BM*b + row;                         // valid-region column of the pixel
 		const float eps = 1e-3f;
-		const int kq = BN*(t-2*b);                  // disparity index of (row 0, column 0) of this tile
-		#pragma unroll
-		for (int ch = 0; ch < 2; ++ch) {
-			// the band 0 <= d < num covers about half of a tile: a 32-row x 16-column chunk wholly outside it is skipped (warp-uniform)
-			const int c0 = cbase+16*ch, row0 = 32*(warp&3);
-			if (kq+c0+15-row0 < 0 || kq+c0-(row0+31) >= num) continue;
+		const int kq = BN*(t-2*b);                          // disparity index of (row 0, column 0) of this tile
+		// the band 0 <= d < num covers about half of a tile: a 32-row x 16-column chunk wholly outside it is skipped (warp-uniform)
+		if (!(kq+c0+15-row0 < 0 || kq+c0-(row0+31) >= num)) {
 			uint32_t s0[16], s1[16], s2[16];
 			const uint32_t ta = tmem + ((uint32_t)row0<<16) + (uint32_t)buf*256u + (uint32_t)c0;
 			tmem_ld16(ta, s0); tmem_ld16(ta+64u, s1); tmem_ld16(ta+128u, s2);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+			// disparities whose right window lies inside the image: 0 <= col + d + dmin, col + d + dmin + 6 < w
+			const int dlo = max(0, -(col+dmin)), dhi = min(num, w-2*HW-col-dmin);
 			#pragma unroll
 			for (int e = 0; e < 16; ++e) {
 				const int d = kq + c0+e - row;            // disparity index of (pixel, column)
@@ -265,10 +262,9 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 					const float sum = __uint_as_float(s0[e]), sumSq = __uint_as_float(s1[e]), nom = __uint_as_float(s2[e]);
 					const float normSq1 = fmaf(-sum*cst.y, sum, sumSq);
 					const float ncc = nom*rsqrtf(fmaf(cst.x, normSq1, eps));
-					// ncc <= 0 ? 255 : floor((1 - min(ncc, 1)) * 255 + .5)
+					// ncc <= 0 ? 255 : floor((1 - min(ncc, 1)) * 255 + .5); 255 for windows that leave the right image
 					int cv = ncc <= 0.f ? 255 : __float2int_rd(fmaf(-255.f, fminf(ncc, 1.f), 255.5f));
-					const int left = col+d+dmin;           // image column of the right window's left edge
-					if (left < 0 || left+2*HW >= w) cv = 255;
+					if (d < dlo || d >= dhi) cv = 255;
 					sTile[row*TILE_PITCH + d] = (uint8_t)cv;
 				}
 			}
@@ -281,12 +277,12 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 		#pragma unroll 1
 		for (int b = 0; b < nBlocks; ++b) {
 			// operands of this block: A by warps 0-3; the tiles not yet in the ring by warps 4-7
-			build_a(r, BM*b, tid>>1, tid&1);
+			build_a(r, BM*b, tid>>2, tid&3);
 			{
-				const int tsel = tid>>7, c = (tid>>1)&63, half = tid&1;   // tile of the pair, column, tap half
+				const int tsel = tid>>8, c = (tid>>2)&63, q = tid&3;      // tile of the pair, column, tap quarter
 				if (b == 0)
-					for (int t = 0; t < nTiles-2; t += 2) build_b_tile(r, t+tsel, c, half);
-				build_b_tile(r, 2*b+nTiles-2+tsel, c, half);
+					for (int t = 0; t < nTiles-2; t += 2) build_b_tile(r, t+tsel, c, q);
+				build_b_tile(r, 2*b+nTiles-2+tsel, c, q);
 			}
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
 			__syncthreads();
