@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200MVS_ABI_VERSION 4 /* struct layouts of this header; b200mvs_abi_version() returns the library's */
+#define B200MVS_ABI_VERSION 5 /* struct layouts of this header; b200mvs_abi_version() returns the library's */
 #define B200MVS_MAX_VIEWS 32 /* neighbours per reference view (MAX_VIEWS, PatchMatchCUDA.inl:35) */
 
 typedef struct b200mvs_ctx b200mvs_ctx;
@@ -93,7 +93,16 @@ typedef struct {
 	int sgmAggregation;  /* 0 auto; 1 general ragged kernel; 2 register-pipelined uniform kernel; 3 bulk-copy ring kernel (one launch
 	                        per direction); 4 front kernel (fused directions, auto default for uniform ranges) */
 	int sgmCost;         /* 0 auto; 1 SIMT cost kernel; 2 tensor-core (tcgen05) cost kernel */
-	int reserved[4];
+	int sweepFourCtas;   /* 1: the 64-register instantiation of the sweep kernel (4 CTAs per SM instead of 3) */
+	int frontLayout;     /* wave-front aggregation: 0 auto; 1 two tilted fronts +-(x+2y), four directions each; 2 four straight
+	                        fronts; 3 eight passes of one direction */
+	int frontSerial;     /* 1: one pass per launch into one sum volume (default: two passes share a launch, each with its own
+	                        volume, added by the winner-takes-all kernel) */
+	int frontBlock;      /* fronts per work item (0: default) */
+	int frontLag;        /* queue distance, in blocks, between the directions of a pass (0: default) */
+	int frontCtas;       /* resident CTAs per SM (0: default) */
+	int frontDepth;      /* steps whose loads are in flight: 4 or 8 (0: default) */
+	int reserved[5];
 } b200mvs_debug;
 
 typedef struct {

@@ -48,7 +48,7 @@ cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks,
 int sgm_front_blocks_per_sm(int num, int pd);
 bool sgm_front_supports(int num);
 cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
-cudaError_t sgm_launch_wta_uniform(const SGMParams& P, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s);
+cudaError_t sgm_launch_wta_uniform(const SGMParams& P, const uint16_t* second, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
 cudaError_t sgm_launch_refine(const SGMPixel* px, const uint16_t* accums, int16_t* disparity, int n, int steps, cudaStream_t s);
@@ -143,9 +143,9 @@ struct b200mvs_ctx {
 	DevBuf plane, cost, best, prior, lowPlane;
 	DevBuf dDepth, dNormal, dConf, dViews;    // level scratch / staging of the maps (host API)
 	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
-	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgDisp, sgCost, sgMax; // SGM staging / scratch
+	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgAccums2, sgDisp, sgCost, sgMax; // SGM staging / scratch
 	// wave-front aggregation: cached schedule of the last (size, mode) and its scratch
-	struct FrontPass { FrontPassDesc desc; DevBuf items; int nItems = 0, nFB = 0, maxBands = 0, fc = 0; };
+	struct FrontPass { FrontLaunch launch; DevBuf items; int nItems = 0; };   // launch.items is emptied once uploaded
 	std::vector<FrontPass> sgFront; int sgFrontKey[6] = {0, 0, 0, 0, 0, 0};
 	DevBuf sgFrontCtl, sgFrontState, sgFrontMeta;
 	const void* sgLastPx = nullptr; uint64_t sgLastNum = 0; // pixel map / size of the volume in sgAccums (b200mvs_sgm_refine_device check)
@@ -324,7 +324,7 @@ int launch_sweep_timed(b200mvs_ctx* ctx, const PMParams& P, bool geom, cudaStrea
 		}
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv], s));
 	}
-	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, !ctx->dbg.scalarTaps, geom, ctx->dbg.reserved[3] != 0, s)); ++ctx->launches;
+	CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, !ctx->dbg.scalarTaps, geom, ctx->dbg.sweepFourCtas != 0, s)); ++ctx->launches;
 	if (ctx->timeSweeps) {
 		CK(cudaEventRecord(ctx->sweepEv[2*ctx->nSweepEv+1], s));
 		++ctx->nSweepEv;
@@ -440,60 +440,72 @@ int estimate_on_device(b200mvs_ctx* ctx, const DView* views, int nViews, float d
 	return B200MVS_OK;
 }
 
-// SGM path aggregation with the wave-front kernel (sgm_front.cu).  Pass layouts (b200mvs_debug.reserved[0]):
-//   0 (default) two tilted fronts f = +-(x + 2y): {right, right-down, down, left-down} then {left, left-up, up, right-up};
-//   1 four straight fronts: top-down {down, right-down, left-down}, bottom-up {up, right-up, left-up}, left-right, right-left;
-//   2 eight passes of one direction each (the traffic of the per-direction kernels with the new step).
-// reserved[1] = fronts per block (default 32), reserved[2] = queue lag between the phases of a block (default 2).
-int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStream_t s) {
-	const int layout = std::min(std::max(ctx->dbg.reserved[0], 0), 2);
-	const int FB = ctx->dbg.reserved[1] > 0 ? ctx->dbg.reserved[1] : (layout == 0 ? 32 : 16);
-	const int lag = ctx->dbg.reserved[2] > 0 ? ctx->dbg.reserved[2] : 2;
+// SGM path aggregation with the wave-front kernel (sgm_front.cu).  Pass layouts (b200mvs_debug.frontLayout, 0 = auto = 1):
+//   1 two tilted fronts f = +-(x + 2y): {right, right-down, down, left-down} and {left, left-up, up, right-up};
+//   2 four straight fronts: top-down {down, right-down, left-down}, bottom-up {up, right-up, left-up}, left-right, right-left;
+//   3 eight passes of one direction each (the traffic of the per-direction kernels with the new step).
+// Unless frontSerial is set, consecutive passes share a launch: pass 2j accumulates into the caller's volume, pass 2j+1 into a
+// second one (ctx->sgAccums2), and `twoVolumes` tells the caller to add them (the winner-takes-all kernel does).
+int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStream_t s, bool& twoVolumes) {
+	const b200mvs_debug& D = ctx->dbg;
+	const int layout = std::min(std::max(D.frontLayout-1, 0), 2);
+	const bool concurrent = !D.frontSerial;
+	const int FB = D.frontBlock > 0 ? D.frontBlock : (layout == 0 ? 32 : 16);
+	const int lag = D.frontLag > 0 ? D.frontLag : 2;
 	const int vw = P.vw, vh = P.vh;
-	const int key[6] = {vw, vh, layout, FB, lag, 1};
+	const int key[6] = {vw, vh, layout, FB, lag, concurrent ? 2 : 1};
 	if (memcmp(key, ctx->sgFrontKey, sizeof(key)) != 0) {
-		const std::vector<FrontPassDesc> descs = sgm_front_layout(layout);
 		for (auto& fp: ctx->sgFront) fp.items.release();
-		ctx->sgFront.clear(); ctx->sgFront.resize(descs.size());
-		std::vector<FrontItem> items;
-		for (size_t i = 0; i < descs.size(); ++i) {
+		ctx->sgFront.clear();
+		std::vector<FrontLaunch> plan = sgm_front_plan(vw, vh, layout, concurrent, FB, lag);
+		ctx->sgFront.resize(plan.size());
+		for (size_t i = 0; i < plan.size(); ++i) {
 			b200mvs_ctx::FrontPass& fp = ctx->sgFront[i];
-			fp.desc = descs[i];
-			// one-direction passes of layout 2 need no blocks: one item per band walks the whole path
-			const int fbSize = layout == 2 ? (1<<28) : FB;
-			sgm_front_build(vw, vh, fp.desc, fbSize, lag, items, fp.nFB, fp.maxBands, fp.fc);
-			fp.nItems = (int)items.size();
-			CK(fp.items.reserve(items.size()*sizeof(FrontItem)));
-			CK(cudaMemcpyAsync(fp.items.p, items.data(), items.size()*sizeof(FrontItem), cudaMemcpyHostToDevice, s));
-			CK(cudaStreamSynchronize(s)); // `items` is reused for the next pass
+			CK(fp.items.reserve(plan[i].items.size()*sizeof(FrontItem)));
+			CK(cudaMemcpyAsync(fp.items.p, plan[i].items.data(), plan[i].items.size()*sizeof(FrontItem), cudaMemcpyHostToDevice, s));
+			fp.nItems = (int)plan[i].items.size();
+			plan[i].items.clear(); plan[i].items.shrink_to_fit();
+			fp.launch = plan[i];
 		}
+		CK(cudaStreamSynchronize(s)); // the pageable source vectors die with `plan`
 		memcpy(ctx->sgFrontKey, key, sizeof(key));
+	}
+	twoVolumes = false;
+	for (auto& fp: ctx->sgFront) twoVolumes |= fp.launch.nPasses > 1;
+	uint16_t* second = nullptr;
+	if (twoVolumes) {
+		CK(ctx->sgAccums2.reserve((size_t)vw*vh*num*sizeof(uint16_t)));
+		second = ctx->sgAccums2.as<uint16_t>();
 	}
 	const int maxPaths = vw+vh+8;
 	int maxCtl = 0;
-	for (auto& fp: ctx->sgFront) maxCtl = std::max(maxCtl, 4*fp.maxBands + 4*fp.nFB);
+	for (auto& fp: ctx->sgFront) maxCtl = std::max(maxCtl, fp.launch.nChains + fp.launch.nCells);
 	CK(ctx->sgFrontCtl.reserve((size_t)(4+maxCtl)*sizeof(int)));
-	CK(ctx->sgFrontState.reserve((size_t)4*maxPaths*num*sizeof(uint16_t)));
-	CK(ctx->sgFrontMeta.reserve((size_t)4*maxPaths*sizeof(float2)));
+	CK(ctx->sgFrontState.reserve((size_t)8*maxPaths*num*sizeof(uint16_t)));
+	CK(ctx->sgFrontMeta.reserve((size_t)8*maxPaths*sizeof(float2)));
 	int* ctl = ctx->sgFrontCtl.as<int>();
-	// resident CTAs: the queue needs no particular number; fewer warps in flight leave more queue distance between an item and
-	// its predecessors (reserved[4] = CTAs per SM, 0 = default), reserved[5] = pipeline depth (4 default, 6)
-	const int pd = ctx->dbg.reserved[5] == 6 ? 6 : 4;
+	// resident CTAs: the queue needs no particular number; frontCtas = CTAs per SM, frontDepth = ring slots per warp (8 default, 4)
+	const int pd = D.frontDepth == 4 ? 4 : 8;
 	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	const int perSm = std::min(sgm_front_blocks_per_sm(num, pd), ctx->dbg.reserved[4] > 0 ? ctx->dbg.reserved[4] : 2);
+	const int perSm = std::min(sgm_front_blocks_per_sm(num, pd), D.frontCtas > 0 ? D.frontCtas : 2);
 	const int blocks = sms*perSm;
 	const int FBeff = layout == 2 ? (1<<28) : FB;
 	for (size_t i = 0; i < ctx->sgFront.size(); ++i) {
 		b200mvs_ctx::FrontPass& fp = ctx->sgFront[i];
-		// [ticket, error, -, - | progress (4 x maxBands) | cellDone (4 x nFB)]; the error word survives the passes of one call
+		const FrontLaunch& L = fp.launch;
+		// [ticket, error, -, - | progress | cellDone]; the error word survives the launches of one call
 		if (i == 0) CK(cudaMemsetAsync(ctl, 0, (size_t)(4+maxCtl)*sizeof(int), s));
 		else { CK(cudaMemsetAsync(ctl, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctl+4, 0, (size_t)maxCtl*sizeof(int), s)); }
-		FrontArgs A;
+		FrontArgs A; memset(&A, 0, sizeof(A));
 		A.items = fp.items.as<FrontItem>(); A.nItems = fp.nItems;
-		A.ticket = ctl; A.error = ctl+1; A.progress = ctl+4; A.cellDone = ctl+4+4*fp.maxBands;
+		A.ticket = ctl; A.error = ctl+1; A.progress = ctl+4; A.cellDone = ctl+4+L.nChains;
 		A.state = ctx->sgFrontState.as<uint16_t>(); A.meta = ctx->sgFrontMeta.as<float2>(); A.maxPaths = maxPaths;
-		A.fa = fp.desc.fa; A.fb = fp.desc.fb; A.fc = fp.fc; A.FB = FBeff;
-		A.storePhase0 = i == 0 ? 1 : 0; A.num = num;
+		A.FB = FBeff; A.num = num;
+		for (int p = 0; p < L.nPasses; ++p) {
+			A.fa[p] = L.pass[p].fa; A.fb[p] = L.pass[p].fb; A.fc[p] = L.fc[p];
+			A.storePhase0[p] = i == 0 ? 1 : 0;
+			A.sum[p] = p == 0 ? P.accums : second;
+		}
 		CK(sgm_front_launch(P, A, blocks, pd, s)); ++ctx->launches;
 	}
 	return B200MVS_OK;
@@ -570,7 +582,7 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto& b: c->pyr) b.release();
 	c->refPad.release(); c->maskBuf.release(); c->maskLevel.release();
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
-	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release();
+	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release(); c->sgAccums2.release();
 	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
 	for (auto& fp: c->sgFront) fp.items.release();
 	c->sgFrontCtl.release(); c->sgFrontState.release(); c->sgFrontMeta.release();
@@ -869,7 +881,7 @@ int b200mvs_pm_sweep(b200mvs_ctx* ctx, const b200mvs_view* views, int nViews, fl
 	for (int colour = 0; colour < 2; ++colour) {
 		if (half >= 0 && half != colour) continue;
 		P.colour = colour;
-		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, !ctx->dbg.scalarTaps, geom, ctx->dbg.reserved[3] != 0, s));
+		CK(pm_launch_sweep(P, ctx->tmapValid ? &ctx->tmapRef : nullptr, !ctx->dbg.scalarTaps, geom, ctx->dbg.sweepFourCtas != 0, s));
 	}
 	return B200MVS_OK;
 }
@@ -905,11 +917,11 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	P.w = width; P.h = height; P.vw = width-6; P.vh = height-6;
 	P.px = (const SGMPixel*)pixels;
 	P.P1 = prm->P1;
-	int minP2 = 1<<30;
+	int minP2 = 1<<30, maxP2 = 0;
 	for (int i = 0; i < 256; ++i) {
 		// GenerateP2s (libs/MVS/SemiGlobalMatcher.cpp:518-524)
 		P.P2s[i] = (uint16_t)(int)std::floor(prm->P2*(1.f+prm->P2alpha*std::exp(-float(i)*float(i)/(2.f*prm->P2beta*prm->P2beta)))+.5f);
-		minP2 = std::min(minP2, (int)P.P2s[i]);
+		minP2 = std::min(minP2, (int)P.P2s[i]); maxP2 = std::max(maxP2, (int)P.P2s[i]);
 	}
 	if (prm->P1 < 0 || prm->P1 > minP2)
 		return fail(ctx, B200MVS_ERR_ARG, "sgm: needs 0 <= P1 <= min(P2s)");
@@ -937,7 +949,8 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 		// every slice 16-byte aligned: bulk-copy ring kernel (one launch per direction)
 		ring = uniform && (st8[0] & 15) == 0 && st8[5] == 0 && !((uintptr_t)P.costs & 15) && !((uintptr_t)P.accums & 15) && mode != 2;
 		// dense volume of a supported width: wave-front kernel (fused directions) — the default
-		front = ring && !st8[6] && sgm_front_supports(st8[0]) && (mode == 0 || mode == 4);
+		// (its step carries P2 + the previous line's minimum in 16 bits: P2 <= 16000; sums of eight paths overflow far earlier)
+		front = ring && !st8[6] && sgm_front_supports(st8[0]) && maxP2 <= 16000 && (mode == 0 || mode == 4);
 		if (mode == 4 && !front)
 			return fail(ctx, B200MVS_ERR_ARG, "sgm: the wave-front kernel needs a dense volume with one range of 64, 128 or 256 disparities");
 	}
@@ -951,9 +964,11 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 		else CK(sgm_launch_cost(P, s));
 		++ctx->launches;
 	}
+	bool twoVolumes = false;   // the wave-front passes ran side by side: accums + ctx->sgAccums2 is the sum
 	if ((stages & 2) && front) {
-		const int rc = sgm_aggregate_fronts(ctx, P, st8[0], s);
+		const int rc = sgm_aggregate_fronts(ctx, P, st8[0], s, twoVolumes);
 		if (rc) return rc;
+		if (twoVolumes && !(stages & 4)) { CK(sgm_launch_wta_uniform(P, ctx->sgAccums2.as<uint16_t>(), st8[1], st8[0], nullptr, nullptr, s)); ++ctx->launches; }
 	} else
 	if (stages & 2) {
 		CK(cudaMemsetAsync(accums, 0, numCosts*sizeof(uint16_t), s));
@@ -966,7 +981,7 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	if (stages & 2) { ctx->sgLastPx = (accums == ctx->sgAccums.as<uint16_t>()) ? (const void*)pixels : nullptr; ctx->sgLastNum = numCosts; }
 	if (stages & 4) {
 		const bool denseWta = uniform && (st8[0] & 15) == 0 && !st8[6] && !((uintptr_t)P.accums & 15);
-		if (denseWta) CK(sgm_launch_wta_uniform(P, st8[1], st8[0], disparity, cost, s));
+		if (denseWta) CK(sgm_launch_wta_uniform(P, twoVolumes ? ctx->sgAccums2.as<uint16_t>() : nullptr, st8[1], st8[0], disparity, cost, s));
 		else CK(sgm_launch_wta(P, disparity, cost, s));
 		++ctx->launches;
 	}

@@ -28,6 +28,7 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <type_traits>
 
 struct SGMPixel { unsigned long long idx; short dmin, dmax; int pad; };
 struct SGMParams {
@@ -46,70 +47,39 @@ namespace {
 
 constexpr int FRONT_WARPS = 4;
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-	int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
 __device__ __forceinline__ void st_release(int* p, int v) {
 	asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg((const uint4*)p); }
 __device__ __forceinline__ void stcg4(void* p, uint4 v) { __stcg((uint4*)p, v); }
+// asynchronous global -> shared copies (LDGSTS): no destination registers, so the prefetch distance does not depend on the
+// register allocator; .cg is served by the L2 (coherent with the other SMs' st.cg after the acquire fence)
+__device__ __forceinline__ void cp16(unsigned dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp8(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp4(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-template <int NW> struct FrontVec;   // NW packed u16x2 words per lane = 2*NW disparities; cost bytes 2*NW, sum bytes 4*NW
-template <> struct FrontVec<8> {
-	struct C { uint4 v; }; struct S { uint4 a, b; };
-	static __device__ __forceinline__ C ldc(const uint8_t* p) { C c; c.v = __ldg((const uint4*)p); return c; }
-	static __device__ __forceinline__ S lds(const uint16_t* p) { S s; s.a = ldcg4(p); s.b = ldcg4(p+8); return s; }
-	static __device__ __forceinline__ void sts(uint16_t* p, const unsigned* w) { stcg4(p, make_uint4(w[0], w[1], w[2], w[3])); stcg4(p+8, make_uint4(w[4], w[5], w[6], w[7])); }
-	static __device__ __forceinline__ void unpackC(const C& c, unsigned* o) {
-		o[0] = __byte_perm(c.v.x, 0u, 0x4140); o[1] = __byte_perm(c.v.x, 0u, 0x4342);
-		o[2] = __byte_perm(c.v.y, 0u, 0x4140); o[3] = __byte_perm(c.v.y, 0u, 0x4342);
-		o[4] = __byte_perm(c.v.z, 0u, 0x4140); o[5] = __byte_perm(c.v.z, 0u, 0x4342);
-		o[6] = __byte_perm(c.v.w, 0u, 0x4140); o[7] = __byte_perm(c.v.w, 0u, 0x4342);
-	}
-	static __device__ __forceinline__ void unpackS(const S& s, unsigned* o) { o[0] = s.a.x; o[1] = s.a.y; o[2] = s.a.z; o[3] = s.a.w; o[4] = s.b.x; o[5] = s.b.y; o[6] = s.b.z; o[7] = s.b.w; }
-};
-template <> struct FrontVec<4> {
-	struct C { uint2 v; }; struct S { uint4 a; };
-	static __device__ __forceinline__ C ldc(const uint8_t* p) { C c; c.v = __ldg((const uint2*)p); return c; }
-	static __device__ __forceinline__ S lds(const uint16_t* p) { S s; s.a = ldcg4(p); return s; }
-	static __device__ __forceinline__ void sts(uint16_t* p, const unsigned* w) { stcg4(p, make_uint4(w[0], w[1], w[2], w[3])); }
-	static __device__ __forceinline__ void unpackC(const C& c, unsigned* o) {
-		o[0] = __byte_perm(c.v.x, 0u, 0x4140); o[1] = __byte_perm(c.v.x, 0u, 0x4342);
-		o[2] = __byte_perm(c.v.y, 0u, 0x4140); o[3] = __byte_perm(c.v.y, 0u, 0x4342);
-	}
-	static __device__ __forceinline__ void unpackS(const S& s, unsigned* o) { o[0] = s.a.x; o[1] = s.a.y; o[2] = s.a.z; o[3] = s.a.w; }
-};
-template <> struct FrontVec<16> {
-	struct C { uint4 v, u; }; struct S { uint4 a, b, c, d; };
-	static __device__ __forceinline__ C ldc(const uint8_t* p) { C c; c.v = __ldg((const uint4*)p); c.u = __ldg((const uint4*)(p+16)); return c; }
-	static __device__ __forceinline__ S lds(const uint16_t* p) { S s; s.a = ldcg4(p); s.b = ldcg4(p+8); s.c = ldcg4(p+16); s.d = ldcg4(p+24); return s; }
-	static __device__ __forceinline__ void sts(uint16_t* p, const unsigned* w) {
-		stcg4(p, make_uint4(w[0], w[1], w[2], w[3])); stcg4(p+8, make_uint4(w[4], w[5], w[6], w[7]));
-		stcg4(p+16, make_uint4(w[8], w[9], w[10], w[11])); stcg4(p+24, make_uint4(w[12], w[13], w[14], w[15]));
-	}
-	static __device__ __forceinline__ void unpackC(const C& c, unsigned* o) {
-		const unsigned s[8] = {c.v.x, c.v.y, c.v.z, c.v.w, c.u.x, c.u.y, c.u.z, c.u.w};
-		#pragma unroll
-		for (int i = 0; i < 8; ++i) { o[2*i] = __byte_perm(s[i], 0u, 0x4140); o[2*i+1] = __byte_perm(s[i], 0u, 0x4342); }
-	}
-	static __device__ __forceinline__ void unpackS(const S& s, unsigned* o) {
-		const uint4 q[4] = {s.a, s.b, s.c, s.d};
-		#pragma unroll
-		for (int i = 0; i < 4; ++i) { o[4*i] = q[i].x; o[4*i+1] = q[i].y; o[4*i+2] = q[i].z; o[4*i+3] = q[i].w; }
-	}
+// One step's inputs of a warp in shared memory: planes of 32 lanes x 16 B (costs: 2*NW bytes per lane, sums: 4*NW bytes per
+// lane), then 32 x 4 B of intensities.  A lane reads back exactly what it copied.
+template <int NW> struct FrontSlot {
+	static constexpr int CB = 2*NW, SB = 4*NW;
+	static constexpr int NC = (CB+15)/16, NS = SB/16;
+	static constexpr int IOFF = (NC+NS)*512;
+	static constexpr int BYTES = IOFF+128;
 };
 
-// NW words per lane, 8 lanes per pixel, 4 pixels (adjacent paths) per warp; PD = steps whose loads are in flight.
-// Dense volumes only: every pixel of the valid region is valid, owns `num` = 16*NW entries at idx = (y*vw + x)*num (checked by
-// the caller).  Per-item overhead is kept off the critical path: the ticket of the item after next and the record of the next item
-// are requested while the current item runs; the read-only loads of the first steps (costs, intensities) are issued before the
-// dependency wait; the wait polls with relaxed loads (no L1 invalidation per poll) and fences once.
+// NW words per lane (2*NW disparities), 8 lanes per pixel, 4 pixels (adjacent paths) per warp; PD = ring slots = steps whose
+// loads are in flight.  Dense volumes only: every pixel of the valid region is valid, owns `num` = 16*NW entries at
+// idx = (y*vw + x)*num (checked by the caller).  Per-item overhead is kept off the critical path: the ticket of the item after
+// next and the record of the next item are requested while the current item runs; the copies of the first steps' read-only
+// inputs (costs, intensities) are issued before the dependency wait; the wait polls with relaxed loads and fences once.
 template <int NW, int PD>
 __global__ void __launch_bounds__(FRONT_WARPS*32)
 sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ FrontArgs A)
 {
-	typedef FrontVec<NW> V;
+	typedef FrontSlot<NW> SL;
+	extern __shared__ uint4 ringMem[];
 	__shared__ unsigned sP2[256];   // adaptive P2 replicated in both halfwords (GenerateP2s, SemiGlobalMatcher.cpp:518-524)
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) sP2[i] = (unsigned)P.P2s[i]*0x10001u;
 	__syncthreads();
@@ -117,6 +87,8 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 	const int g = lane>>3, sub = lane&7;
 	const unsigned P1x2 = (unsigned)P.P1*0x10001u;
 	const int vw = P.vw, vh = P.vh, num = A.num;
+	char* const ring = (char*)ringMem + (size_t)(threadIdx.x>>5)*PD*SL::BYTES;
+	const unsigned ringS = (unsigned)__cvta_generic_to_shared(ring);
 	// queue: `ticket` is being processed, `next` is already claimed, the one after is requested at the top of the loop
 	int ticket = 0, next = 0;
 	if (lane == 0) { ticket = atomicAdd(A.ticket, 1); next = atomicAdd(A.ticket, 1); }
@@ -129,33 +101,45 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 		if (lane == 0) next2 = atomicAdd(A.ticket, 1);
 		uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
 		if (next < A.nItems) { n0 = __ldg((const uint4*)(A.items+next)); n1 = __ldg((const uint4*)(A.items+next)+1); }
-		const int k0 = (int)r0.x, dir = (int)(short)(r0.y&0xFFFFu), ph = (int)(short)(r0.y>>16), fblk = (int)r0.z, seq = (int)r0.w;
+		const int k0 = (int)r0.x, dir = (int)(r0.y&0xFFu), pass = (int)((r0.y>>8)&1u), ph = (int)(short)(r0.y>>16), fblk = (int)r0.z, seq = (int)r0.w;
 		const int chain = (int)r1.x, depCell = (int)r1.y, depNeed = (int)r1.z, cell = (int)r1.w;
 		// geometry of this lane's path
 		int xs = 0, ys = 0, dx = 0, dy = 0;
 		const bool pv = front_path_start(dir, k0+g, vw, vh, xs, ys, dx, dy);
 		const int n = pv ? front_path_len(xs, ys, dx, dy, vw, vh) : 0;
-		const int f0 = A.fa*xs + A.fb*ys + A.fc, df = max(1, A.fa*dx + A.fb*dy);
+		const int f0 = A.fa[pass]*xs + A.fb[pass]*ys + A.fc[pass], df = max(1, A.fa[pass]*dx + A.fb[pass]*dy);
 		const int s0 = min(n, front_first_step(fblk*A.FB, f0, df)), s1 = min(n, front_first_step((fblk+1)*A.FB, f0, df));
 		const int cnt = s1-s0;
 		const int maxcnt = __reduce_max_sync(0xFFFFFFFFu, cnt);
-		const bool add = !(A.storePhase0 && ph == 0);
-		// pipeline stages.  Addresses advance by constant strides along the path: the load pointers run PD steps ahead of the
-		// store pointer (no per-step 64-bit multiplies).
-		typename V::C cs[PD]; typename V::S ss[PD]; float is[PD];
-		const long long pstep = (long long)dy*vw + dx;                    // pixel index stride of one step
-		const long long pix0 = (long long)(ys+s0*dy)*vw + (xs+s0*dx);
-		const uint8_t* cptr = P.costs + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
-		const uint16_t* sptr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
-		uint16_t* optr = P.accums + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
-		const float* iptr = P.lgray + (size_t)(ys+s0*dy)*P.w + (xs+s0*dx);
-		const long long cstep = pstep*num, istep = (long long)dy*P.w + dx;
-		// read-only inputs of the first PD steps: no dependency, issued before the wait
+		const bool add = !(A.storePhase0[pass] && ph == 0);
+		uint16_t* const sum = A.sum[pass];
+		// Step k of this lane's segment lies at base + min(k, last)*stride: every lane takes part in every copy (lanes whose
+		// segment is shorter re-read their last step, lanes without steps the first slice of the volume).
+		const int last = max(cnt-1, 0);
+		const long long pix0 = cnt > 0 ? (long long)(ys+s0*dy)*vw + (xs+s0*dx) : 0;
+		const uint8_t* const cbase = P.costs + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		uint16_t* const sbase = sum + (size_t)pix0*(size_t)num + (size_t)sub*(2*NW);
+		const float* const ibase = P.lgray + (cnt > 0 ? (size_t)(ys+s0*dy)*P.w + (xs+s0*dx) : 0);
+		const int cstep = (dy*vw + dx)*num, istep = dy*P.w + dx;          // element strides of one step (|cstep| < 2^31: checked by the host)
+		auto copy_ci = [&](int j, int k) {   // costs and intensity of step k into slot j
+			const uint8_t* c = cbase + (long long)min(k, last)*cstep;
+			const unsigned d = ringS + (unsigned)(j*SL::BYTES + lane*16);
+			if (SL::CB >= 16) {
+				#pragma unroll
+				for (int p = 0; p < SL::NC; ++p) cp16(d + p*512, c + p*16);
+			} else cp8(d, c);
+			cp4(ringS + (unsigned)(j*SL::BYTES + SL::IOFF + lane*4), ibase + (long long)min(k, last)*istep);
+		};
+		auto copy_s = [&](int j, int k) {    // sums of step k into slot j
+			const uint16_t* sp = sbase + (long long)min(k, last)*cstep;
+			const unsigned d = ringS + (unsigned)(j*SL::BYTES + SL::NC*512 + lane*16);
+			#pragma unroll
+			for (int p = 0; p < SL::NS; ++p) cp16(d + p*512, sp + p*8);
+		};
+		// read-only inputs of the first PD steps: no dependency, requested before the wait (one group)
 		#pragma unroll
-		for (int j = 0; j < PD; ++j) {
-			memset(&cs[j], 0, sizeof(cs[j])); memset(&ss[j], 0, sizeof(ss[j])); is[j] = 0.f;
-			if (j < cnt) { cs[j] = V::ldc(cptr + j*cstep); is[j] = __ldg(iptr + j*istep); }
-		}
+		for (int j = 0; j < PD; ++j) if (j < maxcnt) copy_ci(j, j);
+		cp_commit();
 		// wait for the predecessors: the previous segment of this band, the previous phase of this front block
 		if (lane == 0) {
 			const int* pp = A.progress+chain; const int* pc = A.cellDone+(depCell >= 0 ? depCell : 0);
@@ -166,36 +150,31 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(pp) : "memory");
 				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(pc) : "memory");
 				if (a >= seq && c >= need) break;
-				__nanosleep(256);
+				__nanosleep(64);
 				if (++spins > (1u<<21)) { *A.error = 1; break; }
 			}
-			__threadfence();   // acquire: the predecessors' stores are visible to the loads below (which go to the L2)
+			// acquire: the predecessors' stores are visible to the loads below (ld.cg / cp.async.cg: served by the L2)
+			asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		}
 		__syncwarp();
-		// path state
-		const size_t slot = (size_t)ph*A.maxPaths + (size_t)(k0+g);
+		// the sums of the first PD steps: one group per step (empty when the phase stores)
+		#pragma unroll
+		for (int j = 0; j < PD; ++j) { if (add && j < maxcnt) copy_s(j, j); cp_commit(); }
+		// path state: the previous line minus its minimum (all 0xFFFF at the start of a path: the step then yields C + P2,
+		// SemiGlobalMatcher.cpp:1003-1006) and the previous intensity
+		const size_t slot = (size_t)(pass*4+ph)*A.maxPaths + (size_t)(k0+g);
 		unsigned w[NW];
-		float Ip = 0.5f; bool havePrev = false;
+		float Ip = 0.5f;
 		#pragma unroll
 		for (int i = 0; i < NW; ++i) w[i] = 0xFFFFFFFFu;
 		if (s0 > 0 && cnt > 0) {
-			const float2 m = __ldcg(A.meta+slot);
-			Ip = m.x; havePrev = m.y != 0.f;
+			Ip = __ldcg(A.meta+slot).x;
 			const uint16_t* st = A.state + slot*(size_t)num + (size_t)sub*(2*NW);
 			#pragma unroll
 			for (int i = 0; i < NW; i += 4) { const uint4 v = ldcg4(st+2*i); w[i] = v.x; w[i+1] = v.y; w[i+2] = v.z; w[i+3] = v.w; }
 		}
-		if (add) {
-			#pragma unroll
-			for (int j = 0; j < PD; ++j) if (j < cnt) ss[j] = V::lds(sptr + j*cstep);
-		}
-		cptr += (long long)min(cnt, PD)*cstep; sptr += (long long)min(cnt, PD)*cstep; iptr += (long long)min(cnt, PD)*istep;
-		auto load = [&](int j) {   // loads of the next step not yet requested, then advance
-			cs[j] = V::ldc(cptr);
-			if (add) ss[j] = V::lds(sptr);
-			is[j] = __ldg(iptr);
-			cptr += cstep; sptr += cstep; iptr += istep;
-		};
+		unsigned mp2 = 0u;   // minimum of the line in w, in both halfwords (0: normalised)
+		uint16_t* optr = sbase;
 		#pragma unroll 1
 		for (int t = 0; t < maxcnt; t += PD) {
 			#pragma unroll
@@ -203,64 +182,88 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 				const int tt = t+j;
 				if (tt >= maxcnt) break;
 				const bool act = tt < cnt;
+				// the group of step tt has landed when at most the PD-1 younger ones are pending
+				cp_wait<PD-1>();
+				const char* sl = ring + j*SL::BYTES + lane*16;
 				unsigned C[NW], S[NW];
-				V::unpackC(cs[j], C);
-				V::unpackS(ss[j], S);
-				const float I = is[j];
-				if (tt+PD < cnt) load(j);
-				// penalty of this step: P2s[|round(255 (I - Ip))|] (SemiGlobalMatcher.cpp:1009, 518-524)
-				const int di = min(255, abs((int)floorf(255.f*(I-Ip)+.5f)));
-				const unsigned P2x2 = sP2[di];
-				unsigned L[NW];
-				// neighbours d-1 / d+1 across the lanes of the pixel (0xFFFF beyond the two ends of the range)
-				unsigned below = __shfl_up_sync(0xFFFFFFFFu, w[NW-1]>>16, 1), above = __shfl_down_sync(0xFFFFFFFFu, w[0]&0xFFFFu, 1);
-				if (sub == 0) below = 0xFFFFu;
-				if (sub == 7) above = 0xFFFFu;
-				if (havePrev) {
-					unsigned q[NW+1];
-					q[0] = __byte_perm(below, w[0], 0x5410);               // (L[-1], L[0])
+				if (SL::CB >= 16) {
 					#pragma unroll
-					for (int i = 1; i < NW; ++i) q[i] = __byte_perm(w[i-1], w[i], 0x5432);   // (L[2i-1], L[2i])
-					q[NW] = __byte_perm(w[NW-1], above, 0x5432);
+					for (int p = 0; p < SL::NC; ++p) {
+						const uint4 v = *(const uint4*)(sl + p*512);
+						C[8*p+0] = __byte_perm(v.x, 0u, 0x4140); C[8*p+1] = __byte_perm(v.x, 0u, 0x4342);
+						C[8*p+2] = __byte_perm(v.y, 0u, 0x4140); C[8*p+3] = __byte_perm(v.y, 0u, 0x4342);
+						C[8*p+4] = __byte_perm(v.z, 0u, 0x4140); C[8*p+5] = __byte_perm(v.z, 0u, 0x4342);
+						C[8*p+6] = __byte_perm(v.w, 0u, 0x4140); C[8*p+7] = __byte_perm(v.w, 0u, 0x4342);
+					}
+				} else {
+					const uint2 v = *(const uint2*)sl;
+					C[0] = __byte_perm(v.x, 0u, 0x4140); C[1] = __byte_perm(v.x, 0u, 0x4342);
+					C[2] = __byte_perm(v.y, 0u, 0x4140); C[3] = __byte_perm(v.y, 0u, 0x4342);
+				}
+				if (add) {
 					#pragma unroll
-					for (int i = 0; i < NW; ++i) {
-						const unsigned nb = __vaddus2(__vminu2(q[i], q[i+1]), P1x2);
-						L[i] = __vadd2(C[i], __vimin3_u16x2(w[i], nb, P2x2));
+					for (int p = 0; p < SL::NS; ++p) {
+						const uint4 v = *(const uint4*)(sl + (SL::NC+p)*512);
+						S[4*p] = v.x; S[4*p+1] = v.y; S[4*p+2] = v.z; S[4*p+3] = v.w;
 					}
 				} else {
 					#pragma unroll
-					for (int i = 0; i < NW; ++i) L[i] = __vadd2(C[i], P2x2);
+					for (int i = 0; i < NW; ++i) S[i] = 0u;
 				}
-				// minimum of the new line over the pixel's 8 lanes
+				const float I = *(const float*)(ring + j*SL::BYTES + SL::IOFF + lane*4);
+				// penalty of this step: P2s[|round(255 (I - Ip))|] (SemiGlobalMatcher.cpp:1009, 518-524)
+				const int di = min(255, abs((int)floorf(255.f*(I-Ip)+.5f)));
+				const unsigned P2x2 = sP2[di];
+				// With w = previous line (not normalised) and mp its minimum:
+				//   L = C + min(w - mp, min(w[d-1], w[d+1]) - mp + P1, P2) = C + min(w, min(w[d-1], w[d+1]) + P1, P2 + mp) - mp,
+				// so the neighbour exchange does not wait for the minimum of the previous step (shorter dependent chain).
+				// Neighbours d-1 / d+1 across the lanes of the pixel: 0xFFFF beyond the two ends of the range.
+				unsigned below = __shfl_up_sync(0xFFFFFFFFu, w[NW-1]>>16, 1), above = __shfl_down_sync(0xFFFFFFFFu, w[0]&0xFFFFu, 1);
+				if (sub == 0) below = 0xFFFFu;
+				if (sub == 7) above = 0xFFFFu;
+				unsigned q[NW+1], L[NW];
+				q[0] = __byte_perm(below, w[0], 0x5410);               // (L[-1], L[0])
+				#pragma unroll
+				for (int i = 1; i < NW; ++i) q[i] = __byte_perm(w[i-1], w[i], 0x5432);   // (L[2i-1], L[2i])
+				q[NW] = __byte_perm(w[NW-1], above, 0x5432);
+				const unsigned cap = __vadd2(P2x2, mp2);
+				#pragma unroll
+				for (int i = 0; i < NW; ++i) {
+					const unsigned nb = __vaddus2(__vminu2(q[i], q[i+1]), P1x2);
+					L[i] = __vsub2(__vadd2(C[i], __vimin3_u16x2(w[i], nb, cap)), mp2);
+				}
+				// minimum of the new line: within the lane, then three butterfly steps over the pixel's 8 lanes on the packed pair
+				// (a sub-warp redux.sync with a per-group mask compiles to a WARPSYNC.COLLECTIVE loop: about 2000 cycles per step)
 				unsigned m = L[0];
 				#pragma unroll
 				for (int i = 1; i+1 < NW; i += 2) m = __vimin3_u16x2(m, L[i], L[i+1]);
 				if ((NW&1) == 0) m = __vminu2(m, L[NW-1]);
-				// over the pixel's 8 lanes: three butterfly steps on the packed pair (a sub-warp redux.sync with a per-group mask
-				// compiles to a WARPSYNC.COLLECTIVE loop over the groups: measured at about 2000 cycles per step)
 				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 4));
 				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
 				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
 				m = min(m&0xFFFFu, m>>16);
-				const unsigned mx2 = m*0x10001u;
 				if (act) {
-					unsigned out[NW];
 					#pragma unroll
-					for (int i = 0; i < NW; ++i) { out[i] = add ? __vadd2(S[i], L[i]) : L[i]; w[i] = __vsub2(L[i], mx2); }
-					V::sts(optr, out);
+					for (int i = 0; i < NW; ++i) w[i] = L[i];
+					#pragma unroll
+					for (int i = 0; i < NW; i += 4) stcg4(optr+2*i, make_uint4(__vadd2(S[i], L[i]), __vadd2(S[i+1], L[i+1]), __vadd2(S[i+2], L[i+2]), __vadd2(S[i+3], L[i+3])));
 					optr += cstep;
-					Ip = I; havePrev = true;
+					mp2 = m*0x10001u;
+					Ip = I;
 				}
+				// refill the slot (its contents are in registers that have been consumed) with step tt+PD
+				if (tt+PD < maxcnt) { copy_ci(j, tt+PD); if (add) copy_s(j, tt+PD); }
+				cp_commit();
 			}
 		}
 		// store the state for the next segment of these paths, then publish
 		if (cnt > 0 && s1 < n) {
 			uint16_t* st = A.state + slot*(size_t)num + (size_t)sub*(2*NW);
 			#pragma unroll
-			for (int i = 0; i < NW; i += 4) stcg4(st+2*i, make_uint4(w[i], w[i+1], w[i+2], w[i+3]));
-			if (sub == 0) __stcg(A.meta+slot, make_float2(Ip, havePrev ? 1.f : 0.f));
+			for (int i = 0; i < NW; i += 4) stcg4(st+2*i, make_uint4(__vsub2(w[i], mp2), __vsub2(w[i+1], mp2), __vsub2(w[i+2], mp2), __vsub2(w[i+3], mp2)));
+			if (sub == 0) __stcg(A.meta+slot, make_float2(Ip, 1.f));
 		}
-		__threadfence();
+		// publish: the warp barrier orders the lanes' stores before lane 0's release store (cumulativity of release)
 		__syncwarp();
 		if (lane == 0) {
 			st_release(A.progress+chain, seq+1);
@@ -271,24 +274,37 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 	}
 }
 
+template <int NW, int PD> cudaError_t front_launch(const SGMParams& P, const FrontArgs& A, int blocks, cudaStream_t s) {
+	const int smem = FRONT_WARPS*PD*FrontSlot<NW>::BYTES;
+	cudaError_t e = cudaFuncSetAttribute(sgm_front_kernel<NW, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess) return e;
+	sgm_front_kernel<NW, PD><<<blocks, FRONT_WARPS*32, smem, s>>>(P, A);
+	return cudaGetLastError();
+}
+template <int NW, int PD> int front_blocks_per_sm() {
+	int per = 1;
+	const int smem = FRONT_WARPS*PD*FrontSlot<NW>::BYTES;
+	cudaFuncSetAttribute(sgm_front_kernel<NW, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<NW, PD>, FRONT_WARPS*32, smem);
+	return std::max(1, per);
+}
+
 } // namespace
 
-// pd: software pipeline depth (4 or 6 steps in flight)
+// pd: ring slots per warp (4 or 8 steps in flight)
 cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, int pd, cudaStream_t s) {
 	const int NW = A.num/16;
-	if (NW == 8) { if (pd == 6) sgm_front_kernel<8, 6><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); else sgm_front_kernel<8, 4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); }
-	else if (NW == 4) { if (pd == 6) sgm_front_kernel<4, 6><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); else sgm_front_kernel<4, 4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A); }
-	else if (NW == 16) sgm_front_kernel<16, 4><<<blocks, FRONT_WARPS*32, 0, s>>>(P, A);
-	else return cudaErrorInvalidValue;
-	return cudaGetLastError();
+	if (NW == 8) return pd == 4 ? front_launch<8, 4>(P, A, blocks, s) : front_launch<8, 8>(P, A, blocks, s);
+	if (NW == 4) return pd == 4 ? front_launch<4, 4>(P, A, blocks, s) : front_launch<4, 8>(P, A, blocks, s);
+	if (NW == 16) return pd == 4 ? front_launch<16, 4>(P, A, blocks, s) : front_launch<16, 8>(P, A, blocks, s);
+	return cudaErrorInvalidValue;
 }
 // resident CTAs of the kernel per SM on the current device
 int sgm_front_blocks_per_sm(int num, int pd) {
-	int per = 1;
 	const int NW = num/16;
-	if (NW == 8) { if (pd == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<8, 6>, FRONT_WARPS*32, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<8, 4>, FRONT_WARPS*32, 0); }
-	else if (NW == 4) { if (pd == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<4, 6>, FRONT_WARPS*32, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<4, 4>, FRONT_WARPS*32, 0); }
-	else if (NW == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, sgm_front_kernel<16, 4>, FRONT_WARPS*32, 0);
-	return std::max(1, per);
+	if (NW == 8) return pd == 4 ? front_blocks_per_sm<8, 4>() : front_blocks_per_sm<8, 8>();
+	if (NW == 4) return pd == 4 ? front_blocks_per_sm<4, 4>() : front_blocks_per_sm<4, 8>();
+	if (NW == 16) return pd == 4 ? front_blocks_per_sm<16, 4>() : front_blocks_per_sm<16, 8>();
+	return 1;
 }
 bool sgm_front_supports(int num) { return num == 64 || num == 128 || num == 256; }

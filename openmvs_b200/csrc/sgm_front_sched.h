@@ -14,7 +14,7 @@ using std::min; using std::max;
 struct float2;
 #endif
 
-// one work item: direction `dir` (phase `ph` of its pass), paths k0 .. k0+3, fronts [fb*FB, fb*FB+FB)
+// one work item: direction `dir & 0xFF` (phase `ph` of pass `dir >> 8` of the launch), paths k0 .. k0+3, fronts [fb*FB, fb*FB+FB)
 struct FrontItem {
 	int k0; short dir; short ph;
 	int fb;
@@ -27,15 +27,18 @@ struct FrontItem {
 struct FrontArgs {
 	const FrontItem* items; int nItems;
 	int* ticket;         // queue head
-	int* progress;       // per (phase, band): segments completed
-	int* cellDone;       // per (phase, front block): items completed
+	int* progress;       // per (pass, phase, band): segments completed
+	int* cellDone;       // per (pass, phase, front block): items completed
 	int* error;          // set to 1 when a wait timed out (never in a correct schedule)
-	uint16_t* state;     // per (phase, path): the normalised previous line, num u16
-	float2* meta;        // per (phase, path): {previous intensity, have-previous flag}
+	uint16_t* state;     // per (pass, phase, path): the normalised previous line, num u16
+	float2* meta;        // per (pass, phase, path): {previous intensity, have-previous flag}
 	int maxPaths;        // paths per phase slot in state / meta
-	int fa, fb, fc, FB;  // front f(x,y) = fa*x + fb*y + fc >= 0, block size
-	int storePhase0;     // 1: phase 0 stores the sum instead of adding to it (first pass)
+	int FB;              // fronts per block
 	int num;             // disparities per pixel (16 * NW)
+	// the (up to two) passes that share the launch's queue; each accumulates into its own sum volume
+	int fa[2], fb[2], fc[2];   // front f(x,y) = fa*x + fb*y + fc >= 0
+	int storePhase0[2];        // 1: phase 0 stores the sum instead of adding to it (the volume's first pass)
+	uint16_t* sum[2];
 };
 
 // start pixel and step of scanline `k` of direction `dir` (order of SemiGlobalMatcher.cpp:1084-1199); host and device
@@ -86,12 +89,12 @@ inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int
 		const int dir = pd.dirs[ph];
 		const int nPaths = dir == 0 || dir == 2 ? vw : dir == 1 || dir == 3 ? vh : vw+vh-1;
 		for (int band = 0; band*4 < nPaths; ++band) {
-			int s0v[4], nv[4], f0v[4], dfv[4]; bool pv[4];
+			int nv[4], f0v[4], dfv[4]; bool pv[4];
 			int blo = 0x7FFFFFFF, bhi = -1;
 			for (int g = 0; g < 4; ++g) {
 				int x, y, dx, dy;
 				pv[g] = front_path_start(dir, band*4+g, vw, vh, x, y, dx, dy);
-				nv[g] = 0; f0v[g] = 0; dfv[g] = 1; s0v[g] = 0;
+				nv[g] = 0; f0v[g] = 0; dfv[g] = 1;
 				if (!pv[g]) continue;
 				nv[g] = front_path_len(x, y, dx, dy, vw, vh);
 				f0v[g] = pd.fa*x + pd.fb*y + fc; dfv[g] = pd.fa*dx + pd.fb*dy;
@@ -125,8 +128,40 @@ inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int
 	});
 }
 
+// One kernel launch: one pass, or two passes whose items share one queue (interleaved, each pass in its own order).  Two
+// passes never touch the same sum volume, so they are independent chains of dependencies: while an item of one waits for
+// its predecessors the warps find ready work in the other.
+struct FrontLaunch {
+	int nPasses; FrontPassDesc pass[2];
+	int fc[2], nFB[2], maxBands;
+	int nChains, nCells;           // sizes of progress[] / cellDone[]
+	std::vector<FrontItem> items;
+};
+inline void sgm_front_build_launch(int vw, int vh, const FrontPassDesc* pds, int nPasses, int FB, int lag, FrontLaunch& L) {
+	L.nPasses = nPasses; L.items.clear(); L.nChains = 0; L.nCells = 0; L.maxBands = 0;
+	std::vector<FrontItem> part[2];
+	for (int p = 0; p < nPasses; ++p) {
+		L.pass[p] = pds[p];
+		sgm_front_build(vw, vh, pds[p], FB, lag, part[p], L.nFB[p], L.maxBands, L.fc[p]);
+		for (FrontItem& it: part[p]) {
+			it.dir = (short)(it.dir | (p<<8));
+			it.chain += L.nChains; it.cell += L.nCells;
+			if (it.depCell >= 0) it.depCell += L.nCells;
+		}
+		L.nChains += 4*L.maxBands; L.nCells += 4*L.nFB[p];
+	}
+	if (nPasses == 1) { L.items.swap(part[0]); return; }
+	// proportional interleave: both passes reach the end of their queues together
+	const size_t na = part[0].size(), nb = part[1].size();
+	L.items.reserve(na+nb);
+	size_t ia = 0, ib = 0;
+	while (ia < na || ib < nb) {
+		if (ib >= nb || (ia < na && ia*nb <= ib*na)) L.items.push_back(part[0][ia++]);
+		else L.items.push_back(part[1][ib++]);
+	}
+}
 
-// Pass layouts of the wave-front aggregation (b200mvs_debug.reserved[0]):
+// Pass layouts of the wave-front aggregation (b200mvs_debug.frontLayout - 1):
 //   0 (default) two tilted fronts f = +-(x + 2y): {right, right-down, down, left-down} then {left, left-up, up, right-up};
 //   1 four straight fronts: top-down {down, right-down, left-down}, bottom-up {up, right-up, left-up}, left-right, right-left;
 //   2 eight passes of one direction each (the traffic of the per-direction kernels with the new step).
@@ -145,4 +180,17 @@ inline std::vector<FrontPassDesc> sgm_front_layout(int layout) {
 		for (int d = 0; d < 8; ++d) descs.push_back(FrontPassDesc{f[d][0], f[d][1], 1, {d, 0, 0, 0}});
 	}
 	return descs;
+}
+// The launches of a layout: `concurrent` pairs consecutive passes (pass 2j into volume 0, pass 2j+1 into volume 1; the caller adds
+// the two volumes at the end), otherwise one pass per launch, all into volume 0.
+inline std::vector<FrontLaunch> sgm_front_plan(int vw, int vh, int layout, bool concurrent, int FB, int lag) {
+	const std::vector<FrontPassDesc> descs = sgm_front_layout(layout);
+	const int fbSize = layout == 2 ? (1<<28) : FB;   // one-direction passes need no blocks: one item per band walks the whole path
+	std::vector<FrontLaunch> out;
+	const size_t per = concurrent ? 2 : 1;
+	for (size_t i = 0; i < descs.size(); i += per) {
+		out.emplace_back();
+		sgm_front_build_launch(vw, vh, &descs[i], (int)std::min(per, descs.size()-i), fbSize, lag, out.back());
+	}
+	return out;
 }

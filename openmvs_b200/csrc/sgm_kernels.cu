@@ -591,15 +591,25 @@ __global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int16_t* __r
 }
 
 // Uniform dense volumes (num % 16 == 0, 16-byte aligned slices): 8 lanes per pixel, 16-byte loads, the arg-min carried as
-// (value << 16 | index) per lane.  HBM-bound: one read of the u16 sum volume.
-__global__ void sgm_wta_uniform_kernel(const uint16_t* __restrict__ accums, int nPixels, int dmin, int num, int16_t* __restrict__ disparity, uint16_t* __restrict__ cost)
+// (value << 16 | index) per lane.  HBM-bound: one read of the u16 sum volume.  TWO: the wave-front aggregation ran its two
+// passes side by side into two volumes; their sum is formed here (packed u16x2 adds), written back to the first volume (the
+// caller's accumulated costs, read again by the sub-pixel refinement) and searched in the same pass.
+template <bool TWO>
+__global__ void sgm_wta_uniform_kernel(uint16_t* __restrict__ accums, const uint16_t* __restrict__ second, int nPixels, int dmin, int num,
+	int16_t* __restrict__ disparity, uint16_t* __restrict__ cost)
 {
 	const int gp = (blockIdx.x*blockDim.x + threadIdx.x)>>3, sub = threadIdx.x&7;
 	const bool live = gp < nPixels;                         // every lane stays for the full-mask shuffles
-	const uint16_t* a = accums + (size_t)(live ? gp : 0)*num;
+	uint16_t* a = accums + (size_t)(live ? gp : 0)*num;
+	const uint16_t* b = TWO ? second + (size_t)(live ? gp : 0)*num : nullptr;
 	unsigned best = 0xFFFFFFFFu;
 	for (int k = sub*8; k < num; k += 64) {
-		const uint4 v = __ldcs((const uint4*)(a+k));
+		uint4 v = TWO ? __ldcg((const uint4*)(a+k)) : __ldcs((const uint4*)(a+k));
+		if (TWO) {
+			const uint4 u = __ldcs((const uint4*)(b+k));
+			v.x = __vadd2(v.x, u.x); v.y = __vadd2(v.y, u.y); v.z = __vadd2(v.z, u.z); v.w = __vadd2(v.w, u.w);
+			if (live) __stcs((uint4*)(a+k), v);
+		}
 		const unsigned w[4] = {v.x, v.y, v.z, v.w};
 		#pragma unroll
 		for (int i = 0; i < 4; ++i) {
@@ -610,7 +620,7 @@ __global__ void sgm_wta_uniform_kernel(const uint16_t* __restrict__ accums, int 
 	best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, 4));
 	best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, 2));
 	best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, 1));
-	if (live && sub == 0) { disparity[gp] = (int16_t)(dmin+(int)(best&0xFFFFu)); cost[gp] = (uint16_t)(best>>16); }
+	if (live && sub == 0 && disparity) { disparity[gp] = (int16_t)(dmin+(int)(best&0xFFFFu)); cost[gp] = (uint16_t)(best>>16); }
 }
 
 // ConsistencyCrossCheck (SemiGlobalMatcher.cpp:1449-1489): every pixel reads r2l and writes only
@@ -757,9 +767,11 @@ cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cos
 }
 
 // dense uniform volume: every pixel valid, slice of pixel i at i*num
-cudaError_t sgm_launch_wta_uniform(const SGMParams& P, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
+// second != nullptr: accums += second first (disparity / cost may then be null: the addition alone)
+cudaError_t sgm_launch_wta_uniform(const SGMParams& P, const uint16_t* second, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
 	const long long threads = (long long)P.vw*P.vh*8;
-	sgm_wta_uniform_kernel<<<(unsigned)((threads+255)/256), 256, 0, s>>>(P.accums, P.vw*P.vh, dmin, num, disparity, cost);
+	if (second) sgm_wta_uniform_kernel<true><<<(unsigned)((threads+255)/256), 256, 0, s>>>(P.accums, second, P.vw*P.vh, dmin, num, disparity, cost);
+	else sgm_wta_uniform_kernel<false><<<(unsigned)((threads+255)/256), 256, 0, s>>>(P.accums, nullptr, P.vw*P.vh, dmin, num, disparity, cost);
 	return cudaGetLastError();
 }
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s) {

@@ -263,15 +263,13 @@ class PatchMatchB200:
 		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_params(self._ctx, C.byref(p)), "b200mvs_set_params")
 
 	def SetDebug(self, **kw):
-		"""b200mvs_set_debug: diagnostic kernel switches (scalarTaps, noTMA, sgmAggregation, sgmCost); no arguments = defaults."""
+		"""b200mvs_set_debug: diagnostic kernel switches (the fields of b200mvs_debug: scalarTaps, noTMA, sweepFourCtas, ...);
+		no arguments = defaults."""
 		d = _lib.Debug()
 		for k, v in kw.items():
-			if k == "fourCtas":   # reserved[3]: the 64-register instantiation of the sweep kernel (4 CTAs per SM)
-				d.reserved[3] = int(v)
-			elif not hasattr(d, k):
+			if k == "reserved" or not hasattr(d, k):
 				raise AttributeError(k)
-			else:
-				setattr(d, k, int(v))
+			setattr(d, k, int(v))
 		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_debug(self._ctx, C.byref(d)), "b200mvs_set_debug")
 
 	def SetIgnoreMask(self, mask=None):
@@ -545,15 +543,12 @@ class SemiGlobalMatcher:
 
 	def SetDebug(self, **kw):
 		"""b200mvs_set_debug: sgmAggregation (0 auto, 1 general, 2 register-pipelined uniform, 3 bulk-copy ring, 4 wave fronts),
-		sgmCost, frontLayout / frontBlock / frontLag (reserved[0..2]); no arguments = defaults."""
+		sgmCost, frontLayout / frontSerial / frontBlock / frontLag / frontCtas / frontDepth (b200mvs_debug); no arguments = defaults."""
 		d = _lib.Debug()
 		for k, v in kw.items():
-			if k in ("frontLayout", "frontBlock", "frontLag", "fourCtas", "frontCtas", "frontDepth"):
-				d.reserved[("frontLayout", "frontBlock", "frontLag", "fourCtas", "frontCtas", "frontDepth").index(k)] = int(v)
-			elif hasattr(d, k):
-				setattr(d, k, int(v))
-			else:
+			if k == "reserved" or not hasattr(d, k):
 				raise AttributeError(k)
+			setattr(d, k, int(v))
 		_lib.check(self._lib, self._ctx, self._lib.b200mvs_set_debug(self._ctx, C.byref(d)), "b200mvs_set_debug")
 
 	def Match(self, leftGray, leftColor, rightGray, imagePixels, numCosts: int):

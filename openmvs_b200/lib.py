@@ -8,7 +8,7 @@ import os
 from . import build as _build
 
 MAX_VIEWS = 32
-ABI_VERSION = 4  # B200MVS_ABI_VERSION of include/b200mvs.h these structs mirror
+ABI_VERSION = 5  # B200MVS_ABI_VERSION of include/b200mvs.h these structs mirror
 
 
 class View(C.Structure):
@@ -34,7 +34,9 @@ class Params(C.Structure):
 
 class Debug(C.Structure):
 	"""b200mvs_debug"""
-	_fields_ = [("scalarTaps", C.c_int), ("noTMA", C.c_int), ("sgmAggregation", C.c_int), ("sgmCost", C.c_int), ("reserved", C.c_int*4)]
+	_fields_ = [("scalarTaps", C.c_int), ("noTMA", C.c_int), ("sgmAggregation", C.c_int), ("sgmCost", C.c_int),
+		("sweepFourCtas", C.c_int), ("frontLayout", C.c_int), ("frontSerial", C.c_int), ("frontBlock", C.c_int), ("frontLag", C.c_int),
+		("frontCtas", C.c_int), ("frontDepth", C.c_int), ("reserved", C.c_int*5)]
 
 
 class Stats(C.Structure):

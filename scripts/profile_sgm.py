@@ -17,14 +17,16 @@ costs = torch.zeros(n, dtype=torch.uint8, device="cuda"); accums = torch.zeros(n
 ref = None
 MODES = [("register pipeline", dict(sgmAggregation=2)), ("bulk-copy ring, 8 launches", dict(sgmAggregation=3)),
 	("wave fronts (default)", dict())]
-for layout, name in ((0, "tilted"), (1, "straight")):
-	for fbk in (32, 64):
+for layout, name in ((1, "tilted"), (2, "straight"), (3, "single")):
+	for serial in (0, 1):
+		MODES.append(("fronts %s %s" % (name, "serial" if serial else "paired"), dict(sgmAggregation=4, frontLayout=layout, frontSerial=serial)))
+for layout, name in ((1, "tilted"), (2, "straight")):
+	for fbk in (16, 32, 64):
 		for ctas in (1, 2, 3):
 			for pd in (4, 6):
-				MODES.append(("fronts %s FB %d ctas %d depth %d" % (name, fbk, ctas, pd), dict(sgmAggregation=4, frontLayout=layout, frontBlock=fbk, frontCtas=ctas, frontDepth=pd)))
-MODES += [("fronts tilted FB 32 lag 1 ctas 2", dict(sgmAggregation=4, frontLag=1, frontCtas=2)), ("fronts tilted FB 32 lag 3 ctas 2", dict(sgmAggregation=4, frontLag=3, frontCtas=2)),
-	("fronts tilted FB 128 ctas 2", dict(sgmAggregation=4, frontBlock=128, frontCtas=2)), ("fronts straight FB 8 ctas 2", dict(sgmAggregation=4, frontLayout=1, frontBlock=8, frontCtas=2)),
-	("fronts, 8 single passes", dict(sgmAggregation=4, frontLayout=2))]
+				if (fbk, ctas, pd) == ((32 if layout == 1 else 16), 2, 4): continue
+				MODES.append(("fronts %s paired FB %d ctas %d depth %d" % (name, fbk, ctas, pd), dict(sgmAggregation=4, frontLayout=layout, frontBlock=fbk, frontCtas=ctas, frontDepth=pd)))
+MODES += [("fronts tilted paired lag 1", dict(sgmAggregation=4, frontLag=1)), ("fronts tilted paired lag 3", dict(sgmAggregation=4, frontLag=3))]
 MODES.append(("tensor-core cost kernel + wave fronts", dict(sgmCost=2)))
 if len(sys.argv) > 2 and sys.argv[2] == "default":
 	MODES = MODES[2:3]

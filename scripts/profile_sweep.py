@@ -20,7 +20,7 @@ views = [sc.views[r]]+[sc.views[i] for i in sc.neighbors(r, 9)]
 imgs = [ViewData(torch.from_numpy(v.image).to(dev), Camera(v.K, v.R, v.C)) for v in views]
 OPTDENSE.nSubResolutionLevels = 0; OPTDENSE.nEstimationGeometricIters = 0; OPTDENSE.nEstimationIters = iters
 pm = PatchMatchB200(0)
-pm.SetDebug(fourCtas=FOUR)
+pm.SetDebug(sweepFourCtas=FOUR)
 gt = sc.views[r].depth_gt; gtn = sc.views[r].normal_gt
 for tag in ("random init", "warm, random init", "continued"):
 	dd = DepthData(imgs, sc.dmin, sc.dmax) if tag != "continued" else dd

@@ -13,7 +13,7 @@ int main(int argc, char** argv) {
 	if (argc < 3) { fprintf(stderr, "usage: front_sched in.bin out.bin\n"); return 64; }
 	FILE* f = fopen(argv[1], "rb");
 	if (!f) return 65;
-	int hdr[8]; // w, h, num, layout, FB, lag, P1, reserved
+	int hdr[8]; // w, h, num, layout, FB, lag, P1, concurrent
 	if (fread(hdr, 4, 8, f) != 8) return 66;
 	const int w = hdr[0], h = hdr[1], num = hdr[2], layout = hdr[3], FB = hdr[4], lag = hdr[5], P1 = hdr[6];
 	const int vw = w-6, vh = h-6;
@@ -23,33 +23,38 @@ int main(int argc, char** argv) {
 	std::vector<uint8_t> costs(n);
 	if (fread(P2s.data(), 2, 256, f) != 256 || fread(gray.data(), 4, gray.size(), f) != gray.size() || fread(costs.data(), 1, n, f) != n) return 66;
 	fclose(f);
-	std::vector<uint16_t> S(n, 0xABCD);   // garbage: phase 0 of the first pass must store every entry
+	const bool concurrent = hdr[7] != 0;
+	std::vector<uint16_t> S[2] = {std::vector<uint16_t>(n, 0xABCD), std::vector<uint16_t>(n, 0xABCD)};   // garbage: phase 0 of a volume's first pass must store every entry
 	std::vector<uint32_t> touched(n/num*8, 0);
 	const int maxPaths = vw+vh+8;
-	std::vector<uint16_t> state((size_t)4*maxPaths*num);
-	std::vector<float> metaI((size_t)4*maxPaths); std::vector<int> metaH((size_t)4*maxPaths);
-	const std::vector<FrontPassDesc> descs = sgm_front_layout(layout);
+	std::vector<uint16_t> state((size_t)8*maxPaths*num);
+	std::vector<float> metaI((size_t)8*maxPaths); std::vector<int> metaH((size_t)8*maxPaths);
+	const std::vector<FrontLaunch> plan = sgm_front_plan(vw, vh, layout, concurrent, FB, lag);
+	const int fbSize = layout == 2 ? (1<<28) : FB;
 	long long itemsTotal = 0;
-	for (size_t pi = 0; pi < descs.size(); ++pi) {
-		const FrontPassDesc& pd = descs[pi];
-		std::vector<FrontItem> items; int nFB, maxBands, fc;
-		const int fbSize = layout == 2 ? (1<<28) : FB;
-		sgm_front_build(vw, vh, pd, fbSize, lag, items, nFB, maxBands, fc);
-		itemsTotal += (long long)items.size();
-		std::vector<int> progress((size_t)4*maxBands, 0), cellDone((size_t)4*nFB, 0);
-		for (const FrontItem& it: items) {
+	bool two = false;
+	for (size_t li = 0; li < plan.size(); ++li) {
+		const FrontLaunch& LA = plan[li];
+		two |= LA.nPasses > 1;
+		itemsTotal += (long long)LA.items.size();
+		std::vector<int> progress((size_t)LA.nChains, 0), cellDone((size_t)LA.nCells, 0);
+		for (const FrontItem& it: LA.items) {
+			const int dir = it.dir & 0xFF, pass = (it.dir >> 8) & 1;
+			if (pass >= LA.nPasses) { printf("FAIL: item of pass %d in a launch of %d\n", pass, LA.nPasses); return 2; }
+			const FrontPassDesc& pd = LA.pass[pass];
 			// in-order execution: every dependency must already be complete, or the queue order would deadlock a single worker
-			if (progress[it.chain] < it.seq) { printf("FAIL: band dependency not met (pass %zu dir %d k0 %d fb %d)\n", pi, it.dir, it.k0, it.fb); return 2; }
-			if (it.depCell >= 0 && cellDone[it.depCell] < it.depNeed) { printf("FAIL: phase dependency not met (pass %zu ph %d fb %d)\n", pi, it.ph, it.fb); return 2; }
-			const bool add = !(pi == 0 && it.ph == 0);
+			if (progress[it.chain] < it.seq) { printf("FAIL: band dependency not met (launch %zu dir %d k0 %d fb %d)\n", li, dir, it.k0, it.fb); return 2; }
+			if (it.depCell >= 0 && cellDone[it.depCell] < it.depNeed) { printf("FAIL: phase dependency not met (launch %zu ph %d fb %d)\n", li, it.ph, it.fb); return 2; }
+			const bool add = !(li == 0 && it.ph == 0);
+			std::vector<uint16_t>& V = S[pass];
 			for (int g = 0; g < 4; ++g) {
 				int xs, ys, dx, dy;
-				if (!front_path_start(it.dir, it.k0+g, vw, vh, xs, ys, dx, dy)) continue;
+				if (!front_path_start(dir, it.k0+g, vw, vh, xs, ys, dx, dy)) continue;
 				const int len = front_path_len(xs, ys, dx, dy, vw, vh);
-				const int f0 = pd.fa*xs + pd.fb*ys + fc, df = std::max(1, pd.fa*dx + pd.fb*dy);
+				const int f0 = pd.fa*xs + pd.fb*ys + LA.fc[pass], df = std::max(1, pd.fa*dx + pd.fb*dy);
 				const int s0 = std::min(len, front_first_step(it.fb*fbSize, f0, df)), s1 = std::min(len, front_first_step((it.fb+1)*fbSize, f0, df));
 				if (s1 <= s0) continue;
-				const size_t slot = (size_t)it.ph*maxPaths + (it.k0+g);
+				const size_t slot = (size_t)(pass*4+it.ph)*maxPaths + (it.k0+g);
 				std::vector<unsigned> A(num, 0xFFFFu); float Ip = 0.5f; bool havePrev = false;
 				if (s0 > 0) { for (int d = 0; d < num; ++d) A[d] = state[slot*num+d]; Ip = metaI[slot]; havePrev = metaH[slot] != 0; }
 				for (int s = s0; s < s1; ++s) {
@@ -71,10 +76,10 @@ int main(int argc, char** argv) {
 						m = std::min(m, L[d]);
 					}
 					for (int d = 0; d < num; ++d) {
-						S[idx+d] = (uint16_t)(add ? S[idx+d]+L[d] : L[d]);
+						V[idx+d] = (uint16_t)(add ? V[idx+d]+L[d] : L[d]);
 						A[d] = L[d]-m;
 					}
-					touched[((size_t)y*vw+x)*8 + it.dir] += 1;
+					touched[((size_t)y*vw+x)*8 + dir] += 1;
 					Ip = I; havePrev = true;
 				}
 				if (s1 < len) { for (int d = 0; d < num; ++d) state[slot*num+d] = (uint16_t)A[d]; metaI[slot] = Ip; metaH[slot] = havePrev; }
@@ -83,11 +88,12 @@ int main(int argc, char** argv) {
 			cellDone[it.cell] += 1;
 		}
 	}
+	if (two) for (size_t i = 0; i < n; ++i) S[0][i] = (uint16_t)(S[0][i]+S[1][i]);
 	for (size_t i = 0; i < touched.size(); ++i)
 		if (touched[i] != 1) { printf("FAIL: pixel %zu direction %zu processed %u times\n", i/8, i%8, touched[i]); return 3; }
 	f = fopen(argv[2], "wb");
-	fwrite(S.data(), 2, n, f);
+	fwrite(S[0].data(), 2, n, f);
 	fclose(f);
-	printf("ok: %lld items over %zu passes\n", itemsTotal, descs.size());
+	printf("ok: %lld items over %zu launches\n", itemsTotal, plan.size());
 	return 0;
 }

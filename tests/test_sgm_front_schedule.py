@@ -19,8 +19,8 @@ def exe(tmp_path_factory):
 	return out
 
 
-@pytest.mark.parametrize("layout,block,lag", [(0, 32, 2), (0, 8, 1), (0, 5, 3), (1, 16, 2), (1, 3, 1), (2, 32, 2)])
-def test_schedule_simulation_equals_oracle(exe, tmp_path, layout, block, lag):
+@pytest.mark.parametrize("layout,block,lag,concurrent", [(0, 32, 2, 1), (0, 8, 1, 1), (0, 5, 3, 0), (1, 16, 2, 1), (1, 3, 1, 0), (2, 32, 2, 1), (2, 32, 2, 0), (0, 32, 2, 0)])
+def test_schedule_simulation_equals_oracle(exe, tmp_path, layout, block, lag, concurrent):
 	from oracle import oracle as O
 	from openmvs_b200 import synth
 	num = 64
@@ -38,7 +38,7 @@ def test_schedule_simulation_equals_oracle(exe, tmp_path, layout, block, lag):
 			P2s = np.frombuffer(buf, np.uint16).copy()
 		fin, fout = str(tmp_path/"in.bin"), str(tmp_path/"out.bin")
 		with open(fin, "wb") as f:
-			f.write(struct.pack("8i", w, h, num, layout, block, lag, 3, 0))
+			f.write(struct.pack("8i", w, h, num, layout, block, lag, 3, concurrent))
 			f.write(P2s.tobytes()); f.write(np.ascontiguousarray(lg, np.float32).tobytes()); f.write(costs.tobytes())
 		r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
 		assert r.returncode == 0, r.stdout+r.stderr

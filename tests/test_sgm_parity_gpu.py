@@ -182,12 +182,13 @@ def test_uniform_range_fast_path_bit_exact(sgm, num):
 	assert np.array_equal(gd.cpu().numpy(), disp) and np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
 
 
-@pytest.mark.parametrize("layout,block,lag", [(0, 0, 0), (0, 8, 1), (0, 16, 3), (1, 0, 0), (1, 4, 1), (2, 0, 0)])
+@pytest.mark.parametrize("layout,block,lag,serial", [(0, 0, 0, 0), (1, 0, 0, 1), (1, 8, 1, 0), (1, 16, 3, 1), (2, 0, 0, 0), (2, 4, 1, 1), (3, 0, 0, 0), (3, 0, 0, 1)])
 @pytest.mark.parametrize("num", [64, 128, 256])
-def test_wave_front_aggregation_bit_exact(sgm, num, layout, block, lag):
+def test_wave_front_aggregation_bit_exact(sgm, num, layout, block, lag, serial):
 	"""The wave-front kernel (dense volume, one range of 64 / 128 / 256 disparities; the default of the non-tSGM branch) against the
-	oracle: two tilted fronts (default), four straight fronts, eight single-direction passes; small blocks and lags exercise the
-	ordering of the phases and the hand-over of the path state between the segments of a path."""
+	oracle: two tilted fronts (default), four straight fronts, eight single-direction passes, pairs of passes sharing a launch with
+	one sum volume each (default) or one pass per launch; small blocks and lags exercise the ordering of the phases and the
+	hand-over of the path state between the segments of a path."""
 	m, O = sgm
 	w, h = 151, 92   # valid region 145 x 86: neither a multiple of the 4-path bands
 	rng = np.random.RandomState(num+layout)
@@ -197,7 +198,7 @@ def test_wave_front_aggregation_bit_exact(sgm, num, layout, block, lag):
 	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n, costs=costs)
 	accums = torch.full((n,), -1, dtype=torch.int16, device="cuda")   # phase 0 of the first pass stores: no memset needed
 	try:
-		m.SetDebug(sgmAggregation=4, frontLayout=layout, frontBlock=block, frontLag=lag)
+		m.SetDebug(sgmAggregation=4, frontLayout=layout, frontSerial=serial, frontBlock=block, frontLag=lag)
 		gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
 	finally:
 		m.SetDebug()
@@ -221,7 +222,20 @@ def test_wave_front_aggregation_larger_image_and_variants_agree(sgm):
 			gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
 			assert np.array_equal(accums.cpu().numpy().view(np.uint16), a), mode
 			assert np.array_equal(gd.cpu().numpy(), disp), mode
-			assert m.stats.kernel_launches == (2+2+1 if mode == 0 else 2+8+1)
+			assert m.stats.kernel_launches == (2+1+1 if mode == 0 else 2+8+1)
+		# aggregation alone (stages = 2): the two volumes of the default are added by a launch of their own; then the
+		# winner-takes-all stage alone over the stored sums
+		m.SetDebug()
+		accums = torch.zeros(n, dtype=torch.int16, device="cuda")
+		m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=2, costs=_dev(costs), accums=accums)
+		assert np.array_equal(accums.cpu().numpy().view(np.uint16), a)
+		gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=4, costs=_dev(costs), accums=accums)
+		assert np.array_equal(accums.cpu().numpy().view(np.uint16), a) and np.array_equal(gd.cpu().numpy(), disp)
+		m.SetDebug(frontSerial=1)
+		accums = torch.zeros(n, dtype=torch.int16, device="cuda")
+		gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(costs), accums=accums)
+		assert np.array_equal(accums.cpu().numpy().view(np.uint16), a) and np.array_equal(gd.cpu().numpy(), disp)
+		assert m.stats.kernel_launches == 2+2+1
 	finally:
 		m.SetDebug()
 
