@@ -426,7 +426,7 @@ def main():
 	sweep_share = pm.stats.ms_sweep_kernels/max(1e-9, pm.stats.ms_device)
 	bytes_launch = w*h*(20+10+4*(N_NEIGH+1))
 	achieved = bytes_launch/(k_ms*1e-3)/1e9
-	roof = {"kernel": "pm_sweep_kernel<true,false> (one red-black half-sweep; taps evaluated in FMUL2/FFMA2 pairs)", "bound": "hbm", "achieved": achieved, "peak": peak,
+	roof = {"kernel": "pm_sweep_kernel<1, 0, 3> (packed taps, photometric, 3 CTAs/SM: one red-black half-sweep)", "bound": "hbm", "achieved": achieved, "peak": peak,
 		"unit": "GB/s", "frac": achieved/peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
 		"launch_ms": k_ms, "launches_timed": int(pm.stats.sweep_launches), "share_of_step": sweep_share, "algorithmic_bytes_per_launch": bytes_launch,
 		"secondary": {"bound": "issue / L1 data pipe (gather stencil, AI ~ 280 flop/B): see the committed ncu capture",
@@ -436,7 +436,7 @@ def main():
 	ncu_file = os.path.join(ROOT, "profiles", "ncu_pm_sweep.txt")
 	try:
 		lines = open(ncu_file).read().splitlines()
-		if lines and "pm_sweep_kernel<1, 0>" in lines[0].replace("(bool)", ""):
+		if lines and "pm_sweep_kernel<1, 0, 3>" in lines[0].replace("(bool)", "").replace("(int)", ""):
 			roof["secondary"]["ncu_capture"] = "profiles/ncu_pm_sweep.txt"
 			for line in lines:
 				if line.startswith("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"):

@@ -52,6 +52,10 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 __device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg((const uint4*)p); }
 __device__ __forceinline__ void stcg4(void* p, uint4 v) { __stcg((uint4*)p, v); }
+__device__ __forceinline__ void st_cg4_if(bool on, void* p, unsigned a, unsigned b, unsigned c, unsigned d) {
+	asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %0, 0;\n@q st.global.cg.v4.u32 [%1], {%2, %3, %4, %5};\n}"
+		:: "r"((unsigned)on), "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // asynchronous global -> shared copies (LDGSTS): no destination registers, so the prefetch distance does not depend on the
 // register allocator; .cg is served by the L2 (coherent with the other SMs' st.cg after the acquire fence)
 __device__ __forceinline__ void cp16(unsigned dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); }
@@ -111,7 +115,7 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 		const int s0 = min(n, front_first_step(fblk*A.FB, f0, df)), s1 = min(n, front_first_step((fblk+1)*A.FB, f0, df));
 		const int cnt = s1-s0;
 		const int maxcnt = __reduce_max_sync(0xFFFFFFFFu, cnt);
-		const bool add = !(A.storePhase0[pass] && ph == 0);
+		const bool add = __any_sync(0xFFFFFFFFu, !(A.storePhase0[pass] && ph == 0));   // item-wide, and known to be warp-uniform
 		uint16_t* const sum = A.sum[pass];
 		// Step k of this lane's segment lies at base + min(k, last)*stride: every lane takes part in every copy (lanes whose
 		// segment is shorter re-read their last step, lanes without steps the first slice of the volume).
@@ -140,8 +144,10 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 		#pragma unroll
 		for (int j = 0; j < PD; ++j) if (j < maxcnt) copy_ci(j, j);
 		cp_commit();
-		// wait for the predecessors: the previous segment of this band, the previous phase of this front block
-		if (lane == 0) {
+		// wait for the predecessors: the previous segment of this band, the previous phase of this front block.  Every lane polls
+		// the same two words (one request per warp) and the exit is a vote: a loop run by lane 0 alone leaves the warp split in
+		// two — measured: the steps after it then ran once per half, each shuffle through a collective re-synchronisation.
+		{
 			const int* pp = A.progress+chain; const int* pc = A.cellDone+(depCell >= 0 ? depCell : 0);
 			const int need = depCell >= 0 ? depNeed : 0;
 			unsigned spins = 0;
@@ -149,14 +155,13 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 				int a, c;
 				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(pp) : "memory");
 				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(pc) : "memory");
-				if (a >= seq && c >= need) break;
+				if (__all_sync(0xFFFFFFFFu, a >= seq && c >= need)) break;
 				__nanosleep(64);
-				if (++spins > (1u<<21)) { *A.error = 1; break; }
+				if (++spins > (1u<<21)) { if (lane == 0) *A.error = 1; break; }
 			}
 			// acquire: the predecessors' stores are visible to the loads below (ld.cg / cp.async.cg: served by the L2)
 			asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		}
-		__syncwarp();
 		// the sums of the first PD steps: one group per step (empty when the phase stores)
 		#pragma unroll
 		for (int j = 0; j < PD; ++j) { if (add && j < maxcnt) copy_s(j, j); cp_commit(); }
@@ -242,15 +247,15 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
 				m = __vminu2(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
 				m = min(m&0xFFFFu, m>>16);
-				if (act) {
-					#pragma unroll
-					for (int i = 0; i < NW; ++i) w[i] = L[i];
-					#pragma unroll
-					for (int i = 0; i < NW; i += 4) stcg4(optr+2*i, make_uint4(__vadd2(S[i], L[i]), __vadd2(S[i+1], L[i+1]), __vadd2(S[i+2], L[i+2]), __vadd2(S[i+3], L[i+3])));
-					optr += cstep;
-					mp2 = m*0x10001u;
-					Ip = I;
-				}
+				// lanes whose segment has ended keep their line (predicated moves and stores: no branch, the warp stays converged)
+				#pragma unroll
+				for (int i = 0; i < NW; ++i) w[i] = act ? L[i] : w[i];
+				#pragma unroll
+				for (int i = 0; i < NW; i += 4)
+					st_cg4_if(act, optr+2*i, __vadd2(S[i], L[i]), __vadd2(S[i+1], L[i+1]), __vadd2(S[i+2], L[i+2]), __vadd2(S[i+3], L[i+3]));
+				optr += act ? cstep : 0;
+				mp2 = act ? m*0x10001u : mp2;
+				Ip = act ? I : Ip;
 				// refill the slot (its contents are in registers that have been consumed) with step tt+PD
 				if (tt+PD < maxcnt) { copy_ci(j, tt+PD); if (add) copy_s(j, tt+PD); }
 				cp_commit();

@@ -22,9 +22,9 @@ for layout, name in ((1, "tilted"), (2, "straight"), (3, "single")):
 		MODES.append(("fronts %s %s" % (name, "serial" if serial else "paired"), dict(sgmAggregation=4, frontLayout=layout, frontSerial=serial)))
 for layout, name in ((1, "tilted"), (2, "straight")):
 	for fbk in (16, 32, 64):
-		for ctas in (1, 2, 3):
-			for pd in (4, 6):
-				if (fbk, ctas, pd) == ((32 if layout == 1 else 16), 2, 4): continue
+		for ctas in (1, 2, 4):
+			for pd in (4, 8):
+				if (fbk, ctas, pd) == ((32 if layout == 1 else 16), 2, 8): continue
 				MODES.append(("fronts %s paired FB %d ctas %d depth %d" % (name, fbk, ctas, pd), dict(sgmAggregation=4, frontLayout=layout, frontBlock=fbk, frontCtas=ctas, frontDepth=pd)))
 MODES += [("fronts tilted paired lag 1", dict(sgmAggregation=4, frontLag=1)), ("fronts tilted paired lag 3", dict(sgmAggregation=4, frontLag=3))]
 MODES.append(("tensor-core cost kernel + wave fronts", dict(sgmCost=2)))
