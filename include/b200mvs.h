@@ -84,6 +84,8 @@ typedef struct {
 	uint32_t seed;                          /* Philox key */
 	int nPropagationFar;                    /* 2: per direction the candidate is the lowest-cost pixel at distance 1, 3, .. 2n+1 (0: adjacent only) */
 	int bSkipUnchanged;                     /* 1: a direction whose candidates kept their plane in their last update is not re-tested */
+	int nEvalCap;                           /* 7: a pixel that tests c propagation candidates in a sweep spends at most max(1, nEvalCap - c)
+	                                           refinement tries in it (0: always nRandomIters-derived tries) */
 } b200mvs_params;
 
 /* Diagnostic switches (all zero = the shipped kernels); replaces the environment variables of round 1. */

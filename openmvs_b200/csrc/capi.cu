@@ -200,7 +200,7 @@ void build_params(const b200mvs_params& o, const DView* v, int nViews, float dMi
 	P.depthRatio = o.fRandomDepthRatio; P.angle1Range = d2r(o.fRandomAngle1Range); P.angle2Range = d2r(o.fRandomAngle2Range);
 	P.geomWeight = o.fEstimationGeometricWeight;
 	P.nRandomIters = o.nRandomIters; P.propagation = o.nPropagation;
-	P.farRings = o.nPropagationFar; P.skipUnchanged = 0; // the estimate call turns the changed-flag rule on; building blocks keep costs unsigned
+	P.farRings = o.nPropagationFar; P.evalCap = o.nEvalCap; P.skipUnchanged = 0; // the estimate call turns the changed-flag rule on; building blocks keep costs unsigned
 	P.seed = o.seed;
 	P.lowres = lowres; P.plane = plane; P.cost = cost; P.bestViews = best;
 	double RrT[9], Hr[9], KrRr[9];
@@ -528,7 +528,7 @@ void b200mvs_default_params(b200mvs_params* p) {
 	p->fRandomSmoothDepth = 0.02f; p->fRandomSmoothNormal = 13.f; p->fRandomSmoothBonus = 0.93f;
 	p->fEstimationGeometricWeight = 0.1f;
 	p->nSweepsPerIter = 0; p->nPropagation = 4; p->seed = 1234u;
-	p->nPropagationFar = 2; p->bSkipUnchanged = 1;
+	p->nPropagationFar = 2; p->bSkipUnchanged = 1; p->nEvalCap = 0;
 }
 
 /* bumped whenever a struct of b200mvs.h changes layout; bindings compare it (and the struct sizes) at load time */
@@ -601,7 +601,7 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 int b200mvs_set_params(b200mvs_ctx* ctx, const b200mvs_params* p) {
 	if (!ctx || !p) return B200MVS_ERR_ARG;
 	if (p->nEstimationIters < 0 || p->nRandomIters < 0 || p->nSweepsPerIter < 0 || (p->nPropagation != 2 && p->nPropagation != 4) ||
-		p->nPropagationFar < 0 || p->nPropagationFar > 3 || p->nSubResolutionLevels < 0 || !(p->fNCCThresholdKeep > 0))
+		p->nPropagationFar < 0 || p->nPropagationFar > 3 || p->nEvalCap < 0 || p->nEvalCap > 15 || p->nSubResolutionLevels < 0 || !(p->fNCCThresholdKeep > 0))
 		return fail(ctx, B200MVS_ERR_ARG, "invalid parameter block");
 	ctx->prm = *p;
 	return B200MVS_OK;

@@ -29,6 +29,7 @@ struct PMParams {
 	float depthRatio, angle1Range, angle2Range, geomWeight;
 	int nRandomIters, propagation;           // refinement tries per sweep; directions that propagate (2 causal / 4)
 	int farRings;                            // propagation candidates per direction: distances 1, 3, .. 2*farRings+1
+	int evalCap;                             // > 0: tries per pixel and sweep <= max(1, evalCap - propagation candidates tested)
 	int skipUnchanged;                       // 1: a direction whose candidates kept their plane is not re-tested (sign bit of cost)
 	int sweep, colour;
 	int tma;                                 // reference tile staged by TMA (tensor map passed beside the params)

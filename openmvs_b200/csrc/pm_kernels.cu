@@ -583,13 +583,28 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 	float3 normal = make_float3(pl.x, pl.y, pl.z);
 	uint32_t bestViews = P.bestViews ? P.bestViews[idx] : 0xFFFFFFFFu;
 
-	// ---- propagation (DepthMap.cpp:775-799) ----
+	// ---- propagation (DepthMap.cpp:775-799), then the refinement state machine (DepthMap.cpp:800-852) ----
+	// One loop and one copy of the scoring code for both: a lane first pops its propagation candidates, then runs its
+	// refinement tries; lanes with fewer candidates start refining while the others still propagate.  Per pixel the order is
+	// the reference's (candidates, then tries), and every try has its own Philox slot (restart try k: slot k, refinement try
+	// k: slot nR+k), so the result does not depend on the step at which a lane executes it.
+	// evalCap > 0 (engine schedule, b200mvs_params.nEvalCap): a pixel that tests c candidates spends at most
+	// max(1, evalCap - c) tries of each kind — pixels whose four directions all changed give up their finest perturbation.
+	const int nR = P.nRandomIters;
+	const int nRl = P.evalCap > 0 ? min(nR, max(P.evalCap-__popc(todo), 1)) : nR;
+	const uint2 key = make_uint2(P.seed, 0xB200C0DEu);
+	const uint32_t phase = 1u + (uint32_t)P.sweep;
+	int mode = 0;               // 0 undecided, 1 restart (fully random), 2 refine, 3 done
+	bool entered = false;       // the state machine has taken its first decision
+	bool useClose = true;
+	unsigned idxScale = 0;
+	float scaleRange = 1.f, depthRange = 0.f, pa = 0.f, pb = 0.f;
+	int nRestart = 0, nRefine = 0; // tries spent
 	#pragma unroll 1
 	for (;;) {
-		const bool have = todo != 0u;
-		if (!__any_sync(__activemask(), have))
-			break;
-		if (have) {
+		bool have = false, isRefine = false, alive = false, uc = true;
+		float hd = 0.f, na = 0.f, nb = 0.f; float3 hn = make_float3(0.f, 0.f, 1.f);
+		if (todo != 0u) {
 			const int k = __ffs((int)todo)-1;
 			todo &= todo-1u;
 			const int kk = dir ? (k^2) : k;
@@ -604,82 +619,63 @@ pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUte
 			const float nx1 = vertical ? X0y : fmaf(fx, P.ifx, P.ox0);
 			const float x1 = vertical ? fmaf(float(qy), P.ify, P.oy) : fmaf(float(qx), P.ifx, P.ox0);
 			const float denom = qp.z + nx1*ncomp;
-			float hd = qp.w;
+			hd = qp.w;
 			if (!(fabsf(denom) < 0.0001f)) {
 				const float dn = qp.w*(qp.z + x1*ncomp)/denom;
 				if (P.dMin <= dn && dn < P.dMax)
 					hd = dn;
 			}
-			float3 hn = make_float3(qp.x, qp.y, qp.z);
+			hn = make_float3(qp.x, qp.y, qp.z);
 			correct_normal(hn, X0x, X0y);
-			Hyp h;
-			make_hyp(P, X0x, X0y, hd, hn, cl, true, h);
-			uint32_t bv;
-			const float nconf = score_pixel<PACK, GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
-			if (conf > nconf) { conf = nconf; depth = hd; normal = hn; bestViews = bv; }
-		}
-	}
-
-	// ---- refinement state machine (DepthMap.cpp:800-852) ----
-	// Lanes in restart mode spend their random tries in the same steps in which refine-mode lanes spend their
-	// perturbation tries; every try has its own Philox slot (restart try k: slot k, refinement try k: slot
-	// nR+k), so the result does not depend on the step at which a lane executes it.
-	const int nR = P.nRandomIters;
-	const uint2 key = make_uint2(P.seed, 0xB200C0DEu);
-	const uint32_t phase = 1u + (uint32_t)P.sweep;
-	int mode = 0;               // 0 undecided, 1 restart (fully random), 2 refine, 3 done
-	bool useClose = true;
-	unsigned idxScale = 0;
-	float scaleRange = 1.f, depthRange = 0.f, pa = 0.f, pb = 0.f;
-	int nRestart = 0, nRefine = 0; // tries spent
-	#pragma unroll 1
-	for (int step = 0; step < 2*nR; ++step) {
-		if (step == 0 || (mode == 1 && conf < P.thConfRand)) {
-			// RefineIters: choose the perturbation scale from the current score
-			bool toRefine = true;
-			if (conf <= P.thConfSmall) idxScale = 2;
-			else if (conf <= P.thConfBig) idxScale = 1;
-			else if (conf >= P.thConfRand && mode == 0) { mode = 1; useClose = false; toRefine = false; }
-			if (toRefine) {
-				mode = 2;
-				scaleRange = pow2neg(idxScale);
-				depthRange = depth*P.depthRatio;
-				pa = atan2f(normal.y, normal.x);
-				pb = acosf(normal.z);
+			have = true; alive = true;
+		} else {
+			if (!entered || (mode == 1 && conf < P.thConfRand)) {
+				// RefineIters: choose the perturbation scale from the current score
+				entered = true;
+				bool toRefine = true;
+				if (conf <= P.thConfSmall) idxScale = 2;
+				else if (conf <= P.thConfBig) idxScale = 1;
+				else if (conf >= P.thConfRand && mode == 0) { mode = 1; useClose = false; toRefine = false; }
+				if (toRefine) {
+					mode = 2;
+					scaleRange = pow2neg(idxScale);
+					depthRange = depth*P.depthRatio;
+					pa = atan2f(normal.y, normal.x);
+					pb = acosf(normal.z);
+				}
+			}
+			if (mode == 1 && nRestart >= nRl) mode = 3; // all random tries failed: no refinement this sweep
+			alive = (mode == 1) || (mode == 2 && nRefine < nRl);
+			uc = useClose;
+			if (mode == 1) {
+				// completely random plane (DepthMap.cpp:810-825)
+				const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)nRestart, 0u), key);
+				++nRestart;
+				const float s = P.dMinSqr + (P.dMaxSqr-P.dMinSqr)*u32_to_unit(r.x);
+				hd = s*s;
+				hn = random_normal(u32_to_unit(r.y), u32_to_unit(r.z), X0x, X0y);
+				have = true;
+			} else if (mode == 2 && nRefine < nRl) {
+				// perturb around the current estimate (DepthMap.cpp:832-851)
+				const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)(nR+nRefine), 0u), key);
+				++nRefine;
+				hd = depth + depthRange*scaleRange*(2.f*u32_to_unit(r.x)-1.f);
+				if (P.dMin <= hd && hd < P.dMax) {
+					na = pa + P.angle1Range*scaleRange*(2.f*u32_to_unit(r.y)-1.f);
+					nb = pb + P.angle2Range*scaleRange*(2.f*u32_to_unit(r.z)-1.f);
+					hn = dir2normal(na, nb);
+					have = hn.x*X0x + hn.y*X0y + hn.z < 0.f;
+					isRefine = true;
+				}
 			}
 		}
-		if (mode == 1 && nRestart >= nR) mode = 3; // all random tries failed: no refinement this sweep
-		const bool work = (mode == 1) || (mode == 2 && nRefine < nR);
-		if (!__any_sync(__activemask(), work))
+		if (!__any_sync(__activemask(), alive))
 			break;
-		bool have = false, isRefine = false;
-		float hd = 0.f, na = 0.f, nb = 0.f; float3 hn = make_float3(0.f, 0.f, 1.f);
-		if (mode == 1) {
-			// completely random plane (DepthMap.cpp:810-825)
-			const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)nRestart, 0u), key);
-			++nRestart;
-			const float s = P.dMinSqr + (P.dMaxSqr-P.dMinSqr)*u32_to_unit(r.x);
-			hd = s*s;
-			hn = random_normal(u32_to_unit(r.y), u32_to_unit(r.z), X0x, X0y);
-			have = true;
-		} else if (mode == 2 && nRefine < nR) {
-			// perturb around the current estimate (DepthMap.cpp:832-851)
-			const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, phase, (uint32_t)(nR+nRefine), 0u), key);
-			++nRefine;
-			hd = depth + depthRange*scaleRange*(2.f*u32_to_unit(r.x)-1.f);
-			if (P.dMin <= hd && hd < P.dMax) {
-				na = pa + P.angle1Range*scaleRange*(2.f*u32_to_unit(r.y)-1.f);
-				nb = pb + P.angle2Range*scaleRange*(2.f*u32_to_unit(r.z)-1.f);
-				hn = dir2normal(na, nb);
-				have = hn.x*X0x + hn.y*X0y + hn.z < 0.f;
-				isRefine = true;
-			}
-		}
 		if (!__any_sync(__activemask(), have))
 			continue;
 		if (have) {
 			Hyp h;
-			make_hyp(P, X0x, X0y, hd, hn, cl, useClose, h);
+			make_hyp(P, X0x, X0y, hd, hn, cl, uc, h);
 			uint32_t bv;
 			const float nconf = score_pixel<PACK, GEOM>(P, pt, fx, fy, X0x, X0y, h, priorF, priorD, bv);
 			if (conf > nconf) {

@@ -11,13 +11,17 @@
 // parts (w = wh + wl, error 2^-22) and every sum is three kind::f16 MMAs with fp32 accumulation in TMEM (wh fh + wh fl + wl fh) —
 // the dropped wl fl term is 2^-22 relative — so the uint8 cost stays within the +-1 level of the SIMT kernel.
 //
-// Structure (one 512-thread CTA per SM, persistent over the rows of the valid region):
-//   all 16 warps build A (bilateral weights of the block's 128 pixels: 49 expf per pixel shared by four threads, fp16 split, 16-byte
-//              stores in the UMMA K-major no-swizzle core-matrix layout), then the two new B tiles (im2col of 7 right-image rows);
-//   one thread issues the MMAs of a tile (9 products x 4 K-steps of 128 x 64 x 16) into one of two TMEM accumulator buffers
-//              and commits them to an mbarrier; the next tile's MMAs run while
-//   all 16 warps read the finished buffer (tcgen05.ld 32x32b), turn sums into costs and scatter them into a shared cost tile,
-//              which is finally written to the volume with coalesced 16-byte stores.
+// Structure (one CTA of 16 worker warps + 1 issuing warp per SM, persistent over the rows of the valid region):
+//   the workers stage the seven image rows of the block in shared memory (left colour packed to a word, left and right gray) and
+//              build A (bilateral weights of the block's 128 pixels: one warp-uniform tap quarter per warp, so tap offsets and
+//              spatial weights are immediates; colour distance by VABSDIFF4 + DP4A, weight by one EX2; fp16 split; 16-byte stores
+//              in the UMMA K-major no-swizzle core-matrix layout) and the two new B tiles (im2col of the staged right rows);
+//   the issuing warp waits on a named barrier for the operands and issues the MMAs of a tile (9 products x 4 K-steps of
+//              128 x 64 x 16) into one of two TMEM accumulator buffers, committing them to an mbarrier; it re-uses a buffer as
+//              soon as the workers have signalled (bar.arrive, non-blocking) that they have read it;
+//   the workers read a finished buffer (tcgen05.ld 32x32b), turn sums into costs and scatter them into a shared cost tile,
+//              which is finally written to the volume with coalesced 16-byte stores.  No CTA-wide barrier inside a block's
+//              tile loop: the uneven share of the diagonal band per warp and tile evens out over the block.
 // SASS: UTCHMMA (tcgen05.mma), UTCBAR (commit), LDTM (tcgen05.ld), UTCATOMSWS / UTCALLOC (alloc).
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -41,19 +45,32 @@ constexpr int HW = 3, NT = 49;
 constexpr int BM = 128;          // pixels per block (MMA M)
 constexpr int BN = 64;           // right-image columns per tile (MMA N)
 constexpr int KP = 64;           // taps padded to the MMA K granularity (4 x 16)
-constexpr int TC_THREADS = 512;
+constexpr int TC_WORKERS = 512;  // operand builders and epilogue: 16 warps
+constexpr int TC_THREADS = TC_WORKERS+32;   // + the warp that issues the MMAs
 constexpr int A_ARRAY = BM*KP*2;         // one fp16 operand array of a block: 16 KB
 constexpr int B_ARRAY = BN*KP*2;         // one fp16 operand array of a tile: 8 KB
 constexpr int B_SLOT = 4*B_ARRAY;        // fh, fl, qh, ql
 constexpr int RING = 4;                  // B tiles kept (a block of D <= 128 needs (128+D)/64 <= 4)
 constexpr int TILE_PITCH = 132;          // bytes per pixel row of the shared cost tile (bank-conflict-free byte scatter)
+constexpr int SP = BM+8;                 // pitch of the staged image rows (128 columns + 6 of the window, padded)
 constexpr int SMEM_A = 4*A_ARRAY;        // wh, wl, th, tl
 constexpr int SMEM_B = RING*B_SLOT;
-constexpr int SMEM_TILE = BM*TILE_PITCH;
-constexpr int SMEM_CONST = BM*8;         // {normSq0, 1/sumW} per pixel
+constexpr int SMEM_TILE = BM*TILE_PITCH; // the block's costs; while the operands are built: the staged image rows and partial sums
+constexpr int SMEM_CONST = 4*BM*4 + BM*4;   // normSq0 partial of each tap quarter, 1/sumW per pixel
 constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_TILE + SMEM_CONST + 64;
+// staging area inside the cost tile (free between the store of a block and the epilogue of the next)
+constexpr int ST_LC = 0;                 // left colour rows, packed B | G<<8 | R<<16: 7 x SP u32
+constexpr int ST_LG = ST_LC + 7*SP*4;    // left gray rows: 7 x SP float
+constexpr int ST_RG = ST_LG + 7*SP*4;    // right gray rows of the two new tiles: 7 x SP float
+constexpr int ST_PART = ST_RG + 7*SP*4;  // {sum w g, sum w} of each tap quarter: 4 x BM float2
+static_assert(ST_PART + 4*BM*8 <= SMEM_TILE, "staging area exceeds the cost tile");
+static_assert(SMEM_TOTAL <= 232448, "shared memory of one SM");
+// named barriers (id 0 is __syncthreads)
+constexpr int BAR_WORKERS = 1, BAR_OPS = 2, BAR_DRAIN = 3;   // BAR_DRAIN, BAR_DRAIN+1: accumulator buffers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
 // K-major, no swizzle (INTERLEAVE): a K-chunk of 8 halves (16 B) of row r sits at chunk*rows*16 + r*16; 8 consecutive rows are one
 // 128-byte core matrix: stride between 8-row groups SBO = 128 B, between the two 16-byte K-chunks of one MMA LBO = rows*16 B
@@ -96,6 +113,95 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b)<<16); }
 // x = hi + lo with hi = fp16(x): two fp16 numbers carrying 22 bits of x
 __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) { hi = __float2half_rn(x); lo = __float2half_rn(x-__half2float(hi)); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float SIGMA_COLOR = -1.f/(2.f*(0.3f*255)*(0.3f*255));
+constexpr float SIGMA_SPATIAL = -1.f/(2.f*(0.4f*7)*(0.4f*7));
+
+// One tap quarter (taps 16 Q .. 16 Q + 15; Q = 3: tap 48) of the A operands of pixel `row` of the block, from the staged left
+// rows.  Q is a template parameter so that the tap geometry (i, j) and the spatial weight are compile-time constants.
+// Bilateral weight (SemiGlobalMatcher.cpp:889-905): exp(colour distance^2 sigmaColor + spatial distance^2 sigmaSpatial) as one
+// ex2 of a fused multiply-add; the colour distance is |dB|^2 + |dG|^2 + |dR|^2 = dp4a of the packed absolute differences.
+template <int Q>
+__device__ __forceinline__ void build_a_quarter(unsigned char* sA, const unsigned char* sStage, float* sNorm, float* sInv, int row, bool valid) {
+	constexpr int N0 = 16*Q, NN = Q == 3 ? 1 : 16;
+	const uint32_t* lc = (const uint32_t*)(sStage + ST_LC);
+	const float* lg = (const float*)(sStage + ST_LG);
+	float2* part = (float2*)(sStage + ST_PART);
+	float wv[NN], gv[NN];
+	float sumW = 0.f, acc = 0.f;
+	const uint32_t cc = lc[HW*SP + row+HW];
+	#pragma unroll
+	for (int k = 0; k < NN; ++k) {
+		const int n = N0+k, i = n/7, j = n-7*i;   // compile-time after unrolling
+		const uint32_t d = __vabsdiffu4(lc[i*SP + row+j], cc);
+		const int dist2 = (int)__dp4a(d, d, 0u);
+		const float spatial = float((j-HW)*(j-HW)+(i-HW)*(i-HW))*(SIGMA_SPATIAL*LOG2E);
+		float wgt = ex2_approx(fmaf((float)dist2, SIGMA_COLOR*LOG2E, spatial));
+		if (!valid) wgt = 0.f;
+		const float g = lg[i*SP + row+j];
+		wv[k] = wgt; gv[k] = g;
+		acc = fmaf(g, wgt, acc);
+		sumW += wgt;
+	}
+	part[Q*BM + row] = make_float2(acc, sumW);
+	bar_sync(BAR_WORKERS, TC_WORKERS);
+	{
+		const float2 p0 = part[row], p1 = part[BM+row], p2 = part[2*BM+row], p3 = part[3*BM+row];
+		acc = (p0.x+p1.x)+(p2.x+p3.x); sumW = (p0.y+p1.y)+(p2.y+p3.y);
+	}
+	if (!valid) sumW = 1.f;
+	const float tm = acc/sumW;
+	float normSq0 = 0.f;
+	#pragma unroll
+	for (int k = 0; k < NN; ++k) {
+		const float t = gv[k]-tm;
+		gv[k] = wv[k]*t;          // tempWeight
+		normSq0 = fmaf(gv[k], t, normSq0);
+	}
+	sNorm[Q*BM + row] = normSq0;
+	if (Q == 0) sInv[row] = 1.f/sumW;
+	#pragma unroll
+	for (int c2 = 0; c2 < (Q == 3 ? 1 : 2); ++c2) {
+		const int kc = 2*Q+c2;
+		__half wh[8], wl[8], th[8], tl[8];
+		#pragma unroll
+		for (int e = 0; e < 8; ++e) {
+			const int k = c2*8+e;
+			if (k < NN) { split_h(wv[k], wh[e], wl[e]); split_h(gv[k], th[e], tl[e]); }
+			else { wh[e] = wl[e] = th[e] = tl[e] = __float2half_rn(0.f); }
+		}
+		const size_t off = (size_t)kc*(BM*16) + (size_t)row*16;
+		*(uint4*)(sA+0*A_ARRAY+off) = make_uint4(pack_h2(wh[0], wh[1]), pack_h2(wh[2], wh[3]), pack_h2(wh[4], wh[5]), pack_h2(wh[6], wh[7]));
+		*(uint4*)(sA+1*A_ARRAY+off) = make_uint4(pack_h2(wl[0], wl[1]), pack_h2(wl[2], wl[3]), pack_h2(wl[4], wl[5]), pack_h2(wl[6], wl[7]));
+		*(uint4*)(sA+2*A_ARRAY+off) = make_uint4(pack_h2(th[0], th[1]), pack_h2(th[2], th[3]), pack_h2(th[4], th[5]), pack_h2(th[6], th[7]));
+		*(uint4*)(sA+3*A_ARRAY+off) = make_uint4(pack_h2(tl[0], tl[1]), pack_h2(tl[2], tl[3]), pack_h2(tl[4], tl[5]), pack_h2(tl[6], tl[7]));
+	}
+}
+// One tap quarter of column c of a B tile (slot) from the staged right rows; cs = column of the tile's first window in the stage
+template <int Q>
+__device__ __forceinline__ void build_b_quarter(unsigned char* slot, const unsigned char* sStage, int cs, int c) {
+	const float* rg = (const float*)(sStage + ST_RG);
+	#pragma unroll
+	for (int c2 = 0; c2 < (Q == 3 ? 1 : 2); ++c2) {
+		const int kc = 2*Q+c2;
+		__half fh[8], fl[8], qh[8], ql[8];
+		#pragma unroll
+		for (int e = 0; e < 8; ++e) {
+			const int n = kc*8+e;
+			float f = 0.f;
+			if (n < NT) { const int i = n/7, j = n-7*i; f = rg[i*SP + cs+c+j]; }
+			split_h(f, fh[e], fl[e]);
+			split_h(f*f, qh[e], ql[e]);
+		}
+		const size_t off = (size_t)kc*(BN*16) + (size_t)c*16;
+		*(uint4*)(slot+0*B_ARRAY+off) = make_uint4(pack_h2(fh[0], fh[1]), pack_h2(fh[2], fh[3]), pack_h2(fh[4], fh[5]), pack_h2(fh[6], fh[7]));
+		*(uint4*)(slot+1*B_ARRAY+off) = make_uint4(pack_h2(fl[0], fl[1]), pack_h2(fl[2], fl[3]), pack_h2(fl[4], fl[5]), pack_h2(fl[6], fl[7]));
+		*(uint4*)(slot+2*B_ARRAY+off) = make_uint4(pack_h2(qh[0], qh[1]), pack_h2(qh[2], qh[3]), pack_h2(qh[4], qh[5]), pack_h2(qh[6], qh[7]));
+		*(uint4*)(slot+3*B_ARRAY+off) = make_uint4(pack_h2(ql[0], ql[1]), pack_h2(ql[2], ql[3]), pack_h2(ql[4], ql[5]), pack_h2(ql[6], ql[7]));
+	}
+}
 
 // Dense volumes only (every pixel valid with the range [dmin, dmin+num), idx = pixel index x num); num in {64, 128}.
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -105,8 +211,9 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 	unsigned char* sA = smem;
 	unsigned char* sB = smem + SMEM_A;
 	unsigned char* sTile = sB + SMEM_B;
-	float2* sConst = (float2*)(sTile + SMEM_TILE);
-	uint64_t* bars = (uint64_t*)((unsigned char*)sConst + SMEM_CONST);   // 2 mbarriers
+	float* sNorm = (float*)(sTile + SMEM_TILE);           // 4 x BM: normSq0 of each tap quarter
+	float* sInv = sNorm + 4*BM;                           // 1/sumW
+	uint64_t* bars = (uint64_t*)((unsigned char*)sNorm + SMEM_CONST);   // 2 mbarriers
 	uint32_t* sTmem = (uint32_t*)(bars+2);
 	const int tid = threadIdx.x, warp = tid>>5, lane = tid&31;
 	const int w = P.w, vw = P.vw, vh = P.vh;
@@ -127,189 +234,147 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 	const uint32_t tmem = *sTmem;
 	const int nTiles = (BM+num)/BN;             // u tiles a block needs: 3 (D = 64) or 4 (D = 128)
 	const int nBlocks = (vw+BM-1)/BM;
-	const float sigmaColor = -1.f/(2.f*(0.3f*255)*(0.3f*255));
-	const float sigmaSpatial = -1.f/(2.f*(0.4f*7)*(0.4f*7));
-	unsigned phase[2] = {0u, 0u};
 
-	// Operand builders: every pixel / column is shared by four threads (adjacent lanes); quarter q owns K-chunks 2q and 2q+1
-	// (taps 16q .. 16q+15), quarter 3 the chunk of tap 48 — all 512 threads build: A (128 pixels x 4) first, then the two new B
-	// tiles (2 x 64 columns x 4).
-	// one B tile column: u' = 64 t + c of the band
-	auto build_b_tile = [&](int r, int t, int c, int q) {
-		unsigned char* slot = sB + (size_t)(t&(RING-1))*B_SLOT;
-		const int lcol = BN*t + c + dmin;         // image column of the window's left edge
+	if (warp == TC_WORKERS/32) {
+		// ---- the issuing warp: MMAs of a tile as soon as its operands stand and its accumulator buffer has been read ----
+		// the 36 MMAs of tile t into accumulator buffer `buf` (columns buf*256 + {0, 64, 128}: sum, sumSq, nom), then commit
+		auto issue_tile = [&](int t, int buf) {
+			const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB + (size_t)(t&(RING-1))*B_SLOT);
+			const uint32_t dBase = tmem + (uint32_t)buf*256u;
+			// {A array, B array, accumulator}: wh fh, wh fl, wl fh -> sum | wh qh, wh ql, wl qh -> sumSq | th fh, th fl, tl fh -> nom
+			const int prod[9][3] = {{0, 0, 0}, {0, 1, 0}, {1, 0, 0}, {0, 2, 1}, {0, 3, 1}, {1, 2, 1}, {2, 0, 2}, {2, 1, 2}, {3, 0, 2}};
+			#pragma unroll
+			for (int p = 0; p < 9; ++p) {
+				#pragma unroll
+				for (int kk = 0; kk < KP/16; ++kk) {
+					const uint64_t ad = umma_desc(aBase + prod[p][0]*A_ARRAY + kk*2*(BM*16), BM*16);
+					const uint64_t bd = umma_desc(bBase + prod[p][1]*B_ARRAY + kk*2*(BN*16), BN*16);
+					const bool first = (p == 0 || p == 3 || p == 6) && kk == 0;
+					umma_f16(dBase + (uint32_t)prod[p][2]*64u, ad, bd, first ? 0u : 1u);
+				}
+			}
+			umma_commit(bars+buf);
+		};
 		#pragma unroll 1
-		for (int kc = 2*q; kc < (q == 3 ? 7 : 2*q+2); ++kc) {
-			__half fh[8], fl[8], qh[8], ql[8];
-			#pragma unroll
-			for (int e = 0; e < 8; ++e) {
-				const int n = kc*8+e;
-				float f = 0.f;
-				if (n < NT) {
-					const int i = n/7, j = n-7*i;
-					const int col = min(max(lcol+j, 0), w-1);
-					f = __ldg(P.rgray + (size_t)(r+i)*w + col);
-				}
-				split_h(f, fh[e], fl[e]);
-				split_h(f*f, qh[e], ql[e]);
-			}
-			const size_t off = (size_t)kc*(BN*16) + (size_t)c*16;
-			*(uint4*)(slot+0*B_ARRAY+off) = make_uint4(pack_h2(fh[0], fh[1]), pack_h2(fh[2], fh[3]), pack_h2(fh[4], fh[5]), pack_h2(fh[6], fh[7]));
-			*(uint4*)(slot+1*B_ARRAY+off) = make_uint4(pack_h2(fl[0], fl[1]), pack_h2(fl[2], fl[3]), pack_h2(fl[4], fl[5]), pack_h2(fl[6], fl[7]));
-			*(uint4*)(slot+2*B_ARRAY+off) = make_uint4(pack_h2(qh[0], qh[1]), pack_h2(qh[2], qh[3]), pack_h2(qh[4], qh[5]), pack_h2(qh[6], qh[7]));
-			*(uint4*)(slot+3*B_ARRAY+off) = make_uint4(pack_h2(ql[0], ql[1]), pack_h2(ql[2], ql[3]), pack_h2(ql[4], ql[5]), pack_h2(ql[6], ql[7]));
-		}
-	};
-	// the block's A operands: threads 4*row .. 4*row+3 (adjacent lanes) own pixel x0 + row
-	auto build_a = [&](int r, int x0, int row, int q) {
-		constexpr int NQ = 16;                        // taps per quarter: 16 | 16 | 16 | 1
-		const int n0 = 16*q, nn = q == 3 ? 1 : 16;
-		const int col = x0+row;
-		float wv[NQ], gv[NQ];
-		float sumW = 0.f, acc = 0.f, normSq0 = 0.f;
-		const bool valid = col < vw;
-		#pragma unroll
-		for (int k = 0; k < NQ; ++k) { wv[k] = 0.f; gv[k] = 0.f; }
-		if (valid) {
-			const int ux = col+HW, uy = r+HW;
-			const uchar3 cc = P.lbgr[(size_t)uy*w + ux];
-			#pragma unroll
-			for (int k = 0; k < NQ; ++k) {
-				if (k < nn) {
-					const int n = n0+k, i = n/7, j = n-7*i;
-					const size_t o = (size_t)(uy+i-HW)*w + (ux+j-HW);
-					const uchar3 pc = P.lbgr[o];
-					const int d0 = abs((int)pc.x-(int)cc.x), d1 = abs((int)pc.y-(int)cc.y), d2 = abs((int)pc.z-(int)cc.z);
-					const float wgt = expf(float(d0*d0+d1*d1+d2*d2)*sigmaColor + float((j-HW)*(j-HW)+(i-HW)*(i-HW))*sigmaSpatial);
-					const float g = __ldg(P.lgray + o);
-					wv[k] = wgt; gv[k] = g;
-					acc += g*wgt;
-					sumW += wgt;
-				}
-			}
-		}
-		// the four quarters of a pixel sit in adjacent lanes
-		acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1); acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-		sumW += __shfl_xor_sync(0xFFFFFFFFu, sumW, 1); sumW += __shfl_xor_sync(0xFFFFFFFFu, sumW, 2);
-		if (!valid) sumW = 1.f;
-		const float tm = acc/sumW;
-		#pragma unroll
-		for (int k = 0; k < NQ; ++k) {
-			const float t = gv[k]-tm;
-			gv[k] = wv[k]*t;          // tempWeight (0 for the unused taps: w = 0)
-			normSq0 += gv[k]*t;
-		}
-		normSq0 += __shfl_xor_sync(0xFFFFFFFFu, normSq0, 1); normSq0 += __shfl_xor_sync(0xFFFFFFFFu, normSq0, 2);
-		if (q == 0) sConst[row] = make_float2(normSq0, 1.f/sumW);
-		#pragma unroll
-		for (int c2 = 0; c2 < 2; ++c2) {
-			if (q == 3 && c2 == 1) break;
-			const int kc = 2*q+c2;
-			__half wh[8], wl[8], th[8], tl[8];
-			#pragma unroll
-			for (int e = 0; e < 8; ++e) {
-				const int k = c2*8+e;                   // index into this quarter's taps
-				split_h(wv[k], wh[e], wl[e]);
-				split_h(gv[k], th[e], tl[e]);
-			}
-			const size_t off = (size_t)kc*(BM*16) + (size_t)row*16;
-			*(uint4*)(sA+0*A_ARRAY+off) = make_uint4(pack_h2(wh[0], wh[1]), pack_h2(wh[2], wh[3]), pack_h2(wh[4], wh[5]), pack_h2(wh[6], wh[7]));
-			*(uint4*)(sA+1*A_ARRAY+off) = make_uint4(pack_h2(wl[0], wl[1]), pack_h2(wl[2], wl[3]), pack_h2(wl[4], wl[5]), pack_h2(wl[6], wl[7]));
-			*(uint4*)(sA+2*A_ARRAY+off) = make_uint4(pack_h2(th[0], th[1]), pack_h2(th[2], th[3]), pack_h2(th[4], th[5]), pack_h2(th[6], th[7]));
-			*(uint4*)(sA+3*A_ARRAY+off) = make_uint4(pack_h2(tl[0], tl[1]), pack_h2(tl[2], tl[3]), pack_h2(tl[4], tl[5]), pack_h2(tl[6], tl[7]));
-		}
-	};
-	// the 36 MMAs of tile t into accumulator buffer `buf` (columns buf*256 + {0, 64, 128}: sum, sumSq, nom), then commit
-	auto issue_tile = [&](int t, int buf) {
-		const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB + (size_t)(t&(RING-1))*B_SLOT);
-		const uint32_t dBase = tmem + (uint32_t)buf*256u;
-		// {A array, B array, accumulator}: wh fh, wh fl, wl fh -> sum | wh qh, wh ql, wl qh -> sumSq | th fh, th fl, tl fh -> nom
-		const int prod[9][3] = {{0, 0, 0}, {0, 1, 0}, {1, 0, 0}, {0, 2, 1}, {0, 3, 1}, {1, 2, 1}, {2, 0, 2}, {2, 1, 2}, {3, 0, 2}};
-		#pragma unroll
-		for (int p = 0; p < 9; ++p) {
-			#pragma unroll
-			for (int kk = 0; kk < KP/16; ++kk) {
-				const uint64_t ad = umma_desc(aBase + prod[p][0]*A_ARRAY + kk*2*(BM*16), BM*16);
-				const uint64_t bd = umma_desc(bBase + prod[p][1]*B_ARRAY + kk*2*(BN*16), BN*16);
-				const bool first = (p == 0 || p == 3 || p == 6) && kk == 0;
-				umma_f16(dBase + (uint32_t)prod[p][2]*64u, ad, bd, first ? 0u : 1u);
-			}
-		}
-		umma_commit(bars+buf);
-	};
-	// sums -> costs of tile t (block b) from accumulator buffer `buf` into the shared cost tile
-	auto epilogue = [&](int r, int b, int t, int buf) {
-		mbar_wait(bars+buf, phase[buf]); phase[buf] ^= 1u;
-		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-		const int row0 = 32*(warp&3), row = row0 + lane;   // TMEM lane = pixel of the block
-		const int c0 = 16*(warp>>2);                        // this warp's 16 of the 64 columns
-		const float2 cst = sConst[row];
-		const int col = BM*b + row;                         // valid-region column of the pixel
-		const float eps = 1e-3f;
-		const int kq = BN*(t-2*b);                          // disparity index of (row 0, column 0) of this tile
-		// the band 0 <= d < num covers about half of a tile: a 32-row x 16-column chunk wholly outside it is skipped (warp-uniform)
-		if (!(kq+c0+15-row0 < 0 || kq+c0-(row0+31) >= num)) {
-			uint32_t s0[16], s1[16], s2[16];
-			const uint32_t ta = tmem + ((uint32_t)row0<<16) + (uint32_t)buf*256u + (uint32_t)c0;
-			tmem_ld16(ta, s0); tmem_ld16(ta+64u, s1); tmem_ld16(ta+128u, s2);
-			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-			// disparities whose right window lies inside the image: 0 <= col + d + dmin, col + d + dmin + 6 < w
-			const int dlo = max(0, -(col+dmin)), dhi = min(num, w-2*HW-col-dmin);
-			#pragma unroll
-			for (int e = 0; e < 16; ++e) {
-				const int d = kq + c0+e - row;            // disparity index of (pixel, column)
-				if (d >= 0 && d < num) {
-					const float sum = __uint_as_float(s0[e]), sumSq = __uint_as_float(s1[e]), nom = __uint_as_float(s2[e]);
-					const float normSq1 = fmaf(-sum*cst.y, sum, sumSq);
-					const float ncc = nom*rsqrtf(fmaf(cst.x, normSq1, eps));
-					// ncc <= 0 ? 255 : floor((1 - min(ncc, 1)) * 255 + .5); 255 for windows that leave the right image
-					int cv = ncc <= 0.f ? 255 : __float2int_rd(fmaf(-255.f, fminf(ncc, 1.f), 255.5f));
-					if (d < dlo || d >= dhi) cv = 255;
-					sTile[row*TILE_PITCH + d] = (uint8_t)cv;
-				}
-			}
-		}
-		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-	};
-
-	#pragma unroll 1
-	for (int r = blockIdx.x; r < vh; r += gridDim.x) {
-		#pragma unroll 1
-		for (int b = 0; b < nBlocks; ++b) {
-			// operands of this block: A by warps 0-3; the tiles not yet in the ring by warps 4-7
-			build_a(r, BM*b, tid>>2, tid&3);
-			{
-				const int tsel = tid>>8, c = (tid>>2)&63, q = tid&3;      // tile of the pair, column, tap quarter
-				if (b == 0)
-					for (int t = 0; t < nTiles-2; t += 2) build_b_tile(r, t+tsel, c, q);
-				build_b_tile(r, 2*b+nTiles-2+tsel, c, q);
-			}
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-			__syncthreads();
-			if (tid == 0) {
+		for (int r = blockIdx.x; r < vh; r += gridDim.x) {
+			#pragma unroll 1
+			for (int b = 0; b < nBlocks; ++b) {
+				bar_sync(BAR_OPS, TC_THREADS);                 // the workers have built this block's operands
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				issue_tile(2*b, 0); issue_tile(2*b+1, 1);
-			}
-			for (int k = 0; k < nTiles; ++k) {
-				epilogue(r, b, 2*b+k, k&1);
-				__syncthreads();                               // every warp has drained buffer k&1
-				if (tid == 0 && k+2 < nTiles) {
+				if (lane == 0) { issue_tile(2*b, 0); if (nTiles > 1) issue_tile(2*b+1, 1); }
+				__syncwarp();
+				for (int k = 2; k < nTiles; ++k) {
+					bar_sync(BAR_DRAIN+(k&1), TC_THREADS);     // the workers have read tile k-2 out of this buffer
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-					issue_tile(2*b+k+2, k&1);
+					if (lane == 0) issue_tile(2*b+k, k&1);
+					__syncwarp();
 				}
 			}
-			// the block's costs: num bytes per pixel, coalesced 16-byte stores
-			const int chunks = num/16;
-			for (int i = tid; i < BM*chunks; i += TC_THREADS) {
-				const int row = i/chunks, c16 = i-row*chunks;
-				const int col = BM*b+row;
-				if (col < vw) {
-					const uint32_t* src = (const uint32_t*)(sTile + row*TILE_PITCH + 16*c16);
-					const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
-					*(uint4*)(P.costs + ((size_t)r*vw + col)*(size_t)num + 16*c16) = v;
+		}
+	} else {
+		// ---- the 16 worker warps: operands, then sums -> costs ----
+		unsigned phase[2] = {0u, 0u};
+		const int wq = warp&3;                       // tap quarter of this warp (operand builders)
+		#pragma unroll 1
+		for (int r = blockIdx.x; r < vh; r += gridDim.x) {
+			#pragma unroll 1
+			for (int b = 0; b < nBlocks; ++b) {
+				const int x0 = BM*b;
+				// B tiles not yet in the ring: the last two of the block (all of them for the first block of a row), two at a time
+				for (int t0 = (b == 0 ? 0 : 2*b+nTiles-2); t0 < 2*b+nTiles; t0 += 2) {
+					if (t0 != (b == 0 ? 0 : 2*b+nTiles-2)) bar_sync(BAR_WORKERS, TC_WORKERS);   // the stage is read by the previous pair
+					// stage the image rows r .. r+6: left colour / gray columns x0 .. x0+133 (first pair only), right gray columns of the pair
+					const bool first = t0 == (b == 0 ? 0 : 2*b+nTiles-2);
+					for (int i = tid; i < 7*(BM+6); i += TC_WORKERS) {
+						const int ry = i/(BM+6), cx = i-ry*(BM+6);
+						if (first) {
+							const int col = min(x0+cx, w-1);
+							const uchar3 c3 = P.lbgr[(size_t)(r+ry)*w + col];
+							((uint32_t*)(sTile+ST_LC))[ry*SP+cx] = (uint32_t)c3.x | ((uint32_t)c3.y<<8) | ((uint32_t)c3.z<<16);
+							((float*)(sTile+ST_LG))[ry*SP+cx] = __ldg(P.lgray + (size_t)(r+ry)*w + col);
+						}
+						const int rc = min(max(BN*t0 + cx + dmin, 0), w-1);
+						((float*)(sTile+ST_RG))[ry*SP+cx] = __ldg(P.rgray + (size_t)(r+ry)*w + rc);
+					}
+					bar_sync(BAR_WORKERS, TC_WORKERS);
+					if (first) {
+						const int row = (warp>>2)*32 + lane;
+						const bool valid = x0+row < vw;
+						switch (wq) {
+						case 0: build_a_quarter<0>(sA, sTile, sNorm, sInv, row, valid); break;
+						case 1: build_a_quarter<1>(sA, sTile, sNorm, sInv, row, valid); break;
+						case 2: build_a_quarter<2>(sA, sTile, sNorm, sInv, row, valid); break;
+						default: build_a_quarter<3>(sA, sTile, sNorm, sInv, row, valid); break;
+						}
+					}
+					{
+						const int tsel = warp>>3, q = (warp>>1)&3, c = (warp&1)*32 + lane;
+						if (t0+tsel < 2*b+nTiles) {
+							unsigned char* slot = sB + (size_t)((t0+tsel)&(RING-1))*B_SLOT;
+							switch (q) {
+							case 0: build_b_quarter<0>(slot, sTile, BN*tsel, c); break;
+							case 1: build_b_quarter<1>(slot, sTile, BN*tsel, c); break;
+							case 2: build_b_quarter<2>(slot, sTile, BN*tsel, c); break;
+							default: build_b_quarter<3>(slot, sTile, BN*tsel, c); break;
+							}
+						}
+					}
 				}
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+				bar_sync(BAR_WORKERS, TC_WORKERS);     // every worker is done with the stage (the cost tile is written next)
+				bar_arrive(BAR_OPS, TC_THREADS);
+				// sums -> costs, tile by tile, into the shared cost tile
+				const int row0 = 32*(warp&3), row = row0 + lane;   // TMEM lane = pixel of the block
+				const int c0 = 16*(warp>>2);                        // this warp's 16 of the 64 columns
+				const int col = x0 + row;                           // valid-region column of the pixel
+				// disparities whose right window lies inside the image: 0 <= col + d + dmin, col + d + dmin + 6 < w
+				const int dlo = max(0, -(col+dmin)), dhi = min(num, w-2*HW-col-dmin);
+				float normSq0 = 0.f, invW = 0.f;
+				for (int k = 0; k < nTiles; ++k) {
+					const int buf = k&1;
+					mbar_wait(bars+buf, phase[buf]); phase[buf] ^= 1u;
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					if (k == 0) { normSq0 = (sNorm[row]+sNorm[BM+row])+(sNorm[2*BM+row]+sNorm[3*BM+row]); invW = sInv[row]; }
+					const int kq = BN*k;                             // disparity index of (row 0, column 0) of this tile
+					// the band 0 <= d < num covers about half of a tile: a 32-row x 16-column chunk wholly outside it is skipped (warp-uniform)
+					if (!(kq+c0+15-row0 < 0 || kq+c0-(row0+31) >= num)) {
+						uint32_t s0[16], s1[16], s2[16];
+						const uint32_t ta = tmem + ((uint32_t)row0<<16) + (uint32_t)buf*256u + (uint32_t)c0;
+						tmem_ld16(ta, s0); tmem_ld16(ta+64u, s1); tmem_ld16(ta+128u, s2);
+						asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+						#pragma unroll
+						for (int e = 0; e < 16; ++e) {
+							const int d = kq + c0+e - row;            // disparity index of (pixel, column)
+							if (d >= 0 && d < num) {
+								const float sum = __uint_as_float(s0[e]), sumSq = __uint_as_float(s1[e]), nom = __uint_as_float(s2[e]);
+								const float normSq1 = fmaf(-sum*invW, sum, sumSq);
+								const float ncc = nom*rsqrtf(fmaf(normSq0, normSq1, 1e-3f));
+								// ncc <= 0 ? 255 : floor((1 - min(ncc, 1)) * 255 + .5); 255 for windows that leave the right image
+								int cv = ncc <= 0.f ? 255 : __float2int_rd(fmaf(-255.f, fminf(ncc, 1.f), 255.5f));
+								if (d < dlo || d >= dhi) cv = 255;
+								sTile[row*TILE_PITCH + d] = (uint8_t)cv;
+							}
+						}
+					}
+					if (k+2 < nTiles) {
+						asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+						bar_arrive(BAR_DRAIN+buf, TC_THREADS);      // the issuing warp may overwrite this buffer
+					}
+				}
+				bar_sync(BAR_WORKERS, TC_WORKERS);
+				// the block's costs: num bytes per pixel, coalesced 16-byte stores
+				const int chunks = num/16;
+				for (int i = tid; i < BM*chunks; i += TC_WORKERS) {
+					const int prow = i/chunks, c16 = i-prow*chunks;
+					const int pcol = x0+prow;
+					if (pcol < vw) {
+						const uint32_t* src = (const uint32_t*)(sTile + prow*TILE_PITCH + 16*c16);
+						const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+						*(uint4*)(P.costs + ((size_t)r*vw + pcol)*(size_t)num + 16*c16) = v;
+					}
+				}
+				bar_sync(BAR_WORKERS, TC_WORKERS);                  // the tile is free: the next block stages into it
 			}
-			__syncthreads();                                   // tile and A are free for the next block
 		}
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

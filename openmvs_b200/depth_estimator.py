@@ -55,6 +55,7 @@ class OPTDENSE:
 	nPropagation = 4
 	nPropagationFar = 2
 	bSkipUnchanged = 1
+	nEvalCap = 0
 	nSeed = 1234
 
 	@classmethod

@@ -29,7 +29,7 @@ class Params(C.Structure):
 		("fRandomSmoothDepth", C.c_float), ("fRandomSmoothNormal", C.c_float), ("fRandomSmoothBonus", C.c_float),
 		("fEstimationGeometricWeight", C.c_float),
 		("nSweepsPerIter", C.c_int), ("nPropagation", C.c_int), ("seed", C.c_uint32),
-		("nPropagationFar", C.c_int), ("bSkipUnchanged", C.c_int)]
+		("nPropagationFar", C.c_int), ("bSkipUnchanged", C.c_int), ("nEvalCap", C.c_int)]
 
 
 class Debug(C.Structure):

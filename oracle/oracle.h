@@ -53,7 +53,8 @@ typedef struct {
 	int propagation; /* RB only (the engine's schedule): bits 0-3: 2 = the two causal neighbours of the reference
 	                    direction, 4 = all four 4-neighbours; bits 4-7: F far rings, the candidate of a direction is the
 	                    lowest-cost pixel at distance 1, 3, .. 2F+1; bit 8 (0x100): a direction whose candidates kept
-	                    their plane in their last update is not re-tested */
+	                    their plane in their last update is not re-tested; bits 12-15: E > 0 = a pixel that scored c
+	                    candidates spends at most max(1, E - c) refinement tries in the sweep */
 	uint32_t seed;
 	int threads;     /* ZZ: number of worker threads pulling from the shared counter */
 } oracle_params;

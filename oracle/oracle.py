@@ -172,9 +172,9 @@ def pm_iterate_flags(views, prm, dmin, dmax, depth, normal, conf, changed, it, h
 	return d, n, c, f
 
 
-def rb_propagation(nPropagation=4, nPropagationFar=2, bSkipUnchanged=1):
+def rb_propagation(nPropagation=4, nPropagationFar=2, bSkipUnchanged=1, nEvalCap=0):
 	"""oracle_params.propagation for the engine's red-black schedule (include/b200mvs.h b200mvs_params)"""
-	return int(nPropagation) | (int(nPropagationFar) << 4) | (0x100 if bSkipUnchanged else 0)
+	return int(nPropagation) | (int(nPropagationFar) << 4) | (0x100 if bSkipUnchanged else 0) | (int(nEvalCap) << 12)
 
 
 def pm_estimate_range(views, prm, dmin, dmax, it_begin, it_end, geometric=False, mask=None, depth=None, normal=None, depths=None):

@@ -535,6 +535,7 @@ struct Estimator {
 			~FlagSetter() { if (J.changed) J.changed[i] = (d != d0 || pn[0] != n0.x || pn[1] != n0.y || pn[2] != n0.z) ? 1 : 0; }
 		} flagSetter{J, i0, depth, pn, depthIn, normalIn};
 		// propagation
+		int nTested = 0;   // candidates scored (engine schedule: bounds the refinement tries, see below)
 		for (int p=0; p<nProp; ++p) {
 			const int c = prop[p][0], k = prop[p][1];
 			if (!dirChanged[k]) { g_propSkipped.fetch_add(1, std::memory_order_relaxed); continue; }
@@ -549,6 +550,7 @@ struct Estimator {
 				nb = close[c];
 			if (J.conf[(size_t)ny*w+nx] >= J.prm.fNCCThresholdKeep)
 				continue;
+			++nTested;
 			nb.depth = InterpolatePixel(nx, ny, nb.depth, nb.normal);
 			CorrectNormal(nb.normal);
 			InitPlane(nb.depth, nb.normal);
@@ -556,6 +558,10 @@ struct Estimator {
 			if (conf > nconf) { conf = nconf; depth = nb.depth; normal = nb.normal; }
 		}
 		// refinement
+		// RB engine schedule, propagation bits 12-15 = evaluation cap E > 0 (not in the reference): a pixel that scored c
+		// candidates above spends at most max(1, E - c) random / perturbation tries; the Philox slots keep their numbering
+		const int evalCap = J.prm.schedule == 1 ? ((J.prm.propagation >> 12) & 15) : 0;
+		const int nTries = evalCap > 0 ? std::min(J.prm.nRandomIters, std::max(evalCap-nTested, 1)) : J.prm.nRandomIters;
 		const uint32_t phase = 1u+(uint32_t)iter;
 		unsigned idxScaleRange = 0;
 		static const float scaleRanges[12] = {1.f, 0.5f, 0.25f, 0.125f, 0.0625f, 0.03125f, 0.015625f, 0.0078125f, 0.00390625f, 0.001953125f, 0.0009765625f, 0.00048828125f};
@@ -570,7 +576,7 @@ struct Estimator {
 				restarted = true;
 				nClose = 0;
 				bool again = false;
-				for (int it=0; it<J.prm.nRandomIters; ++it) {
+				for (int it=0; it<nTries; ++it) {
 					rngBegin(phase, (uint32_t)it);
 					const float ndepth = RandomDepth();
 					const V3 nnormal = RandomNormal(vd);
@@ -590,7 +596,7 @@ struct Estimator {
 		const float depthRange = depth*J.prm.fRandomDepthRatio;
 		float pa, pb;
 		normal2dir(normal, pa, pb);
-		for (int it=0; it<J.prm.nRandomIters; ++it) {
+		for (int it=0; it<nTries; ++it) {
 			rngBegin(phase, (uint32_t)(J.prm.nRandomIters+it));
 			const float ndepth = randomMeanRange(depth, depthRange*scaleRange);
 			if (!(J.dMin <= ndepth && ndepth < J.dMax))

@@ -1,6 +1,6 @@
 """Single-view 1080p run (one reference view, 9 neighbours) for ncu captures and schedule comparisons: prints the per-sweep
 kernel times of the engine's schedule, from random initialisation and continuing from the converged state.
-usage: profile_sweep.py [iters] [far] [skip] [sweepsPerIter]"""
+usage: profile_sweep.py [iters] [far] [skip] [sweepsPerIter] [fourCtas] [evalCap]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,6 +13,7 @@ OPTDENSE.nPropagationFar = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 OPTDENSE.bSkipUnchanged = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 OPTDENSE.nSweepsPerIter = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 FOUR = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+if len(sys.argv) > 6: OPTDENSE.nEvalCap = int(sys.argv[6])
 dev = torch.device("cuda:0")
 sc = synth.make_scene(1920, 1080, 12, step_deg=4.0, device=dev)
 r = 5
@@ -27,7 +28,7 @@ for tag in ("random init", "warm, random init", "continued"):
 	pm.EstimateDepthMap(dd)
 	gd = dd.depthMap.cpu().numpy(); gn = dd.normalMap.cpu().numpy(); m = gd > 0
 	ang = np.degrees(np.arccos(np.clip((gn*gtn).sum(-1), -1, 1)))[m]
-	print("%-18s 4ctas %d schedule %s far %d skip %d | device ms %.2f launches %d | sweep launches %d avg %.3f ms | valid %.4f gt<1e-3 %.4f med ang %.2f" % (
-		tag, FOUR, OPTDENSE.schedule(), OPTDENSE.nPropagationFar, OPTDENSE.bSkipUnchanged, pm.stats.ms_device, pm.stats.kernel_launches,
+	print("%-18s 4ctas %d cap %d schedule %s far %d skip %d | device ms %.2f launches %d | sweep launches %d avg %.3f ms | valid %.4f gt<1e-3 %.4f med ang %.2f" % (
+		tag, FOUR, OPTDENSE.nEvalCap, OPTDENSE.schedule(), OPTDENSE.nPropagationFar, OPTDENSE.bSkipUnchanged, pm.stats.ms_device, pm.stats.kernel_launches,
 		pm.stats.sweep_launches, pm.stats.ms_sweep_kernels/max(1, pm.stats.sweep_launches), m.mean(),
 		(np.abs(gd-gt)[m]/gt[m] < 1e-3).mean(), np.median(ang)), flush=True)

@@ -52,7 +52,7 @@ def rb_oracle(views, dmin, dmax, geometric_iter=-1, threads=8, mask=None, depth=
 	T, nR = OPT.schedule(False)
 	S, nRg = OPT.schedule(True)
 	geo = geometric_iter >= 0
-	prm = O.default_params(schedule=1, propagation=O.rb_propagation(OPT.nPropagation, OPT.nPropagationFar, OPT.bSkipUnchanged),
+	prm = O.default_params(schedule=1, propagation=O.rb_propagation(OPT.nPropagation, OPT.nPropagationFar, OPT.bSkipUnchanged, OPT.nEvalCap),
 		nRandomIters=nRg if geo else nR, nSubResolutionLevels=OPT.nSubResolutionLevels, nEstimationGeometricIters=OPT.nEstimationGeometricIters,
 		fEstimationGeometricWeight=OPT.fEstimationGeometricWeight, fNCCThresholdKeep=OPT.fNCCThresholdKeep, seed=OPT.nSeed, threads=threads)
 	b, e = (T+geometric_iter*S, T+(geometric_iter+1)*S) if geo else (0, T)

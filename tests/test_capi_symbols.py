@@ -32,7 +32,7 @@ def test_struct_layouts_match_header_sizes():
 	from openmvs_b200 import lib
 	# b200mvs_view: pointer, 3 ints (+pad), 21 doubles, pointer, 3 ints (+pad), 21 doubles
 	assert C.sizeof(lib.View) == 8+16+21*8+8+16+21*8-8+8 or C.sizeof(lib.View) % 8 == 0
-	assert C.sizeof(lib.Params) == 18*4
+	assert C.sizeof(lib.Params) == 19*4
 	assert C.sizeof(lib.Stats) == 8+8+8+8+4+4+8+4+4
 
 
