@@ -450,7 +450,7 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 	const b200mvs_debug& D = ctx->dbg;
 	const int layout = std::min(std::max(D.frontLayout-1, 0), 2);
 	const bool concurrent = !D.frontSerial;
-	const int FB = D.frontBlock > 0 ? D.frontBlock : (layout == 0 ? 32 : 16);
+	const int FB = D.frontBlock > 0 ? D.frontBlock : 64;   // measured: profiles/sgm_variants_r02d.txt
 	const int lag = D.frontLag > 0 ? D.frontLag : 2;
 	const int vw = P.vw, vh = P.vh;
 	const int key[6] = {vw, vh, layout, FB, lag, concurrent ? 2 : 1};
@@ -957,7 +957,7 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	if (stages & 1) {
 		// dense volume with one range of 64 / 128 disparities: the banded-GEMM cost kernel on the tensor cores (sgm_cost_tc.cu)
 		const bool dense = uniform && (st8[0] & 15) == 0 && !st8[6] && !((uintptr_t)P.costs & 15);
-		const bool tc = dense && sgm_cost_tc_supports(st8[0]) && ctx->dbg.sgmCost == 2;
+		const bool tc = dense && sgm_cost_tc_supports(st8[0]) && ctx->dbg.sgmCost != 1;   // auto: the tensor-core kernel where it applies
 		if (ctx->dbg.sgmCost == 2 && !tc)
 			return fail(ctx, B200MVS_ERR_ARG, "sgm: the tensor-core cost kernel needs a dense volume with one range of 64 or 128 disparities");
 		if (tc) CK(sgm_cost_tc_launch(P, st8[1], st8[0], s));

@@ -159,8 +159,12 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 				__nanosleep(64);
 				if (++spins > (1u<<21)) { if (lane == 0) *A.error = 1; break; }
 			}
-			// acquire: the predecessors' stores are visible to the loads below (ld.cg / cp.async.cg: served by the L2)
-			asm volatile("fence.acq_rel.gpu;" ::: "memory");
+			// acquire: one acquire load of each word once they are satisfied (not a fence: a fence would also wait for the cost
+			// copies requested above); the predecessors' stores are then visible to the loads below (ld.cg / cp.async.cg: L2)
+			int a, c;
+			asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(pp) : "memory");
+			asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(pc) : "memory");
+			if (a < seq || c < need) *A.error = 2;   // cannot happen: the counters only grow
 		}
 		// the sums of the first PD steps: one group per step (empty when the phase stores)
 		#pragma unroll

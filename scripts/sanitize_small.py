@@ -32,7 +32,7 @@ if ONLY == "":
 if ONLY in ("", "sgm"):
 	# uniform 16-byte aligned ranges: the bulk-copy ring aggregation kernel (mbarrier + cp.async.bulk)
 	lg, lc, rg, d = synth.make_stereo_pair(150, 90)
-	for num in (32, 144):
+	for num in (32, 144, 64, 128):   # ring kernel; wave-front aggregation + tensor-core cost kernel
 		px, n = synth.sgm_pixel_map(150, 90, -8, -8+num)
 		m = SemiGlobalMatcher(); disp, cost = m.Match(lg, lc, rg, px, n); m.Release()
 		print("sgm ring num", num, "ok", int((disp != 32767).sum()))

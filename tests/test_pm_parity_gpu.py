@@ -199,6 +199,31 @@ def test_full_estimate_parity_rb_and_zz(env, small_scene):
 	assert np.all(vm[m][two, 0] < vm[m][two, 1])  # view ids ascending, like PatchMatchCUDA.cpp:374-391
 
 
+def test_evaluation_cap_parity(env, small_scene):
+	"""b200mvs_params.nEvalCap = 7 (a pixel that tests c propagation candidates spends at most max(1, 7 - c) refinement tries in
+	the sweep; an option, off by default): same rule in the oracle's RB schedule, same Philox slots -> same agreement as the
+	uncapped schedule; and the result differs from the uncapped one (the option does something)."""
+	e = env
+	sc, ref, views = small_scene
+	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=0, nEstimationIters=6, nSweepsPerIter=0, nRandomIters=6, nPropagation=4)
+	dd0 = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+	e.pm.EstimateDepthMap(dd0)
+	try:
+		_set(e, nEvalCap=7)
+		dd = e.DepthData(_dev_views(e, views), sc.dmin, sc.dmax)
+		e.pm.EstimateDepthMap(dd)
+		od, on, oc = rb_oracle(views, sc.dmin, sc.dmax, threads=4)
+	finally:
+		_set(e, nEvalCap=0)
+	gd, g0 = dd.depthMap.cpu().numpy(), dd0.depthMap.cpu().numpy()
+	iou, agree = agreement(od, gd)
+	gt = sc.views[ref].depth_gt
+	acc = (np.abs(gd-gt)[gd > 0]/gt[gd > 0] < 1e-3).mean(); acc0 = (np.abs(g0-gt)[g0 > 0]/gt[g0 > 0] < 1e-3).mean()
+	_record("eval_cap7_320x240_N4_I6", iou_rb=iou, agree_rb=agree, acc_cap7=acc, acc_cap0=acc0, frac_differs_from_cap0=float((gd != g0).mean()))
+	assert iou > 0.999 and agree > 0.98
+	assert (gd != g0).mean() > 0.05 and abs(acc-acc0) < 0.01
+
+
 def test_host_api_equals_device_api_and_is_deterministic(env, small_scene):
 	e = env
 	sc, ref, views = small_scene
