@@ -74,3 +74,115 @@ def ImportDepthDataRaw(fileName, flags: int = 15) -> dict:
 				if flags & flag:
 					out[key] = np.frombuffer(raw, dt).reshape(shape).copy()
 	return out
+
+
+class AsyncDepthDataWriter:
+	"""Asynchronous emission of `.dmap` files (second half).
+
+	The reference saves a depth-map from its event loop after the estimation of the next image has been queued
+	(EVT_SAVEDEPTHMAP, libs/MVS/SceneDensify.cpp:2065,2092-2113; DepthData::Save libs/MVS/DepthMap.cpp:237-251), so the disk
+	write overlaps the next estimation.  Here `submit()` returns at once: device-resident maps (torch CUDA tensors) are copied to
+	pinned host buffers on a side stream that waits for the producing stream, and a worker thread writes the file when the copy
+	has landed; host arrays go straight to the worker.  `flush()` waits for everything submitted and re-raises the first error.
+	At most `max_pending` files are in flight (their pinned buffers are recycled), so a slow disk throttles the caller instead of
+	growing memory without bound."""
+
+	def __init__(self, max_pending: int = 4):
+		import queue, threading
+		self._q = queue.Queue()
+		self._slots = threading.Semaphore(max_pending)
+		self._errors = []
+		self._pool = {}          # (shape, dtype) -> list of free pinned tensors
+		self._lock = threading.Lock()
+		self._stream = None
+		self._thread = threading.Thread(target=self._run, name="dmap-writer", daemon=True)
+		self._thread.start()
+		self.files_written = 0
+
+	def _pinned(self, t):
+		import torch
+		key = (tuple(t.shape), t.dtype)
+		with self._lock:
+			free = self._pool.setdefault(key, [])
+			if free:
+				return free.pop()
+		return torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+
+	def _release(self, bufs):
+		with self._lock:
+			for b in bufs:
+				self._pool.setdefault((tuple(b.shape), b.dtype), []).append(b)
+
+	def submit(self, fileName, imageFileName, IDs, imageSize, K, R, C, dMin, dMax, depthMap, normalMap=None, confMap=None, viewsMap=None):
+		"""Queue one file; the maps may be numpy arrays or torch tensors (CUDA tensors are read in the current stream's order:
+		work queued on it before this call is finished before the copy starts, work queued after it waits for the copy)."""
+		# host arrays are snapshotted here, device maps by the ordered copy below: the caller may reuse both right away
+		maps = [m if (m is None or hasattr(m, "is_cuda")) else np.array(m, copy=True) for m in (depthMap, normalMap, confMap, viewsMap)]
+		self._slots.acquire()
+		event, bufs = None, []
+		try:
+			import torch
+			cuda = [m for m in maps if m is not None and hasattr(m, "is_cuda") and m.is_cuda]
+			if cuda:
+				dev = cuda[0].device
+				if self._stream is None or self._stream.device != dev:
+					self._stream = torch.cuda.Stream(device=dev)
+				self._stream.wait_stream(torch.cuda.current_stream(dev))
+				with torch.cuda.stream(self._stream):
+					for i, m in enumerate(maps):
+						if m is not None and hasattr(m, "is_cuda") and m.is_cuda:
+							m = m.contiguous()
+							m.record_stream(self._stream)
+							b = self._pinned(m)
+							b.copy_(m, non_blocking=True)
+							bufs.append(b); maps[i] = b
+					event = torch.cuda.Event()
+					event.record(self._stream)
+				# later work on the producing stream must not overwrite the maps before the copy has read them
+				torch.cuda.current_stream(dev).wait_event(event)
+		except ImportError:
+			pass
+		self._q.put((fileName, imageFileName, list(IDs), tuple(imageSize), np.array(K, np.float64), np.array(R, np.float64), np.array(C, np.float64),
+			float(dMin), float(dMax), maps, event, bufs))
+
+	def _run(self):
+		while True:
+			job = self._q.get()
+			if job is None:
+				self._q.task_done()
+				return
+			fileName, imageFileName, IDs, imageSize, K, R, C, dMin, dMax, maps, event, bufs = job
+			try:
+				if event is not None:
+					event.synchronize()
+				host = [None if m is None else (m.numpy() if hasattr(m, "numpy") else np.asarray(m)) for m in maps]
+				ExportDepthDataRaw(fileName, imageFileName, IDs, imageSize, K, R, C, dMin, dMax, host[0], host[1], host[2], host[3])
+				self.files_written += 1
+			except Exception as e:   # reported by flush()
+				self._errors.append((fileName, e))
+			finally:
+				self._release(bufs)
+				self._slots.release()
+				self._q.task_done()
+
+	def flush(self):
+		self._q.join()
+		if self._errors:
+			name, e = self._errors[0]
+			self._errors = []
+			raise RuntimeError("writing %s failed: %r" % (name, e))
+
+	def close(self):
+		self._q.join()
+		self._q.put(None)
+		self._thread.join()
+		if self._errors:
+			name, e = self._errors[0]
+			raise RuntimeError("writing %s failed: %r" % (name, e))
+
+	def __enter__(self):
+		return self
+
+	def __exit__(self, *exc):
+		self.close()
+		return False

@@ -241,8 +241,12 @@ class SceneEstimator:
 	"""estimate() callable for compute_depth_maps on one GPU: images resident in HBM, one PatchMatchB200.
 	views: list of objects with .image (numpy HxW float32) .K .R .C; neighbors: list of index lists."""
 
-	def __init__(self, views, neighbors, dmin: float, dmax: float, device=None):
+	def __init__(self, views, neighbors, dmin: float, dmax: float, device=None, writer=None, path_of=None, image_names=None):
+		"""writer / path_of: emit every estimated view as a `.dmap` file without waiting for the disk — writer is a
+		dmap_io.AsyncDepthDataWriter, path_of(view, nGeometricIter) the file name (the reference writes depthNNNN.dmap after pass 1
+		and depthNNNN.geo.dmap after a geometric pass, SceneDensify.cpp:2113); image_names[v]: the image file of view v."""
 		from .depth_estimator import Camera, PatchMatchB200
+		self.writer, self.path_of, self.image_names = writer, path_of, image_names
 		self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
 		self.pm = PatchMatchB200(self.dev.index or 0)
 		self.cams = [Camera(v.K, v.R, v.C) for v in views]
@@ -263,4 +267,11 @@ class SceneEstimator:
 			dd.depthMap = previous["depth"].clone(); dd.normalMap = previous["normal"].clone()
 		self.pm.Init(nGeometricIter >= 0)
 		self.pm.EstimateDepthMap(dd, nGeometricIter)
+		if self.writer is not None:
+			# EVT_SAVEDEPTHMAP (SceneDensify.cpp:2095-2113): the copy to pinned memory is ordered after the estimation on this
+			# stream, the file is written by the writer's thread while the next view is estimated
+			h, w = dd.depthMap.shape
+			cam = self.cams[v]
+			self.writer.submit(self.path_of(v, nGeometricIter), self.image_names[v] if self.image_names else "%05d.jpg" % v,
+				[v]+list(self.neighbors[v]), (w, h), cam.K, cam.R, cam.C, self.dmin, self.dmax, dd.depthMap, dd.normalMap, dd.confMap, dd.viewsMap)
 		return dict(depth=dd.depthMap, normal=dd.normalMap, conf=dd.confMap)

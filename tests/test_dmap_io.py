@@ -67,3 +67,54 @@ def test_reference_reader_reads_our_files(tmp_path):
 	assert np.array_equal(d["confidence_map"], conf) and np.array_equal(d["views_map"], views)
 	assert np.array_equal(d["K"], K) and np.array_equal(d["R"], R) and np.array_equal(d["C"], C)
 	assert d["depth_min"] == np.float32(0.25) and d["file_name"] == "img.jpg"
+
+
+def test_async_writer_host_arrays_and_errors(tmp_path):
+	"""AsyncDepthDataWriter: files submitted from host arrays equal the synchronous writer's byte for byte, the queue is bounded,
+	an unwritable path surfaces in flush()."""
+	rng = np.random.RandomState(1)
+	samples = [_sample(rng) for _ in range(7)]
+	with dmap_io.AsyncDepthDataWriter(max_pending=2) as wr:
+		for i, (depth, normal, conf, views, K, R, C) in enumerate(samples):
+			wr.submit(str(tmp_path/("a%02d.dmap" % i)), str(tmp_path/"img.jpg"), [i, i+1], (17, 12), K, R, C, 0.5, 9.5, depth, normal, conf, views)
+			depth[:] = -1   # submit() snapshots host arrays: reuse is allowed at once
+		wr.flush()
+		assert wr.files_written == 7
+	rng = np.random.RandomState(1)
+	for i in range(7):
+		depth, normal, conf, views, K, R, C = _sample(rng)
+		d = dmap_io.ImportDepthDataRaw(str(tmp_path/("a%02d.dmap" % i)))
+		assert np.array_equal(d["depthMap"], depth) and np.array_equal(d["normalMap"], normal) and np.array_equal(d["viewsMap"], views) and list(d["IDs"]) == [i, i+1]
+	wr = dmap_io.AsyncDepthDataWriter()
+	depth, normal, conf, views, K, R, C = samples[0]
+	wr.submit(str(tmp_path/"no_such_dir"/"x.dmap"), "img.jpg", [0, 1], (17, 12), K, R, C, 1, 2, depth)
+	with pytest.raises(RuntimeError):
+		wr.flush()
+	wr.close()
+
+
+@pytest.mark.gpu
+def test_async_writer_device_maps_overlap_and_equal_sync(tmp_path):
+	"""Device-resident maps: submit() returns before the file exists, later writes to the same tensors on the producing stream
+	do not leak into the file, and the file equals the synchronous export of the maps as they were at submit time."""
+	import torch
+	if not torch.cuda.is_available():
+		pytest.skip("no CUDA device")
+	rng = np.random.RandomState(2)
+	h, w = 1080, 1920
+	depth = torch.from_numpy((rng.rand(h, w).astype(np.float32)*5+1)).cuda()
+	normal = torch.from_numpy(rng.randn(h, w, 3).astype(np.float32)).cuda()
+	conf = torch.from_numpy(rng.rand(h, w).astype(np.float32)).cuda()
+	views = torch.from_numpy(rng.randint(0, 255, (h, w, 4)).astype(np.uint8)).cuda()
+	K = np.array([[1700.0, 0, 959.5], [0, 1700.0, 539.5], [0, 0, 1]]); R = np.eye(3); C = np.zeros(3)
+	want = [t.cpu().numpy().copy() for t in (depth, normal, conf, views)]
+	with dmap_io.AsyncDepthDataWriter(max_pending=3) as wr:
+		for i in range(3):
+			wr.submit(str(tmp_path/("d%d.dmap" % i)), str(tmp_path/"img.jpg"), [0, 1, 2], (w, h), K, R, C, 0.5, 9.5, depth, normal, conf, views)
+		# overwrite on the producing stream right after the submits: ordered after the copies
+		depth.zero_(); normal.zero_()
+		wr.flush()
+	for i in range(3):
+		d = dmap_io.ImportDepthDataRaw(str(tmp_path/("d%d.dmap" % i)))
+		assert np.array_equal(d["depthMap"], want[0]) and np.array_equal(d["normalMap"], want[1])
+		assert np.array_equal(d["confMap"], want[2]) and np.array_equal(d["viewsMap"], want[3])

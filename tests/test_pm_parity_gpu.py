@@ -549,20 +549,32 @@ def test_batch_call_over_two_contexts_equals_single_calls(env, small_scene):
 		assert np.array_equal(a.depthMap, b.depthMap) and np.array_equal(a.confMap, b.confMap) and np.array_equal(a.viewsMap, b.viewsMap)
 
 
-def test_scene_pipeline_with_geometric_passes(env, small_scene):
+def test_scene_pipeline_with_geometric_passes(env, small_scene, tmp_path):
 	"""Pass 1 for every view, then geometric-consistency passes fed by the other views' depth-maps
-	(compute_depth_maps, the estimation part of Scene::ComputeDepthMaps) on one GPU."""
+	(compute_depth_maps, the estimation part of Scene::ComputeDepthMaps) on one GPU; every estimated view is emitted as a
+	.dmap file by the asynchronous writer (depthNNNN.dmap / depthNNNN.geo.dmap like SceneDensify.cpp:2113)."""
 	e = env
-	from openmvs_b200 import multi_gpu
+	from openmvs_b200 import multi_gpu, dmap_io
 	sc, ref, _ = small_scene
 	n = len(sc.views)
 	nbrs = [sc.neighbors(v, 3) for v in range(n)]
 	_set(e, nSubResolutionLevels=0, nEstimationGeometricIters=2, nEstimationIters=4, nSweepsPerIter=2, nRandomIters=6)
-	est = multi_gpu.SceneEstimator(sc.views, nbrs, sc.dmin, sc.dmax, device=e.dev)
+	wr = dmap_io.AsyncDepthDataWriter()
+	est = multi_gpu.SceneEstimator(sc.views, nbrs, sc.dmin, sc.dmax, device=e.dev, writer=wr,
+		path_of=lambda v, g: str(tmp_path/("depth%04d.%sdmap" % (v, "" if g < 0 else "geo."))))
 	pass1 = multi_gpu.compute_depth_maps(n, est, n_geometric_iters=0)
+	wr.flush()
+	for v in range(n):   # the files of pass 1 hold exactly the maps the pass returned
+		f = dmap_io.ImportDepthDataRaw(str(tmp_path/("depth%04d.dmap" % v)))
+		assert np.array_equal(f["depthMap"], pass1[v][..., 0].cpu().numpy()) and np.array_equal(f["confMap"], pass1[v][..., 4].cpu().numpy())
+		assert list(f["IDs"]) == [v]+list(nbrs[v]) and f["viewsMap"].shape == f["depthMap"].shape+(4,)
 	full = multi_gpu.compute_depth_maps(n, est, n_geometric_iters=2)
+	wr.close()
+	assert wr.files_written == n + 3*n
 	est.pm.Release()
 	for v in range(n):
+		f = dmap_io.ImportDepthDataRaw(str(tmp_path/("depth%04d.geo.dmap" % v)))
+		assert np.array_equal(f["depthMap"], full[v][..., 0].cpu().numpy())   # the last geometric pass wrote last
 		gt = sc.views[v].depth_gt
 		d1 = pass1[v][..., 0].cpu().numpy(); d2 = full[v][..., 0].cpu().numpy()
 		m1, m2 = d1 > 0, d2 > 0
