@@ -102,7 +102,7 @@ typedef struct {
 	int frontSerial;     /* 1: one pass per launch into one sum volume (default: two passes share a launch, each with its own
 	                        volume, added by the winner-takes-all kernel) */
 	int frontBlock;      /* fronts per work item (0: default) */
-	int frontLag;        /* queue distance, in blocks, between the directions of a pass (0: default) */
+	int frontLag;        /* 1 + queue distance, in blocks, between the directions of a pass (0: default = distance 0) */
 	int frontCtas;       /* resident CTAs per SM (0: default) */
 	int frontDepth;      /* steps whose loads are in flight: 4 or 8 (0: default) */
 	int reserved[5];
@@ -322,6 +322,43 @@ int b200mvs_to_gray_device(b200mvs_ctx* ctx, const uint8_t* image, int width, in
 int b200mvs_scaled_size(int width, int height, float scale, int* scaledWidth, int* scaledHeight);
 int b200mvs_scale_image_device(b200mvs_ctx* ctx, const float* image, int width, int height, int stride_bytes, float scale,
 	float* scaled, int* applied, void* stream);
+
+/* ---- fusion of the depth-maps into a point cloud -----------------------
+ * DepthMapsData::FuseDepthMaps (libs/MVS/SceneDensify.cpp:1372-1646): HOST arrays, host code — the result depends on the order in
+ * which points claim pixels and zero blocking depths, so the reference's sequential loop is the specification (best connected
+ * images first, pixels in raster order).  One b200mvs_fuse_view per scene image (index = image ID); images without a depth-map
+ * have depth = NULL.  `depth` is modified like the reference modifies its depth-maps (depths behind an accepted point become 0). */
+typedef struct {
+	int width, height;            /* size of the maps (and of `color`) */
+	float* depth;                 /* in/out; NULL: no depth-map */
+	const float* normal;          /* camera-space unit normals, 3 floats per pixel, or NULL */
+	const float* conf;            /* confidence in [0,1] or NULL (weight 1) */
+	const uint8_t* color;         /* 3 bytes per pixel (the image at map resolution) or NULL */
+	double K[9], R[9], C[3];      /* camera at map resolution */
+	const uint32_t* neighbors;    /* depthData.neighbors: image IDs, best first */
+	int nNeighbors;
+	int nSceneNeighbors;          /* scene.images[i].neighbors.size(): the connection score (images are fused best connected first) */
+} b200mvs_fuse_view;
+typedef struct {
+	int nMinViewsFuse;            /* 2 (OPTDENSE::nMinViewsFuse, libs/MVS/DepthMap.cpp:75) */
+	float fDepthDiffThreshold;    /* 0.01 */
+	float fNormalDiffThreshold;   /* 25 (degrees) */
+	int bEstimateColor;           /* 1 */
+	int bEstimateNormal;          /* 1 */
+} b200mvs_fuse_params;
+typedef struct b200mvs_pointcloud b200mvs_pointcloud;   /* PointCloud: points, pointViews, pointWeights, colors, normals */
+void b200mvs_fuse_default_params(b200mvs_fuse_params* p);
+int b200mvs_fuse_depth_maps(b200mvs_fuse_view* views, int nViews, const b200mvs_fuse_params* prm, b200mvs_pointcloud** cloud);
+uint64_t b200mvs_pointcloud_size(const b200mvs_pointcloud* cloud);
+uint64_t b200mvs_pointcloud_depths(const b200mvs_pointcloud* cloud);               /* valid depths visited (the reference's nDepths) */
+const float* b200mvs_pointcloud_points(const b200mvs_pointcloud* cloud);           /* 3 floats per point */
+const float* b200mvs_pointcloud_normals(const b200mvs_pointcloud* cloud);          /* 3 floats per point or NULL */
+const uint8_t* b200mvs_pointcloud_colors(const b200mvs_pointcloud* cloud);         /* 3 bytes per point or NULL */
+const uint32_t* b200mvs_pointcloud_view_offsets(const b200mvs_pointcloud* cloud);  /* size+1 entries: views / weights of point i are [o[i], o[i+1]) */
+const uint32_t* b200mvs_pointcloud_views(const b200mvs_pointcloud* cloud);         /* image IDs, ascending per point */
+const float* b200mvs_pointcloud_weights(const b200mvs_pointcloud* cloud);
+const uint16_t* b200mvs_pointcloud_projs(const b200mvs_pointcloud* cloud);         /* pixel (x, y) of every view of every point */
+void b200mvs_pointcloud_free(b200mvs_pointcloud* cloud);
 
 #ifdef __cplusplus
 }

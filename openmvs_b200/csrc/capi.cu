@@ -145,7 +145,7 @@ struct b200mvs_ctx {
 	DevBuf mapD, mapN;                        // full-resolution in/out maps (host API)
 	DevBuf sgL, sgC, sgR, sgPx, sgCosts, sgAccums, sgAccums2, sgDisp, sgCost, sgMax; // SGM staging / scratch
 	// wave-front aggregation: cached schedule of the last (size, mode) and its scratch
-	struct FrontPass { FrontLaunch launch; DevBuf items; int nItems = 0; };   // launch.items is emptied once uploaded
+	struct FrontPass { FrontLaunch launch; DevBuf items, need; int nItems = 0; };   // launch.items is emptied once uploaded
 	std::vector<FrontPass> sgFront; int sgFrontKey[6] = {0, 0, 0, 0, 0, 0};
 	DevBuf sgFrontCtl, sgFrontState, sgFrontMeta;
 	const void* sgLastPx = nullptr; uint64_t sgLastNum = 0; // pixel map / size of the volume in sgAccums (b200mvs_sgm_refine_device check)
@@ -451,11 +451,11 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 	const int layout = std::min(std::max(D.frontLayout-1, 0), 2);
 	const bool concurrent = !D.frontSerial;
 	const int FB = D.frontBlock > 0 ? D.frontBlock : 64;   // measured: profiles/sgm_variants_r02d.txt
-	const int lag = D.frontLag > 0 ? D.frontLag : 2;
+	const int lag = D.frontLag > 0 ? D.frontLag-1 : 0;     // frontLag = lag + 1; default lag 0: the phases of a block are adjacent
 	const int vw = P.vw, vh = P.vh;
 	const int key[6] = {vw, vh, layout, FB, lag, concurrent ? 2 : 1};
 	if (memcmp(key, ctx->sgFrontKey, sizeof(key)) != 0) {
-		for (auto& fp: ctx->sgFront) fp.items.release();
+		for (auto& fp: ctx->sgFront) { fp.items.release(); fp.need.release(); }
 		ctx->sgFront.clear();
 		std::vector<FrontLaunch> plan = sgm_front_plan(vw, vh, layout, concurrent, FB, lag);
 		ctx->sgFront.resize(plan.size());
@@ -463,8 +463,11 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 			b200mvs_ctx::FrontPass& fp = ctx->sgFront[i];
 			CK(fp.items.reserve(plan[i].items.size()*sizeof(FrontItem)));
 			CK(cudaMemcpyAsync(fp.items.p, plan[i].items.data(), plan[i].items.size()*sizeof(FrontItem), cudaMemcpyHostToDevice, s));
+			CK(fp.need.reserve(std::max<size_t>(1, plan[i].cellNeed.size())*sizeof(int)));
+			CK(cudaMemcpyAsync(fp.need.p, plan[i].cellNeed.data(), plan[i].cellNeed.size()*sizeof(int), cudaMemcpyHostToDevice, s));
+			CK(cudaStreamSynchronize(s)); // the pageable source vectors are released below
 			fp.nItems = (int)plan[i].items.size();
-			plan[i].items.clear(); plan[i].items.shrink_to_fit();
+			plan[i].items.clear(); plan[i].items.shrink_to_fit(); plan[i].cellNeed.clear(); plan[i].cellNeed.shrink_to_fit();
 			fp.launch = plan[i];
 		}
 		CK(cudaStreamSynchronize(s)); // the pageable source vectors die with `plan`
@@ -498,7 +501,7 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 		else { CK(cudaMemsetAsync(ctl, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctl+4, 0, (size_t)maxCtl*sizeof(int), s)); }
 		FrontArgs A; memset(&A, 0, sizeof(A));
 		A.items = fp.items.as<FrontItem>(); A.nItems = fp.nItems;
-		A.ticket = ctl; A.error = ctl+1; A.progress = ctl+4; A.cellDone = ctl+4+L.nChains;
+		A.ticket = ctl; A.error = ctl+1; A.progress = ctl+4; A.cellDone = ctl+4+L.nChains; A.cellNeed = fp.need.as<int>();
 		A.state = ctx->sgFrontState.as<uint16_t>(); A.meta = ctx->sgFrontMeta.as<float2>(); A.maxPaths = maxPaths;
 		A.FB = FBeff; A.num = num;
 		for (int p = 0; p < L.nPasses; ++p) {
@@ -584,7 +587,7 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	for (auto e: c->sweepEv) cudaEventDestroy(e);
 	c->sgL.release(); c->sgC.release(); c->sgR.release(); c->sgPx.release(); c->sgCosts.release(); c->sgAccums.release(); c->sgAccums2.release();
 	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
-	for (auto& fp: c->sgFront) fp.items.release();
+	for (auto& fp: c->sgFront) { fp.items.release(); fp.need.release(); }
 	c->sgFrontCtl.release(); c->sgFrontState.release(); c->sgFrontMeta.release();
 	c->fltZ.release(); c->fltIn.release(); c->fltOutD.release(); c->fltOutC.release();
 	c->ppA.release(); c->ppB.release(); c->ppD.release(); c->ppN.release(); c->ppC.release();
@@ -993,6 +996,12 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 		stats->ms_device = ms;
 		stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now()-t0).count();
 		stats->kernel_launches = ctx->launches; stats->levels = 1;
+		if ((stages & 2) && front) {
+			// the wave-front kernel flags a dependency wait that timed out (never in a correct schedule): the stream is idle here
+			int err = 0;
+			CK(cudaMemcpy(&err, ctx->sgFrontCtl.as<int>()+1, sizeof(int), cudaMemcpyDeviceToHost));
+			if (err) return fail(ctx, B200MVS_ERR_CUDA, "sgm: the wave-front aggregation timed out waiting for a predecessor");
+		}
 	}
 	return B200MVS_OK;
 }

@@ -47,9 +47,6 @@ namespace {
 
 constexpr int FRONT_WARPS = 4;
 
-__device__ __forceinline__ void st_release(int* p, int v) {
-	asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg((const uint4*)p); }
 __device__ __forceinline__ void stcg4(void* p, uint4 v) { __stcg((uint4*)p, v); }
 __device__ __forceinline__ void st_cg4_if(bool on, void* p, unsigned a, unsigned b, unsigned c, unsigned d) {
@@ -144,27 +141,28 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 		#pragma unroll
 		for (int j = 0; j < PD; ++j) if (j < maxcnt) copy_ci(j, j);
 		cp_commit();
-		// wait for the predecessors: the previous segment of this band, the previous phase of this front block.  Every lane polls
-		// the same two words (one request per warp) and the exit is a vote: a loop run by lane 0 alone leaves the warp split in
-		// two — measured: the steps after it then ran once per half, each shuffle through a collective re-synchronisation.
+		// wait for the predecessors: the previous segment of this band (progress[chain] >= seq) and the items of the previous phase
+		// that touch this item's sub-cells (cellDone >= cellNeed for nDep consecutive counters).  Lane i < nDep polls counter i,
+		// the other lanes the band's progress word — one load instruction per poll — and the exit is a vote: a loop run by one
+		// lane alone leaves the warp split in two (measured: the steps after it then ran once per half, every shuffle through a
+		// collective re-synchronisation).
 		{
-			const int* pp = A.progress+chain; const int* pc = A.cellDone+(depCell >= 0 ? depCell : 0);
-			const int need = depCell >= 0 ? depNeed : 0;
+			const int nDep = depCell >= 0 ? (depNeed & 0xFF) : 0;
+			const int* pw = lane < nDep ? A.cellDone+depCell+lane : A.progress+chain;
+			const int need = lane < nDep ? __ldg(A.cellNeed+depCell+lane) : seq;
 			unsigned spins = 0;
 			for (;;) {
-				int a, c;
-				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(pp) : "memory");
-				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(pc) : "memory");
-				if (__all_sync(0xFFFFFFFFu, a >= seq && c >= need)) break;
+				int v;
+				asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(pw) : "memory");
+				if (__all_sync(0xFFFFFFFFu, v >= need)) break;
 				__nanosleep(64);
 				if (++spins > (1u<<21)) { if (lane == 0) *A.error = 1; break; }
 			}
-			// acquire: one acquire load of each word once they are satisfied (not a fence: a fence would also wait for the cost
-			// copies requested above); the predecessors' stores are then visible to the loads below (ld.cg / cp.async.cg: L2)
-			int a, c;
-			asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(pp) : "memory");
-			asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(pc) : "memory");
-			if (a < seq || c < need) *A.error = 2;   // cannot happen: the counters only grow
+			// acquire: one acquire load per lane once satisfied (not a fence: a fence would also wait for the cost copies requested
+			// above); the predecessors' stores are then visible to the loads below (ld.cg / cp.async.cg: served by the L2)
+			int v;
+			asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(pw) : "memory");
+			if (v < need) *A.error = 2;   // cannot happen: the counters only grow
 		}
 		// the sums of the first PD steps: one group per step (empty when the phase stores)
 		#pragma unroll
@@ -272,11 +270,14 @@ sgm_front_kernel(const __grid_constant__ SGMParams P, const __grid_constant__ Fr
 			for (int i = 0; i < NW; i += 4) stcg4(st+2*i, make_uint4(__vsub2(w[i], mp2), __vsub2(w[i+1], mp2), __vsub2(w[i+2], mp2), __vsub2(w[i+3], mp2)));
 			if (sub == 0) __stcg(A.meta+slot, make_float2(Ip, 1.f));
 		}
-		// publish: the warp barrier orders the lanes' stores before lane 0's release store (cumulativity of release)
+		// publish: every lane fences its own stores (one MEMBAR per warp), the barrier makes all of them happen before the signals
+		// that lane 0 (band progress) and lanes < nOwn (sub-cell counters) then send
+		asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		__syncwarp();
-		if (lane == 0) {
-			st_release(A.progress+chain, seq+1);
-			atomicAdd(A.cellDone+cell, 1);
+		{
+			const int nOwn = (depNeed>>8) & 0xFF;
+			if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(A.progress+chain), "r"(seq+1) : "memory");
+			if (lane < nOwn) asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" :: "l"(A.cellDone+cell+lane) : "memory");
 		}
 		ticket = next; next = __shfl_sync(0xFFFFFFFFu, next2, 0);
 		r0 = n0; r1 = n1;

@@ -20,15 +20,16 @@ struct FrontItem {
 	int fb;
 	int seq;       // number of earlier items of the same band: wait until progress[chain] >= seq
 	int chain;     // index into progress[]
-	int depCell;   // cell (phase - 1, fb) whose completion this item waits for, or -1
-	int depNeed;   // number of items in that cell
-	int cell;      // this item's cell (completion counter to bump)
+	int depCell;   // first sub-cell of (phase - 1, fb) whose completion this item waits for, or -1
+	int depNeed;   // bits 0-7: number of consecutive sub-cells waited for (each until cellDone >= cellNeed); bits 8-15: own sub-cells
+	int cell;      // this item's first sub-cell (completion counters to bump)
 };
 struct FrontArgs {
 	const FrontItem* items; int nItems;
 	int* ticket;         // queue head
 	int* progress;       // per (pass, phase, band): segments completed
-	int* cellDone;       // per (pass, phase, front block): items completed
+	int* cellDone;       // per (pass, phase, front block, sub-cell): items completed
+	const int* cellNeed; // ... items that touch it
 	int* error;          // set to 1 when a wait timed out (never in a correct schedule)
 	uint16_t* state;     // per (pass, phase, path): the normalised previous line, num u16
 	float2* meta;        // per (pass, phase, path): {previous intensity, have-previous flag}
@@ -73,9 +74,19 @@ FRONT_HD inline int front_first_step(int lo, int f0, int df) {
 // ---- host side: schedule --------------------------------------------------------------------------------------------
 struct FrontPassDesc { int fa, fb; int nDirs; int dirs[4]; };
 
-// Work items of one pass in queue order; returns the number of front blocks and chains through nFB / nChains.
-// lag: queue distance (in front blocks) between consecutive phases of the same block.
-inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc) {
+// Phase dependencies are tracked per SUB-CELL: a front block cut into column ranges of FRONT_SW pixels.  An item touches the one
+// to three sub-cells its pixels fall into (its paths are adjacent and its segment is at most a block long); it waits until every
+// item of the previous phase that touches one of them is complete, and bumps the counters of its own when it is done.  With
+// dependencies this local the phases of a block can follow each other directly in the queue (lag 0): the slice of the sum
+// volume a block owns is read-modify-written by its four directions while it sits in the L2.
+constexpr int FRONT_SW = 128;
+
+// Work items of one pass in queue order; returns the number of front blocks, bands and sub-cell columns through nFB / maxBands /
+// nSX, and the number of items touching each sub-cell through cellCount (index (ph*nFB + fb)*nSX + sx).
+// lag: queue distance (in front blocks) between consecutive phases of the same block (0: the phases of a block are adjacent).
+inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc,
+	int& nSX, std::vector<int>& cellCount)
+{
 	// offset that makes the front coordinate non-negative
 	const int cx[2] = {0, vw-1}, cy[2] = {0, vh-1};
 	int fmin = 0x7FFFFFFF, fmax = -0x7FFFFFFF;
@@ -83,50 +94,58 @@ inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int
 	fc = -fmin;
 	nFB = (fmax-fmin)/FB + 1;
 	maxBands = (vw+vh+3)/4 + 1;
+	nSX = (vw+FRONT_SW-1)/FRONT_SW;
+	const bool phases = pd.nDirs > 1;      // a pass of one direction has no phase dependencies: no counters
 	items.clear();
-	std::vector<int> cellCount((size_t)pd.nDirs*nFB, 0);
+	cellCount.assign((size_t)pd.nDirs*nFB*nSX, 0);
 	for (int ph = 0; ph < pd.nDirs; ++ph) {
 		const int dir = pd.dirs[ph];
 		const int nPaths = dir == 0 || dir == 2 ? vw : dir == 1 || dir == 3 ? vh : vw+vh-1;
 		for (int band = 0; band*4 < nPaths; ++band) {
-			int nv[4], f0v[4], dfv[4]; bool pv[4];
+			int nv[4], f0v[4], dfv[4], xsv[4], dxv[4]; bool pv[4];
 			int blo = 0x7FFFFFFF, bhi = -1;
 			for (int g = 0; g < 4; ++g) {
 				int x, y, dx, dy;
 				pv[g] = front_path_start(dir, band*4+g, vw, vh, x, y, dx, dy);
-				nv[g] = 0; f0v[g] = 0; dfv[g] = 1;
+				nv[g] = 0; f0v[g] = 0; dfv[g] = 1; xsv[g] = 0; dxv[g] = 0;
 				if (!pv[g]) continue;
 				nv[g] = front_path_len(x, y, dx, dy, vw, vh);
 				f0v[g] = pd.fa*x + pd.fb*y + fc; dfv[g] = pd.fa*dx + pd.fb*dy;
+				xsv[g] = x; dxv[g] = dx;
 				blo = std::min(blo, f0v[g]/FB); bhi = std::max(bhi, (f0v[g]+(nv[g]-1)*dfv[g])/FB);
 			}
 			int seq = 0;
 			for (int fb = blo; fb <= bhi; ++fb) {
-				bool any = false;
-				for (int g = 0; g < 4 && !any; ++g) {
+				int xlo = 0x7FFFFFFF, xhi = -1;
+				for (int g = 0; g < 4; ++g) {
 					if (!pv[g]) continue;
 					const int a = std::min(nv[g], front_first_step(fb*FB, f0v[g], dfv[g])), b = std::min(nv[g], front_first_step((fb+1)*FB, f0v[g], dfv[g]));
-					any = b > a;
+					if (b <= a) continue;
+					const int xa = xsv[g]+a*dxv[g], xb = xsv[g]+(b-1)*dxv[g];
+					xlo = std::min(xlo, std::min(xa, xb)); xhi = std::max(xhi, std::max(xa, xb));
 				}
-				if (!any) continue;
+				if (xhi < 0) continue;
+				const int sx0 = xlo/FRONT_SW, nsx = phases ? xhi/FRONT_SW-sx0+1 : 0;
 				FrontItem it;
 				it.k0 = band*4; it.dir = (short)dir; it.ph = (short)ph; it.fb = fb; it.seq = seq++;
 				it.chain = ph*maxBands + band;
-				it.cell = ph*nFB + fb;
-				it.depCell = ph > 0 ? (ph-1)*nFB + fb : -1; it.depNeed = 0;
+				it.cell = (ph*nFB + fb)*nSX + sx0;                                   // first own sub-cell
+				it.depCell = ph > 0 ? ((ph-1)*nFB + fb)*nSX + sx0 : -1;              // first sub-cell of the previous phase waited for
+				it.depNeed = (ph > 0 ? nsx : 0) | (nsx<<8);                           // number of sub-cells waited for | number of own sub-cells
 				items.push_back(it);
-				++cellCount[it.cell];
+				for (int i = 0; i < nsx; ++i) ++cellCount[(size_t)it.cell+i];
 			}
 		}
 	}
-	for (auto& it: items) if (it.depCell >= 0) it.depNeed = cellCount[it.depCell];
 	// queue order: front blocks advance, phase ph runs `lag` blocks behind phase ph-1; every dependency is earlier in the queue
 	std::stable_sort(items.begin(), items.end(), [lag](const FrontItem& a, const FrontItem& b) {
 		const int ta = a.fb + lag*a.ph, tb = b.fb + lag*b.ph;
 		if (ta != tb) return ta < tb;
-		return a.ph > b.ph;
+		if (a.fb != b.fb) return a.fb < b.fb;
+		return a.ph < b.ph;
 	});
 }
+
 
 // One kernel launch: one pass, or two passes whose items share one queue (interleaved, each pass in its own order).  Two
 // passes never touch the same sum volume, so they are independent chains of dependencies: while an item of one waits for
@@ -136,19 +155,22 @@ struct FrontLaunch {
 	int fc[2], nFB[2], maxBands;
 	int nChains, nCells;           // sizes of progress[] / cellDone[]
 	std::vector<FrontItem> items;
+	std::vector<int> cellNeed;     // items touching each sub-cell (nCells entries)
 };
 inline void sgm_front_build_launch(int vw, int vh, const FrontPassDesc* pds, int nPasses, int FB, int lag, FrontLaunch& L) {
-	L.nPasses = nPasses; L.items.clear(); L.nChains = 0; L.nCells = 0; L.maxBands = 0;
+	L.nPasses = nPasses; L.items.clear(); L.cellNeed.clear(); L.nChains = 0; L.nCells = 0; L.maxBands = 0;
 	std::vector<FrontItem> part[2];
 	for (int p = 0; p < nPasses; ++p) {
 		L.pass[p] = pds[p];
-		sgm_front_build(vw, vh, pds[p], FB, lag, part[p], L.nFB[p], L.maxBands, L.fc[p]);
+		int nSX = 0; std::vector<int> cnt;
+		sgm_front_build(vw, vh, pds[p], FB, lag, part[p], L.nFB[p], L.maxBands, L.fc[p], nSX, cnt);
 		for (FrontItem& it: part[p]) {
 			it.dir = (short)(it.dir | (p<<8));
 			it.chain += L.nChains; it.cell += L.nCells;
 			if (it.depCell >= 0) it.depCell += L.nCells;
 		}
-		L.nChains += 4*L.maxBands; L.nCells += 4*L.nFB[p];
+		L.cellNeed.insert(L.cellNeed.end(), cnt.begin(), cnt.end());
+		L.nChains += 4*L.maxBands; L.nCells += (int)cnt.size();
 	}
 	if (nPasses == 1) { L.items.swap(part[0]); return; }
 	// proportional interleave: both passes reach the end of their queues together

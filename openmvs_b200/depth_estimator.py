@@ -623,3 +623,71 @@ class SemiGlobalMatcher:
 		self.RefineDisparityMap(ldisp, pxl, None, subpixelSteps)  # accumulated costs of the last (left) match
 		torch.cuda.current_stream(leftGray.device).synchronize()
 		return ldisp, rdisp
+
+
+@dataclasses.dataclass
+class PointCloud:
+	"""MVS::PointCloud as FuseDepthMaps fills it: points, pointViews, pointWeights, colors, normals."""
+	points: np.ndarray            # (n, 3) float32
+	pointViews: list              # per point: ascending image IDs (np.uint32 arrays)
+	pointWeights: list            # per point: float32 weights, parallel to pointViews
+	colors: object = None         # (n, 3) uint8
+	normals: object = None        # (n, 3) float32
+	projs: list = None            # per point: (k, 2) uint16 pixel coordinates of its views
+	nDepths: int = 0
+
+
+def FuseDepthMaps(views, nMinViewsFuse: int = 2, fDepthDiffThreshold: float = 0.01, fNormalDiffThreshold: float = 25.0,
+		bEstimateColor: bool = True, bEstimateNormal: bool = True) -> PointCloud:
+	"""DepthMapsData::FuseDepthMaps (libs/MVS/SceneDensify.cpp:1372-1646) through b200mvs_fuse_depth_maps (host arrays, host code:
+	the sequential greedy order is the specification).  views[i] (index = image ID): dict with depth (h, w) float32 — MODIFIED in
+	place like the reference's depth-maps (depths behind an accepted point are zeroed) — or None, normal (h, w, 3) / conf (h, w) /
+	color (h, w, 3) uint8 or None, K R C, neighbors (image IDs, best first) and n_scene_neighbors (the connection score)."""
+	lib = _lib.load()
+	n = len(views)
+	arr = (_lib.FuseView*n)()
+	keep = []
+	for i, v in enumerate(views):
+		o = arr[i]
+		d = v.get("depth")
+		if d is not None:
+			if not (isinstance(d, np.ndarray) and d.dtype == np.float32 and d.flags.c_contiguous and d.flags.writeable):
+				raise ValueError("views[%d].depth must be a writeable C-contiguous float32 array (it is modified in place)" % i)
+			o.height, o.width = d.shape
+			o.depth = d.ctypes.data
+			for key, dt, shape in (("normal", np.float32, d.shape+(3,)), ("conf", np.float32, d.shape), ("color", np.uint8, d.shape+(3,))):
+				a = v.get(key)
+				if a is not None:
+					a = np.ascontiguousarray(a, dt)
+					if a.shape != shape:
+						raise ValueError("views[%d].%s has shape %s, expected %s" % (i, key, a.shape, shape))
+					keep.append(a); setattr(o, key, a.ctypes.data)
+		for name in ("K", "R", "C"):
+			getattr(o, name)[:] = list(np.asarray(v[name], np.float64).ravel())
+		nb = np.ascontiguousarray(v.get("neighbors", []), np.uint32)
+		keep.append(nb)
+		o.neighbors = nb.ctypes.data if nb.size else None
+		o.nNeighbors = int(nb.size)
+		o.nSceneNeighbors = int(v.get("n_scene_neighbors", nb.size))
+	prm = _lib.FuseParams(int(nMinViewsFuse), float(fDepthDiffThreshold), float(fNormalDiffThreshold), int(bool(bEstimateColor)), int(bool(bEstimateNormal)))
+	cloud = C.c_void_p()
+	rc = lib.b200mvs_fuse_depth_maps(arr, n, C.byref(prm), C.byref(cloud))
+	if rc:
+		raise _lib.B200MVSError("b200mvs_fuse_depth_maps failed with status %d (bad view description)" % rc)
+	try:
+		m = int(lib.b200mvs_pointcloud_size(cloud))
+		def take(fn, count, dt):
+			p = fn(cloud)
+			return np.ctypeslib.as_array(p, shape=(count,)).astype(dt, copy=True) if (count and p) else None
+		off = take(lib.b200mvs_pointcloud_view_offsets, m+1, np.uint32)
+		total = int(off[-1]) if off is not None else 0
+		pts = take(lib.b200mvs_pointcloud_points, 3*m, np.float32)
+		vs = take(lib.b200mvs_pointcloud_views, total, np.uint32); ws = take(lib.b200mvs_pointcloud_weights, total, np.float32)
+		pj = take(lib.b200mvs_pointcloud_projs, 2*total, np.uint16)
+		nr = take(lib.b200mvs_pointcloud_normals, 3*m, np.float32); cl = take(lib.b200mvs_pointcloud_colors, 3*m, np.uint8)
+		return PointCloud(points=pts.reshape(-1, 3) if pts is not None else np.zeros((0, 3), np.float32),
+			pointViews=[vs[off[i]:off[i+1]] for i in range(m)], pointWeights=[ws[off[i]:off[i+1]] for i in range(m)],
+			colors=None if cl is None else cl.reshape(-1, 3), normals=None if nr is None else nr.reshape(-1, 3),
+			projs=[pj[2*off[i]:2*off[i+1]].reshape(-1, 2) for i in range(m)], nDepths=int(lib.b200mvs_pointcloud_depths(cloud)))
+	finally:
+		lib.b200mvs_pointcloud_free(cloud)

@@ -73,6 +73,19 @@ class FilterParams(C.Structure):
 	_fields_ = [("nMinViews", C.c_int), ("nMinViewsAdjust", C.c_int), ("fDepthDiffThreshold", C.c_float), ("bAdjust", C.c_int)]
 
 
+class FuseView(C.Structure):
+	"""b200mvs_fuse_view"""
+	_fields_ = [("width", C.c_int), ("height", C.c_int), ("depth", C.c_void_p), ("normal", C.c_void_p), ("conf", C.c_void_p),
+		("color", C.c_void_p), ("K", C.c_double*9), ("R", C.c_double*9), ("C", C.c_double*3), ("neighbors", C.c_void_p),
+		("nNeighbors", C.c_int), ("nSceneNeighbors", C.c_int)]
+
+
+class FuseParams(C.Structure):
+	"""b200mvs_fuse_params"""
+	_fields_ = [("nMinViewsFuse", C.c_int), ("fDepthDiffThreshold", C.c_float), ("fNormalDiffThreshold", C.c_float),
+		("bEstimateColor", C.c_int), ("bEstimateNormal", C.c_int)]
+
+
 MAX_FILTER_VIEWS = 16
 
 # every symbol include/b200mvs.h declares (checked by tests/test_capi_symbols.py)
@@ -87,6 +100,9 @@ SYMBOLS = [
 	"b200mvs_remove_small_segments", "b200mvs_remove_small_segments_device",
 	"b200mvs_gap_interpolation", "b200mvs_gap_interpolation_device",
 	"b200mvs_to_gray_device", "b200mvs_scaled_size", "b200mvs_scale_image_device",
+	"b200mvs_fuse_default_params", "b200mvs_fuse_depth_maps", "b200mvs_pointcloud_size", "b200mvs_pointcloud_depths",
+	"b200mvs_pointcloud_points", "b200mvs_pointcloud_normals", "b200mvs_pointcloud_colors", "b200mvs_pointcloud_view_offsets",
+	"b200mvs_pointcloud_views", "b200mvs_pointcloud_weights", "b200mvs_pointcloud_projs", "b200mvs_pointcloud_free",
 ]
 
 _LIB = None
@@ -136,6 +152,15 @@ def load(build_if_missing: bool = True):
 	lib.b200mvs_sgm_default_params.argtypes = [C.POINTER(SgmParams)]
 	lib.b200mvs_sgm_match.argtypes = [P, P, P, P, C.c_int, C.c_int, P, C.c_uint64, C.POINTER(SgmParams), P, P, C.POINTER(Stats)]
 	lib.b200mvs_sgm_match_device.argtypes = [P, P, P, P, C.c_int, C.c_int, P, C.c_uint64, C.POINTER(SgmParams), C.c_int, P, P, P, P, P, C.POINTER(Stats)]
+	lib.b200mvs_fuse_default_params.argtypes = [C.POINTER(FuseParams)]
+	lib.b200mvs_fuse_depth_maps.argtypes = [C.POINTER(FuseView), C.c_int, C.POINTER(FuseParams), C.POINTER(C.c_void_p)]
+	for name, rt in (("size", C.c_uint64), ("depths", C.c_uint64), ("points", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)),
+			("colors", C.POINTER(C.c_uint8)), ("view_offsets", C.POINTER(C.c_uint32)), ("views", C.POINTER(C.c_uint32)),
+			("weights", C.POINTER(C.c_float)), ("projs", C.POINTER(C.c_uint16))):
+		f = getattr(lib, "b200mvs_pointcloud_"+name)
+		f.restype = rt; f.argtypes = [C.c_void_p]
+	lib.b200mvs_pointcloud_free.argtypes = [C.c_void_p]
+	lib.b200mvs_pointcloud_free.restype = None
 	lib.b200mvs_sgm_cross_check_device.argtypes = [P, P, P, C.c_int, C.c_int, C.c_int, P]
 	lib.b200mvs_sgm_refine_device.argtypes = [P, P, P, P, C.c_int, C.c_int, P]
 	lib.b200mvs_filter_default_params.argtypes = [C.POINTER(FilterParams)]

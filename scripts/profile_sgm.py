@@ -21,13 +21,14 @@ for layout, name in ((1, "tilted"), (2, "straight"), (3, "single")):
 	for serial in (0, 1):
 		MODES.append(("fronts %s %s" % (name, "serial" if serial else "paired"), dict(sgmAggregation=4, frontLayout=layout, frontSerial=serial)))
 for layout, name in ((1, "tilted"), (2, "straight")):
-	for fbk in (16, 32, 64):
-		for ctas in (1, 2, 4):
-			for pd in (4, 8):
-				if (fbk, ctas, pd) == ((32 if layout == 1 else 16), 2, 8): continue
-				MODES.append(("fronts %s paired FB %d ctas %d depth %d" % (name, fbk, ctas, pd), dict(sgmAggregation=4, frontLayout=layout, frontBlock=fbk, frontCtas=ctas, frontDepth=pd)))
-MODES += [("fronts tilted paired lag 1", dict(sgmAggregation=4, frontLag=1)), ("fronts tilted paired lag 3", dict(sgmAggregation=4, frontLag=3))]
-MODES.append(("tensor-core cost kernel + wave fronts", dict(sgmCost=2)))
+	for fbk in (32, 64):
+		for lag in (0, 1, 2):
+			for ctas in (2, 4):
+				MODES.append(("fronts %s paired FB %d lag %d ctas %d" % (name, fbk, lag, ctas), dict(sgmAggregation=4, frontLayout=layout, frontBlock=fbk, frontLag=lag+1, frontCtas=ctas)))
+MODES += [("fronts tilted paired FB 16 lag 0", dict(sgmAggregation=4, frontBlock=16)), ("fronts tilted paired FB 128 lag 0", dict(sgmAggregation=4, frontBlock=128)),
+	("fronts tilted paired FB 64 lag 0 depth 4", dict(sgmAggregation=4, frontDepth=4)), ("fronts tilted paired FB 64 lag 0 ctas 1", dict(sgmAggregation=4, frontCtas=1)),
+	("fronts tilted paired FB 64 lag 0 ctas 3", dict(sgmAggregation=4, frontCtas=3))]
+MODES.append(("SIMT cost kernel + wave fronts", dict(sgmCost=1)))
 if len(sys.argv) > 2 and sys.argv[2] == "default":
 	MODES = MODES[2:3]
 if len(sys.argv) > 2 and sys.argv[2] == "tc":
@@ -45,5 +46,5 @@ for name, dbg in MODES:
 	else:
 		same = "| identical to the register pipeline: %s" % (torch.equal(ref[0], accums) and torch.equal(ref[1], disp))
 		if "sgmCost" in dbg:
-			same = "| disparities equal to the SIMT-cost run on %.4f of the pixels" % float((ref[1] == disp).float().mean())
+			same = "| disparities equal to the tensor-core-cost run on %.4f of the pixels" % float((ref[1] == disp).float().mean())
 	print("D=%d %-40s" % (D, name), " ".join("%s %.2f ms" % kv for kv in t.items()), "| %.2f G(px.d)/s" % (n/t["all"]/1e6), same, flush=True)

@@ -44,7 +44,11 @@ int main(int argc, char** argv) {
 			const FrontPassDesc& pd = LA.pass[pass];
 			// in-order execution: every dependency must already be complete, or the queue order would deadlock a single worker
 			if (progress[it.chain] < it.seq) { printf("FAIL: band dependency not met (launch %zu dir %d k0 %d fb %d)\n", li, dir, it.k0, it.fb); return 2; }
-			if (it.depCell >= 0 && cellDone[it.depCell] < it.depNeed) { printf("FAIL: phase dependency not met (launch %zu ph %d fb %d)\n", li, it.ph, it.fb); return 2; }
+			const int nDep = it.depCell >= 0 ? (it.depNeed & 0xFF) : 0, nOwn = (it.depNeed >> 8) & 0xFF;
+			if (nOwn > 31 || nDep > 31) { printf("FAIL: an item touches %d sub-cells (one lane polls one counter)\n", nOwn); return 2; }
+			for (int i = 0; i < nDep; ++i)
+				if (cellDone[it.depCell+i] < LA.cellNeed[it.depCell+i]) { printf("FAIL: phase dependency not met (launch %zu ph %d fb %d sub-cell %d)\n", li, it.ph, it.fb, i); return 2; }
+			if (LA.pass[pass].nDirs > 1 && nOwn == 0) { printf("FAIL: an item of a multi-direction pass touches no sub-cell\n"); return 2; }
 			const bool add = !(li == 0 && it.ph == 0);
 			std::vector<uint16_t>& V = S[pass];
 			for (int g = 0; g < 4; ++g) {
@@ -80,12 +84,18 @@ int main(int argc, char** argv) {
 						A[d] = L[d]-m;
 					}
 					touched[((size_t)y*vw+x)*8 + dir] += 1;
+					if (LA.pass[pass].nDirs > 1) {
+						// the counters this item bumps must include the sub-cell of every pixel it writes
+						const int nSX = (vw+FRONT_SW-1)/FRONT_SW, sx = x/FRONT_SW, first = it.cell % nSX;
+						if (sx < first || sx >= first+nOwn) { printf("FAIL: pixel outside the item's sub-cells\n"); return 2; }
+					}
 					Ip = I; havePrev = true;
 				}
 				if (s1 < len) { for (int d = 0; d < num; ++d) state[slot*num+d] = (uint16_t)A[d]; metaI[slot] = Ip; metaH[slot] = havePrev; }
 			}
+			// every pixel of the item must lie in one of its own sub-cells (checked in the pixel loop through `covered`)
 			progress[it.chain] = it.seq+1;
-			cellDone[it.cell] += 1;
+			for (int i = 0; i < nOwn; ++i) cellDone[it.cell+i] += 1;
 		}
 	}
 	if (two) for (size_t i = 0; i < n; ++i) S[0][i] = (uint16_t)(S[0][i]+S[1][i]);

@@ -42,7 +42,7 @@ def test_struct_layouts_match_a_c_compiler(tmp_path):
 	from openmvs_b200 import lib
 	structs = {"b200mvs_view": lib.View, "b200mvs_params": lib.Params, "b200mvs_stats": lib.Stats, "b200mvs_job": lib.Job,
 		"b200mvs_sgm_params": lib.SgmParams, "b200mvs_dmap": lib.DMap, "b200mvs_filter_params": lib.FilterParams,
-		"b200mvs_debug": lib.Debug, "b200mvs_sgm_pixel": lib.SgmPixel}
+		"b200mvs_debug": lib.Debug, "b200mvs_sgm_pixel": lib.SgmPixel, "b200mvs_fuse_view": lib.FuseView, "b200mvs_fuse_params": lib.FuseParams}
 	lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200mvs.h"', 'int main(void) {']
 	for cname, ct in structs.items():
 		lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

@@ -19,12 +19,12 @@ def exe(tmp_path_factory):
 	return out
 
 
-@pytest.mark.parametrize("layout,block,lag,concurrent", [(0, 32, 2, 1), (0, 8, 1, 1), (0, 5, 3, 0), (1, 16, 2, 1), (1, 3, 1, 0), (2, 32, 2, 1), (2, 32, 2, 0), (0, 32, 2, 0)])
+@pytest.mark.parametrize("layout,block,lag,concurrent", [(0, 64, 0, 1), (0, 32, 2, 1), (0, 8, 1, 1), (0, 5, 3, 0), (0, 7, 0, 0), (1, 16, 0, 1), (1, 3, 1, 0), (2, 32, 2, 1), (2, 32, 0, 0), (0, 32, 2, 0)])
 def test_schedule_simulation_equals_oracle(exe, tmp_path, layout, block, lag, concurrent):
 	from oracle import oracle as O
 	from openmvs_b200 import synth
 	num = 64
-	for (w, h) in ((61, 47), (38, 73)):   # wider than high and higher than wide; valid regions not multiples of 4
+	for (w, h) in ((61, 47), (38, 73), (301, 40)):   # the last one spans three sub-cell columns   # wider than high and higher than wide; valid regions not multiples of 4
 		rng = np.random.RandomState(w+layout)
 		lg, lc, rg, d = synth.make_stereo_pair(w, h)
 		px, n = synth.sgm_pixel_map(w, h, -5, -5+num)

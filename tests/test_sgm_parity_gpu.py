@@ -182,7 +182,7 @@ def test_uniform_range_fast_path_bit_exact(sgm, num):
 	assert np.array_equal(gd.cpu().numpy(), disp) and np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
 
 
-@pytest.mark.parametrize("layout,block,lag,serial", [(0, 0, 0, 0), (1, 0, 0, 1), (1, 8, 1, 0), (1, 16, 3, 1), (2, 0, 0, 0), (2, 4, 1, 1), (3, 0, 0, 0), (3, 0, 0, 1)])
+@pytest.mark.parametrize("layout,block,lag,serial", [(0, 0, 0, 0), (1, 0, 0, 1), (1, 8, 1, 0), (1, 16, 3, 1), (2, 0, 0, 0), (2, 4, 2, 1), (3, 0, 0, 0), (3, 0, 0, 1)])
 @pytest.mark.parametrize("num", [64, 128, 256])
 def test_wave_front_aggregation_bit_exact(sgm, num, layout, block, lag, serial):
 	"""The wave-front kernel (dense volume, one range of 64 / 128 / 256 disparities; the default of the non-tSGM branch) against the
