@@ -137,9 +137,9 @@ def host_info(threads):
 	return info
 
 
-def build_scene(device, w, h, n_views=N_VIEWS, seed=1234):
+def build_scene(device, w, h, n_views=N_VIEWS, seed=1234, gt_views=None):
 	from openmvs_b200 import synth
-	return synth.make_scene(w, h, n_views, seed=seed, step_deg=4.0, device=device)
+	return synth.make_scene(w, h, n_views, seed=seed, step_deg=4.0, device=device, gt_views=gt_views)
 
 
 def cpu_sample(scene, w, h, band_rows, threads):
@@ -493,7 +493,8 @@ def run_scene_workload(args, dev, rank, world, local_rank, peak):
 	n_views = args.views or (50 if c5 else 200)
 	n_neigh = N_NEIGH if not c5 else 8
 	OPTDENSE.nEstimationGeometricIters = 1 if c5 else 0   # pass 1 keeps with the x1.333 threshold when a geometric pass follows
-	scene = build_scene(dev, w, h, n_views=n_views)
+	# ground truth only for the two views of this rank whose accuracy is reported (200 x 1080p of it would be 6.6 GB of host memory per rank)
+	scene = build_scene(dev, w, h, n_views=n_views, gt_views=set(multi_gpu.shard_views(n_views, rank, world)[:2]))
 	nbrs = [scene.neighbors(r, n_neigh) for r in range(n_views)]
 	cams = [Camera(v.K, v.R, v.C) for v in scene.views]
 	imgs = [torch.from_numpy(v.image).to(dev) for v in scene.views]

@@ -102,7 +102,7 @@ typedef struct {
 	int frontSerial;     /* 1: one pass per launch into one sum volume (default: two passes share a launch, each with its own
 	                        volume, added by the winner-takes-all kernel) */
 	int frontBlock;      /* fronts per work item (0: default) */
-	int frontLag;        /* 1 + queue distance, in blocks, between the directions of a pass (0: default = distance 0) */
+	int frontLag;        /* 1 + queue distance, in blocks, between the directions of a pass (0: default = distance 2) */
 	int frontCtas;       /* resident CTAs per SM (0: default) */
 	int frontDepth;      /* steps whose loads are in flight: 4 or 8 (0: default) */
 	int reserved[5];

@@ -41,13 +41,13 @@ cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s);
 cudaError_t sgm_cost_tc_configure();
 bool sgm_cost_tc_supports(int num);
 cudaError_t sgm_cost_tc_launch(const SGMParams& P, int dmin, int num, cudaStream_t s);
-cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s);
+cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, bool store, cudaStream_t s);
 cudaError_t sgm_launch_aggregate_uniform(const SGMParams& P, int dir, int dmin, int num, bool ring, cudaStream_t s);
 // wave-front aggregation (sgm_front.cu)
 cudaError_t sgm_front_launch(const SGMParams& P, const FrontArgs& A, int blocks, int pd, cudaStream_t s);
 int sgm_front_blocks_per_sm(int num, int pd);
 bool sgm_front_supports(int num);
-cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s);
+cudaError_t sgm_launch_wta(const SGMParams& P, int nVol, unsigned long long volStride, const uint16_t* more, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 cudaError_t sgm_launch_wta_uniform(const SGMParams& P, const uint16_t* second, int dmin, int num, int16_t* disparity, uint16_t* cost, cudaStream_t s);
 int sgm_max_disparities();
 cudaError_t sgm_launch_cross_check(int16_t* l2r, const int16_t* r2l, int w, int h, int th, cudaStream_t s);
@@ -148,6 +148,8 @@ struct b200mvs_ctx {
 	struct FrontPass { FrontLaunch launch; DevBuf items, need; int nItems = 0; };   // launch.items is emptied once uploaded
 	std::vector<FrontPass> sgFront; int sgFrontKey[6] = {0, 0, 0, 0, 0, 0};
 	DevBuf sgFrontCtl, sgFrontState, sgFrontMeta;
+	cudaStream_t sgSide[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // side streams of the ragged aggregation
+	cudaEvent_t sgJoin[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, sgFork = nullptr;
 	const void* sgLastPx = nullptr; uint64_t sgLastNum = 0; // pixel map / size of the volume in sgAccums (b200mvs_sgm_refine_device check)
 	DevBuf fltZ, fltIn, fltOutD, fltOutC;     // FilterDepthMap: z-buffer keys, staged maps (host API), outputs
 	DevBuf ppA, ppB, ppD, ppN, ppC;           // RemoveSmallSegments labels/sizes, GapInterpolation temporaries, staging
@@ -450,8 +452,10 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 	const b200mvs_debug& D = ctx->dbg;
 	const int layout = std::min(std::max(D.frontLayout-1, 0), 2);
 	const bool concurrent = !D.frontSerial;
-	const int FB = D.frontBlock > 0 ? D.frontBlock : 64;   // measured: profiles/sgm_variants_r02d.txt
-	const int lag = D.frontLag > 0 ? D.frontLag-1 : 0;     // frontLag = lag + 1; default lag 0: the phases of a block are adjacent
+	const int FB = D.frontBlock > 0 ? D.frontBlock : 32;   // measured: profiles/sgm_variants_r02e.txt (64: same time, a third more DRAM traffic)
+	// frontLag = lag + 1.  The sub-cell dependencies allow lag 0 (the phases of a block adjacent in the queue: DRAM traffic falls to
+	// the algorithmic 2.2 GB) but the warps then wait for each other: 5.6 ms against 2.6 ms at lag 2 (profiles/sgm_variants_r02e.txt)
+	const int lag = D.frontLag > 0 ? D.frontLag-1 : 2;
 	const int vw = P.vw, vh = P.vh;
 	const int key[6] = {vw, vh, layout, FB, lag, concurrent ? 2 : 1};
 	if (memcmp(key, ctx->sgFrontKey, sizeof(key)) != 0) {
@@ -589,6 +593,8 @@ int b200mvs_destroy(b200mvs_ctx* c) {
 	c->sgDisp.release(); c->sgCost.release(); c->sgMax.release();
 	for (auto& fp: c->sgFront) { fp.items.release(); fp.need.release(); }
 	c->sgFrontCtl.release(); c->sgFrontState.release(); c->sgFrontMeta.release();
+	for (int i = 0; i < 7; ++i) { if (c->sgSide[i]) cudaStreamDestroy(c->sgSide[i]); if (c->sgJoin[i]) cudaEventDestroy(c->sgJoin[i]); }
+	if (c->sgFork) cudaEventDestroy(c->sgFork);
 	c->fltZ.release(); c->fltIn.release(); c->fltOutD.release(); c->fltOutC.release();
 	c->ppA.release(); c->ppB.release(); c->ppD.release(); c->ppN.release(); c->ppC.release();
 	c->ppK.release(); c->ppArcs.release(); c->ppPatch.release();
@@ -968,16 +974,42 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 		++ctx->launches;
 	}
 	bool twoVolumes = false;   // the wave-front passes ran side by side: accums + ctx->sgAccums2 is the sum
+	bool eightVolumes = false; // ragged ranges: one volume per direction, accums + the seven of ctx->sgAccums2
 	if ((stages & 2) && front) {
 		const int rc = sgm_aggregate_fronts(ctx, P, st8[0], s, twoVolumes);
 		if (rc) return rc;
 		if (twoVolumes && !(stages & 4)) { CK(sgm_launch_wta_uniform(P, ctx->sgAccums2.as<uint16_t>(), st8[1], st8[0], nullptr, nullptr, s)); ++ctx->launches; }
 	} else
+	if ((stages & 2) && !uniform && numCosts <= (1ull<<28)) {
+		// ragged (tSGM) ranges: a direction has only 1000-3000 scanlines, one warp each — far too few to fill the GPU.  The eight
+		// directions run side by side on eight streams, each STORING its path costs into a volume of its own (no memset, no
+		// read-modify-write, no races); the winner-takes-all kernel adds the volumes.
+		eightVolumes = true;
+		CK(ctx->sgAccums2.reserve((size_t)7*numCosts*sizeof(uint16_t)));
+		if (!ctx->sgSide[0]) {
+			for (int i = 0; i < 7; ++i) { CK(cudaStreamCreateWithFlags(&ctx->sgSide[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->sgJoin[i], cudaEventDisableTiming)); }
+			CK(cudaEventCreateWithFlags(&ctx->sgFork, cudaEventDisableTiming));
+		}
+		CK(cudaEventRecord(ctx->sgFork, s));
+		for (int dir = 0; dir < 8; ++dir) {
+			SGMParams Pd = P;
+			cudaStream_t sd = s;
+			if (dir > 0) {
+				Pd.accums = ctx->sgAccums2.as<uint16_t>() + (size_t)(dir-1)*numCosts;
+				sd = ctx->sgSide[dir-1];
+				CK(cudaStreamWaitEvent(sd, ctx->sgFork, 0));
+			}
+			CK(sgm_launch_aggregate(Pd, dir, true, sd));
+			++ctx->launches;
+			if (dir > 0) { CK(cudaEventRecord(ctx->sgJoin[dir-1], sd)); CK(cudaStreamWaitEvent(s, ctx->sgJoin[dir-1], 0)); }
+		}
+		if (!(stages & 4)) { CK(sgm_launch_wta(P, 8, numCosts, ctx->sgAccums2.as<uint16_t>(), nullptr, nullptr, s)); ++ctx->launches; }
+	} else
 	if (stages & 2) {
 		CK(cudaMemsetAsync(accums, 0, numCosts*sizeof(uint16_t), s));
 		for (int dir = 0; dir < 8; ++dir) {
 			if (uniform) CK(sgm_launch_aggregate_uniform(P, dir, st8[1], st8[0], ring, s));
-			else CK(sgm_launch_aggregate(P, dir, s));
+			else CK(sgm_launch_aggregate(P, dir, false, s));
 			++ctx->launches;
 		}
 	}
@@ -985,7 +1017,7 @@ int b200mvs_sgm_match_device(b200mvs_ctx* ctx, const float* leftGray, const uint
 	if (stages & 4) {
 		const bool denseWta = uniform && (st8[0] & 15) == 0 && !st8[6] && !((uintptr_t)P.accums & 15);
 		if (denseWta) CK(sgm_launch_wta_uniform(P, twoVolumes ? ctx->sgAccums2.as<uint16_t>() : nullptr, st8[1], st8[0], disparity, cost, s));
-		else CK(sgm_launch_wta(P, disparity, cost, s));
+		else CK(sgm_launch_wta(P, eightVolumes ? 8 : 1, numCosts, eightVolumes ? ctx->sgAccums2.as<uint16_t>() : nullptr, disparity, cost, s));
 		++ctx->launches;
 	}
 	if (stats) {

@@ -148,7 +148,9 @@ __device__ __forceinline__ bool path_start(int dir, int k, int W, int H, int& x,
 // One warp walks one scanline; lane l owns disparities l, l+32, ... (NPL per lane) of every pixel.
 // The scanline is a chain of dependent steps, so it is software-pipelined: the pixel record of
 // step t+PD+1 and the cost / accumulator values of step t+PD are in flight while step t computes.
-template <int NPL, int PD>
+// ADD = false: the launch owns its sum volume (P.accums) and stores the path costs instead of adding them — the eight directions
+// then run side by side on eight streams, and the winner-takes-all kernel adds the volumes (sgm_wta_kernel, nVol = 8).
+template <int NPL, int PD, bool ADD>
 __global__ void __launch_bounds__(AGG_WARPS*32)
 sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 {
@@ -180,7 +182,7 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 		for (int j = 0; j < NPL; ++j) {
 			const int kk = lane+32*j;
 			const bool v = kk < pr[i].dmax-pr[i].dmin;
-			c[i][j] = v ? P.costs[pr[i].idx+kk] : 0; a[i][j] = v ? P.accums[pr[i].idx+kk] : 0;
+			c[i][j] = v ? P.costs[pr[i].idx+kk] : 0; a[i][j] = (ADD && v) ? P.accums[pr[i].idx+kk] : 0;
 		}
 	}
 	for (; inside(x, y); x += dx, y += dy) {
@@ -196,7 +198,7 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 		for (int j = 0; j < NPL; ++j) {
 			const int kk = lane+32*j;
 			const bool v = kk < pr[PD].dmax-pr[PD].dmin;
-			cn[j] = v ? P.costs[pr[PD].idx+kk] : 0; an[j] = v ? P.accums[pr[PD].idx+kk] : 0;
+			cn[j] = v ? P.costs[pr[PD].idx+kk] : 0; an[j] = (ADD && v) ? P.accums[pr[PD].idx+kk] : 0;
 		}
 		uint8_t* c0 = c[0]; uint16_t* a0 = a[0];
 		const float I0 = Ir[0];
@@ -573,21 +575,30 @@ sgm_aggregate_uniform_ring_kernel(const __grid_constant__ SGMParams P, int dir, 
 }
 
 // ---- (3) winner takes all ------------------------------------------------------------------------
-__global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int16_t* __restrict__ disparity, uint16_t* __restrict__ cost)
+__global__ void sgm_wta_kernel(const __grid_constant__ SGMParams P, int nVol, unsigned long long volStride, const uint16_t* __restrict__ more,
+	int16_t* __restrict__ disparity, uint16_t* __restrict__ cost)
 {
 	const int gw = (blockIdx.x*blockDim.x + threadIdx.x)>>5, lane = threadIdx.x&31;
 	if (gw >= P.vw*P.vh) return;
 	const SGMPixel p = P.px[gw];
 	if (!(p.dmin < p.dmax)) {
-		if (lane == 0) { disparity[gw] = p.dmin; cost[gw] = 0xFFFFu; }
+		if (lane == 0 && disparity) { disparity[gw] = p.dmin; cost[gw] = 0xFFFFu; }
 		return;
 	}
-	const uint16_t* a = P.accums + p.idx;
+	uint16_t* a = P.accums + p.idx;
 	unsigned best = 0xFFFFFFFFu; // (value << 16) | index: the minimum is the first arg-min
-	for (int k = lane; k < p.dmax-p.dmin; k += 32)
-		best = min(best, ((unsigned)a[k]<<16) | (unsigned)k);
+	for (int k = lane; k < p.dmax-p.dmin; k += 32) {
+		unsigned v = a[k];
+		if (nVol > 1) {
+			// the directions ran side by side into their own volumes (`more` holds volumes 1 .. nVol-1): the sum goes back to volume 0
+			for (int i = 0; i+1 < nVol; ++i) v += more[(size_t)i*volStride + p.idx + k];
+			v &= 0xFFFFu;
+			a[k] = (uint16_t)v;
+		}
+		best = min(best, (v<<16) | (unsigned)k);
+	}
 	best = __reduce_min_sync(0xFFFFFFFFu, best); // redux.sync: one instruction instead of a 5-shuffle chain
-	if (lane == 0) { disparity[gw] = (int16_t)(p.dmin+(int)(best&0xFFFFu)); cost[gw] = (uint16_t)(best>>16); }
+	if (lane == 0 && disparity) { disparity[gw] = (int16_t)(p.dmin+(int)(best&0xFFFFu)); cost[gw] = (uint16_t)(best>>16); }
 }
 
 // Uniform dense volumes (num % 16 == 0, 16-byte aligned slices): 8 lanes per pixel, 16-byte loads, the arg-min carried as
@@ -749,20 +760,26 @@ cudaError_t sgm_launch_cost(const SGMParams& P, cudaStream_t s) {
 	return cudaGetLastError();
 }
 int sgm_max_disparities() { return MAXD; }
-cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, cudaStream_t s) {
+template <bool ADD>
+static void launch_aggregate(const SGMParams& P, int dir, int grid, cudaStream_t s) {
+	const int npl = (P.maxNumDisp+31)/32;
+	if (npl <= 1) sgm_aggregate_kernel<1, AGG_PD, ADD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+	else if (npl <= 2) sgm_aggregate_kernel<2, AGG_PD, ADD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+	else if (npl <= 4) sgm_aggregate_kernel<4, AGG_PD, ADD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+	else sgm_aggregate_kernel<8, AGG_PD, ADD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+}
+// store: P.accums is this direction's own volume, written without reading it (see sgm_aggregate_kernel)
+cudaError_t sgm_launch_aggregate(const SGMParams& P, int dir, bool store, cudaStream_t s) {
 	const int W = P.vw, H = P.vh;
 	const int paths = dir == 0 || dir == 2 ? W : dir == 1 || dir == 3 ? H : W+H-1;
 	const int grid = (paths+AGG_WARPS-1)/AGG_WARPS;
-	const int npl = (P.maxNumDisp+31)/32;
-	if (npl <= 1) sgm_aggregate_kernel<1, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
-	else if (npl <= 2) sgm_aggregate_kernel<2, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
-	else if (npl <= 4) sgm_aggregate_kernel<4, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
-	else sgm_aggregate_kernel<8, AGG_PD><<<grid, AGG_WARPS*32, 0, s>>>(P, dir);
+	if (store) launch_aggregate<false>(P, dir, grid, s); else launch_aggregate<true>(P, dir, grid, s);
 	return cudaGetLastError();
 }
-cudaError_t sgm_launch_wta(const SGMParams& P, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
+// nVol > 1: P.accums += the nVol-1 volumes at more + i*volStride first (disparity / cost may then be null: the addition alone)
+cudaError_t sgm_launch_wta(const SGMParams& P, int nVol, unsigned long long volStride, const uint16_t* more, int16_t* disparity, uint16_t* cost, cudaStream_t s) {
 	const long long threads = (long long)P.vw*P.vh*32;
-	sgm_wta_kernel<<<(unsigned)((threads+255)/256), 256, 0, s>>>(P, disparity, cost);
+	sgm_wta_kernel<<<(unsigned)((threads+255)/256), 256, 0, s>>>(P, nVol, volStride, more, disparity, cost);
 	return cudaGetLastError();
 }
 

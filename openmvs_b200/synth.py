@@ -77,7 +77,7 @@ def look_at(C, target=np.zeros(3)):
 
 
 def make_scene(width: int, height: int, n_views: int, seed: int = 1234, radius: float = 5.5,
-		step_deg: float = 4.0, focal_ratio: float = 0.9, cols: int | None = None, device=None) -> Scene:
+		step_deg: float = 4.0, focal_ratio: float = 0.9, cols: int | None = None, device=None, gt_views=None) -> Scene:
 	"""n_views cameras on a (rows x cols) angular grid `step_deg` apart, radius `radius`.
 	device: None -> numpy float64 (bit-reproducible inputs for the parity tests);
 	a torch device -> the same arithmetic in torch float64 on that device (fast, for the bench)."""
@@ -121,10 +121,11 @@ def make_scene(width: int, height: int, n_views: int, seed: int = 1234, radius: 
 		nw = [-hx*inv, -hy*inv, inv]
 		nc = xp.stack([nw[0]*R[k, 0] + nw[1]*R[k, 1] + nw[2]*R[k, 2] for k in range(3)], -1)
 		img = tex(px, py, xp)
+		keep = gt_views is None or i in gt_views   # large scenes: ground truth only for the views that are checked (16 B per pixel)
 		if device is None:
-			views.append(View(img.astype(np.float32), K.copy(), R, C, t.astype(np.float32), nc.astype(np.float32)))
+			views.append(View(img.astype(np.float32), K.copy(), R, C, t.astype(np.float32) if keep else None, nc.astype(np.float32) if keep else None))
 		else:
-			views.append(View(img.float().cpu().numpy(), K.copy(), R, C, t.float().cpu().numpy(), nc.float().cpu().numpy()))
+			views.append(View(img.float().cpu().numpy(), K.copy(), R, C, t.float().cpu().numpy() if keep else None, nc.float().cpu().numpy() if keep else None))
 	return Scene(views, dmin=float(radius-1.5), dmax=float(radius+1.5))
 
 
