@@ -105,7 +105,8 @@ typedef struct {
 	int frontLag;        /* 1 + queue distance, in blocks, between the directions of a pass (0: default = distance 2) */
 	int frontCtas;       /* resident CTAs per SM (0: default) */
 	int frontDepth;      /* steps whose loads are in flight: 4 or 8 (0: default) */
-	int reserved[5];
+	int frontSubCell;    /* columns per sub-cell of the phase dependencies (0: default 128) */
+	int reserved[4];
 } b200mvs_debug;
 
 typedef struct {

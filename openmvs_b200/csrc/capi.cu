@@ -457,11 +457,12 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 	// the algorithmic 2.2 GB) but the warps then wait for each other: 5.6 ms against 2.6 ms at lag 2 (profiles/sgm_variants_r02e.txt)
 	const int lag = D.frontLag > 0 ? D.frontLag-1 : 2;
 	const int vw = P.vw, vh = P.vh;
-	const int key[6] = {vw, vh, layout, FB, lag, concurrent ? 2 : 1};
+	const int SW = D.frontSubCell >= 16 ? D.frontSubCell : FRONT_SW;
+	const int key[6] = {vw, vh, layout, FB, lag | (SW<<8), concurrent ? 2 : 1};
 	if (memcmp(key, ctx->sgFrontKey, sizeof(key)) != 0) {
 		for (auto& fp: ctx->sgFront) { fp.items.release(); fp.need.release(); }
 		ctx->sgFront.clear();
-		std::vector<FrontLaunch> plan = sgm_front_plan(vw, vh, layout, concurrent, FB, lag);
+		std::vector<FrontLaunch> plan = sgm_front_plan(vw, vh, layout, concurrent, FB, lag, SW);
 		ctx->sgFront.resize(plan.size());
 		for (size_t i = 0; i < plan.size(); ++i) {
 			b200mvs_ctx::FrontPass& fp = ctx->sgFront[i];

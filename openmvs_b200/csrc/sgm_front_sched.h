@@ -79,12 +79,12 @@ struct FrontPassDesc { int fa, fb; int nDirs; int dirs[4]; };
 // item of the previous phase that touches one of them is complete, and bumps the counters of its own when it is done.  With
 // dependencies this local the phases of a block can follow each other directly in the queue (lag 0): the slice of the sum
 // volume a block owns is read-modify-written by its four directions while it sits in the L2.
-constexpr int FRONT_SW = 128;
+constexpr int FRONT_SW = 128;   // default width; b200mvs_debug.frontSubCell overrides it
 
 // Work items of one pass in queue order; returns the number of front blocks, bands and sub-cell columns through nFB / maxBands /
 // nSX, and the number of items touching each sub-cell through cellCount (index (ph*nFB + fb)*nSX + sx).
 // lag: queue distance (in front blocks) between consecutive phases of the same block (0: the phases of a block are adjacent).
-inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc,
+inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int lag, int SW, std::vector<FrontItem>& items, int& nFB, int& maxBands, int& fc,
 	int& nSX, std::vector<int>& cellCount)
 {
 	// offset that makes the front coordinate non-negative
@@ -94,9 +94,10 @@ inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int
 	fc = -fmin;
 	nFB = (fmax-fmin)/FB + 1;
 	maxBands = (vw+vh+3)/4 + 1;
-	nSX = (vw+FRONT_SW-1)/FRONT_SW;
+	nSX = (vw+SW-1)/SW;
 	const bool phases = pd.nDirs > 1;      // a pass of one direction has no phase dependencies: no counters
 	items.clear();
+	std::vector<int> xkey;                // first column of every item: position along the front
 	cellCount.assign((size_t)pd.nDirs*nFB*nSX, 0);
 	for (int ph = 0; ph < pd.nDirs; ++ph) {
 		const int dir = pd.dirs[ph];
@@ -125,25 +126,34 @@ inline void sgm_front_build(int vw, int vh, const FrontPassDesc& pd, int FB, int
 					xlo = std::min(xlo, std::min(xa, xb)); xhi = std::max(xhi, std::max(xa, xb));
 				}
 				if (xhi < 0) continue;
-				const int sx0 = xlo/FRONT_SW, nsx = phases ? xhi/FRONT_SW-sx0+1 : 0;
+				const int sx0 = xlo/SW, nsx = phases ? xhi/SW-sx0+1 : 0;
 				FrontItem it;
 				it.k0 = band*4; it.dir = (short)dir; it.ph = (short)ph; it.fb = fb; it.seq = seq++;
 				it.chain = ph*maxBands + band;
 				it.cell = (ph*nFB + fb)*nSX + sx0;                                   // first own sub-cell
 				it.depCell = ph > 0 ? ((ph-1)*nFB + fb)*nSX + sx0 : -1;              // first sub-cell of the previous phase waited for
 				it.depNeed = (ph > 0 ? nsx : 0) | (nsx<<8);                           // number of sub-cells waited for | number of own sub-cells
-				items.push_back(it);
+				items.push_back(it); xkey.push_back(xlo);
 				for (int i = 0; i < nsx; ++i) ++cellCount[(size_t)it.cell+i];
 			}
 		}
 	}
-	// queue order: front blocks advance, phase ph runs `lag` blocks behind phase ph-1; every dependency is earlier in the queue
-	std::stable_sort(items.begin(), items.end(), [lag](const FrontItem& a, const FrontItem& b) {
+	// queue order: front blocks advance, phase ph runs `lag` blocks behind phase ph-1; every dependency is earlier in the queue.
+	// Within a (block, phase) the items run along the front in the same direction (ascending column) in every phase, so the
+	// sub-cells of the previous phase complete in the order in which their dependents are handed out.
+	std::vector<int> order(items.size());
+	for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+	std::stable_sort(order.begin(), order.end(), [&](int ia, int ib) {
+		const FrontItem& a = items[ia]; const FrontItem& b = items[ib];
 		const int ta = a.fb + lag*a.ph, tb = b.fb + lag*b.ph;
 		if (ta != tb) return ta < tb;
 		if (a.fb != b.fb) return a.fb < b.fb;
-		return a.ph < b.ph;
+		if (a.ph != b.ph) return a.ph < b.ph;
+		return xkey[ia] < xkey[ib];
 	});
+	std::vector<FrontItem> sorted(items.size());
+	for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
+	items.swap(sorted);
 }
 
 
@@ -154,16 +164,18 @@ struct FrontLaunch {
 	int nPasses; FrontPassDesc pass[2];
 	int fc[2], nFB[2], maxBands;
 	int nChains, nCells;           // sizes of progress[] / cellDone[]
+	int subCell;                   // width of a sub-cell in columns
 	std::vector<FrontItem> items;
 	std::vector<int> cellNeed;     // items touching each sub-cell (nCells entries)
 };
-inline void sgm_front_build_launch(int vw, int vh, const FrontPassDesc* pds, int nPasses, int FB, int lag, FrontLaunch& L) {
+inline void sgm_front_build_launch(int vw, int vh, const FrontPassDesc* pds, int nPasses, int FB, int lag, int SW, FrontLaunch& L) {
+	L.subCell = SW;
 	L.nPasses = nPasses; L.items.clear(); L.cellNeed.clear(); L.nChains = 0; L.nCells = 0; L.maxBands = 0;
 	std::vector<FrontItem> part[2];
 	for (int p = 0; p < nPasses; ++p) {
 		L.pass[p] = pds[p];
 		int nSX = 0; std::vector<int> cnt;
-		sgm_front_build(vw, vh, pds[p], FB, lag, part[p], L.nFB[p], L.maxBands, L.fc[p], nSX, cnt);
+		sgm_front_build(vw, vh, pds[p], FB, lag, SW, part[p], L.nFB[p], L.maxBands, L.fc[p], nSX, cnt);
 		for (FrontItem& it: part[p]) {
 			it.dir = (short)(it.dir | (p<<8));
 			it.chain += L.nChains; it.cell += L.nCells;
@@ -205,14 +217,14 @@ inline std::vector<FrontPassDesc> sgm_front_layout(int layout) {
 }
 // The launches of a layout: `concurrent` pairs consecutive passes (pass 2j into volume 0, pass 2j+1 into volume 1; the caller adds
 // the two volumes at the end), otherwise one pass per launch, all into volume 0.
-inline std::vector<FrontLaunch> sgm_front_plan(int vw, int vh, int layout, bool concurrent, int FB, int lag) {
+inline std::vector<FrontLaunch> sgm_front_plan(int vw, int vh, int layout, bool concurrent, int FB, int lag, int SW = FRONT_SW) {
 	const std::vector<FrontPassDesc> descs = sgm_front_layout(layout);
 	const int fbSize = layout == 2 ? (1<<28) : FB;   // one-direction passes need no blocks: one item per band walks the whole path
 	std::vector<FrontLaunch> out;
 	const size_t per = concurrent ? 2 : 1;
 	for (size_t i = 0; i < descs.size(); i += per) {
 		out.emplace_back();
-		sgm_front_build_launch(vw, vh, &descs[i], (int)std::min(per, descs.size()-i), fbSize, lag, out.back());
+		sgm_front_build_launch(vw, vh, &descs[i], (int)std::min(per, descs.size()-i), fbSize, lag, SW, out.back());
 	}
 	return out;
 }

@@ -36,7 +36,7 @@ class Debug(C.Structure):
 	"""b200mvs_debug"""
 	_fields_ = [("scalarTaps", C.c_int), ("noTMA", C.c_int), ("sgmAggregation", C.c_int), ("sgmCost", C.c_int),
 		("sweepFourCtas", C.c_int), ("frontLayout", C.c_int), ("frontSerial", C.c_int), ("frontBlock", C.c_int), ("frontLag", C.c_int),
-		("frontCtas", C.c_int), ("frontDepth", C.c_int), ("reserved", C.c_int*5)]
+		("frontCtas", C.c_int), ("frontDepth", C.c_int), ("frontSubCell", C.c_int), ("reserved", C.c_int*4)]
 
 
 class Stats(C.Structure):

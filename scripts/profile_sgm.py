@@ -35,6 +35,16 @@ if len(sys.argv) > 2 and sys.argv[2] == "lag1":
 	MODES = [("fronts FB 32 lag 1", dict(sgmAggregation=4, frontLag=2))]
 if len(sys.argv) > 2 and sys.argv[2] == "fb64":
 	MODES = [("fronts FB 64 lag 2", dict(sgmAggregation=4, frontBlock=64))]
+if len(sys.argv) > 2 and sys.argv[2] == "order":
+	MODES = MODES[:1]+[("fronts default (FB 32 lag 2)", dict())]
+	for fbk in (32, 64):
+		for lag in (0, 1, 2):
+			for sw in (128, 64):
+				for ctas in (2, 3):
+					MODES.append(("fronts FB %d lag %d subcell %d ctas %d" % (fbk, lag, sw, ctas), dict(sgmAggregation=4, frontBlock=fbk, frontLag=lag+1, frontSubCell=sw, frontCtas=ctas)))
+	MODES.append(("fronts FB 32 lag 1 subcell 32", dict(sgmAggregation=4, frontLag=2, frontSubCell=32)))
+	MODES.append(("fronts FB 32 lag 1 ctas 1", dict(sgmAggregation=4, frontLag=2, frontCtas=1)))
+	MODES.append(("fronts straight FB 32 lag 1", dict(sgmAggregation=4, frontLayout=2, frontLag=2)))
 if len(sys.argv) > 2 and sys.argv[2] == "tc":
 	MODES = MODES[-1:]
 for name, dbg in MODES:

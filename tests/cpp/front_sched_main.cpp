@@ -23,13 +23,13 @@ int main(int argc, char** argv) {
 	std::vector<uint8_t> costs(n);
 	if (fread(P2s.data(), 2, 256, f) != 256 || fread(gray.data(), 4, gray.size(), f) != gray.size() || fread(costs.data(), 1, n, f) != n) return 66;
 	fclose(f);
-	const bool concurrent = hdr[7] != 0;
+	const bool concurrent = (hdr[7] & 0xFF) != 0;   // bits 8..: sub-cell width (0: default)
 	std::vector<uint16_t> S[2] = {std::vector<uint16_t>(n, 0xABCD), std::vector<uint16_t>(n, 0xABCD)};   // garbage: phase 0 of a volume's first pass must store every entry
 	std::vector<uint32_t> touched(n/num*8, 0);
 	const int maxPaths = vw+vh+8;
 	std::vector<uint16_t> state((size_t)8*maxPaths*num);
 	std::vector<float> metaI((size_t)8*maxPaths); std::vector<int> metaH((size_t)8*maxPaths);
-	const std::vector<FrontLaunch> plan = sgm_front_plan(vw, vh, layout, concurrent, FB, lag);
+	const std::vector<FrontLaunch> plan = sgm_front_plan(vw, vh, layout, concurrent, FB, lag, (hdr[7]>>8) ? (hdr[7]>>8) : FRONT_SW);
 	const int fbSize = layout == 2 ? (1<<28) : FB;
 	long long itemsTotal = 0;
 	bool two = false;
@@ -86,7 +86,7 @@ int main(int argc, char** argv) {
 					touched[((size_t)y*vw+x)*8 + dir] += 1;
 					if (LA.pass[pass].nDirs > 1) {
 						// the counters this item bumps must include the sub-cell of every pixel it writes
-						const int nSX = (vw+FRONT_SW-1)/FRONT_SW, sx = x/FRONT_SW, first = it.cell % nSX;
+						const int nSX = (vw+LA.subCell-1)/LA.subCell, sx = x/LA.subCell, first = it.cell % nSX;
 						if (sx < first || sx >= first+nOwn) { printf("FAIL: pixel outside the item's sub-cells\n"); return 2; }
 					}
 					Ip = I; havePrev = true;

@@ -19,7 +19,7 @@ def exe(tmp_path_factory):
 	return out
 
 
-@pytest.mark.parametrize("layout,block,lag,concurrent", [(0, 64, 0, 1), (0, 32, 2, 1), (0, 8, 1, 1), (0, 5, 3, 0), (0, 7, 0, 0), (1, 16, 0, 1), (1, 3, 1, 0), (2, 32, 2, 1), (2, 32, 0, 0), (0, 32, 2, 0)])
+@pytest.mark.parametrize("layout,block,lag,concurrent", [(0, 32, 1, 1 | (48 << 8)), (0, 64, 0, 1), (0, 32, 2, 1), (0, 8, 1, 1), (0, 5, 3, 0), (0, 7, 0, 0), (1, 16, 0, 1), (1, 3, 1, 0), (2, 32, 2, 1), (2, 32, 0, 0), (0, 32, 2, 0)])
 def test_schedule_simulation_equals_oracle(exe, tmp_path, layout, block, lag, concurrent):
 	from oracle import oracle as O
 	from openmvs_b200 import synth
