@@ -102,10 +102,10 @@ typedef struct {
 	int frontSerial;     /* 1: one pass per launch into one sum volume (default: two passes share a launch, each with its own
 	                        volume, added by the winner-takes-all kernel) */
 	int frontBlock;      /* fronts per work item (0: default) */
-	int frontLag;        /* 1 + queue distance, in blocks, between the directions of a pass (0: default = distance 2) */
+	int frontLag;        /* 1 + queue distance, in blocks, between the directions of a pass (0: default = distance 1) */
 	int frontCtas;       /* resident CTAs per SM (0: default) */
 	int frontDepth;      /* steps whose loads are in flight: 4 or 8 (0: default) */
-	int frontSubCell;    /* columns per sub-cell of the phase dependencies (0: default 128) */
+	int frontSubCell;    /* columns per sub-cell of the phase dependencies (0: default 64; never fewer than width / 30) */
 	int reserved[4];
 } b200mvs_debug;
 

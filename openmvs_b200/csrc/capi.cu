@@ -452,12 +452,15 @@ int sgm_aggregate_fronts(b200mvs_ctx* ctx, const SGMParams& P, int num, cudaStre
 	const b200mvs_debug& D = ctx->dbg;
 	const int layout = std::min(std::max(D.frontLayout-1, 0), 2);
 	const bool concurrent = !D.frontSerial;
-	const int FB = D.frontBlock > 0 ? D.frontBlock : 32;   // measured: profiles/sgm_variants_r02e.txt (64: same time, a third more DRAM traffic)
-	// frontLag = lag + 1.  The sub-cell dependencies allow lag 0 (the phases of a block adjacent in the queue: DRAM traffic falls to
-	// the algorithmic 2.2 GB) but the warps then wait for each other: 5.6 ms against 2.6 ms at lag 2 (profiles/sgm_variants_r02e.txt)
-	const int lag = D.frontLag > 0 ? D.frontLag-1 : 2;
+	const int FB = D.frontBlock > 0 ? D.frontBlock : 32;   // measured: profiles/sgm_variants_r02f.txt (64: 4 % faster, a third more DRAM traffic at lag 2)
+	// frontLag = lag + 1.  The sub-cell dependencies make every lag legal; measured for 1914x1074x128 (profiles/sgm_variants_r02f.txt,
+	// profiles/front_traffic_*_r02.csv): lag 2: 2.6 ms with 6.4 GB of DRAM traffic (the window of blocks between a block's first and
+	// last phase exceeds the L2); lag 1: 2.9 ms with 2.0 GB — the algorithmic volume; lag 0: 2.2 GB but 5.1 ms (the resident warps all
+	// hold items of one block and wait for each other).  Default: lag 1.
+	const int lag = D.frontLag > 0 ? D.frontLag-1 : 1;
 	const int vw = P.vw, vh = P.vh;
-	const int SW = D.frontSubCell >= 16 ? D.frontSubCell : FRONT_SW;
+	// sub-cell width: one lane polls one counter, and a band at an image corner can span the whole width: at most 30 sub-cell columns
+	const int SW = std::max(D.frontSubCell >= 16 ? D.frontSubCell : FRONT_SW, (vw+29)/30);
 	const int key[6] = {vw, vh, layout, FB, lag | (SW<<8), concurrent ? 2 : 1};
 	if (memcmp(key, ctx->sgFrontKey, sizeof(key)) != 0) {
 		for (auto& fp: ctx->sgFront) { fp.items.release(); fp.need.release(); }

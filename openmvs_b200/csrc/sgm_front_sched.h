@@ -74,12 +74,12 @@ FRONT_HD inline int front_first_step(int lo, int f0, int df) {
 // ---- host side: schedule --------------------------------------------------------------------------------------------
 struct FrontPassDesc { int fa, fb; int nDirs; int dirs[4]; };
 
-// Phase dependencies are tracked per SUB-CELL: a front block cut into column ranges of FRONT_SW pixels.  An item touches the one
+// Phase dependencies are tracked per SUB-CELL: a front block cut into column ranges of SW (default FRONT_SW) pixels.  An item touches the one
 // to three sub-cells its pixels fall into (its paths are adjacent and its segment is at most a block long); it waits until every
 // item of the previous phase that touches one of them is complete, and bumps the counters of its own when it is done.  With
 // dependencies this local the phases of a block can follow each other directly in the queue (lag 0): the slice of the sum
 // volume a block owns is read-modify-written by its four directions while it sits in the L2.
-constexpr int FRONT_SW = 128;   // default width; b200mvs_debug.frontSubCell overrides it
+constexpr int FRONT_SW = 64;    // default width; b200mvs_debug.frontSubCell overrides it (the driver keeps at most 30 columns of sub-cells)
 
 // Work items of one pass in queue order; returns the number of front blocks, bands and sub-cell columns through nFB / maxBands /
 // nSX, and the number of items touching each sub-cell through cellCount (index (ph*nFB + fb)*nSX + sx).
