@@ -569,17 +569,20 @@ def run_scene_workload(args, dev, rank, world, local_rank, peak):
 	acc = []
 	for v in sampled:
 		gd = stack.maps(v)["depth"].cpu().numpy(); gt = scene.views[v].depth_gt; mm = gd > 0
-		acc.append((float(mm.mean()), float((np.abs(gd-gt)[mm]/gt[mm] < 1e-3).mean())))
+		# accuracy over the pixels whose true depth lies inside the search range [dmin, dmax) (oblique views of the large camera grid
+		# see parts of the surface beyond it; no estimator can return those depths)
+		inr = mm & (gt >= scene.dmin) & (gt < scene.dmax)
+		acc.append((float(mm.mean()), float((np.abs(gd-gt)[inr]/gt[inr] < 1e-3).mean()), float(inr.sum()/max(1, mm.sum()))))
 	if rank == 0:
 		cfg = {"workload": ("C5: %d views %dx%d, 8 neighbours, pass 1 (6 iters) + 1 geometric-consistency pass with the depth all-gather" if c5 else
 			"C4: %d views %dx%d, 9 neighbours, PatchMatch 6 iters, sharded per reference view") % (n_views, w, h),
 			"parallelism": "reference views round-robin over %d GPU(s), images replicated, NCCL gather of the maps to rank 0" % world,
-			"views_sampled_valid_and_within_1e-3_of_ground_truth": acc}
+			"views_sampled_valid__within_1e-3_of_ground_truth__fraction_with_true_depth_in_range": acc}
 		out = {"metric": "Mpix/sec depth+normal (%dx%d, %d neighbours%s)" % (w, h, n_neigh, ", incl. one geometric pass" if c5 else ""), "value": value, "unit": "Mpix/s",
 			"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
 			"vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches[0]),
 			"passes_per_view": passes}
-		if c5:
+		if c5 and world > 1:
 			cm = float(np.median(coll_ms)) if coll_ms else None
 			out["collective"] = {"name": "ncclAllGather of the depth-maps before the geometric pass", "ms": cm, "bytes": stack.bytes_all_gather(),
 				"GB_per_s": (stack.bytes_all_gather()/1e9/(cm/1e3)) if cm else None}
