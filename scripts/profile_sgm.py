@@ -31,6 +31,10 @@ MODES += [("fronts tilted paired FB 16 lag 0", dict(sgmAggregation=4, frontBlock
 MODES.append(("SIMT cost kernel + wave fronts", dict(sgmCost=1)))
 if len(sys.argv) > 2 and sys.argv[2] == "default":
 	MODES = MODES[2:3]
+if len(sys.argv) > 2 and sys.argv[2] == "lag0":
+	MODES = [("fronts FB 32 lag 0", dict(sgmAggregation=4, frontLag=1))]
+if len(sys.argv) > 2 and sys.argv[2] == "lag2":
+	MODES = [("fronts FB 32 lag 2", dict(sgmAggregation=4, frontLag=3))]
 if len(sys.argv) > 2 and sys.argv[2] == "lag1":
 	MODES = [("fronts FB 32 lag 1", dict(sgmAggregation=4, frontLag=2))]
 if len(sys.argv) > 2 and sys.argv[2] == "fb64":
