@@ -275,6 +275,27 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 		// ---- the 16 worker warps: operands, then sums -> costs ----
 		unsigned phase[2] = {0u, 0u};
 		const int wq = warp&3;                       // tap quarter of this warp (operand builders)
+		// The staged pixels of a block's first tile pair are loaded into registers while the block before it is in its epilogue:
+		// thread t owns elements t and t + 512 of the 7 x 134 window (left colour packed to a word, left gray, right gray).
+		struct Pre { uint32_t c[2]; float lg[2], rg[2]; } pre;
+		auto prefetch = [&](int rr, int bb) {
+			const int xx0 = BM*bb, tt0 = bb == 0 ? 0 : 2*bb+nTiles-2;
+			#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				const int i = tid + k*TC_WORKERS;
+				pre.c[k] = 0u; pre.lg[k] = 0.f; pre.rg[k] = 0.f;
+				if (i < 7*(BM+6)) {
+					const int ry = i/(BM+6), cx = i-ry*(BM+6);
+					const int col = min(xx0+cx, w-1);
+					const uchar3 c3 = P.lbgr[(size_t)(rr+ry)*w + col];
+					pre.c[k] = (uint32_t)c3.x | ((uint32_t)c3.y<<8) | ((uint32_t)c3.z<<16);
+					pre.lg[k] = __ldg(P.lgray + (size_t)(rr+ry)*w + col);
+					const int rc = min(max(BN*tt0 + cx + dmin, 0), w-1);
+					pre.rg[k] = __ldg(P.rgray + (size_t)(rr+ry)*w + rc);
+				}
+			}
+		};
+		if ((int)blockIdx.x < vh) prefetch((int)blockIdx.x, 0);
 		#pragma unroll 1
 		for (int r = blockIdx.x; r < vh; r += gridDim.x) {
 			#pragma unroll 1
@@ -283,18 +304,26 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 				// B tiles not yet in the ring: the last two of the block (all of them for the first block of a row), two at a time
 				for (int t0 = (b == 0 ? 0 : 2*b+nTiles-2); t0 < 2*b+nTiles; t0 += 2) {
 					if (t0 != (b == 0 ? 0 : 2*b+nTiles-2)) bar_sync(BAR_WORKERS, TC_WORKERS);   // the stage is read by the previous pair
-					// stage the image rows r .. r+6: left colour / gray columns x0 .. x0+133 (first pair only), right gray columns of the pair
+					// stage the image rows r .. r+6: left colour / gray columns x0 .. x0+133 (first pair only), right gray columns of the pair.
+					// The first pair of a block comes out of registers: its global loads were issued a block earlier (see below).
 					const bool first = t0 == (b == 0 ? 0 : 2*b+nTiles-2);
-					for (int i = tid; i < 7*(BM+6); i += TC_WORKERS) {
-						const int ry = i/(BM+6), cx = i-ry*(BM+6);
-						if (first) {
-							const int col = min(x0+cx, w-1);
-							const uchar3 c3 = P.lbgr[(size_t)(r+ry)*w + col];
-							((uint32_t*)(sTile+ST_LC))[ry*SP+cx] = (uint32_t)c3.x | ((uint32_t)c3.y<<8) | ((uint32_t)c3.z<<16);
-							((float*)(sTile+ST_LG))[ry*SP+cx] = __ldg(P.lgray + (size_t)(r+ry)*w + col);
+					if (first) {
+						#pragma unroll
+						for (int k = 0; k < 2; ++k) {
+							const int i = tid + k*TC_WORKERS;
+							if (i < 7*(BM+6)) {
+								const int ry = i/(BM+6), cx = i-ry*(BM+6);
+								((uint32_t*)(sTile+ST_LC))[ry*SP+cx] = pre.c[k];
+								((float*)(sTile+ST_LG))[ry*SP+cx] = pre.lg[k];
+								((float*)(sTile+ST_RG))[ry*SP+cx] = pre.rg[k];
+							}
 						}
-						const int rc = min(max(BN*t0 + cx + dmin, 0), w-1);
-						((float*)(sTile+ST_RG))[ry*SP+cx] = __ldg(P.rgray + (size_t)(r+ry)*w + rc);
+					} else {
+						for (int i = tid; i < 7*(BM+6); i += TC_WORKERS) {
+							const int ry = i/(BM+6), cx = i-ry*(BM+6);
+							const int rc = min(max(BN*t0 + cx + dmin, 0), w-1);
+							((float*)(sTile+ST_RG))[ry*SP+cx] = __ldg(P.rgray + (size_t)(r+ry)*w + rc);
+						}
 					}
 					bar_sync(BAR_WORKERS, TC_WORKERS);
 					if (first) {
@@ -323,6 +352,9 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
 				bar_sync(BAR_WORKERS, TC_WORKERS);     // every worker is done with the stage (the cost tile is written next)
 				bar_arrive(BAR_OPS, TC_THREADS);
+				// the next block's window: requested now, consumed after this block's epilogue
+				if (b+1 < nBlocks) prefetch(r, b+1);
+				else if (r+(int)gridDim.x < vh) prefetch(r+(int)gridDim.x, 0);
 				// sums -> costs, tile by tile, into the shared cost tile
 				const int row0 = 32*(warp&3), row = row0 + lane;   // TMEM lane = pixel of the block
 				const int c0 = 16*(warp>>2);                        // this warp's 16 of the 64 columns
