@@ -94,7 +94,7 @@ typedef struct {
 	int noTMA;           /* 1: the sweep kernel reads the reference patch with plain loads instead of the TMA-staged tile */
 	int sgmAggregation;  /* 0 auto; 1 general ragged kernel; 2 register-pipelined uniform kernel; 3 bulk-copy ring kernel (one launch
 	                        per direction); 4 front kernel (fused directions, auto default for uniform ranges) */
-	int sgmCost;         /* 0 auto (tensor-core kernel for dense volumes with one range of 64 / 128 disparities, SIMT otherwise);
+	int sgmCost;         /* 0 auto (tensor-core kernel for dense volumes with one range of 64 / 128 / 192 / 256 disparities, SIMT otherwise);
 	                        1 SIMT cost kernel; 2 tensor-core (tcgen05) cost kernel or an error */
 	int sweepFourCtas;   /* 1: the 64-register instantiation of the sweep kernel (4 CTAs per SM instead of 3) */
 	int frontLayout;     /* wave-front aggregation: 0 auto; 1 two tilted fronts +-(x+2y), four directions each; 2 four straight

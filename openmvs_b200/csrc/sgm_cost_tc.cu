@@ -203,9 +203,11 @@ __device__ __forceinline__ void build_b_quarter(unsigned char* slot, const unsig
 	}
 }
 
-// Dense volumes only (every pixel valid with the range [dmin, dmin+num), idx = pixel index x num); num in {64, 128}.
+// Dense volumes only (every pixel valid with one range, idx = pixel index x numAll).  One launch computes the disparities
+// [dmin, dmin+num), num in {64, 128}, and stores them at offset dOff of every pixel's numAll-wide slice: wider ranges (192, 256)
+// are covered by two launches.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
+sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num, int numAll, int dOff)
 {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	unsigned char* sA = smem;
@@ -402,7 +404,7 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 					if (pcol < vw) {
 						const uint32_t* src = (const uint32_t*)(sTile + prow*TILE_PITCH + 16*c16);
 						const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
-						*(uint4*)(P.costs + ((size_t)r*vw + pcol)*(size_t)num + 16*c16) = v;
+						*(uint4*)(P.costs + ((size_t)r*vw + pcol)*(size_t)numAll + dOff + 16*c16) = v;
 					}
 				}
 				bar_sync(BAR_WORKERS, TC_WORKERS);                  // the tile is free: the next block stages into it
@@ -420,11 +422,13 @@ sgm_cost_tc_kernel(const __grid_constant__ SGMParams P, int dmin, int num)
 cudaError_t sgm_cost_tc_configure() {
 	return cudaFuncSetAttribute(sgm_cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
 }
-bool sgm_cost_tc_supports(int num) { return num == 64 || num == 128; }
+bool sgm_cost_tc_supports(int num) { return num == 64 || num == 128 || num == 192 || num == 256; }
 cudaError_t sgm_cost_tc_launch(const SGMParams& P, int dmin, int num, cudaStream_t s) {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	sgm_cost_tc_kernel<<<sms, TC_THREADS, SMEM_TOTAL, s>>>(P, dmin, num);
+	// slices of at most 128 disparities (the ring holds the four B tiles a block of 128 pixels x 128 disparities needs)
+	for (int off = 0; off < num; off += 128)
+		sgm_cost_tc_kernel<<<sms, TC_THREADS, SMEM_TOTAL, s>>>(P, dmin+off, num-off >= 128 ? 128 : num-off, num, off);
 	return cudaGetLastError();
 }

@@ -19,6 +19,3 @@ timeout 200 python scripts/profile_sgm.py 256 default 2>&1 | tail -1 | tee -a gp
 echo "== ncu --set full: wave-front kernel (shipped defaults)"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sgm_front_kernel -s 1 -c 1 -o gpurun_out/sgm_front -f python scripts/profile_sgm.py 128 default > gpurun_out/ncu_front.log 2>&1
 timeout 60 python scripts/ncu_summary.py gpurun_out/sgm_front.ncu-rep 0 > gpurun_out/ncu_sgm_front.txt 2>&1; head -8 gpurun_out/ncu_sgm_front.txt
-echo "== C4 / C5 on one GPU (strong-scaling reference of profiles/scale_r02_c4_n8.json / c5_n8.json)"
-timeout 900 python bench.py --workload c4 --steps 2 --warmup 3 2> gpurun_out/c4_n1.err | tail -1 > gpurun_out/scale_c4_n1.json; cut -c1-400 gpurun_out/scale_c4_n1.json
-timeout 900 python bench.py --workload c5 --steps 2 --warmup 3 2> gpurun_out/c5_n1.err | tail -1 > gpurun_out/scale_c5_n1.json; cut -c1-400 gpurun_out/scale_c5_n1.json

@@ -43,7 +43,7 @@ def test_cost_volume_parity(sgm):
 	assert np.array_equal(g == 255, c == 255) or ((g == 255) != (c == 255)).mean() < 1e-4
 
 
-@pytest.mark.parametrize("num,dmin,w", [(128, 0, 403), (128, -40, 300), (64, 5, 261), (64, -70, 200)])
+@pytest.mark.parametrize("num,dmin,w", [(128, 0, 403), (128, -40, 300), (64, 5, 261), (64, -70, 200), (256, -100, 330), (192, 3, 290)])
 def test_cost_volume_on_tensor_cores(sgm, num, dmin, w):
 	"""The banded-GEMM cost kernel (tcgen05, fp16 hi/lo split operands, fp32 accumulation in TMEM; sgm_cost_tc.cu) against the
 	oracle and against the SIMT kernel: within one uint8 level on a small fraction of the entries, out-of-image windows exact."""
