@@ -248,6 +248,9 @@ def test_pair_pipeline_matches_oracle_and_ground_truth(sgm):
 	lg, lc, rg, d, rc = synth.make_stereo_pair(w, h, right_color=True)
 	# left(x) = right(x + d): the left->right disparity is +d, the right->left one about -d
 	ld, rd = m.MatchPairDevice(_dev(lg), _dev(lc), _dev(rg), _dev(rc), -32, 0)
+	# default: the two matches on two contexts / streams; one after the other on one context gives the same integers
+	ld1, rd1 = m.MatchPairDevice(_dev(lg), _dev(lc), _dev(rg), _dev(rc), -32, 0, overlap=False)
+	assert torch.equal(ld, ld1) and torch.equal(rd, rd1)
 	ld, rd = ld.cpu().numpy(), rd.cpu().numpy()
 	pxr, n = synth.sgm_pixel_map(w, h, -32, 0)
 	cr, ar, odr, _ = O.sgm_match(rg, rc, lg, pxr, n)
