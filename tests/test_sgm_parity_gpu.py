@@ -206,6 +206,24 @@ def test_wave_front_aggregation_bit_exact(sgm, num, layout, block, lag, serial):
 	assert np.array_equal(gd.cpu().numpy(), disp) and np.array_equal(gc.cpu().numpy().view(np.uint16), cost)
 
 
+def test_wide_image_tensor_core_cost_and_wave_fronts(sgm):
+	"""A 4100-pixel-wide strip (wider than C5's 4032): 32 pixel blocks per row in the tensor-core cost kernel, sub-cell columns of
+	the wave-front dependencies clamped to 30 (137 pixels each), bands at the image corners that span every sub-cell column."""
+	m, O = sgm
+	w, h, num = 4100, 61, 64
+	lg, lc, rg, d = synth.make_stereo_pair(w, h, d0=20.0, amp=8.0)
+	px, n = synth.sgm_pixel_map(w, h, 0, num)
+	c, a, disp, cost = O.sgm_match(lg, lc, rg, px, n)
+	costs = torch.zeros(n, dtype=torch.uint8, device="cuda"); accums = torch.full((n,), -1, dtype=torch.int16, device="cuda")
+	m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=1, costs=costs)
+	diff = np.abs(costs.cpu().numpy().astype(np.int32)-c.astype(np.int32))
+	assert diff.max() <= 1 and (diff > 0).mean() < 5e-3
+	# aggregation + WTA on the ORACLE's cost volume: bit-exact
+	gd, gc = m.MatchDevice(_dev(lg), _dev(lc), _dev(rg), _px_dev(px), n, stages=6, costs=_dev(c), accums=accums)
+	assert np.array_equal(accums.cpu().numpy().view(np.uint16), a)
+	assert np.array_equal(gd.cpu().numpy(), disp)
+
+
 def test_wave_front_aggregation_larger_image_and_variants_agree(sgm):
 	"""403 x 251, D = 128: default (wave fronts) == bulk-copy ring kernel == register-pipelined kernel == general kernel == oracle"""
 	m, O = sgm
