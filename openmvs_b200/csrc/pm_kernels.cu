@@ -486,7 +486,7 @@ pm_score_kernel(const __grid_constant__ PMParams P)
 //   3. the refinement state machine (DepthMap.cpp:800-852).
 // Every lane keeps its own to-do list of directions, so a warp runs max-over-lanes(list length) test steps.
 // MINB: resident CTAs per SM the register allocation aims at: 3 (80 registers, the default) or 4 (64 registers: one more CTA of
-// latency hiding against more spill traffic — b200mvs_debug.reserved[3], measured in profiles/)
+// latency hiding against more spill traffic — b200mvs_debug.sweepFourCtas, measured in profiles/pm_4ctas_r02.txt: slower)
 template <bool PACK, bool GEOM, int MINB>
 __global__ void __launch_bounds__(BLOCK_X*BLOCK_Y, MINB)
 pm_sweep_kernel(const __grid_constant__ PMParams P, const __grid_constant__ CUtensorMap tmapRef)

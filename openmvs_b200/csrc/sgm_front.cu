@@ -12,15 +12,20 @@
 //     fixed cost (penalty lookup, neighbour shuffles, minimum reduction, loop) is shared by 4 pixels: about 25 warp
 //     instructions per pixel and direction;
 //   * directions whose step moves a tilted wave front f = x + 2y forward (right, right-down, down, left-down — and their
-//     mirror images in a second pass) are processed TOGETHER, front block by front block: a work item is (direction,
+//     mirror images in the other pass) are processed TOGETHER, front block by front block: a work item is (direction,
 //     band of 4 adjacent paths, block of FB consecutive fronts); items are handed out from one queue in front order, so all
-//     four directions touch a block's slice of the sum volume while it is resident in the 126 MB L2 — the volume
-//     crosses HBM once per pass instead of once per direction (2 passes: 2 x 263 MB of costs + 526 MB written + 526 MB
-//     read-modify-written for 1914 x 1074 x 128, instead of 8 x 1.3 GB);
-//   * ordering instead of atomics: within a block the directions are phases; an item waits (rarely — its predecessors are
-//     thousands of queue positions ahead) until the previous phase of its block is complete and until its own paths'
+//     four directions touch a block's slice of the sum volume while it is resident in the 126 MB L2 (2 x 263 MB of costs
+//     read, 2 x 526 MB of sums written, the other phases' read-modify-writes in the L2, for 1914 x 1074 x 128; measured
+//     2.0 GB of DRAM traffic instead of 8 x 1.3 GB);
+//   * the two passes share ONE launch and one queue, each accumulating into its own sum volume (the winner-takes-all kernel
+//     adds them): two independent chains of dependencies keep the warps busy;
+//   * ordering instead of atomics: within a block the directions are phases; an item waits until the items of the previous
+//     phase that touch its sub-cells (column ranges of the block, sgm_front_sched.h) are complete and until its own paths'
 //     previous segment has been stored (path state: the normalised previous line, 256 B per path, kept in a small L2-resident
-//     buffer between the segments).  Phase 0 of the first pass stores the sum, so the volume needs no memset.
+//     buffer between the segments).  Phase 0 stores the sum, so the volumes need no memset;
+//   * the inputs of a step reach the warp through a ring in shared memory filled by cp.async (no destination registers:
+//     the prefetch distance does not depend on the register allocator), and the whole step is branch-free, so that the warp
+//     never splits (a split warp runs every shuffle through a collective re-synchronisation).
 // Bit-exact against the oracle (tests/test_sgm_parity_gpu.py); the per-direction kernels of sgm_kernels.cu remain for
 // ragged (tSGM) ranges and as debug variants (b200mvs_debug.sgmAggregation).
 #include <cuda_runtime.h>
