@@ -247,8 +247,12 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 			} else {
 				// general (ragged) path: min of the previous line over the intersection
 				unsigned m = 0xFFFFu;
-				for (int d = imin+lane; d < imax; d += 32)
-					m = min(m, (unsigned)Lp[d-pmin]);
+				// the intersection is at most as wide as the current range (<= 32*NPL): NPL predicated reads, no loop control
+				#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int d = imin+lane+32*j;
+					if (d < imax) m = min(m, (unsigned)Lp[d-pmin]);
+				}
 				m = __reduce_min_sync(0xFFFFFFFFu, m); // redux.sync: one instruction instead of a 5-shuffle chain
 				const int minLp = (int)m;
 				#pragma unroll
