@@ -216,6 +216,23 @@ def sgm_block(dev, peak, threads):
 	m.Match(lg, lc, rg, px, n)   # warm-up: the host path's staging buffers are allocated on first use
 	t0 = time.perf_counter(); m.Match(lg, lc, rg, px, n); m.Match(lg, lc, rg, px, n); fixed["ms_host_api"] = (time.perf_counter()-t0)*500
 	out["fixed_range_D128"] = fixed
+	# the unit the reference works in: a PAIR (right->left match, left->right match with mirrored ranges, cross-check, sub-pixel
+	# refinement; SemiGlobalMatcher.cpp:643-725), the two matches on two contexts / streams
+	try:
+		lg2, lc2, rg2, d2, rc2 = synth.make_stereo_pair(w, h, d0=40.0, amp=25.0, right_color=True)
+		RC = todev(rc2)
+		ms = []
+		for rep in range(5):
+			e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			torch.cuda.synchronize(dev); e0.record()
+			ld, rd = m.MatchPairDevice(L, C3, R, RC, -D, 0)
+			e1.record(); torch.cuda.synchronize(dev)
+			if rep >= 2:
+				ms.append(e0.elapsed_time(e1))
+		out["pair_D128"] = {"ms_pair": float(np.median(ms)), "gpxd_per_s": 2*n/float(np.median(ms))/1e6,
+			"left_within_1px_of_ground_truth": float((np.abs(ld.cpu().numpy()/4.0-gt)[8:-8, 8:-140] <= 1).mean())}
+	except Exception as e:
+		out["pair_D128"] = {"error": repr(e)}
 	# tSGM-like ragged ranges around the true disparity (per-pixel [dmin, dmax), 10..48 wide), 3 % invalid pixels
 	rng = np.random.RandomState(3)
 	base = np.rint(gt).astype(np.int16)
