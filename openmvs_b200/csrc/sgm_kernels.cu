@@ -164,7 +164,10 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 	int pmin = 0, pmax = 0;     // previous range (empty at the start of a scanline)
 	unsigned minPrev = 0xFFFFu; // minimum of the previous line over its whole range
 	float Ip = 0.5f;
-	auto inside = [&](int xx, int yy) { return xx >= 0 && yy >= 0 && xx < P.vw && yy < P.vh; };
+	// pixels of the scanline: the steps until x or y leaves the valid region (one comparison per step instead of four)
+	int len = 0x7FFFFFFF;
+	if (dx > 0) len = min(len, P.vw-x); else if (dx < 0) len = min(len, x+1);
+	if (dy > 0) len = min(len, P.vh-y); else if (dy < 0) len = min(len, y+1);
 	SGMPixel none; none.idx = 0; none.dmin = 0; none.dmax = 0; none.pad = 0;
 	// pipeline registers: pr[i] / Ir[i] = record and intensity of pixel t+i (i <= PD),
 	// c[i] / a[i] = its costs and accumulators (i < PD)
@@ -174,7 +177,7 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 	for (int i = 0; i <= PD; ++i) {
 		pr[i] = none; Ir[i] = 0.f;
 		const int xx = x+i*dx, yy = y+i*dy;
-		if (inside(xx, yy)) { pr[i] = P.px[(size_t)yy*P.vw + xx]; Ir[i] = __ldg(P.lgray + (size_t)yy*P.w + xx); }
+		if (i < len) { pr[i] = P.px[(size_t)yy*P.vw + xx]; Ir[i] = __ldg(P.lgray + (size_t)yy*P.w + xx); }
 	}
 	#pragma unroll
 	for (int i = 0; i < PD; ++i) {
@@ -185,12 +188,12 @@ sgm_aggregate_kernel(const __grid_constant__ SGMParams P, int dir)
 			c[i][j] = v ? P.costs[pr[i].idx+kk] : 0; a[i][j] = (ADD && v) ? P.accums[pr[i].idx+kk] : 0;
 		}
 	}
-	for (; inside(x, y); x += dx, y += dy) {
+	for (int t = 0; t < len; ++t, x += dx, y += dy) {
 		// stage A: pixel record PD+1 steps ahead
 		SGMPixel pnew = none; float Inew = 0.f;
 		{
 			const int xx = x+(PD+1)*dx, yy = y+(PD+1)*dy;
-			if (inside(xx, yy)) { pnew = P.px[(size_t)yy*P.vw + xx]; Inew = __ldg(P.lgray + (size_t)yy*P.w + xx); }
+			if (t+PD+1 < len) { pnew = P.px[(size_t)yy*P.vw + xx]; Inew = __ldg(P.lgray + (size_t)yy*P.w + xx); }
 		}
 		// stage B: costs and accumulators PD steps ahead
 		uint8_t cn[NPL]; uint16_t an[NPL];
